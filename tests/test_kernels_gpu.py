@@ -1,0 +1,173 @@
+"""-m gpu: every CUDA kernel, called through the C ABI, against an fp32 torch restatement of the same op.
+
+Tolerances (written per test): outputs are stored in fp16 (rel. rounding 4.9e-4) and MMA operands are fp16, so the
+reference uses fp16-rounded operands with fp32 accumulation; the bound covers fp16 output rounding plus rare
+1-ulp operand flips caused by the fast GELU (2.5e-5 abs error) in the prologue.
+"""
+import ctypes as C
+
+import pytest
+import torch
+
+import gpu_utils as G
+from wav2sleep_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-6)).item()
+
+
+def test_pack_conv_weight_layout(cuda_device):
+    w = torch.randn(32, 16, 3, device=cuda_device)
+    p = G.pack_conv(w).view(3, 2, 32, 8)  # [tap][cin/8][cout][8]
+    torch.cuda.synchronize()
+    ref = w.permute(2, 1, 0).reshape(3, 2, 8, 32).permute(0, 1, 3, 2).half()
+    assert torch.equal(p, ref)
+    # Linear(4C -> F) viewed as taps=4 (input index = tap*C + c)
+    wl = torch.randn(128, 4 * 64, device=cuda_device)
+    pl = G.pack_conv(wl, taps_major=1, taps=4).view(4, 8, 128, 8)
+    ref = wl.view(128, 4, 8, 8).permute(1, 2, 0, 3).half()
+    assert torch.equal(pl, ref)
+
+
+@pytest.mark.parametrize("B,T", [(2, 4096), (3, 1024 + 256), (1, 2048)])
+def test_first_conv(cuda_device, B, T):
+    """first_conv_kernel vs conv1d(k3,pad1) + 1x1 stride-2 branch + sums + -inf row detection."""
+    from wav2sleep_b200 import build_default
+    torch.manual_seed(1)
+    model = build_default({"ABD": "ABD"}, 4, seed=3).to(cuda_device).eval()
+    enc = model.signal_encoders.encoders["ABD"]
+    x = torch.randn(B, T, device=cuda_device)
+    if B > 1:
+        x[1] = float("-inf")
+    # run the whole encoder in keep mode and look at block 0's first tensors in the workspace
+    from wav2sleep_b200.engine import _PackedEncoder
+    lib = _lib.load()
+    pe = _PackedEncoder(lib, enc, cuda_device)
+    ws_bytes = lib.w2s_encoder_workspace_bytes(C.byref(pe.desc), B, T, 1)
+    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=cuda_device)
+    z = torch.zeros(B, T // 256, 128, dtype=torch.float16, device=cuda_device)
+    mask = torch.zeros(B, dtype=torch.uint8, device=cuda_device)
+    _lib.check(lib.w2s_encoder_fwd(C.byref(pe.desc), x.data_ptr(), B, T, ws.data_ptr(), ws_bytes, 1, z.data_ptr(),
+                                   mask.data_ptr(), G.stream()))
+    torch.cuda.synchronize()
+    assert mask.tolist() == [0] + ([1] if B > 1 else []) + [0] * max(0, B - 2)
+    n_stats = sum(3 * B * c * 2 for c in enc.channels)
+    stats_bytes = (n_stats * 4 + 255) // 256 * 256
+    y1 = ws[stats_bytes: stats_bytes + B * T * 16 * 2].view(torch.float16).view(B, T, 16)
+    off_r = stats_bytes + (B * T * 16 * 2 + 255) // 256 * 256
+    r0 = ws[off_r: off_r + B * (T // 2) * 16 * 2].view(torch.float16).view(B, T // 2, 16)
+    s1 = ws[: B * 16 * 2 * 4].view(torch.float32).view(B, 16, 2)
+    w1 = enc.cnn[0].conv1.conv.weight
+    wd = enc.cnn[0].downsample.weight
+    live = [b for b in range(B) if not (B > 1 and b == 1)]
+    xr = x[live]
+    ref = torch.nn.functional.conv1d(xr[:, None], w1, padding=1).transpose(1, 2)
+    refr = torch.nn.functional.conv1d(xr[:, None], wd, stride=2).transpose(1, 2)
+    assert (y1[live].float() - ref).abs().max().item() < 2e-3 * ref.abs().max().item()  # fp16 storage
+    assert (r0[live].float() - refr).abs().max().item() < 2e-3 * refr.abs().max().item()
+    assert torch.allclose(s1[live][..., 0], ref.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(s1[live][..., 1], (ref * ref).sum(1), rtol=1e-4, atol=1e-2)
+
+
+ENC_CASES = [
+    # cin, cout, stride, has_ds, L
+    (16, 16, 1, 0, 2500), (32, 32, 1, 0, 1100), (64, 64, 1, 0, 700), (128, 128, 1, 0, 300),
+    (16, 16, 2, 0, 4096), (32, 32, 2, 0, 1030), (64, 64, 2, 0, 512), (128, 128, 2, 0, 258),
+    (16, 16, 1, 1, 2048), (16, 32, 1, 1, 1000), (32, 32, 1, 1, 600), (32, 64, 1, 1, 512),
+    (64, 64, 1, 1, 256), (64, 128, 1, 1, 384), (128, 128, 1, 1, 130),
+]
+
+
+@pytest.mark.parametrize("cin,cout,stride,has_ds,L", ENC_CASES)
+def test_encoder_conv_layer(cuda_device, cin, cout, stride, has_ds, L):
+    """conv_igemm_kernel, EPI_STATS: prologue norm+GELU(+res), k3 conv (tcgen05), fp16 store, sums, fused 1x1."""
+    torch.manual_seed(cin * 1000 + cout + stride)
+    B = 2
+    dev = cuda_device
+    y = (torch.randn(B, L, cin, device=dev) * 1.5 + 0.3).half()
+    r = torch.randn(B, L, cin, device=dev).half() if has_ds else None
+    w = torch.randn(cout, cin, 3, device=dev) / (3 * cin) ** 0.5
+    wd = torch.randn(cout, cin, 1, device=dev) / cin ** 0.5 if has_ds else None
+    L_out = (L + 2 - 3) // stride + 1
+    out = torch.full((B, L_out, cout), float("nan"), dtype=torch.float16, device=dev)
+    out_ds = torch.full((B, L_out // 2, cout), float("nan"), dtype=torch.float16, device=dev) if has_ds else None
+    stats = torch.zeros(B, cout, 2, device=dev)
+    G.run_conv(cin=cin, cout=cout, taps=3, stride=stride, dilation=1, pad=1,
+               prologue=_lib.PRO_NORM_RES if has_ds else _lib.PRO_NORM, epilogue=_lib.EPI_STATS, has_ds=has_ds,
+               B=B, L_in=L, L_out=L_out, **{"in": y}, in_res=r, in_stats=G.sums(y), w=G.pack_conv(w),
+               w_ds=G.pack_conv(wd) if has_ds else None, out=out, out_ds=out_ds, out_stats=stats, in_eps=1e-2)
+    a = G.prologue_ref(y, r)
+    ref = G.conv_ref(a, w, stride=stride)
+    assert ref.shape == out.shape
+    assert not torch.isnan(out.float()).any()
+    assert rel_err(out, ref) < 4e-3
+    assert torch.allclose(stats[..., 0], ref.sum(1), rtol=2e-3, atol=0.05 * L ** 0.5)
+    assert torch.allclose(stats[..., 1], (ref * ref).sum(1), rtol=2e-3, atol=1e-2)
+    if has_ds:
+        refd = G.conv_ref(a, wd, stride=2, pad=0)
+        assert refd.shape == out_ds.shape
+        assert rel_err(out_ds, refd) < 4e-3
+
+
+def test_encoder_conv_row_mask_skips_sample(cuda_device):
+    dev = cuda_device
+    B, L, c = 3, 1024, 16
+    y = torch.randn(B, L, c, device=dev).half()
+    w = torch.randn(c, c, 3, device=dev) / 7
+    out = torch.zeros(B, L, c, dtype=torch.float16, device=dev)
+    stats = torch.zeros(B, c, 2, device=dev)
+    mask = torch.tensor([0, 1, 0], dtype=torch.uint8, device=dev)
+    G.run_conv(cin=c, cout=c, taps=3, stride=1, dilation=1, pad=1, prologue=_lib.PRO_NORM, epilogue=_lib.EPI_STATS,
+               has_ds=0, B=B, L_in=L, L_out=L, **{"in": y}, in_stats=G.sums(y), w=G.pack_conv(w), out=out,
+               out_stats=stats, row_mask=mask, in_eps=1e-2)
+    assert out[1].abs().max().item() == 0 and stats[1].abs().max().item() == 0
+    assert out[0].abs().max().item() > 0 and out[2].abs().max().item() > 0
+
+
+@pytest.mark.parametrize("cin,S", [(64, 37), (128, 130), (128, 16)])
+def test_encoder_linear(cuda_device, cin, S):
+    """Linear(4C -> 128) + bias + GELU as a 4-tap stride-4 conv (reference models/wav2sleep.py:261-265)."""
+    torch.manual_seed(cin + S)
+    dev, B, L = cuda_device, 2, 4 * S
+    y = torch.randn(B, L, cin, device=dev).half()
+    r = torch.randn(B, L, cin, device=dev).half()
+    w = torch.randn(128, 4 * cin, device=dev) / (4 * cin) ** 0.5
+    bias = torch.randn(128, device=dev)
+    out = torch.full((B, S, 128), float("nan"), dtype=torch.float16, device=dev)
+    G.run_conv(cin=cin, cout=128, taps=4, stride=4, dilation=1, pad=0, prologue=_lib.PRO_NORM_RES,
+               epilogue=_lib.EPI_BIAS_GELU, has_ds=0, B=B, L_in=L, L_out=S, **{"in": y}, in_res=r,
+               in_stats=G.sums(y), w=G.pack_conv(w, taps_major=1, taps=4), bias=bias, out=out, in_eps=1e-2)
+    a = G.prologue_ref(y, r).half().float().reshape(B, S, 4 * cin)
+    ref = G.gelu(a @ w.half().float().t() + bias)
+    assert rel_err(out, ref) < 4e-3
+
+
+@pytest.mark.parametrize("dil,S,res", [(1, 200, 0), (4, 130, 0), (32, 300, 0), (32, 1200, 1), (2, 50, 1)])
+def test_seq_conv_layer(cuda_device, dil, S, res):
+    """Dilated k7 conv + ConvLayerNorm + GELU (+ residual + GELU + classifier head)."""
+    torch.manual_seed(dil + S)
+    dev, B = cuda_device, 2
+    x = torch.randn(B, S, 128, device=dev).half()
+    w = torch.randn(128, 128, 7, device=dev) / (7 * 128) ** 0.5
+    g, b = torch.randn(128, device=dev) * 0.2 + 1, torch.randn(128, device=dev) * 0.1
+    xin = torch.randn(B, S, 128, device=dev).half() if res else None
+    hw, hb = torch.randn(5, 128, device=dev) / 11, torch.randn(5, device=dev)
+    out = torch.full((B, S, 128), float("nan"), dtype=torch.float16, device=dev)
+    logits = torch.full((B, S, 5), float("nan"), device=dev)
+    G.run_conv(cin=128, cout=128, taps=7, stride=1, dilation=dil, pad=3 * dil, prologue=_lib.PRO_NONE,
+               epilogue=_lib.EPI_LN_GELU_RES if res else _lib.EPI_LN_GELU, has_ds=0, B=B, L_in=S, L_out=S,
+               **{"in": x}, w=G.pack_conv(w), ln_w=g, ln_b=b, res=xin, head_w=hw if res else None,
+               head_b=hb if res else None, logits=logits if res else None, n_classes=5 if res else 0, out=out,
+               ln_eps=1e-5)
+    c = G.conv_ref(x, w, stride=1, pad=3 * dil, dil=dil)
+    mu = c.mean(-1, keepdim=True)
+    var = (c - mu).pow(2).mean(-1, keepdim=True)
+    ref = G.gelu((c - mu) / torch.sqrt(var + 1e-5) * g + b)
+    if res:
+        ref = G.gelu(ref + xin.float())
+    assert (out.float() - ref).abs().max().item() < 5e-3
+    if res:
+        assert (logits - (ref @ hw.t() + hb)).abs().max().item() < 5e-3

@@ -1,0 +1,154 @@
+"""Build + ctypes binding of ``libw2s_b200.so`` (C ABI declared in ``include/w2s_b200.h``).
+
+The shared library is compiled in-tree with ``nvcc`` for sm_100a only.  There is no CPU fallback: if the
+library cannot be loaded every compute entry point raises ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+REPO_DIR = PKG_DIR.parent
+LIB_PATH = PKG_DIR / "libw2s_b200.so"
+SOURCES = [PKG_DIR / "csrc" / "capi.cu"]
+HEADERS = sorted((PKG_DIR / "csrc").glob("*.cuh")) + [REPO_DIR / "include" / "w2s_b200.h"]
+
+MAX_BLOCKS = 12
+MAX_MIXER_LAYERS = 8
+MAX_SIGNALS = 4
+MAX_SEQ_BLOCKS = 4
+MAX_DILATIONS = 8
+ABI_VERSION = 1
+
+PRO_NONE, PRO_NORM, PRO_NORM_RES = 0, 1, 2
+EPI_STATS, EPI_BIAS_GELU, EPI_LN_GELU, EPI_LN_GELU_RES = 0, 1, 2, 3
+
+
+def nvcc_path() -> str:
+    p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(p):
+        raise RuntimeError("nvcc not found; cannot build libw2s_b200.so")
+    return p
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile the CUDA library for sm_100a (cross-compiles without a GPU)."""
+    if not force and LIB_PATH.exists():
+        newest = max(p.stat().st_mtime for p in SOURCES + HEADERS)
+        if LIB_PATH.stat().st_mtime >= newest:
+            return LIB_PATH
+    cmd = [
+        nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+        "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "1886", "-o", str(LIB_PATH),
+    ] + [str(s) for s in SOURCES]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+class ConvCall(C.Structure):
+    _fields_ = [
+        ("cin", C.c_int32), ("cout", C.c_int32), ("taps", C.c_int32), ("stride", C.c_int32),
+        ("dilation", C.c_int32), ("pad", C.c_int32),
+        ("prologue", C.c_int32), ("epilogue", C.c_int32), ("has_ds", C.c_int32),
+        ("B", C.c_int32), ("L_in", C.c_int32), ("L_out", C.c_int32),
+        ("in_", C.c_void_p), ("in_res", C.c_void_p), ("in_stats", C.c_void_p),
+        ("w", C.c_void_p), ("w_ds", C.c_void_p),
+        ("out", C.c_void_p), ("out_ds", C.c_void_p), ("out_stats", C.c_void_p),
+        ("row_mask", C.c_void_p), ("bias", C.c_void_p), ("ln_w", C.c_void_p), ("ln_b", C.c_void_p),
+        ("res", C.c_void_p), ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("logits", C.c_void_p),
+        ("n_classes", C.c_int32), ("in_eps", C.c_float), ("ln_eps", C.c_float),
+    ]
+
+
+class EncoderDesc(C.Structure):
+    _fields_ = [
+        ("n_blocks", C.c_int32), ("channels", C.c_int32 * MAX_BLOCKS), ("feature_dim", C.c_int32),
+        ("norm_eps", C.c_float),
+        ("w_first", C.c_void_p), ("w_first_ds", C.c_void_p),
+        ("w_conv", (C.c_void_p * 3) * MAX_BLOCKS), ("w_ds", C.c_void_p * MAX_BLOCKS),
+        ("w_lin", C.c_void_p), ("b_lin", C.c_void_p),
+    ]
+
+
+class MixerLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "in_w", "out_w", "ff1_w", "ff2_w", "in_b", "out_b", "ff1_b", "ff2_b", "ln1_w", "ln1_b", "ln2_w", "ln2_b")]
+
+
+class MixerDesc(C.Structure):
+    _fields_ = [
+        ("n_layers", C.c_int32), ("feature_dim", C.c_int32), ("n_heads", C.c_int32), ("dim_ff", C.c_int32),
+        ("ln_eps", C.c_float), ("cls", C.c_void_p), ("layer", MixerLayer * MAX_MIXER_LAYERS),
+    ]
+
+
+class SeqDesc(C.Structure):
+    _fields_ = [
+        ("n_blocks", C.c_int32), ("n_dilations", C.c_int32), ("kernel_size", C.c_int32),
+        ("feature_dim", C.c_int32), ("n_classes", C.c_int32), ("ln_eps", C.c_float),
+        ("w", (C.c_void_p * MAX_DILATIONS) * MAX_SEQ_BLOCKS),
+        ("ln_w", (C.c_void_p * MAX_DILATIONS) * MAX_SEQ_BLOCKS),
+        ("ln_b", (C.c_void_p * MAX_DILATIONS) * MAX_SEQ_BLOCKS),
+        ("head_w", C.c_void_p), ("head_b", C.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); every symbol declared in include/w2s_b200.h
+SYMBOLS = {
+    "w2s_abi_version": (C.c_int, []),
+    "w2s_last_error": (C.c_char_p, []),
+    "w2s_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "w2s_packed_conv_weight_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "w2s_pack_linear_frag": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "w2s_conv1d_fwd": (C.c_int, [C.POINTER(ConvCall), C.c_void_p]),
+    "w2s_encoder_workspace_bytes": (C.c_size_t, [C.POINTER(EncoderDesc), C.c_int, C.c_int64, C.c_int]),
+    "w2s_encoder_fwd": (C.c_int, [C.POINTER(EncoderDesc), C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_size_t,
+                                  C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "w2s_epoch_mixer_fwd": (C.c_int, [C.POINTER(MixerDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int,
+                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "w2s_seqmixer_workspace_bytes": (C.c_size_t, [C.POINTER(SeqDesc), C.c_int, C.c_int, C.c_int]),
+    "w2s_seqmixer_head_fwd": (C.c_int, [C.POINTER(SeqDesc), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "w2s_argmax": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    """Load the shared library (building it first if needed).  Raises RuntimeError on any failure."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        if not build_if_missing:
+            raise RuntimeError(f"{LIB_PATH} is missing; run `python -c 'import __graft_entry__ as g; g.build()'`")
+        build()
+    try:
+        lib = C.CDLL(str(LIB_PATH))
+    except OSError as e:  # no silent fallback
+        raise RuntimeError(f"cannot load {LIB_PATH}: {e}") from e
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.w2s_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"ABI mismatch: library {lib.w2s_abi_version()} vs binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, exc=RuntimeError) -> None:
+    if rc != 0:
+        msg = load().w2s_last_error().decode()
+        raise exc(msg)

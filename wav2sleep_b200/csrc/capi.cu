@@ -1,0 +1,474 @@
+// C ABI of libw2s_b200 (see include/w2s_b200.h).  Host-side orchestration only: shape checks, workspace
+// carving, kernel dispatch.  No allocation, no synchronisation, no CPU fallback.
+#include "../../include/w2s_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "conv_igemm.cuh"
+#include "epoch_mixer.cuh"
+#include "first_conv.cuh"
+
+using namespace w2s;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+int cuda_fail(cudaError_t e, const char* what) { return fail("%s: %s", what, cudaGetErrorString(e)); }
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------
+// packing kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_conv_kernel(const float* __restrict__ w, int cout, int cin, int taps, int taps_major,
+                                 __half* __restrict__ out) {
+  const int total = taps * cin * cout;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int k = idx & 7;
+    int r = idx >> 3;
+    const int n = r % cout;
+    r /= cout;
+    const int c8 = r % (cin / 8);
+    const int t = r / (cin / 8);
+    const int c = c8 * 8 + k;
+    const float v = taps_major ? w[(size_t)n * taps * cin + (size_t)t * cin + c] : w[((size_t)n * cin + c) * taps + t];
+    out[idx] = __float2half_rn(v);
+  }
+}
+
+__global__ void pack_frag_kernel(const float* __restrict__ w, int n, int k, __half* __restrict__ out) {
+  const int total = n * k;
+  const int KT = k / 16;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int q = idx & 3;
+    const int lane = (idx >> 2) & 31;
+    const int tile = idx >> 7;
+    const int kt = tile % KT, nt = tile / KT;
+    const int row = nt * 8 + (lane >> 2);
+    const int col = kt * 16 + (q >> 1) * 8 + (lane & 3) * 2 + (q & 1);
+    out[idx] = __float2half_rn(w[(size_t)row * k + col]);
+  }
+}
+
+__global__ void argmax_kernel(const float* __restrict__ logits, long long n, int c, long long* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float* row = logits + i * c;
+    int best = 0;
+    float bv = row[0];
+    for (int j = 1; j < c; ++j) {
+      const float v = row[j];
+      if (v > bv) {  // first maximum wins, like torch.argmax
+        bv = v;
+        best = j;
+      }
+    }
+    out[i] = best;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic conv dispatch
+// ------------------------------------------------------------------------------------------------
+int ilog2_exact(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return (1 << l) == v ? l : -1;
+}
+
+ConvArgs to_args(const w2s_conv_call& c) {
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.in = (const act_t*)c.in;
+  a.in_res = (const act_t*)c.in_res;
+  a.in_stats = c.in_stats;
+  a.w = (const act_t*)c.w;
+  a.w_ds = (const act_t*)c.w_ds;
+  a.out = (act_t*)c.out;
+  a.out_ds = (act_t*)c.out_ds;
+  a.out_stats = c.out_stats;
+  a.row_mask = c.row_mask;
+  a.bias = c.bias;
+  a.ln_w = c.ln_w;
+  a.ln_b = c.ln_b;
+  a.res = (const act_t*)c.res;
+  a.head_w = c.head_w;
+  a.head_b = c.head_b;
+  a.logits = c.logits;
+  a.n_classes = c.n_classes;
+  a.L_in = c.L_in;
+  a.L_out = c.L_out;
+  a.stride_log2 = ilog2_exact(c.stride);
+  a.dil = c.dilation;
+  a.pad = c.pad;
+  a.in_inv_len = 1.0f / (float)c.L_in;
+  a.in_eps = c.in_eps;
+  a.ln_eps = c.ln_eps;
+  return a;
+}
+
+int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
+  if (c.B <= 0 || c.L_in <= 0 || c.L_out <= 0) return fail("conv1d: empty shape B=%d L_in=%d L_out=%d", c.B, c.L_in, c.L_out);
+  if (ilog2_exact(c.stride) < 0 || c.stride > 4) return fail("conv1d: stride %d unsupported", c.stride);
+  if (c.B > 65535) return fail("conv1d: B=%d exceeds grid.y", c.B);
+  if (c.n_classes > 8) return fail("conv1d: n_classes=%d > 8", c.n_classes);
+  const ConvArgs a = to_args(c);
+  cudaError_t e = cudaErrorInvalidValue;
+  bool found = false;
+#define W2S_CASE(CIN, COUT, TAPS, GT, PRO, EPI, DS)                                                       \
+  if (!found && c.cin == CIN && c.cout == COUT && c.taps == TAPS && c.prologue == PRO && c.epilogue == EPI && \
+      (c.has_ds != 0) == DS) {                                                                            \
+    found = true;                                                                                         \
+    e = launch_conv_igemm<CIN, COUT, TAPS, GT, PRO, EPI, DS>(a, c.B, st);                                  \
+  }
+  // encoder conv1 (block input = previous block's conv3 output + residual branch), with fused downsample
+  W2S_CASE(16, 16, 3, 3, PRO_NORM_RES, EPI_STATS, true)
+  W2S_CASE(16, 32, 3, 3, PRO_NORM_RES, EPI_STATS, true)
+  W2S_CASE(32, 32, 3, 3, PRO_NORM_RES, EPI_STATS, true)
+  W2S_CASE(32, 64, 3, 3, PRO_NORM_RES, EPI_STATS, true)
+  W2S_CASE(64, 64, 3, 3, PRO_NORM_RES, EPI_STATS, true)
+  W2S_CASE(64, 128, 3, 3, PRO_NORM_RES, EPI_STATS, true)
+  W2S_CASE(128, 128, 3, 3, PRO_NORM_RES, EPI_STATS, true)
+  // encoder conv2 / conv3 (stride is a runtime argument)
+  W2S_CASE(16, 16, 3, 3, PRO_NORM, EPI_STATS, false)
+  W2S_CASE(32, 32, 3, 3, PRO_NORM, EPI_STATS, false)
+  W2S_CASE(64, 64, 3, 3, PRO_NORM, EPI_STATS, false)
+  W2S_CASE(128, 128, 3, 3, PRO_NORM, EPI_STATS, false)
+  // encoder Linear(4C -> 128) + GELU as a 4-tap stride-4 conv
+  W2S_CASE(64, 128, 4, 4, PRO_NORM_RES, EPI_BIAS_GELU, false)
+  W2S_CASE(128, 128, 4, 2, PRO_NORM_RES, EPI_BIAS_GELU, false)
+  // sequence mixer dilated convs
+  W2S_CASE(128, 128, 7, 4, PRO_NONE, EPI_LN_GELU, false)
+  W2S_CASE(128, 128, 7, 4, PRO_NONE, EPI_LN_GELU_RES, false)
+#undef W2S_CASE
+  if (!found)
+    return fail("conv1d: no kernel for cin=%d cout=%d taps=%d pro=%d epi=%d ds=%d", c.cin, c.cout, c.taps, c.prologue,
+                c.epilogue, c.has_ds);
+  if (e != cudaSuccess) return cuda_fail(e, "conv1d launch");
+  return 0;
+}
+
+// Rotating slot allocator for inference workspaces.
+struct Slots {
+  uint8_t* base;
+  size_t slot_bytes;
+  int n;
+  bool busy[8];
+  void* get() {
+    for (int i = 0; i < n; ++i)
+      if (!busy[i]) {
+        busy[i] = true;
+        return base + (size_t)i * slot_bytes;
+      }
+    return nullptr;
+  }
+  void put(const void* p) {
+    if (p == nullptr) return;
+    const size_t i = ((const uint8_t*)p - base) / slot_bytes;
+    if (i < (size_t)n) busy[i] = false;
+  }
+};
+
+constexpr int kEncSlots = 5;
+
+size_t enc_stats_floats(const w2s_encoder_desc* d, int B) {
+  size_t n = 0;
+  for (int i = 0; i < d->n_blocks; ++i) n += (size_t)3 * B * d->channels[i] * 2;
+  return n;
+}
+
+int check_encoder_desc(const w2s_encoder_desc* d) {
+  if (d == nullptr) return fail("encoder: null descriptor");
+  if (d->n_blocks < 1 || d->n_blocks > W2S_MAX_BLOCKS) return fail("encoder: n_blocks=%d out of range", d->n_blocks);
+  if (d->feature_dim != 128) return fail("encoder: feature_dim=%d (only 128 is built)", d->feature_dim);
+  if (d->channels[0] != 16) return fail("encoder: initial_channels=%d (only 16 is built)", d->channels[0]);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int w2s_abi_version(void) { return 1; }
+const char* w2s_last_error(void) { return g_err.c_str(); }
+
+size_t w2s_packed_conv_weight_bytes(int cout, int cin, int taps) { return (size_t)cout * cin * taps * sizeof(__half); }
+
+int w2s_pack_conv_weight(const float* w, int cout, int cin, int taps, int taps_major, void* out, void* stream) {
+  if (cin % 8 != 0 || cout <= 0 || taps <= 0) return fail("pack_conv: cin=%d cout=%d taps=%d", cin, cout, taps);
+  const int total = cout * cin * taps;
+  pack_conv_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, cout, cin, taps, taps_major, (__half*)out);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "pack_conv");
+}
+
+int w2s_pack_linear_frag(const float* w, int n, int k, void* out, void* stream) {
+  if (n % 8 != 0 || k % 16 != 0) return fail("pack_frag: n=%d k=%d", n, k);
+  const int total = n * k;
+  pack_frag_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, n, k, (__half*)out);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "pack_frag");
+}
+
+int w2s_conv1d_fwd(const w2s_conv_call* call, void* stream) {
+  if (call == nullptr) return fail("conv1d: null call");
+  return conv_dispatch(*call, (cudaStream_t)stream);
+}
+
+size_t w2s_encoder_workspace_bytes(const w2s_encoder_desc* d, int B, int64_t T, int keep) {
+  if (check_encoder_desc(d) != 0 || B <= 0 || T <= 0) return 0;
+  const size_t stats = align_up(enc_stats_floats(d, B) * sizeof(float), 256);
+  const size_t e = sizeof(__half);
+  if (!keep) return stats + (size_t)kEncSlots * align_up((size_t)B * T * 16 * e, 256);
+  size_t act = 0;
+  int64_t L = T;
+  for (int i = 0; i < d->n_blocks; ++i) {
+    const size_t c = d->channels[i];
+    act += 2 * align_up((size_t)B * L * c * e, 256);        // y1, y2
+    act += 2 * align_up((size_t)B * (L / 2) * c * e, 256);  // y3, r
+    L /= 2;
+  }
+  return stats + act;
+}
+
+int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T, void* workspace, size_t ws_bytes,
+                    int keep, void* z_out, uint8_t* row_mask, void* stream) {
+  if (check_encoder_desc(d) != 0) return 1;
+  if (x == nullptr || z_out == nullptr || row_mask == nullptr || workspace == nullptr) return fail("encoder: null pointer");
+  const int64_t spe = (int64_t)4 << d->n_blocks;  // samples per epoch = 2^(n_blocks+2)
+  if (B <= 0 || T <= 0) return fail("encoder: empty input B=%d T=%lld", B, (long long)T);
+  if (T % spe != 0) return fail("Input length %lld must be divisible by samples_per_epoch=%lld.", (long long)T, (long long)spe);
+  if (T > 0x7fffffff / 2) return fail("encoder: T=%lld too long", (long long)T);
+  const size_t need = w2s_encoder_workspace_bytes(d, B, T, keep);
+  if (ws_bytes < need) return fail("encoder: workspace %zu < required %zu", ws_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+
+  const size_t stats_bytes = align_up(enc_stats_floats(d, B) * sizeof(float), 256);
+  float* stats = (float*)workspace;
+  cudaError_t ce = cudaMemsetAsync(stats, 0, stats_bytes, st);
+  if (ce != cudaSuccess) return cuda_fail(ce, "encoder memset");
+  uint8_t* act_base = (uint8_t*)workspace + stats_bytes;
+
+  Slots slots;
+  memset(&slots, 0, sizeof(slots));
+  slots.base = act_base;
+  slots.slot_bytes = align_up((size_t)B * T * 16 * sizeof(__half), 256);
+  slots.n = kEncSlots;
+  size_t bump = 0;
+  auto alloc = [&](size_t bytes) -> void* {
+    if (!keep) return slots.get();
+    void* p = act_base + bump;
+    bump += align_up(bytes, 256);
+    return p;
+  };
+  auto release = [&](const void* p) {
+    if (!keep) slots.put(p);
+  };
+
+  float* st_ptr = stats;
+  auto next_stats = [&](int c) {
+    float* p = st_ptr;
+    st_ptr += (size_t)B * c * 2;
+    return p;
+  };
+
+  int L = (int)T;
+  const void* prev_y3 = nullptr;
+  const void* prev_r = nullptr;
+  const float* prev_s3 = nullptr;
+  int prev_c = 1;
+  for (int i = 0; i < d->n_blocks; ++i) {
+    const int c = d->channels[i];
+    const size_t e = sizeof(__half);
+    void* y1 = alloc((size_t)B * L * c * e);
+    void* r = alloc((size_t)B * (L / 2) * c * e);
+    float* s1 = next_stats(c);
+    float* s2 = next_stats(c);
+    float* s3 = next_stats(c);
+    if (y1 == nullptr || r == nullptr) return fail("encoder: slot allocator exhausted");
+    if (i == 0) {
+      FirstConvArgs fa;
+      fa.x = x;
+      fa.w = d->w_first;
+      fa.w_ds = d->w_first_ds;
+      fa.y1 = (act_t*)y1;
+      fa.r0 = (act_t*)r;
+      fa.stats = s1;
+      fa.row_mask = row_mask;
+      fa.T = L;
+      ce = launch_first_conv(fa, B, st);
+      if (ce != cudaSuccess) return cuda_fail(ce, "first_conv launch");
+    } else {
+      w2s_conv_call cc;
+      memset(&cc, 0, sizeof(cc));
+      cc.cin = prev_c; cc.cout = c; cc.taps = 3; cc.stride = 1; cc.dilation = 1; cc.pad = 1;
+      cc.prologue = W2S_PRO_NORM_RES; cc.epilogue = W2S_EPI_STATS; cc.has_ds = 1;
+      cc.B = B; cc.L_in = L; cc.L_out = L;
+      cc.in = prev_y3; cc.in_res = prev_r; cc.in_stats = prev_s3;
+      cc.w = d->w_conv[i][0]; cc.w_ds = d->w_ds[i];
+      cc.out = y1; cc.out_ds = r; cc.out_stats = s1; cc.row_mask = row_mask; cc.in_eps = d->norm_eps;
+      if (conv_dispatch(cc, st) != 0) return 1;
+      release(prev_y3);
+      release(prev_r);
+    }
+    void* y2 = alloc((size_t)B * L * c * e);
+    if (y2 == nullptr) return fail("encoder: slot allocator exhausted");
+    {
+      w2s_conv_call cc;
+      memset(&cc, 0, sizeof(cc));
+      cc.cin = c; cc.cout = c; cc.taps = 3; cc.stride = 1; cc.dilation = 1; cc.pad = 1;
+      cc.prologue = W2S_PRO_NORM; cc.epilogue = W2S_EPI_STATS;
+      cc.B = B; cc.L_in = L; cc.L_out = L;
+      cc.in = y1; cc.in_stats = s1; cc.w = d->w_conv[i][1];
+      cc.out = y2; cc.out_stats = s2; cc.row_mask = row_mask; cc.in_eps = d->norm_eps;
+      if (conv_dispatch(cc, st) != 0) return 1;
+    }
+    release(y1);
+    void* y3 = alloc((size_t)B * (L / 2) * c * e);
+    if (y3 == nullptr) return fail("encoder: slot allocator exhausted");
+    {
+      w2s_conv_call cc;
+      memset(&cc, 0, sizeof(cc));
+      cc.cin = c; cc.cout = c; cc.taps = 3; cc.stride = 2; cc.dilation = 1; cc.pad = 1;
+      cc.prologue = W2S_PRO_NORM; cc.epilogue = W2S_EPI_STATS;
+      cc.B = B; cc.L_in = L; cc.L_out = L / 2;
+      cc.in = y2; cc.in_stats = s2; cc.w = d->w_conv[i][2];
+      cc.out = y3; cc.out_stats = s3; cc.row_mask = row_mask; cc.in_eps = d->norm_eps;
+      if (conv_dispatch(cc, st) != 0) return 1;
+    }
+    release(y2);
+    prev_y3 = y3;
+    prev_r = r;
+    prev_s3 = s3;
+    prev_c = c;
+    L /= 2;
+  }
+  {  // time-distributed Linear(4C -> F) + GELU  (models/wav2sleep.py:261-265)
+    w2s_conv_call cc;
+    memset(&cc, 0, sizeof(cc));
+    cc.cin = prev_c; cc.cout = d->feature_dim; cc.taps = 4; cc.stride = 4; cc.dilation = 1; cc.pad = 0;
+    cc.prologue = W2S_PRO_NORM_RES; cc.epilogue = W2S_EPI_BIAS_GELU;
+    cc.B = B; cc.L_in = L; cc.L_out = L / 4;
+    cc.in = prev_y3; cc.in_res = prev_r; cc.in_stats = prev_s3; cc.w = d->w_lin; cc.bias = d->b_lin;
+    cc.out = z_out; cc.row_mask = row_mask; cc.in_eps = d->norm_eps;
+    if (conv_dispatch(cc, st) != 0) return 1;
+  }
+  return 0;
+}
+
+int w2s_epoch_mixer_fwd(const w2s_mixer_desc* d, const void* const* z, const uint8_t* const* row_mask, int n_signals,
+                        int B, int S, void* out, void* stream) {
+  if (d == nullptr || z == nullptr || out == nullptr) return fail("epoch_mixer: null pointer");
+  if (n_signals < 1) return fail("No signals provided to MultiModalAttentionEmbedder.");
+  if (n_signals > W2S_MAX_SIGNALS) return fail("epoch_mixer: %d signals > %d", n_signals, W2S_MAX_SIGNALS);
+  if (d->feature_dim != kMixF || d->n_heads != kMixHeads || d->dim_ff != kMixFF)
+    return fail("epoch_mixer: only feature_dim=128, nhead=8, dim_ff=512 is built (got %d, %d, %d)", d->feature_dim,
+                d->n_heads, d->dim_ff);
+  if (d->n_layers < 1 || d->n_layers > W2S_MAX_MIXER_LAYERS) return fail("epoch_mixer: n_layers=%d", d->n_layers);
+  if (B <= 0 || S <= 0) return fail("epoch_mixer: empty input");
+  MixerArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_layers = d->n_layers;
+  for (int l = 0; l < d->n_layers; ++l) {
+    const w2s_mixer_layer& s = d->layer[l];
+    MixerLayerW& w = a.layer[l];
+    w.in_w = (const uint2*)s.in_w; w.out_w = (const uint2*)s.out_w;
+    w.ff1_w = (const uint2*)s.ff1_w; w.ff2_w = (const uint2*)s.ff2_w;
+    w.in_b = s.in_b; w.out_b = s.out_b; w.ff1_b = s.ff1_b; w.ff2_b = s.ff2_b;
+    w.ln1_w = s.ln1_w; w.ln1_b = s.ln1_b; w.ln2_w = s.ln2_w; w.ln2_b = s.ln2_b;
+  }
+  for (int i = 0; i < n_signals; ++i) {
+    if (z[i] == nullptr) return fail("epoch_mixer: z[%d] is null", i);
+    a.z[i] = (const act_t*)z[i];
+    a.row_mask[i] = row_mask ? row_mask[i] : nullptr;
+  }
+  a.cls = d->cls;
+  a.out = (act_t*)out;
+  a.n_epochs = B * S;
+  a.S = S;
+  a.ln_eps = d->ln_eps;
+  cudaError_t e = launch_epoch_mixer(a, n_signals, sm_count(), (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "epoch_mixer launch");
+}
+
+size_t w2s_seqmixer_workspace_bytes(const w2s_seq_desc* d, int B, int S, int keep) {
+  if (d == nullptr || B <= 0 || S <= 0) return 0;
+  const size_t t = align_up((size_t)B * S * 128 * sizeof(__half), 256);
+  return keep ? t * ((size_t)d->n_blocks * d->n_dilations + 1) : t * 4;
+}
+
+int w2s_seqmixer_head_fwd(const w2s_seq_desc* d, const void* x, int B, int S, void* workspace, size_t ws_bytes,
+                          int keep, void* feat_out, float* logits, void* stream) {
+  if (d == nullptr || x == nullptr || workspace == nullptr || logits == nullptr) return fail("seqmixer: null pointer");
+  if (d->feature_dim != 128 || d->kernel_size != 7) return fail("seqmixer: only feature_dim=128, kernel_size=7 is built");
+  if (d->n_blocks < 1 || d->n_blocks > W2S_MAX_SEQ_BLOCKS || d->n_dilations < 1 || d->n_dilations > W2S_MAX_DILATIONS)
+    return fail("seqmixer: n_blocks=%d n_dilations=%d", d->n_blocks, d->n_dilations);
+  if (d->n_classes < 1 || d->n_classes > 8) return fail("seqmixer: n_classes=%d", d->n_classes);
+  if (ws_bytes < w2s_seqmixer_workspace_bytes(d, B, S, keep)) return fail("seqmixer: workspace too small");
+  const size_t t = align_up((size_t)B * S * 128 * sizeof(__half), 256);
+  uint8_t* ws = (uint8_t*)workspace;
+  // keep = 0: slots 0/1 ping-pong inside a block, slots 2/3 alternate as block outputs (a block's input is the
+  // previous block's output or x, so it is never overwritten while it is still the residual source).
+  int next = 0;
+  const void* block_in = x;
+  for (int bl = 0; bl < d->n_blocks; ++bl) {
+    const void* cur = block_in;
+    for (int k = 0; k < d->n_dilations; ++k) {
+      const bool last_layer = (k == d->n_dilations - 1);
+      const bool last_block = (bl == d->n_blocks - 1);
+      void* o;
+      if (last_layer && last_block && feat_out != nullptr) o = feat_out;
+      else if (keep) o = ws + (size_t)(next++) * t;
+      else o = ws + (size_t)(last_layer ? 2 + (bl & 1) : (k & 1)) * t;
+      w2s_conv_call cc;
+      memset(&cc, 0, sizeof(cc));
+      cc.cin = 128; cc.cout = 128; cc.taps = 7; cc.stride = 1; cc.dilation = 1 << k; cc.pad = 3 << k;
+      cc.prologue = W2S_PRO_NONE;
+      cc.epilogue = last_layer ? W2S_EPI_LN_GELU_RES : W2S_EPI_LN_GELU;
+      cc.B = B; cc.L_in = S; cc.L_out = S;
+      cc.in = cur; cc.w = d->w[bl][k]; cc.ln_w = d->ln_w[bl][k]; cc.ln_b = d->ln_b[bl][k];
+      cc.out = o; cc.ln_eps = d->ln_eps;
+      if (last_layer) cc.res = block_in;
+      if (last_layer && last_block) {
+        cc.head_w = d->head_w; cc.head_b = d->head_b; cc.logits = logits; cc.n_classes = d->n_classes;
+      }
+      if (conv_dispatch(cc, (cudaStream_t)stream) != 0) return 1;
+      cur = o;
+    }
+    block_in = cur;
+  }
+  return 0;
+}
+
+int w2s_argmax(const float* logits, int64_t n, int n_classes, int64_t* out, void* stream) {
+  if (logits == nullptr || out == nullptr || n <= 0 || n_classes <= 0) return fail("argmax: bad arguments");
+  const int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  argmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, (long long)n, n_classes, (long long*)out);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "argmax");
+}
+
+}  // extern "C"

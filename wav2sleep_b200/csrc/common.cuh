@@ -1,0 +1,191 @@
+// Shared device helpers for the wav2sleep B200 kernels (sm_100a only).
+//
+// Everything here is a thin inline-PTX wrapper: mbarrier, proxy fences, tcgen05
+// (TMEM alloc / MMA / commit / ld), UMMA descriptors for the no-swizzle K-major
+// canonical layout, fp16 packing and the fast GELU used in conv prologues.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace w2s {
+
+// Storage/operand element type of every activation tensor and MMA operand.
+// fp16 (not bf16): measured with the reference model, bf16 storage of the encoder
+// activations gives 7.6e-2 max-abs logit error / 98.6 % argmax agreement, fp16 gives
+// 1.0e-2 / 99.9 % (DESIGN.md "Numerics").  fp32 accumulation everywhere.
+typedef __half act_t;
+
+#define W2S_DEVINL __device__ __forceinline__
+
+W2S_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ----------------------------------------------------------------------------------------------
+// mbarrier
+// ----------------------------------------------------------------------------------------------
+W2S_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+W2S_DEVINL void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+W2S_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a lost arrive turns into a trap (launch error) instead of a hung GPU.
+W2S_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// fences
+// ----------------------------------------------------------------------------------------------
+// generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
+W2S_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+W2S_DEVINL void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+W2S_DEVINL void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
+// TMEM
+// ----------------------------------------------------------------------------------------------
+// Whole warp must call.  ncols: power of two in [32, 512].
+W2S_DEVINL void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+W2S_DEVINL void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers fp16 and bf16 operands, fp32 accum.
+W2S_DEVINL void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrives (count 1) on the mbarrier once every previously issued tcgen05.mma of this thread is done.
+W2S_DEVINL void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// 32 lanes x 16 consecutive fp32 columns: thread i of warp w reads TMEM lane 32*(w%4)+i.
+W2S_DEVINL void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ----------------------------------------------------------------------------------------------
+// UMMA descriptors (cute/arch/mma_sm100_desc.hpp bit layout; SWIZZLE_NONE, K-major)
+// ----------------------------------------------------------------------------------------------
+// Canonical no-swizzle K-major operand: core matrix = 8 rows x 16 bytes, rows 16 B apart.
+//   LBO = byte distance between the two 16-byte K chunks of one K=16 step
+//   SBO = byte distance between consecutive 8-row groups along M/N
+// With "chunk-major" staging [chunk][row][16 B] the rows of one chunk are contiguous, so SBO = 128 and
+// a start address may be shifted by any number of rows (16 B each): that is how conv taps are addressed.
+W2S_DEVINL uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (sm_100)
+  return d;                // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
+}
+// kind::f16 instruction descriptor: fp32 accumulate, A/B both K-major, M x N tile.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, bool bf16) {
+  return (1u << 4)                      // c_format = F32
+         | ((bf16 ? 1u : 0u) << 7)      // a_format
+         | ((bf16 ? 1u : 0u) << 10)     // b_format
+         | ((uint32_t)(N >> 3) << 17)   // n_dim
+         | ((uint32_t)(M >> 4) << 24);  // m_dim
+}
+
+// ----------------------------------------------------------------------------------------------
+// math
+// ----------------------------------------------------------------------------------------------
+// GELU(x) = x * Phi(x) with Phi(x) ~= 1 / (1 + exp(-2 xc (a + b xc^2 + c xc^4))), xc = clamp(x, +-5).
+// Fitted against the erf form (reference models/utils.py:67-68 -> nn.GELU()): max abs error 2.5e-5 over R,
+// 10x below fp16 rounding of the result.  One ex2 + one rcp on the MUFU pipe.
+W2S_DEVINL float gelu_fast(float x) {
+  const float xc = fminf(fmaxf(x, -5.0f), 5.0f);
+  const float t = xc * xc;
+  // coefficients pre-multiplied by -2*log2(e)
+  float q = fmaf(t, 1.01448193e-3f, -0.10677673f);
+  q = fmaf(q, t, -2.30112048f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xc * q));
+  return __fdividef(x, 1.0f + e);
+}
+// Exact-erf GELU for low-volume epilogues.
+W2S_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// {lo, hi} -> packed fp16x2, round-to-nearest, saturating to +-65504 instead of inf.
+W2S_DEVINL uint32_t pack_h2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+W2S_DEVINL float2 unpack_h2(uint32_t u) {
+  __half2 h = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(h);
+}
+
+// Transposing butterfly reduction over the 32 lanes of a warp for 16 per-lane values.
+// On return lane l holds in v[0] the full 32-lane sum of channel ((l >> 1) & 15).
+W2S_DEVINL int butterfly16_channel(int lane) { return (lane >> 1) & 15; }
+W2S_DEVINL void butterfly16(float* v, int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool hi = lane & 16;
+    float send = hi ? v[i] : v[i + 8];
+    float keep = hi ? v[i + 8] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool hi = lane & 8;
+    float send = hi ? v[i] : v[i + 4];
+    float keep = hi ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool hi = lane & 4;
+    float send = hi ? v[i] : v[i + 2];
+    float keep = hi ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const bool hi = lane & 2;
+    float send = hi ? v[0] : v[1];
+    float keep = hi ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+}  // namespace w2s

@@ -1,0 +1,445 @@
+// Implicit-GEMM 1-D convolution on tcgen05 tensor cores (sm_100a), channels-last fp16 activations.
+//
+// One kernel template covers every dense contraction of the wav2sleep forward:
+//   * encoder ConvLayer1D  k=3, stride 1|2            (reference models/blocks.py:173-186, 25-44)
+//   * encoder 1x1 stride-2 residual "downsample"      (blocks.py:46-53) as a 2nd accumulator of conv1
+//   * encoder time-distributed Linear(4C -> F) + GELU (models/wav2sleep.py:261-265) as taps=4, stride=4
+//   * sequence-mixer dilated conv k=7 + ConvLayerNorm + GELU (+ residual + GELU [+ classifier])
+//                                                     (blocks.py:93-126, utils.py:9-23, wav2sleep.py:66)
+//
+// GEMM view: M = output positions (128 per UMMA), N = COUT, K = TAPS * CIN.
+// A (activations) is staged by the CTA's threads - not TMA - because the whole-night InstanceNorm of the
+// producing layer (utils.py:89-92, eps 1e-2) can only be applied by the consumer: the prologue turns the stored
+// pre-norm fp16 values into GELU((y - mu) * rstd) [optionally GELU(. + residual)] on the way to shared memory.
+// Staging layout is [stride phase][16-byte channel chunk][row][8 halfs] ("chunk-major", no swizzle), so a conv
+// tap is just a row offset of the UMMA shared-memory descriptor: im2col costs nothing.
+// B (weights) is pre-packed on the host as [tap][chunk][cout][8 halfs] and copied linearly.
+// Accumulators live in TMEM; the epilogue reads them with tcgen05.ld (thread == output position) and
+//   EPI_STATS     : stores pre-norm fp16 + accumulates sum / sum-of-squares per (sample, channel)
+//   EPI_BIAS_GELU : + bias, exact GELU, stores fp16
+//   EPI_LN_GELU   : LayerNorm over the 128 channels of the thread's row, affine, GELU
+//   EPI_LN_GELU_RES: ... + block input, GELU, optional fused classifier head
+#pragma once
+#include "common.cuh"
+
+namespace w2s {
+
+enum : int { PRO_NONE = 0, PRO_NORM = 1, PRO_NORM_RES = 2 };
+enum : int { EPI_STATS = 0, EPI_BIAS_GELU = 1, EPI_LN_GELU = 2, EPI_LN_GELU_RES = 3 };
+
+struct ConvArgs {
+  // input side
+  const act_t* in;        // [B, L_in, CIN]  pre-norm (PRO_NORM*) or final (PRO_NONE)
+  const act_t* in_res;    // [B, L_in, CIN]  residual branch of the producing block (PRO_NORM_RES)
+  const float* in_stats;  // [B, CIN, 2]     sum, sum of squares over L_in of `in`
+  const act_t* w;         // packed [TAPS][CIN/8][COUT][8]
+  const act_t* w_ds;      // packed [CIN/8][COUT][8] (HAS_DS)
+  // output side
+  act_t* out;             // [B, L_out, COUT]
+  act_t* out_ds;          // [B, L_out/2, COUT] (HAS_DS)
+  float* out_stats;       // [B, COUT, 2] (EPI_STATS), must be zeroed by the caller
+  const uint8_t* row_mask;  // [B] non-zero => sample has no such signal: skip (may be null)
+  const float* bias;      // [COUT] (EPI_BIAS_GELU)
+  const float* ln_w;      // [COUT] (EPI_LN_*)
+  const float* ln_b;      // [COUT]
+  const act_t* res;       // [B, L_out, COUT] block input (EPI_LN_GELU_RES)
+  const float* head_w;    // [n_classes, COUT] or null
+  const float* head_b;    // [n_classes]
+  float* logits;          // [B, L_out, n_classes]
+  int n_classes;
+  int L_in, L_out;
+  int stride_log2;        // stride = 1 << stride_log2
+  int dil, pad;
+  float in_inv_len;       // 1 / L_in (count behind in_stats)
+  float in_eps;           // InstanceNorm eps (1e-2)
+  float ln_eps;           // ConvLayerNorm eps (1e-5)
+};
+
+constexpr int kConvThreads = 256;
+
+template <int COUT>
+struct ConvTile {
+  static constexpr int MT = 128 / COUT;    // 128-row UMMA sub-tiles per CTA
+  static constexpr int POS = 128 * MT;     // output positions per CTA
+};
+
+// Rows of staged input per stride phase for a CTA tile.
+__host__ __device__ inline int conv_rows_per_phase(int pos, int stride, int taps, int dil) {
+  const int R = (pos - 1) * stride + (taps - 1) * dil + 1;
+  return (R + stride - 1) / stride;
+}
+template <int CIN, int COUT, int GT, bool HAS_DS>
+__host__ __device__ inline size_t conv_smem_bytes(int stride, int taps, int dil) {
+  const int rp = conv_rows_per_phase(ConvTile<COUT>::POS, stride, taps, dil);
+  size_t a = (size_t)stride * (CIN / 8) * rp * 16;
+  size_t b = (size_t)(GT + (HAS_DS ? 1 : 0)) * (CIN / 8) * COUT * 16;
+  return a + b + 1152;  // + control block (barrier, tmem ptr, norm scale/shift, stats)
+}
+
+template <int CIN, int COUT, int TAPS, int GT /*taps resident per weight group*/, int PRO, int EPI, bool HAS_DS>
+__global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs p) {
+  static_assert(CIN % 16 == 0 && COUT % 16 == 0 && COUT <= 128, "UMMA shape");
+  static_assert(EPI == EPI_STATS || COUT == 128, "row-wise epilogues need the full channel dim in one tile");
+  constexpr int CH = CIN / 8;                 // 16-byte chunks per input row
+  constexpr int MT = ConvTile<COUT>::MT;
+  constexpr int POS = ConvTile<COUT>::POS;
+  constexpr int KSTEPS = CIN / 16;            // UMMA K=16 steps per tap
+  constexpr int NGROUPS = (TAPS + GT - 1) / GT;
+  constexpr uint32_t TMEM_COLS = HAS_DS ? 256 : 128;
+  constexpr uint32_t IDESC = umma_idesc_f16(128, COUT, false);
+
+  const int b = blockIdx.y;
+  if (p.row_mask != nullptr && p.row_mask[b]) return;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int stride = 1 << p.stride_log2;
+  const int o0 = blockIdx.x * POS;            // first output position of this tile
+  const int i0 = o0 * stride - p.pad;         // input row staged at u = 0
+  const int R = (POS - 1) * stride + (TAPS - 1) * p.dil + 1;
+  const int Rp = (R + stride - 1) >> p.stride_log2;
+
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + (size_t)stride * CH * Rp * 16;
+  uint8_t* sCtl = sB + (size_t)(GT + (HAS_DS ? 1 : 0)) * CH * COUT * 16;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sCtl);            // 8 B
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sCtl + 8);  // 4 B
+  float* sScale = reinterpret_cast<float*>(sCtl + 16);          // [<=128]  (CIN <= 128)
+  float* sShift = sScale + 128;                                 //          (aliased by epilogue stats)
+  float* sSum = sScale;                                         // [COUT] after the prologue is done
+  float* sSq = sShift;
+
+  // ---------------- setup ----------------
+  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (tid == 32) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (PRO != PRO_NONE && tid >= 64 && tid < 64 + CIN) {
+    const int c = tid - 64;
+    const float s0 = p.in_stats[((size_t)b * CIN + c) * 2 + 0];
+    const float s1 = p.in_stats[((size_t)b * CIN + c) * 2 + 1];
+    const float mean = s0 * p.in_inv_len;
+    const float var = fmaxf(s1 * p.in_inv_len - mean * mean, 0.0f);
+    const float rstd = rsqrtf(var + p.in_eps);
+    sScale[c] = rstd;
+    sShift[c] = -mean * rstd;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---------------- prologue: global -> (norm, GELU) -> smem A ----------------
+  {
+    const int cch = tid & (CH - 1);  // this thread's channel chunk is fixed (256 % CH == 0)
+    float sc[8], sh[8];
+    if (PRO != PRO_NONE) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        sc[k] = sScale[cch * 8 + k];
+        sh[k] = sShift[cch * 8 + k];
+      }
+    }
+    const int total = R * CH;
+    const act_t* inb = p.in + (size_t)b * p.L_in * CIN;
+    const act_t* resb = (PRO == PRO_NORM_RES) ? p.in_res + (size_t)b * p.L_in * CIN : nullptr;
+    constexpr int UN = (PRO == PRO_NORM_RES) ? 4 : 8;
+    for (int base = tid; base < total; base += kConvThreads * UN) {
+      uint4 y[UN], r[UN];
+#pragma unroll
+      for (int k = 0; k < UN; ++k) {
+        const int id = base + k * kConvThreads;
+        const int u = id / CH;
+        const int i = i0 + u;
+        y[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (PRO == PRO_NORM_RES) r[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (id < total && i >= 0 && i < p.L_in) {
+          const size_t off = (size_t)i * CIN + cch * 8;
+          y[k] = __ldg(reinterpret_cast<const uint4*>(inb + off));
+          if (PRO == PRO_NORM_RES) r[k] = __ldg(reinterpret_cast<const uint4*>(resb + off));
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < UN; ++k) {
+        const int id = base + k * kConvThreads;
+        if (id >= total) break;
+        const int u = id / CH;
+        const int i = i0 + u;
+        uint4 o = y[k];
+        if (PRO != PRO_NONE) {
+          if (i >= 0 && i < p.L_in) {  // zero padding applies to the *activated* signal
+            uint32_t* yy = reinterpret_cast<uint32_t*>(&y[k]);
+            uint32_t* rr = reinterpret_cast<uint32_t*>(&r[k]);
+            uint32_t* oo = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float2 v = unpack_h2(yy[q]);
+              float a0 = gelu_fast(fmaf(v.x, sc[2 * q], sh[2 * q]));
+              float a1 = gelu_fast(fmaf(v.y, sc[2 * q + 1], sh[2 * q + 1]));
+              if (PRO == PRO_NORM_RES) {
+                float2 rv = unpack_h2(rr[q]);
+                a0 = gelu_fast(a0 + rv.x);
+                a1 = gelu_fast(a1 + rv.y);
+              }
+              oo[q] = pack_h2(a0, a1);
+            }
+          }
+        }
+        const int phase = u & (stride - 1);
+        const int row = u >> p.stride_log2;
+        *reinterpret_cast<uint4*>(sA + ((size_t)(phase * CH + cch) * Rp + row) * 16) = o;
+      }
+    }
+  }
+
+  // ---------------- main loop over weight groups ----------------
+  uint32_t parity = 0;
+#pragma unroll 1
+  for (int g = 0; g < NGROUPS; ++g) {
+    const int t_begin = g * GT;
+    const int t_end = (t_begin + GT < TAPS) ? t_begin + GT : TAPS;
+    {  // weights of this tap group -> smem B (linear copy of the packed layout)
+      const int n16 = (t_end - t_begin) * CH * COUT;
+      const uint4* src = reinterpret_cast<const uint4*>(p.w) + (size_t)t_begin * CH * COUT;
+      uint4* dst = reinterpret_cast<uint4*>(sB);
+      for (int k = tid; k < n16; k += kConvThreads) dst[k] = __ldg(src + k);
+      if (HAS_DS && g == 0) {
+        const uint4* srcd = reinterpret_cast<const uint4*>(p.w_ds);
+        uint4* dstd = dst + (size_t)GT * CH * COUT;
+        for (int k = tid; k < CH * COUT; k += kConvThreads) dstd[k] = __ldg(srcd + k);
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+
+    if (tid == 0) {
+      tc_fence_after_sync();
+      const uint32_t a_base = smem_u32(sA);
+      const uint32_t b_base = smem_u32(sB);
+      const uint32_t lbo_a = (uint32_t)Rp * 16;
+      constexpr uint32_t lbo_b = COUT * 16;
+#pragma unroll 1
+      for (int j = 0; j < MT; ++j) {
+        for (int t = t_begin; t < t_end; ++t) {
+          const int uoff = t * p.dil;
+          const int phase = uoff & (stride - 1);
+          const int rowoff = (uoff >> p.stride_log2) + j * 128;
+#pragma unroll
+          for (int kk = 0; kk < KSTEPS; ++kk) {
+            const uint32_t a_addr = a_base + ((uint32_t)(phase * CH + 2 * kk) * Rp + rowoff) * 16;
+            const uint32_t b_addr = b_base + (uint32_t)((t - t_begin) * CH + 2 * kk) * COUT * 16;
+            umma_f16(tmem_base + j * COUT, umma_smem_desc(a_addr, lbo_a, 128), umma_smem_desc(b_addr, lbo_b, 128),
+                     IDESC, (t > 0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        if (HAS_DS && g == 0) {
+          // 1x1 stride-2 residual conv: centre tap rows (input position == output position of conv1);
+          // computed for every row, only even positions are kept by the epilogue.
+          const int rowoff = p.pad + j * 128;
+#pragma unroll
+          for (int kk = 0; kk < KSTEPS; ++kk) {
+            const uint32_t a_addr = a_base + ((uint32_t)(2 * kk) * Rp + rowoff) * 16;
+            const uint32_t b_addr = b_base + (uint32_t)(GT * CH + 2 * kk) * COUT * 16;
+            umma_f16(tmem_base + 128 + j * COUT, umma_smem_desc(a_addr, lbo_a, 128),
+                     umma_smem_desc(b_addr, lbo_b, 128), IDESC, kk > 0 ? 1u : 0u);
+          }
+        }
+      }
+      umma_commit(bar);
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    tc_fence_after_sync();
+  }
+
+  // ---------------- epilogue ----------------
+  const int quad = warp & 3;   // TMEM lane quadrant this warp may read
+  const int wg = warp >> 2;    // warpgroup 0/1
+  const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
+
+  if (EPI == EPI_STATS) {
+    if (tid < COUT) {
+      sSum[tid] = 0.0f;
+      sSq[tid] = 0.0f;
+    }
+    __syncthreads();
+    act_t* outb = p.out + (size_t)b * p.L_out * COUT;
+    constexpr int UNITS = MT * (COUT / 16);  // == 8
+#pragma unroll 1
+    for (int unit = wg; unit < UNITS; unit += 2) {
+      const int j = unit / (COUT / 16);
+      const int cg = unit % (COUT / 16);
+      float v[16];
+      tmem_ld16(tmem_base + t_lane + j * COUT + cg * 16, v);
+      const int o = o0 + j * 128 + quad * 32 + lane;
+      const bool valid = o < p.L_out;
+      if (valid) {
+        uint4 s0 = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+        uint4 s1 =
+            make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+        uint4* dst = reinterpret_cast<uint4*>(outb + (size_t)o * COUT + cg * 16);
+        dst[0] = s0;
+        dst[1] = s1;
+      }
+      float sq[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        v[k] = valid ? v[k] : 0.0f;
+        sq[k] = v[k] * v[k];
+      }
+      butterfly16(v, lane);
+      butterfly16(sq, lane);
+      if ((lane & 1) == 0) {
+        const int c = cg * 16 + butterfly16_channel(lane);
+        atomicAdd(&sSum[c], v[0]);
+        atomicAdd(&sSq[c], sq[0]);
+      }
+    }
+    if (HAS_DS) {
+      act_t* dsb = p.out_ds + (size_t)b * (p.L_out >> 1) * COUT;
+#pragma unroll 1
+      for (int unit = wg; unit < UNITS; unit += 2) {
+        const int j = unit / (COUT / 16);
+        const int cg = unit % (COUT / 16);
+        float v[16];
+        tmem_ld16(tmem_base + t_lane + 128 + j * COUT + cg * 16, v);
+        const int o = o0 + j * 128 + quad * 32 + lane;
+        if (o < p.L_out && (o & 1) == 0) {
+          uint4 s0 = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+          uint4 s1 =
+              make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+          uint4* dst = reinterpret_cast<uint4*>(dsb + (size_t)(o >> 1) * COUT + cg * 16);
+          dst[0] = s0;
+          dst[1] = s1;
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < COUT) {
+      atomicAdd(&p.out_stats[((size_t)b * COUT + tid) * 2 + 0], sSum[tid]);
+      atomicAdd(&p.out_stats[((size_t)b * COUT + tid) * 2 + 1], sSq[tid]);
+    }
+  } else if (EPI == EPI_BIAS_GELU) {
+    act_t* outb = p.out + (size_t)b * p.L_out * COUT;
+    const int o = o0 + quad * 32 + lane;
+#pragma unroll 1
+    for (int cg = wg; cg < COUT / 16; cg += 2) {
+      float v[16];
+      tmem_ld16(tmem_base + t_lane + cg * 16, v);
+      if (o < p.L_out) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = gelu_erf(v[k] + __ldg(p.bias + cg * 16 + k));
+        uint4 s0 = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+        uint4 s1 =
+            make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+        uint4* dst = reinterpret_cast<uint4*>(outb + (size_t)o * COUT + cg * 16);
+        dst[0] = s0;
+        dst[1] = s1;
+      }
+    }
+  } else {  // EPI_LN_GELU / EPI_LN_GELU_RES : thread owns one row of all 128 channels
+    if (wg == 0) {
+      const int o = o0 + quad * 32 + lane;
+      const bool valid = o < p.L_out;
+      // Three passes over TMEM (cheap) keep the two-pass variance of ConvLayerNorm (utils.py:17-21).
+      float mean = 0.0f;
+#pragma unroll 1
+      for (int cg = 0; cg < 8; ++cg) {
+        float v[16];
+        tmem_ld16(tmem_base + t_lane + cg * 16, v);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) mean += v[k];
+      }
+      mean *= (1.0f / 128.0f);
+      float var = 0.0f;
+#pragma unroll 1
+      for (int cg = 0; cg < 8; ++cg) {
+        float v[16];
+        tmem_ld16(tmem_base + t_lane + cg * 16, v);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float d = v[k] - mean;
+          var = fmaf(d, d, var);
+        }
+      }
+      const float rstd = rsqrtf(var * (1.0f / 128.0f) + p.ln_eps);
+      float lg[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) lg[c] = 0.0f;
+      const size_t rowoff = ((size_t)b * p.L_out + (valid ? o : 0)) * COUT;
+#pragma unroll 1
+      for (int cg = 0; cg < 8; ++cg) {
+        float v[16];
+        tmem_ld16(tmem_base + t_lane + cg * 16, v);
+        uint4 rz[2];
+        if (EPI == EPI_LN_GELU_RES) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.res + rowoff + cg * 16);
+          rz[0] = __ldg(rp);
+          rz[1] = __ldg(rp + 1);
+        }
+        const uint32_t* rr = reinterpret_cast<const uint32_t*>(rz);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int c = cg * 16 + k;
+          float y = (v[k] - mean) * rstd * __ldg(p.ln_w + c) + __ldg(p.ln_b + c);
+          y = gelu_erf(y);
+          if (EPI == EPI_LN_GELU_RES) {
+            const float2 r2 = unpack_h2(rr[k >> 1]);
+            y = gelu_erf(y + ((k & 1) ? r2.y : r2.x));
+          }
+          v[k] = y;
+        }
+        if (EPI == EPI_LN_GELU_RES && p.head_w != nullptr) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            if (c < p.n_classes) {
+              float acc = lg[c];
+#pragma unroll
+              for (int k = 0; k < 16; ++k) acc = fmaf(v[k], __ldg(p.head_w + c * COUT + cg * 16 + k), acc);
+              lg[c] = acc;
+            }
+          }
+        }
+        if (valid) {
+          uint4 s0 = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+          uint4 s1 =
+              make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+          uint4* dst = reinterpret_cast<uint4*>(p.out + rowoff + cg * 16);
+          dst[0] = s0;
+          dst[1] = s1;
+        }
+      }
+      if (EPI == EPI_LN_GELU_RES && p.head_w != nullptr && valid) {
+        float* lrow = p.logits + ((size_t)b * p.L_out + o) * p.n_classes;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < p.n_classes) lrow[c] = lg[c] + __ldg(p.head_b + c);
+      }
+    }
+  }
+
+  // ---------------- teardown ----------------
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// Host-side launcher.  Returns cudaError_t of the launch.
+template <int CIN, int COUT, int TAPS, int GT, int PRO, int EPI, bool HAS_DS>
+inline cudaError_t launch_conv_igemm(const ConvArgs& a, int B, cudaStream_t stream) {
+  auto kern = conv_igemm_kernel<CIN, COUT, TAPS, GT, PRO, EPI, HAS_DS>;
+  const int stride = 1 << a.stride_log2;
+  const size_t smem = conv_smem_bytes<CIN, COUT, GT, HAS_DS>(stride, TAPS, a.dil);
+  static size_t configured = 0;  // per instantiation
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  dim3 grid((a.L_out + ConvTile<COUT>::POS - 1) / ConvTile<COUT>::POS, B);
+  kern<<<grid, kConvThreads, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace w2s

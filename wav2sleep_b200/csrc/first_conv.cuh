@@ -1,0 +1,103 @@
+// First encoder layer: raw fp32 signal (Cin = 1) -> 16 channels, k=3, pad=1, stride 1, no bias.
+// reference: SignalEncoders.forward (models/wav2sleep.py:146-161) for the -inf handling,
+//            ConvBlock1D.conv1 / downsample of block 0 (models/blocks.py:39-53).
+//
+// A 3-tap FIR with 16 outputs per sample is not a tensor-core shape (K = 3); it runs on CUDA cores in fp32
+// and is purely HBM-bound: 4 B read, 32 B (+16 B residual branch) written per sample.
+// Outputs:  y1   [B, T, 16]   fp16 pre-norm conv1 output
+//           r0   [B, T/2, 16] fp16 1x1 stride-2 residual branch  w_ds[c] * x[2j]
+//           stats[B, 16, 2]   sum / sum-of-squares of y1 over T (InstanceNorm, utils.py:89-92)
+//           row_mask[B]       1 where the sample's signal is missing (x[b,0] is +-inf)
+#pragma once
+#include "common.cuh"
+
+namespace w2s {
+
+struct FirstConvArgs {
+  const float* x;       // [B, T]
+  const float* w;       // [16, 3]  (conv1.conv.weight[:, 0, :])
+  const float* w_ds;    // [16]     (downsample.weight[:, 0, 0])
+  act_t* y1;            // [B, T, 16]
+  act_t* r0;            // [B, T/2, 16]
+  float* stats;         // [B, 16, 2]  zeroed by caller
+  uint8_t* row_mask;    // [B]
+  int T;
+};
+
+constexpr int kFirstConvThreads = 256;
+constexpr int kFirstConvPerThread = 4;
+constexpr int kFirstConvPos = kFirstConvThreads * kFirstConvPerThread;
+
+__global__ void __launch_bounds__(kFirstConvThreads) first_conv_kernel(const FirstConvArgs p) {
+  const int b = blockIdx.y;
+  const float* xb = p.x + (size_t)b * p.T;
+  const bool masked = isinf(__ldg(xb));
+  if (blockIdx.x == 0 && threadIdx.x == 0) p.row_mask[b] = masked ? 1 : 0;
+  if (masked) return;
+
+  __shared__ float sw[16 * 3 + 16];
+  __shared__ float sSum[16], sSq[16];
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid < 48) sw[tid] = __ldg(p.w + tid);
+  if (tid >= 64 && tid < 80) sw[48 + tid - 64] = __ldg(p.w_ds + tid - 64);
+  if (tid >= 96 && tid < 112) {
+    sSum[tid - 96] = 0.0f;
+    sSq[tid - 96] = 0.0f;
+  }
+  __syncthreads();
+
+  float acc[16], acc2[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = acc2[c] = 0.0f;
+
+  const int p0 = blockIdx.x * kFirstConvPos;
+#pragma unroll
+  for (int k = 0; k < kFirstConvPerThread; ++k) {
+    const int pos = p0 + k * kFirstConvThreads + tid;
+    if (pos < p.T) {
+      float xm = pos > 0 ? __ldg(xb + pos - 1) : 0.0f;
+      float x0 = __ldg(xb + pos);
+      float xp = pos + 1 < p.T ? __ldg(xb + pos + 1) : 0.0f;
+      xm = isinf(xm) ? 0.0f : xm;  // wav2sleep.py:151
+      x0 = isinf(x0) ? 0.0f : x0;
+      xp = isinf(xp) ? 0.0f : xp;
+      float v[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        v[c] = fmaf(sw[c * 3 + 2], xp, fmaf(sw[c * 3 + 1], x0, sw[c * 3] * xm));
+        acc[c] += v[c];
+        acc2[c] = fmaf(v[c], v[c], acc2[c]);
+      }
+      uint4* dst = reinterpret_cast<uint4*>(p.y1 + ((size_t)b * p.T + pos) * 16);
+      dst[0] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+      dst[1] = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+      if ((pos & 1) == 0) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = sw[48 + c] * x0;
+        uint4* dr = reinterpret_cast<uint4*>(p.r0 + ((size_t)b * (p.T >> 1) + (pos >> 1)) * 16);
+        dr[0] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+        dr[1] = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+      }
+    }
+  }
+  butterfly16(acc, lane);
+  butterfly16(acc2, lane);
+  if ((lane & 1) == 0) {
+    const int c = butterfly16_channel(lane);
+    atomicAdd(&sSum[c], acc[0]);
+    atomicAdd(&sSq[c], acc2[0]);
+  }
+  __syncthreads();
+  if (tid < 16) {
+    atomicAdd(&p.stats[((size_t)b * 16 + tid) * 2 + 0], sSum[tid]);
+    atomicAdd(&p.stats[((size_t)b * 16 + tid) * 2 + 1], sSq[tid]);
+  }
+}
+
+inline cudaError_t launch_first_conv(const FirstConvArgs& a, int B, cudaStream_t stream) {
+  dim3 grid((a.T + kFirstConvPos - 1) / kFirstConvPos, B);
+  first_conv_kernel<<<grid, kFirstConvThreads, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace w2s

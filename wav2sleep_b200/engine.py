@@ -1,0 +1,231 @@
+"""Host-side driver of the CUDA forward: packs weights, carves workspaces, calls the C ABI stage by stage.
+
+PyTorch is plumbing here (device memory, current stream); every FLOP of the forward runs in
+``libw2s_b200.so``.  Mirrors the call ``model(x)`` of the reference (api.py:181-183, trainer/main.py:114).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import EncoderDesc, MixerDesc, SeqDesc
+
+
+def _ptr(t: Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _PackedEncoder:
+    """fp16 UMMA-layout copies of one SignalEncoder's weights + the C descriptor pointing at them."""
+
+    def __init__(self, lib, enc, device):
+        self.keep: list[Tensor] = []
+        d = EncoderDesc()
+        d.n_blocks = len(enc.channels)
+        for i, c in enumerate(enc.channels):
+            d.channels[i] = c
+        d.feature_dim = enc.feature_dim
+        d.norm_eps = enc.norm_eps
+        st = _stream()
+
+        def f32(t):
+            t = t.detach().to(device=device, dtype=torch.float32).contiguous()
+            self.keep.append(t)
+            return t
+
+        def pack(w, taps_major=0, taps=None):
+            w = f32(w)
+            if taps_major:
+                cout, cin = w.shape[0], w.shape[1] // taps
+            else:
+                cout, cin, taps = w.shape
+            out = torch.empty(taps * cin * cout, dtype=torch.float16, device=device)
+            _lib.check(lib.w2s_pack_conv_weight(w.data_ptr(), cout, cin, taps, taps_major, out.data_ptr(), st))
+            self.keep.append(out)
+            return out.data_ptr()
+
+        blk0 = enc.cnn[0]
+        d.w_first = f32(blk0.conv1.conv.weight[:, 0, :]).data_ptr()
+        d.w_first_ds = f32(blk0.downsample.weight[:, 0, 0]).data_ptr()
+        for i, blk in enumerate(enc.cnn):
+            if i > 0:
+                d.w_conv[i][0] = pack(blk.conv1.conv.weight)
+                d.w_ds[i] = pack(blk.downsample.weight)
+            d.w_conv[i][1] = pack(blk.conv2.conv.weight)
+            d.w_conv[i][2] = pack(blk.conv3.conv.weight)
+        d.w_lin = pack(enc.linear.weight, taps_major=1, taps=4)
+        d.b_lin = f32(enc.linear.bias).data_ptr()
+        self.desc = d
+        self.samples_per_epoch = enc.samples_per_epoch
+
+
+class ForwardEngine:
+    """Inference forward of ``Wav2Sleep`` on one CUDA device."""
+
+    def __init__(self, model):
+        self.model = model
+        self.lib = _lib.load()
+        self._weights_key = None
+        self._ws: dict = {}
+
+    # ------------------------------------------------------------------ weights
+    def _params_key(self, device):
+        return (str(device),) + tuple((p.data_ptr(), p._version) for p in self.model.parameters())
+
+    def _ensure_packed(self, device):
+        key = self._params_key(device)
+        if key == self._weights_key:
+            return
+        m, lib, st = self.model, self.lib, _stream()
+        self.keep: list[Tensor] = []
+        self.enc = {name: _PackedEncoder(lib, enc, device) for name, enc in m.signal_encoders.encoders.items()}
+
+        def f32(t):
+            t = t.detach().to(device=device, dtype=torch.float32).contiguous()
+            self.keep.append(t)
+            return t
+
+        def frag(w):
+            w = f32(w)
+            out = torch.empty(w.numel(), dtype=torch.float16, device=device)
+            _lib.check(lib.w2s_pack_linear_frag(w.data_ptr(), w.shape[0], w.shape[1], out.data_ptr(), st))
+            self.keep.append(out)
+            return out.data_ptr()
+
+        mix = m.epoch_mixer
+        md = MixerDesc()
+        md.n_layers = mix.num_layers
+        md.feature_dim, md.n_heads, md.dim_ff = mix.feature_dim, mix.nhead, mix.dim_ff
+        md.ln_eps = mix.transformer_encoder.layers[0].norm1.eps
+        md.cls = f32(mix.register_tokens[0, 0, :, 0]).data_ptr()
+        for l, layer in enumerate(mix.transformer_encoder.layers):
+            L = md.layer[l]
+            L.in_w = frag(layer.self_attn.in_proj_weight)
+            L.out_w = frag(layer.self_attn.out_proj.weight)
+            L.ff1_w = frag(layer.linear1.weight)
+            L.ff2_w = frag(layer.linear2.weight)
+            L.in_b = f32(layer.self_attn.in_proj_bias).data_ptr()
+            L.out_b = f32(layer.self_attn.out_proj.bias).data_ptr()
+            L.ff1_b = f32(layer.linear1.bias).data_ptr()
+            L.ff2_b = f32(layer.linear2.bias).data_ptr()
+            L.ln1_w, L.ln1_b = f32(layer.norm1.weight).data_ptr(), f32(layer.norm1.bias).data_ptr()
+            L.ln2_w, L.ln2_b = f32(layer.norm2.weight).data_ptr(), f32(layer.norm2.bias).data_ptr()
+        self.mixer_desc = md
+
+        seq = m.sequence_mixer
+        sd = SeqDesc()
+        sd.n_blocks = len(seq.dilated_convs)
+        sd.n_dilations = len(seq.dilated_convs[0].conv_layers)
+        sd.kernel_size = seq.dilated_convs[0].kernel_size
+        sd.feature_dim = seq.feature_dim
+        sd.n_classes = m.num_classes
+        sd.ln_eps = seq.dilated_convs[0].conv_layers[0].norm.eps
+        for b, blk in enumerate(seq.dilated_convs):
+            for k, layer in enumerate(blk.conv_layers):
+                w = f32(layer.conv.weight)
+                cout, cin, taps = w.shape
+                out = torch.empty(w.numel(), dtype=torch.float16, device=device)
+                _lib.check(lib.w2s_pack_conv_weight(w.data_ptr(), cout, cin, taps, 0, out.data_ptr(), st))
+                self.keep.append(out)
+                sd.w[b][k] = out.data_ptr()
+                sd.ln_w[b][k] = f32(layer.norm.weight.reshape(-1)).data_ptr()
+                sd.ln_b[b][k] = f32(layer.norm.bias.reshape(-1)).data_ptr()
+        sd.head_w = f32(m.classifier.weight).data_ptr()
+        sd.head_b = f32(m.classifier.bias).data_ptr()
+        self.seq_desc = sd
+        self._weights_key = key
+
+    # ------------------------------------------------------------------ buffers
+    def _buffers(self, device, names, B, S):
+        key = (str(device), tuple(names), B, S)
+        buf = self._ws.get(key)
+        if buf is not None:
+            return buf
+        self._ws.clear()  # one live shape at a time keeps the footprint bounded
+        lib = self.lib
+        enc_ws = 0
+        for n in names:
+            pe = self.enc[self.model.signal_encoders.signal_map[n]]
+            enc_ws = max(enc_ws, lib.w2s_encoder_workspace_bytes(C.byref(pe.desc), B, S * pe.samples_per_epoch, 0))
+        seq_ws = lib.w2s_seqmixer_workspace_bytes(C.byref(self.seq_desc), B, S, 0)
+        buf = {
+            "enc_ws": torch.empty(enc_ws, dtype=torch.uint8, device=device),
+            "seq_ws": torch.empty(seq_ws, dtype=torch.uint8, device=device),
+            "z": {n: torch.empty(B, S, 128, dtype=torch.float16, device=device) for n in names},
+            "mask": {n: torch.zeros(B, dtype=torch.uint8, device=device) for n in names},
+            "mix": torch.empty(B, S, 128, dtype=torch.float16, device=device),
+        }
+        self._ws[key] = buf
+        return buf
+
+    # ------------------------------------------------------------------ forward
+    def _check_inputs(self, x):
+        if not isinstance(x, dict) or len(x) == 0:
+            raise ValueError("No signals provided to MultiModalAttentionEmbedder.")  # wav2sleep.py:312-313
+        smap = self.model.signal_encoders.signal_map
+        B = S = device = None
+        for name, t in x.items():
+            if name not in smap:
+                raise KeyError(f"Signal {name!r} has no encoder (valid: {list(smap)})")
+            if not isinstance(t, Tensor) or t.dim() != 2:
+                raise ValueError(f"{name}: expected a [B, T] tensor")
+            if not t.is_cuda:
+                raise RuntimeError("wav2sleep_b200 runs on CUDA (sm_100a) only: move inputs with .to('cuda'); "
+                                   "there is no CPU fallback")
+            spe = self.model.signal_encoders.get_encoder(name).samples_per_epoch
+            if t.size(-1) % spe:
+                raise ValueError(f"Input length {t.size(-1)} must be divisible by self.samples_per_epoch={spe}.")
+            b, s = t.size(0), t.size(-1) // spe
+            if B is None:
+                B, S, device = b, s, t.device
+            elif (b, s) != (B, S) or t.device != device:
+                raise ValueError(f"{name}: batch/epoch count {(b, s)} differs from {(B, S)}")
+        if B == 0 or S == 0:
+            raise ValueError("empty batch")
+        return B, S, device
+
+    @torch.no_grad()
+    def forward(self, x: dict[str, Tensor]) -> Tensor:
+        if self.model.training and torch.is_grad_enabled():
+            raise NotImplementedError("wav2sleep_b200: backward kernels are not built yet; call under "
+                                      "model.eval() / torch.no_grad() (DESIGN.md, scope)")
+        B, S, device = self._check_inputs(x)
+        lib = self.lib
+        with torch.cuda.device(device):
+            self._ensure_packed(device)
+            names = sorted(x.keys())  # token order of the mixer, wav2sleep.py:311
+            buf = self._buffers(device, names, B, S)
+            st = _stream()
+            for n in names:
+                pe = self.enc[self.model.signal_encoders.signal_map[n]]
+                xs = x[n].detach()
+                if xs.dtype != torch.float32 or not xs.is_contiguous():
+                    xs = xs.to(torch.float32).contiguous()
+                _lib.check(lib.w2s_encoder_fwd(C.byref(pe.desc), xs.data_ptr(), B, xs.size(1), buf["enc_ws"].data_ptr(),
+                                               buf["enc_ws"].numel(), 0, buf["z"][n].data_ptr(),
+                                               buf["mask"][n].data_ptr(), st), ValueError)
+            zs = (C.c_void_p * len(names))(*[buf["z"][n].data_ptr() for n in names])
+            ms = (C.c_void_p * len(names))(*[buf["mask"][n].data_ptr() for n in names])
+            _lib.check(lib.w2s_epoch_mixer_fwd(C.byref(self.mixer_desc), zs, ms, len(names), B, S,
+                                               buf["mix"].data_ptr(), st))
+            logits = torch.empty(B, S, self.model.num_classes, dtype=torch.float32, device=device)
+            _lib.check(lib.w2s_seqmixer_head_fwd(C.byref(self.seq_desc), buf["mix"].data_ptr(), B, S,
+                                                 buf["seq_ws"].data_ptr(), buf["seq_ws"].numel(), 0, None,
+                                                 logits.data_ptr(), st))
+        return logits
+
+    @torch.no_grad()
+    def predict(self, x: dict[str, Tensor]) -> Tensor:
+        logits = self.forward(x)
+        B, S, Cn = logits.shape
+        out = torch.empty(B, S, dtype=torch.int64, device=logits.device)
+        with torch.cuda.device(logits.device):
+            _lib.check(self.lib.w2s_argmax(logits.data_ptr(), B * S, Cn, out.data_ptr(), _stream()))
+        return out

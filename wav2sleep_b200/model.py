@@ -1,0 +1,247 @@
+"""Drop-in mirror of ``wav2sleep.models.wav2sleep`` whose forward runs on hand-written sm_100a kernels.
+
+Same class names, constructor keywords, attribute names and ``state_dict`` keys as the reference
+(/root/reference/src/wav2sleep/models/wav2sleep.py:16-390, blocks.py, utils.py), so that
+``hydra.utils.instantiate`` configs, ``load_state_dict(torch.load('state_dict.pth'))`` and the Lightning module
+of the reference keep working when ``_target_`` is pointed at this module.
+
+The ``torch.nn`` leaf modules below (``nn.Conv1d``, ``nn.Linear``, ``nn.TransformerEncoderLayer`` ...) are
+*parameter containers only*: they give identical parameter names, shapes and default initialisation (same RNG
+consumption order as the reference, so ``torch.manual_seed(s)`` reproduces the reference's random init
+bit-for-bit), but their ``forward`` is never called.  All compute goes through ``engine.ForwardEngine`` ->
+``libw2s_b200.so``.  There is no CPU or eager fallback: a CPU tensor or a missing library raises.
+
+Options of the reference that the CUDA path does not build yet raise ``NotImplementedError`` at construction
+(SURVEY.md section 8f, row N3): causal / chunk-causal mode, norms other than ``instance`` (encoders) and
+``layer`` (sequence mixer), activations other than ``gelu``, ``embed_signals``, ``register_tokens > 0``,
+``output_norm``, ``use_residual=False``, widths other than 16..128 / feature_dim 128.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import Tensor, nn
+
+# settings.py:16-26 of the reference: samples per 30-s epoch after resampling.
+COLS_TO_SAMPLES_PER_EPOCH = {"ABD": 256, "THX": 256, "ECG": 1024, "PPG": 1024, "EOG-L": 4096, "EOG-R": 4096}
+
+
+def _require(cond: bool, what: str) -> None:
+    if not cond:
+        raise NotImplementedError(f"wav2sleep_b200: {what} is not built on the CUDA path")
+
+
+class ConvLayerNorm(nn.Module):
+    """Parameters of the channel-first LayerNorm (reference models/utils.py:9-23); applied inside the conv epilogue."""
+
+    def __init__(self, num_features: int, eps: float = 1e-5):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(1, num_features, 1))
+        self.bias = nn.Parameter(torch.zeros(1, num_features, 1))
+        self.eps = eps
+
+
+class ConvLayer1D(nn.Module):
+    """conv -> norm -> activation; holds ``conv.weight`` (+ ``norm.*``).  reference models/blocks.py:129-186."""
+
+    def __init__(self, input_dim: int, output_dim: int, kernel_size: int = 3, stride: int = 1, padding: int = 1,
+                 dilation: int = 1, norm: str = "instance", norm_eps: float | None = None):
+        super().__init__()
+        self.conv = nn.Conv1d(input_dim, output_dim, kernel_size=kernel_size, stride=stride, padding=padding,
+                              dilation=dilation, bias=False)
+        if norm == "instance":
+            self.norm = nn.InstanceNorm1d(output_dim, **({"eps": norm_eps} if norm_eps is not None else {}))
+        elif norm == "layer":
+            self.norm = ConvLayerNorm(output_dim)
+        else:
+            _require(False, f"norm={norm!r}")
+
+
+class ConvBlock1D(nn.Module):
+    """Three conv layers + 1x1 stride-2 residual; out = GELU(conv3(conv2(conv1(x))) + downsample(x)).  blocks.py:8-71."""
+
+    def __init__(self, input_dim: int, output_dim: int, norm_eps: float | None):
+        super().__init__()
+        self.conv1 = ConvLayer1D(input_dim, output_dim, norm_eps=norm_eps)
+        self.conv2 = ConvLayer1D(output_dim, output_dim, norm_eps=norm_eps)
+        self.conv3 = ConvLayer1D(output_dim, output_dim, stride=2, norm_eps=norm_eps)
+        self.downsample = nn.Conv1d(input_dim, output_dim, kernel_size=1, stride=2, padding=0, bias=False)
+
+
+class SignalEncoder(nn.Module):
+    """Per-signal CNN: log2(samples_per_epoch)-2 ConvBlock1D + Linear(4C -> F).  models/wav2sleep.py:164-267."""
+
+    def __init__(self, input_dim: int = 1, feature_dim: int = 256, activation: str = "gelu",
+                 samples_per_epoch: int = 1024, norm: str = "instance", initial_channels: int = 16,
+                 max_channels: int = 128, causal: bool = False, chunk_causal: bool = True, output_norm: bool = False,
+                 use_residual: bool = True) -> None:
+        super().__init__()
+        if samples_per_epoch & (samples_per_epoch - 1) != 0:
+            raise ValueError(f"samples_per_epoch must be a power of 2, got {samples_per_epoch}")
+        _require(input_dim == 1, f"input_dim={input_dim}")
+        _require(activation == "gelu", f"activation={activation!r}")
+        _require(norm == "instance", f"encoder norm={norm!r}")
+        _require(not causal, "causal=True")
+        _require(not output_norm, "output_norm=True")
+        _require(use_residual, "use_residual=False")
+        _require(initial_channels == 16 and max_channels == 128, f"channels {initial_channels}..{max_channels}")
+        _require(feature_dim == 128, f"feature_dim={feature_dim}")
+        self.feature_dim = feature_dim
+        self.samples_per_epoch = samples_per_epoch
+        self.causal = causal
+        self.chunk_causal = chunk_causal
+        num_blocks = int(math.log2(samples_per_epoch)) - 2
+        _require(1 <= num_blocks <= 12, f"samples_per_epoch={samples_per_epoch}")
+        self.channels = [min(initial_channels * 2 ** (i // 2), max_channels) for i in range(num_blocks)]
+        self.norm_eps = 1e-2  # models/wav2sleep.py:213-215
+        blocks, cin = [], input_dim
+        for cout in self.channels:
+            blocks.append(ConvBlock1D(cin, cout, norm_eps=self.norm_eps))
+            cin = cout
+        self.cnn = nn.Sequential(*blocks)
+        self.epoch_dim = self.channels[-1] * 4
+        self.linear = nn.Linear(self.epoch_dim, feature_dim)
+        self.activation = nn.GELU()
+        self.output_norm = nn.Identity()
+
+
+class SignalEncoders(nn.Module):
+    """Container of the per-signal encoders.  models/wav2sleep.py:83-161."""
+
+    def __init__(self, signal_map: dict[str, str], feature_dim: int, activation: str, norm: str = "instance",
+                 causal: bool = False, chunk_causal: bool = True, embed_signals: bool = False,
+                 initial_channels: int = 16, max_channels: int = 128, output_norm: bool = False,
+                 use_residual: bool = True) -> None:
+        super().__init__()
+        _require(not embed_signals, "embed_signals=True")
+        self.feature_dim = feature_dim
+        self.signal_map = dict(signal_map)
+        self.causal = causal
+        encoders = {}
+        for signal_name, encoder_name in self.signal_map.items():
+            if encoder_name in encoders:
+                continue
+            if signal_name not in COLS_TO_SAMPLES_PER_EPOCH:
+                raise ValueError(f"Column {signal_name} unrecognised. Doesn't have a sampling rate.")
+            encoders[encoder_name] = SignalEncoder(
+                input_dim=1, feature_dim=feature_dim, samples_per_epoch=COLS_TO_SAMPLES_PER_EPOCH[signal_name],
+                activation=activation, norm=norm, causal=causal, chunk_causal=chunk_causal,
+                initial_channels=initial_channels, max_channels=max_channels, output_norm=output_norm,
+                use_residual=use_residual)
+        self.encoders = nn.ModuleDict(encoders)
+        self.embed_signals = embed_signals
+        self.sig_to_embedding_idx = {sig: i for i, sig in enumerate(sorted(self.signal_map.keys()))}
+        self.register_parameter("embedder", None)
+
+    def __len__(self) -> int:
+        return len(self.encoders)
+
+    def get_encoder(self, signal_name: str) -> SignalEncoder:
+        return self.encoders[self.signal_map[signal_name]]  # type: ignore[return-value]
+
+
+class MultiModalAttentionEmbedder(nn.Module):
+    """CLS-token set transformer over the modality tokens of one epoch.  models/wav2sleep.py:270-346."""
+
+    def __init__(self, feature_dim: int, layers: int = 4, dropout: float = 0.0, dim_ff: int = 512,
+                 activation: str = "gelu", norm_first: bool = True, nhead: int = 4, register_tokens: int = 0):
+        super().__init__()
+        _require(feature_dim == 128 and nhead == 8 and dim_ff == 512,
+                 f"epoch mixer shape feature_dim={feature_dim}, nhead={nhead}, dim_ff={dim_ff}")
+        _require(activation == "gelu", f"activation={activation!r}")
+        _require(norm_first, "norm_first=False")
+        _require(register_tokens == 0, f"register_tokens={register_tokens}")
+        _require(1 <= layers <= 8, f"layers={layers}")
+        self.feature_dim = feature_dim
+        self.dropout = dropout
+        self.nhead = nhead
+        self.dim_ff = dim_ff
+        encoder_layer = nn.TransformerEncoderLayer(d_model=feature_dim, dim_feedforward=dim_ff, activation=nn.GELU(),
+                                                   nhead=nhead, batch_first=True, dropout=dropout,
+                                                   norm_first=norm_first)
+        self.num_layers = layers
+        self.transformer_encoder = nn.TransformerEncoder(encoder_layer, num_layers=layers, enable_nested_tensor=False)
+        self.num_register_tokens = register_tokens
+        self.register_tokens = nn.Parameter(torch.randn(1, 1, feature_dim, register_tokens + 1))
+
+
+class DilatedConvBlock(nn.Module):
+    """num_dilations x (dilated conv k -> ConvLayerNorm -> GELU), dropout, + input, GELU.  models/blocks.py:74-126."""
+
+    def __init__(self, feature_dim: int = 128, dropout: float = 0.2, kernel_size: int = 7, num_dilations: int = 6):
+        super().__init__()
+        self.kernel_size = kernel_size
+        self.dilations = [2 ** i for i in range(num_dilations)]
+        layers = []
+        for d in self.dilations:
+            k_eff = kernel_size + (kernel_size - 1) * (d - 1)
+            layers.append(ConvLayer1D(feature_dim, feature_dim, kernel_size=kernel_size, stride=1, dilation=d,
+                                      padding=k_eff // 2, norm="layer"))
+        self.dropout = nn.Dropout(p=dropout)
+        self.conv_layers = nn.Sequential(*layers)
+        self.activation = nn.GELU()
+
+
+class SequenceCNN(nn.Module):
+    """Dilated-CNN sequence mixer.  models/wav2sleep.py:349-390."""
+
+    def __init__(self, feature_dim: int = 128, dropout: float = 0.2, num_layers: int = 2, activation: str = "gelu",
+                 norm: str = "batch", causal: bool = False, num_dilations: int = 6, kernel_size: int = 7) -> None:
+        super().__init__()
+        _require(feature_dim == 128 and kernel_size == 7, f"sequence mixer feature_dim={feature_dim}, k={kernel_size}")
+        _require(activation == "gelu", f"activation={activation!r}")
+        _require(norm == "layer", f"sequence mixer norm={norm!r}")
+        _require(not causal, "causal=True")
+        _require(1 <= num_layers <= 4 and 1 <= num_dilations <= 8, f"num_layers={num_layers}, num_dilations={num_dilations}")
+        self.feature_dim = feature_dim
+        self.dilated_convs = nn.Sequential(*[
+            DilatedConvBlock(feature_dim=feature_dim, dropout=dropout, kernel_size=kernel_size,
+                             num_dilations=num_dilations) for _ in range(num_layers)])
+
+
+class Wav2Sleep(nn.Module):
+    """Sleep-staging model: encoders -> epoch mixer -> sequence mixer -> classifier.  models/wav2sleep.py:16-80."""
+
+    def __init__(self, signal_encoders: SignalEncoders, epoch_mixer: MultiModalAttentionEmbedder,
+                 sequence_mixer: SequenceCNN, num_classes: int):
+        super().__init__()
+        _require(1 <= num_classes <= 8, f"num_classes={num_classes}")
+        self.signal_encoders = signal_encoders
+        self.epoch_mixer = epoch_mixer
+        self.sequence_mixer = sequence_mixer
+        self.feature_dim = self.epoch_mixer.feature_dim
+        self.num_classes = num_classes
+        self.classifier = nn.Linear(in_features=self.feature_dim, out_features=num_classes)
+        self._engine = None
+
+    @property
+    def valid_signals(self) -> list[str]:
+        return list(self.signal_encoders.signal_map.keys())
+
+    def _get_engine(self):
+        from .engine import ForwardEngine  # deferred: loads the CUDA library
+        if self._engine is None:
+            object.__setattr__(self, "_engine", ForwardEngine(self))
+        return self._engine
+
+    def forward(self, x: dict[str, Tensor]) -> Tensor:
+        """dict of [B, S * samples_per_epoch] fp32 (rows of -inf = missing signal) -> logits [B, S, num_classes]."""
+        return self._get_engine().forward(x)
+
+    def predict(self, x: dict[str, Tensor]) -> Tensor:
+        """Most likely class per epoch, int64 [B, S]  (argmax kernel on the logits)."""
+        return self._get_engine().predict(x)
+
+
+def build_default(signal_map: dict[str, str], num_classes: int, seed: int | None = None) -> Wav2Sleep:
+    """The model of scripts/config/model/wav2sleep.yaml + main.yaml (feature_dim 128, non-causal)."""
+    if seed is not None:
+        torch.manual_seed(seed)
+    enc = SignalEncoders(signal_map=signal_map, feature_dim=128, activation="gelu", norm="instance", causal=False,
+                         chunk_causal=False, initial_channels=16, max_channels=128, output_norm=False,
+                         use_residual=True)
+    mix = MultiModalAttentionEmbedder(feature_dim=128, dropout=0.1, activation="gelu", layers=2, dim_ff=512, nhead=8)
+    seq = SequenceCNN(feature_dim=128, dropout=0.1, activation="gelu", norm="layer", causal=False, num_layers=2,
+                      kernel_size=7, num_dilations=6)
+    return Wav2Sleep(enc, mix, seq, num_classes)
