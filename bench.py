@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Benchmark of the wav2sleep forward hot path on B200 (BASELINE.json metric: recording-hours/sec, forward).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                    # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]              # reference algorithm on host CPU cores
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N   # N > 1, one rank per GPU
+
+Workload (config.workload): BASELINE.json configs[2] - cardio model (ABD, THX, ECG, PPG; 4 classes), batch of
+16 synthetic 10-hour nights per GPU (S = 1200 epochs; ECG/PPG 1 228 800 samples, ABD/THX 307 200 samples per
+night, N(0,1) fp32), random-init weights.  Recordings are independent, so N GPUs = N replicas on disjoint shards
+with no data-path collective ("scaling": "weak").
+
+One "step" = one forward pass (signal encoders -> epoch mixer -> sequence mixer -> classifier -> argmax) over one
+batch.  `value` times K steps with inputs resident in HBM (CUDA events, barrier + synchronize on both sides, max
+over ranks).  `e2e` times the same K steps through the public API with HOST (pinned) inputs: every step copies its
+196.6 MB of inputs host->device and reads the int64 predictions back; copies are double-buffered on a side stream
+but all inside the timed region.  Inputs (196.6 MB/step) and activations (GBs) exceed the 126 MB L2, so no
+explicit L2 flush is needed ("l2": "inputs+activations > L2").
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+CARDIO = {"ABD": "ABD", "THX": "THX", "ECG": "ECG", "PPG": "PPG"}
+SPE = {"ABD": 256, "THX": 256, "ECG": 1024, "PPG": 1024}
+S_EPOCHS = 1200          # 10-hour night
+HOURS_PER_NIGHT = 10.0
+BATCH = 16               # nights per GPU per step
+METRIC = "recording-hours/sec fwd"
+UNIT = "recording-hours/s"
+WORKLOAD = "cardio 4-signal (ABD,THX,ECG,PPG) 4-class inference, 16 synthetic 10-h nights per GPU (BASELINE configs[2])"
+
+
+def make_night_batch(B, seed, pin=False):
+    g = torch.Generator().manual_seed(seed)
+    x = {}
+    for name in CARDIO:
+        t = torch.randn(B, S_EPOCHS * SPE[name], generator=g)
+        x[name] = t.pin_memory() if pin else t
+    return x
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))), "measured"
+    return 6650.0, 1400.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([f.strip() for f in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = max((int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(self.samples)}
+
+
+def cpu_reference_time(steps, warmup, nights_per_step=1):
+    """The reference algorithm (oracle port, same torch CPU kernels as the reference) on the host cores."""
+    from oracle import wav2sleep_oracle as oracle
+    from wav2sleep_b200 import build_default
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = build_default(CARDIO, 4, seed=0)
+    sd = model.state_dict()
+    cfg = oracle.cardio_config()
+    x = make_night_batch(nights_per_step, seed=42)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        oracle.forward(x, sd, cfg).argmax(-1)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    times.sort()
+    med = times[len(times) // 2]
+    return {"value": nights_per_step * HOURS_PER_NIGHT / med, "unit": UNIT, "cores": torch.get_num_threads(),
+            "kind": "port", "s_per_step": med,
+            "sample": f"{nights_per_step} night(s) of the workload per step (B={nights_per_step}, S={S_EPOCHS}), "
+                      f"fp32 torch CPU, median of {steps} after {warmup} warm-up"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_time(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["s_per_step"] * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "nights_per_step": 1, "epochs_per_night": S_EPOCHS},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def collect_profile(lib):
+    n = lib.w2s_profile_count()
+    recs = []
+    buf = C.create_string_buffer(128)
+    ms, by, fl = C.c_float(), C.c_double(), C.c_double()
+    for i in range(n):
+        if lib.w2s_profile_get(i, buf, 128, C.byref(ms), C.byref(by), C.byref(fl)) == 0:
+            recs.append((buf.value.decode(), ms.value, by.value, fl.value))
+    return recs
+
+
+def run_cuda(args):
+    import torch.distributed as dist
+    from wav2sleep_b200 import _lib, build_default
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run --nproc-per-node N")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    hbm_peak, tf_peak, peak_src = measured_peaks()
+
+    model = build_default(CARDIO, 4, seed=0).to(dev).eval()
+    # two distinct host batches (pinned) so that consecutive steps never reuse data
+    host = [make_night_batch(BATCH, seed=42 + rank * 2 + i, pin=True) for i in range(2)]
+    devb = [{k: v.to(dev, non_blocking=True) for k, v in h.items()} for h in host]
+    h2d_bytes = sum(v.numel() * 4 for v in host[0].values())
+    d2h_bytes = BATCH * S_EPOCHS * 8
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---------------- device-resident timing ----------------
+    with torch.inference_mode():
+        for i in range(args.warmup):
+            model.predict(devb[i % 2])
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        l0 = lib.w2s_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            pred = model.predict(devb[i % 2])
+        e1.record()
+        barrier()
+        launches = lib.w2s_launch_count() - l0
+        ms_dev = max_over_ranks(e0.elapsed_time(e1))
+
+        # ---------------- end-to-end timing: pinned host inputs -> predictions on host ----------------
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream()
+        stage = [{k: torch.empty_like(v) for k, v in devb[0].items()} for _ in range(2)]
+        out_host = [torch.empty(BATCH, S_EPOCHS, dtype=torch.int64).pin_memory() for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+
+        def upload(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[i % 2])
+                for k in stage[i % 2]:
+                    stage[i % 2][k].copy_(host[i % 2][k], non_blocking=True)
+                ready[i % 2].record(copy_stream)
+
+        def e2e_loop(n):
+            for b in range(2):
+                consumed[b].record(main)
+            upload(0)
+            for i in range(n):
+                if i + 1 < n:
+                    upload(i + 1)
+                main.wait_event(ready[i % 2])
+                p = model.predict(stage[i % 2])
+                consumed[i % 2].record(main)
+                out_host[i % 2].copy_(p, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_loop(min(args.warmup, 3))
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        e2e_loop(args.steps)
+        t1.record()
+        barrier()
+        ms_e2e = max_over_ranks(t0.elapsed_time(t1))
+        sampler.stop_flag.set()
+        sampler.join(timeout=3)
+
+        # ---------------- per-kernel profile (CUDA events around every launch, 2 extra steps) ----------------
+        prof = []
+        if rank == 0:
+            lib.w2s_profile_enable(1)
+            for i in range(2):
+                model.predict(devb[i % 2])
+            torch.cuda.synchronize()
+            prof = collect_profile(lib)
+            lib.w2s_profile_enable(0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hours_per_step = BATCH * HOURS_PER_NIGHT * world
+    value = hours_per_step * args.steps / (ms_dev * 1e-3)
+    e2e_value = hours_per_step * args.steps / (ms_e2e * 1e-3)
+
+    # aggregate the profile by kernel label: share of the step and achieved algorithmic bandwidth / flop rate
+    agg = {}
+    for label, ms, by, fl in prof:
+        a = agg.setdefault(label, [0.0, 0.0, 0.0, 0])
+        a[0] += ms; a[1] += by; a[2] += fl; a[3] += 1
+    total_ms = sum(a[0] for a in agg.values()) or 1.0
+    kernels = []
+    for label, (ms, by, fl, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        kernels.append({"kernel": label, "launches_per_step": n // 2, "share": ms / total_ms,
+                        "avg_ms": ms / n, "algo_GBps": by / ms * 1e-6 if ms > 0 else None,
+                        "algo_TFLOPs": fl / ms * 1e-9 if ms > 0 else None})
+    roofline = None
+    if kernels:
+        k = kernels[0]
+        roofline = {"bound": "hbm", "achieved": k["algo_GBps"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": k["algo_GBps"] / hbm_peak, "traffic": None, "kernel": k["kernel"],
+                    "share_of_step": k["share"], "avg_launch_ms": k["avg_ms"], "peak_source": peak_src,
+                    "whole_step": {"algo_GBps": sum(a[1] for a in agg.values()) / total_ms * 1e-6,
+                                   "algo_TFLOPs": sum(a[2] for a in agg.values()) / total_ms * 1e-9,
+                                   "kernel_ms_per_step": total_ms / 2}}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_time(steps=3, warmup=1)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "nights_per_gpu_per_step": BATCH, "epochs_per_night": S_EPOCHS,
+                   "parallelism": f"replicas x{world} (no data-path collective)",
+                   "l2": "inputs+activations > L2, 2 alternating batches"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "roofline": roofline,
+        "kernels": kernels[:8],
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "cuda" else max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -41,8 +41,12 @@ const char* w2s_last_error(void);
 /* nn.Conv1d weight [cout, cin, taps] fp32 -> fp16 UMMA operand layout [taps][cin/8][cout][8].
  * Also used for nn.Linear(4*C -> F) of SignalEncoder (models/wav2sleep.py:230,264) by viewing its
  * weight [F, 4*C] as [F, taps=4, C] -> pass taps_major = 1 (input index = tap*cin + c). */
-int w2s_pack_conv_weight(const float* w, int cout, int cin, int taps, int taps_major, void* out_fp16, void* stream);
-size_t w2s_packed_conv_weight_bytes(int cout, int cin, int taps);
+int w2s_pack_conv_weight(const float* w, int cout, int cin, int taps, int taps_major, int split, void* out_fp16,
+                         void* stream);
+size_t w2s_packed_conv_weight_bytes(int cout, int cin, int taps, int split);
+/* 1 if the (cin, cout) encoder conv kernels carry operands as fp16 hi + fp16 lo pairs; their weights must then be
+ * packed with split = 1 (hi block followed by lo block, twice the bytes).  True for cin <= 32 and cout <= 32. */
+int w2s_conv_uses_split(int cin, int cout);
 
 /* nn.Linear weight [n, k] fp32 -> fp16 mma.sync B-fragment order [n/8][k/16][32 lanes][4] (epoch mixer). */
 int w2s_pack_linear_frag(const float* w, int n, int k, void* out_fp16, void* stream);
@@ -60,12 +64,12 @@ typedef struct w2s_conv_call {
   int32_t B, L_in, L_out;
   const void* in;         /* fp16 [B, L_in, cin] */
   const void* in_res;     /* fp16 [B, L_in, cin]      (W2S_PRO_NORM_RES) */
-  const float* in_stats;  /* [B, cin, 2] sum, sumsq   (W2S_PRO_NORM*)    */
+  const double* in_stats; /* [B, cin, 2] sum, sumsq   (W2S_PRO_NORM*)    */
   const void* w;          /* packed fp16 */
   const void* w_ds;       /* packed fp16 1x1          (has_ds) */
   void* out;              /* fp16 [B, L_out, cout] */
   void* out_ds;           /* fp16 [B, L_out/2, cout]  (has_ds) */
-  float* out_stats;       /* [B, cout, 2], pre-zeroed (W2S_EPI_STATS) */
+  double* out_stats;      /* [B, cout, 2], pre-zeroed (W2S_EPI_STATS) */
   const uint8_t* row_mask;/* [B] or NULL */
   const float* bias;      /* [cout] (W2S_EPI_BIAS_GELU) */
   const float* ln_w;      /* [cout] (W2S_EPI_LN_*) */
@@ -161,6 +165,17 @@ size_t w2s_seqmixer_workspace_bytes(const w2s_seq_desc* d, int B, int S, int kee
  * logits: fp32 [B, S, n_classes]. */
 int w2s_seqmixer_head_fwd(const w2s_seq_desc* d, const void* x, int B, int S, void* workspace, size_t workspace_bytes,
                           int keep_activations, void* feat_out, float* logits, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Measurement hooks (bench.py).  Not part of the data path.
+ * ------------------------------------------------------------------------------------------------------- */
+/* Number of kernels this library has launched in this process (monotonic). */
+long long w2s_launch_count(void);
+/* on = 1: every later launch is bracketed by CUDA events on its stream and recorded; on = 0: stop and clear. */
+int w2s_profile_enable(int on);
+int w2s_profile_count(void);
+/* Record i: label (host buffer), elapsed ms (synchronises on the record's end event), algorithmic bytes / flops. */
+int w2s_profile_get(int i, char* label, int label_cap, float* ms, double* bytes, double* flops);
 
 /* argmax over classes (Wav2Sleep.predict, models/wav2sleep.py:69-80): logits fp32 [n, c] -> int64 [n]. */
 int w2s_argmax(const float* logits, int64_t n, int n_classes, int64_t* out, void* stream);

@@ -12,21 +12,25 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def pack_conv(w, taps_major=0, taps=None):
+def pack_conv(w, taps_major=0, taps=None, split=0):
     lib = _lib.load()
     w = w.detach().float().contiguous()
     if taps_major:
         cout, cin = w.shape[0], w.shape[1] // taps
     else:
         cout, cin, taps = w.shape
-    out = torch.empty(taps * cin * cout, dtype=torch.float16, device=w.device)
-    _lib.check(lib.w2s_pack_conv_weight(w.data_ptr(), cout, cin, taps, taps_major, out.data_ptr(), stream()))
+    out = torch.empty(taps * cin * cout * (2 if split else 1), dtype=torch.float16, device=w.device)
+    _lib.check(lib.w2s_pack_conv_weight(w.data_ptr(), cout, cin, taps, taps_major, split, out.data_ptr(), stream()))
     return out
 
 
+def uses_split(cin, cout):
+    return _lib.load().w2s_conv_uses_split(cin, cout)
+
+
 def sums(y_h):
-    """[B, L, C] fp16 -> [B, C, 2] fp32 (sum, sum of squares over L), as the producing kernel would emit."""
-    y = y_h.float()
+    """[B, L, C] fp16 -> [B, C, 2] fp64 (sum, sum of squares over L), as the producing kernel would emit."""
+    y = y_h.double()
     return torch.stack([y.sum(1), (y * y).sum(1)], dim=-1).contiguous()
 
 
@@ -45,10 +49,12 @@ def prologue_ref(y_h, r_h=None, eps=1e-2):
     return a
 
 
-def conv_ref(a_BLC, w, stride=1, pad=1, dil=1):
-    """fp32 conv of fp16-rounded operands (the tensor core multiplies fp16 x fp16 exactly, accumulates in fp32)."""
-    a = a_BLC.half().float().transpose(1, 2)
-    return F.conv1d(a, w.half().float(), None, stride=stride, padding=pad, dilation=dil).transpose(1, 2).contiguous()
+def conv_ref(a_BLC, w, stride=1, pad=1, dil=1, split=0):
+    """fp32 conv of fp16-rounded operands (the tensor core multiplies fp16 x fp16 exactly, accumulates in fp32).
+    split: operands are carried as fp16 hi+lo pairs in the kernel, i.e. effectively unrounded."""
+    a = (a_BLC if split else a_BLC.half().float()).transpose(1, 2)
+    w = w if split else w.half().float()
+    return F.conv1d(a, w, None, stride=stride, padding=pad, dilation=dil).transpose(1, 2).contiguous()
 
 
 def run_conv(**kw):

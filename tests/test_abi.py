@@ -34,7 +34,7 @@ def test_abi_version_and_error_channel():
     # argument validation happens before any CUDA call, so it is testable without a GPU
     assert lib.w2s_conv1d_fwd(None, None) != 0
     assert b"null" in lib.w2s_last_error()
-    assert lib.w2s_pack_conv_weight(None, 16, 12, 3, 0, None, None) != 0
+    assert lib.w2s_pack_conv_weight(None, 16, 12, 3, 0, 0, None, None) != 0
     assert b"pack_conv" in lib.w2s_last_error()
 
 

@@ -74,7 +74,7 @@ def test_masked_equals_absent_and_batch_independence(cuda_device):
     xa = {k: v for k, v in x.items() if k != "ABD"}
     a = run_cuda(model, xm, cuda_device)
     b = run_cuda(model, xa, cuda_device)
-    assert (a - b).abs().max().item() < 1e-5  # identical work, only atomics order differs
+    assert (a - b).abs().max().item() < 1e-5  # identical arithmetic; fp64 stats atomics make it order-independent
     full = run_cuda(model, x, cuda_device)
     one = run_cuda(model, {k: v[1:2] for k, v in x.items()}, cuda_device)
     assert (full[1:2] - one).abs().max().item() < 2e-3  # fp32 atomic-order noise through fp16 re-rounding
@@ -114,8 +114,8 @@ def test_stage_outputs_match_oracle(cuda_device):
         z = buf["z"][n].float().cpu()
         live = ~torch.isinf(zref).any(-1).any(-1)
         e = (z[live] - zref[live]).abs().max().item()
-        print(n, "encoder feature max-abs", e)
-        assert e < 2e-2
+        print(n, "encoder feature max-abs", e, "of max", zref[live].abs().max().item())
+        assert e < 1e-2 * zref[live].abs().max().item()  # features are O(5): relative bound
         assert buf["mask"][n].cpu().bool().tolist() == (~live).tolist()
     e = (buf["mix"].float().cpu() - inter["mixer"]).abs().max().item()
     print("mixer max-abs", e)

@@ -107,8 +107,10 @@ class SeqDesc(C.Structure):
 SYMBOLS = {
     "w2s_abi_version": (C.c_int, []),
     "w2s_last_error": (C.c_char_p, []),
-    "w2s_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
-    "w2s_packed_conv_weight_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "w2s_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p]),
+    "w2s_packed_conv_weight_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "w2s_conv_uses_split": (C.c_int, [C.c_int, C.c_int]),
     "w2s_pack_linear_frag": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "w2s_conv1d_fwd": (C.c_int, [C.POINTER(ConvCall), C.c_void_p]),
     "w2s_encoder_workspace_bytes": (C.c_size_t, [C.POINTER(EncoderDesc), C.c_int, C.c_int64, C.c_int]),
@@ -120,6 +122,11 @@ SYMBOLS = {
     "w2s_seqmixer_head_fwd": (C.c_int, [C.POINTER(SeqDesc), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "w2s_argmax": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "w2s_launch_count": (C.c_longlong, []),
+    "w2s_profile_enable": (C.c_int, [C.c_int]),
+    "w2s_profile_count": (C.c_int, []),
+    "w2s_profile_get": (C.c_int, [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double),
+                                  C.POINTER(C.c_double)]),
 }
 
 _lib = None

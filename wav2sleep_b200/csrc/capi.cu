@@ -2,10 +2,13 @@
 // carving, kernel dispatch.  No allocation, no synchronisation, no CPU fallback.
 #include "../../include/w2s_b200.h"
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "conv_igemm.cuh"
 #include "epoch_mixer.cuh"
@@ -42,9 +45,48 @@ int sm_count() {
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ------------------------------------------------------------------------------------------------
+// launch accounting + optional per-launch CUDA-event profile (bench.py reads it; off by default)
+// ------------------------------------------------------------------------------------------------
+std::atomic<long long> g_launches{0};
+struct ProfRec {
+  std::string label;
+  cudaEvent_t e0, e1;
+  double bytes, flops;
+};
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+
+// RAII around one kernel launch: counts it and, when profiling, brackets it with events on its stream.
+struct LaunchScope {
+  cudaStream_t st;
+  bool on;
+  size_t idx;
+  LaunchScope(cudaStream_t s, const char* label, double bytes, double flops) : st(s), on(false), idx(0) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfRec r;
+    r.label = label;
+    r.bytes = bytes;
+    r.flops = flops;
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    cudaEventRecord(r.e0, st);
+    g_prof.push_back(r);
+    idx = g_prof.size() - 1;
+    on = true;
+  }
+  ~LaunchScope() {
+    if (!on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEventRecord(g_prof[idx].e1, st);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
 // packing kernels
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_conv_kernel(const float* __restrict__ w, int cout, int cin, int taps, int taps_major,
+__global__ void pack_conv_kernel(const float* __restrict__ w, int cout, int cin, int taps, int taps_major, int split,
                                  __half* __restrict__ out) {
   const int total = taps * cin * cout;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -56,7 +98,9 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, int cout, int cin,
     const int t = r / (cin / 8);
     const int c = c8 * 8 + k;
     const float v = taps_major ? w[(size_t)n * taps * cin + (size_t)t * cin + c] : w[((size_t)n * cin + c) * taps + t];
-    out[idx] = __float2half_rn(v);
+    const __half hi = __float2half_rn(v);
+    out[idx] = hi;
+    if (split) out[total + idx] = __float2half_rn(v - __half2float(hi));  // W = hi + lo
   }
 }
 
@@ -124,7 +168,6 @@ ConvArgs to_args(const w2s_conv_call& c) {
   a.stride_log2 = ilog2_exact(c.stride);
   a.dil = c.dilation;
   a.pad = c.pad;
-  a.in_inv_len = 1.0f / (float)c.L_in;
   a.in_eps = c.in_eps;
   a.ln_eps = c.ln_eps;
   return a;
@@ -138,6 +181,15 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
   const ConvArgs a = to_args(c);
   cudaError_t e = cudaErrorInvalidValue;
   bool found = false;
+  char label[96];
+  snprintf(label, sizeof(label), "conv_igemm c%d->%d k%d s%d d%d pro%d epi%d%s", c.cin, c.cout, c.taps, c.stride,
+           c.dilation, c.prologue, c.epilogue, c.has_ds ? " +ds" : "");
+  // algorithmic traffic: every input element read once (+ residual), every output written once; fp16
+  const double in_b = (double)c.B * c.L_in * c.cin * 2.0 * (c.prologue == W2S_PRO_NORM_RES ? 2.0 : 1.0);
+  const double out_b = (double)c.B * c.L_out * c.cout * 2.0 * (c.has_ds ? 1.5 : 1.0) +
+                       (c.epilogue == W2S_EPI_LN_GELU_RES ? (double)c.B * c.L_out * c.cout * 2.0 : 0.0);
+  const double fl = 2.0 * c.B * (double)c.L_out * c.cout * c.cin * (c.taps + (c.has_ds ? 0.5 : 0.0));
+  LaunchScope scope(st, label, in_b + out_b, fl);
 #define W2S_CASE(CIN, COUT, TAPS, GT, PRO, EPI, DS)                                                       \
   if (!found && c.cin == CIN && c.cout == COUT && c.taps == TAPS && c.prologue == PRO && c.epilogue == EPI && \
       (c.has_ds != 0) == DS) {                                                                            \
@@ -194,7 +246,7 @@ struct Slots {
 
 constexpr int kEncSlots = 5;
 
-size_t enc_stats_floats(const w2s_encoder_desc* d, int B) {
+size_t enc_stats_count(const w2s_encoder_desc* d, int B) {  // number of fp64 accumulators
   size_t n = 0;
   for (int i = 0; i < d->n_blocks; ++i) n += (size_t)3 * B * d->channels[i] * 2;
   return n;
@@ -215,18 +267,23 @@ extern "C" {
 int w2s_abi_version(void) { return 1; }
 const char* w2s_last_error(void) { return g_err.c_str(); }
 
-size_t w2s_packed_conv_weight_bytes(int cout, int cin, int taps) { return (size_t)cout * cin * taps * sizeof(__half); }
+int w2s_conv_uses_split(int cin, int cout) { return (cin <= 32 && cout <= 32) ? 1 : 0; }
 
-int w2s_pack_conv_weight(const float* w, int cout, int cin, int taps, int taps_major, void* out, void* stream) {
-  if (cin % 8 != 0 || cout <= 0 || taps <= 0) return fail("pack_conv: cin=%d cout=%d taps=%d", cin, cout, taps);
+size_t w2s_packed_conv_weight_bytes(int cout, int cin, int taps, int split) {
+  return (size_t)cout * cin * taps * sizeof(__half) * (split ? 2 : 1);
+}
+
+int w2s_pack_conv_weight(const float* w, int cout, int cin, int taps, int taps_major, int split, void* out, void* stream) {
+  if (w == nullptr || out == nullptr || cin % 8 != 0 || cout <= 0 || taps <= 0)
+    return fail("pack_conv: bad arguments cin=%d cout=%d taps=%d", cin, cout, taps);
   const int total = cout * cin * taps;
-  pack_conv_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, cout, cin, taps, taps_major, (__half*)out);
+  pack_conv_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, cout, cin, taps, taps_major, split, (__half*)out);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "pack_conv");
 }
 
 int w2s_pack_linear_frag(const float* w, int n, int k, void* out, void* stream) {
-  if (n % 8 != 0 || k % 16 != 0) return fail("pack_frag: n=%d k=%d", n, k);
+  if (w == nullptr || out == nullptr || n % 8 != 0 || k % 16 != 0) return fail("pack_frag: bad arguments n=%d k=%d", n, k);
   const int total = n * k;
   pack_frag_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, n, k, (__half*)out);
   cudaError_t e = cudaGetLastError();
@@ -240,7 +297,7 @@ int w2s_conv1d_fwd(const w2s_conv_call* call, void* stream) {
 
 size_t w2s_encoder_workspace_bytes(const w2s_encoder_desc* d, int B, int64_t T, int keep) {
   if (check_encoder_desc(d) != 0 || B <= 0 || T <= 0) return 0;
-  const size_t stats = align_up(enc_stats_floats(d, B) * sizeof(float), 256);
+  const size_t stats = align_up(enc_stats_count(d, B) * sizeof(double), 256);
   const size_t e = sizeof(__half);
   if (!keep) return stats + (size_t)kEncSlots * align_up((size_t)B * T * 16 * e, 256);
   size_t act = 0;
@@ -266,8 +323,8 @@ int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T,
   if (ws_bytes < need) return fail("encoder: workspace %zu < required %zu", ws_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
 
-  const size_t stats_bytes = align_up(enc_stats_floats(d, B) * sizeof(float), 256);
-  float* stats = (float*)workspace;
+  const size_t stats_bytes = align_up(enc_stats_count(d, B) * sizeof(double), 256);
+  double* stats = (double*)workspace;
   cudaError_t ce = cudaMemsetAsync(stats, 0, stats_bytes, st);
   if (ce != cudaSuccess) return cuda_fail(ce, "encoder memset");
   uint8_t* act_base = (uint8_t*)workspace + stats_bytes;
@@ -288,9 +345,9 @@ int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T,
     if (!keep) slots.put(p);
   };
 
-  float* st_ptr = stats;
+  double* st_ptr = stats;
   auto next_stats = [&](int c) {
-    float* p = st_ptr;
+    double* p = st_ptr;
     st_ptr += (size_t)B * c * 2;
     return p;
   };
@@ -298,16 +355,16 @@ int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T,
   int L = (int)T;
   const void* prev_y3 = nullptr;
   const void* prev_r = nullptr;
-  const float* prev_s3 = nullptr;
+  const double* prev_s3 = nullptr;
   int prev_c = 1;
   for (int i = 0; i < d->n_blocks; ++i) {
     const int c = d->channels[i];
     const size_t e = sizeof(__half);
     void* y1 = alloc((size_t)B * L * c * e);
     void* r = alloc((size_t)B * (L / 2) * c * e);
-    float* s1 = next_stats(c);
-    float* s2 = next_stats(c);
-    float* s3 = next_stats(c);
+    double* s1 = next_stats(c);
+    double* s2 = next_stats(c);
+    double* s3 = next_stats(c);
     if (y1 == nullptr || r == nullptr) return fail("encoder: slot allocator exhausted");
     if (i == 0) {
       FirstConvArgs fa;
@@ -319,7 +376,10 @@ int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T,
       fa.stats = s1;
       fa.row_mask = row_mask;
       fa.T = L;
-      ce = launch_first_conv(fa, B, st);
+      {
+        LaunchScope scope(st, "first_conv c1->16 k3", (double)B * L * (4.0 + 32.0 + 16.0), 2.0 * B * (double)L * 16 * 3.5);
+        ce = launch_first_conv(fa, B, st);
+      }
       if (ce != cudaSuccess) return cuda_fail(ce, "first_conv launch");
     } else {
       w2s_conv_call cc;
@@ -410,7 +470,16 @@ int w2s_epoch_mixer_fwd(const w2s_mixer_desc* d, const void* const* z, const uin
   a.n_epochs = B * S;
   a.S = S;
   a.ln_eps = d->ln_eps;
-  cudaError_t e = launch_epoch_mixer(a, n_signals, sm_count(), (cudaStream_t)stream);
+  cudaError_t e;
+  {
+    const double D = n_signals + 1;
+    // layer flops (2*MAC): qkv 3F^2, out F^2, ffn 2*F*FF per token; last layer only K,V for all tokens + CLS row
+    const double per_tok_full = 2.0 * (4.0 * 128 * 128 + 2.0 * 128 * 512);
+    const double last = 2.0 * (D * 2.0 * 128 * 128 + 2.0 * 128 * 128 + 2.0 * 128 * 512);
+    const double fl = (double)B * S * ((d->n_layers - 1) * D * per_tok_full + last);
+    LaunchScope scope((cudaStream_t)stream, "epoch_mixer", (double)B * S * 128 * 2.0 * (n_signals + 1), fl);
+    e = launch_epoch_mixer(a, n_signals, sm_count(), (cudaStream_t)stream);
+  }
   return e == cudaSuccess ? 0 : cuda_fail(e, "epoch_mixer launch");
 }
 
@@ -463,9 +532,42 @@ int w2s_seqmixer_head_fwd(const w2s_seq_desc* d, const void* x, int B, int S, vo
   return 0;
 }
 
+long long w2s_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int w2s_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  g_prof_on = on != 0;
+  return 0;
+}
+
+int w2s_profile_count(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  return (int)g_prof.size();
+}
+
+int w2s_profile_get(int i, char* label, int label_cap, float* ms, double* bytes, double* flops) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (i < 0 || i >= (int)g_prof.size() || label == nullptr || ms == nullptr) return fail("profile_get: bad index %d", i);
+  const ProfRec& r = g_prof[i];
+  cudaError_t e = cudaEventSynchronize(r.e1);
+  if (e != cudaSuccess) return cuda_fail(e, "profile_get sync");
+  e = cudaEventElapsedTime(ms, r.e0, r.e1);
+  if (e != cudaSuccess) return cuda_fail(e, "profile_get elapsed");
+  snprintf(label, label_cap, "%s", r.label.c_str());
+  if (bytes) *bytes = r.bytes;
+  if (flops) *flops = r.flops;
+  return 0;
+}
+
 int w2s_argmax(const float* logits, int64_t n, int n_classes, int64_t* out, void* stream) {
   if (logits == nullptr || out == nullptr || n <= 0 || n_classes <= 0) return fail("argmax: bad arguments");
   const int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  LaunchScope scope((cudaStream_t)stream, "argmax", (double)n * (n_classes * 4.0 + 8.0), 0.0);
   argmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, (long long)n, n_classes, (long long*)out);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "argmax");

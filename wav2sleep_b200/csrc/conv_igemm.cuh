@@ -31,13 +31,13 @@ struct ConvArgs {
   // input side
   const act_t* in;        // [B, L_in, CIN]  pre-norm (PRO_NORM*) or final (PRO_NONE)
   const act_t* in_res;    // [B, L_in, CIN]  residual branch of the producing block (PRO_NORM_RES)
-  const float* in_stats;  // [B, CIN, 2]     sum, sum of squares over L_in of `in`
-  const act_t* w;         // packed [TAPS][CIN/8][COUT][8]
-  const act_t* w_ds;      // packed [CIN/8][COUT][8] (HAS_DS)
+  const double* in_stats; // [B, CIN, 2]     sum, sum of squares over L_in of `in` (fp64: order-independent)
+  const act_t* w;         // packed [TAPS][CIN/8][COUT][8]  (SPLIT: hi block followed by lo block)
+  const act_t* w_ds;      // packed [CIN/8][COUT][8] (HAS_DS; SPLIT: hi then lo)
   // output side
   act_t* out;             // [B, L_out, COUT]
   act_t* out_ds;          // [B, L_out/2, COUT] (HAS_DS)
-  float* out_stats;       // [B, COUT, 2] (EPI_STATS), must be zeroed by the caller
+  double* out_stats;      // [B, COUT, 2] (EPI_STATS), must be zeroed by the caller
   const uint8_t* row_mask;  // [B] non-zero => sample has no such signal: skip (may be null)
   const float* bias;      // [COUT] (EPI_BIAS_GELU)
   const float* ln_w;      // [COUT] (EPI_LN_*)
@@ -50,7 +50,6 @@ struct ConvArgs {
   int L_in, L_out;
   int stride_log2;        // stride = 1 << stride_log2
   int dil, pad;
-  float in_inv_len;       // 1 / L_in (count behind in_stats)
   float in_eps;           // InstanceNorm eps (1e-2)
   float ln_eps;           // ConvLayerNorm eps (1e-5)
 };
@@ -68,16 +67,26 @@ __host__ __device__ inline int conv_rows_per_phase(int pos, int stride, int taps
   const int R = (pos - 1) * stride + (taps - 1) * dil + 1;
   return (R + stride - 1) / stride;
 }
-template <int CIN, int COUT, int GT, bool HAS_DS>
+// SPLIT: operands are carried as fp16 hi + fp16 lo (A = A_hi + A_lo, W = W_hi + W_lo) and the product is
+// A_hi*W_hi + A_lo*W_hi + A_hi*W_lo: ~22-bit operands on the fp16 tensor pipe.  Used for the C<=32 layers, where
+// operand rounding dominates the logit error (DESIGN.md "Numerics") and the tensor pipe is idle anyway.
+template <int CIN, int COUT>
+struct ConvSplit {
+  static constexpr bool value = (CIN <= 32 && COUT <= 32);
+};
+constexpr int kConvCtlBytes = 16 + 2 * 128 * 4 + 2 * 512 * 4;  // barrier+tmem slot, scale/shift, stats partials
+template <int CIN, int COUT, int GT, bool HAS_DS, bool SPLIT>
 __host__ __device__ inline size_t conv_smem_bytes(int stride, int taps, int dil) {
   const int rp = conv_rows_per_phase(ConvTile<COUT>::POS, stride, taps, dil);
   size_t a = (size_t)stride * (CIN / 8) * rp * 16;
   size_t b = (size_t)(GT + (HAS_DS ? 1 : 0)) * (CIN / 8) * COUT * 16;
-  return a + b + 1152;  // + control block (barrier, tmem ptr, norm scale/shift, stats)
+  return (SPLIT ? 2 : 1) * (a + b) + kConvCtlBytes;
 }
 
-template <int CIN, int COUT, int TAPS, int GT /*taps resident per weight group*/, int PRO, int EPI, bool HAS_DS>
+template <int CIN, int COUT, int TAPS, int GT /*taps resident per weight group*/, int PRO, int EPI, bool HAS_DS,
+          bool SPLIT>
 __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs p) {
+  static_assert(!SPLIT || (GT == TAPS && PRO != PRO_NONE), "split operands: single weight group, computed prologue");
   static_assert(CIN % 16 == 0 && COUT % 16 == 0 && COUT <= 128, "UMMA shape");
   static_assert(EPI == EPI_STATS || COUT == 128, "row-wise epilogues need the full channel dim in one tile");
   constexpr int CH = CIN / 8;                 // 16-byte chunks per input row
@@ -99,15 +108,19 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs
   const int Rp = (R + stride - 1) >> p.stride_log2;
 
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* sA = smem;
-  uint8_t* sB = sA + (size_t)stride * CH * Rp * 16;
-  uint8_t* sCtl = sB + (size_t)(GT + (HAS_DS ? 1 : 0)) * CH * COUT * 16;
+  const size_t a_bytes = (size_t)stride * CH * Rp * 16;
+  constexpr size_t b_bytes = (size_t)(GT + (HAS_DS ? 1 : 0)) * CH * COUT * 16;
+  uint8_t* sA = smem;                                  // hi (or only) activations
+  uint8_t* sAlo = sA + a_bytes;                        // lo activations (SPLIT)
+  uint8_t* sB = sA + (SPLIT ? 2 : 1) * a_bytes;        // hi weights [GT taps (+ds)][CH][COUT][8]
+  uint8_t* sBlo = sB + b_bytes;                        // lo weights (SPLIT)
+  uint8_t* sCtl = sB + (SPLIT ? 2 : 1) * b_bytes;
   uint64_t* bar = reinterpret_cast<uint64_t*>(sCtl);            // 8 B
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sCtl + 8);  // 4 B
-  float* sScale = reinterpret_cast<float*>(sCtl + 16);          // [<=128]  (CIN <= 128)
-  float* sShift = sScale + 128;                                 //          (aliased by epilogue stats)
-  float* sSum = sScale;                                         // [COUT] after the prologue is done
-  float* sSq = sShift;
+  float* sScale = reinterpret_cast<float*>(sCtl + 16);          // [128]
+  float* sShift = sScale + 128;                                 // [128]
+  float* sPartSum = sShift + 128;                               // [8 warps][4 units][16 ch]
+  float* sPartSq = sPartSum + 512;
 
   // ---------------- setup ----------------
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -117,13 +130,14 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs
   }
   if (PRO != PRO_NONE && tid >= 64 && tid < 64 + CIN) {
     const int c = tid - 64;
-    const float s0 = p.in_stats[((size_t)b * CIN + c) * 2 + 0];
-    const float s1 = p.in_stats[((size_t)b * CIN + c) * 2 + 1];
-    const float mean = s0 * p.in_inv_len;
-    const float var = fmaxf(s1 * p.in_inv_len - mean * mean, 0.0f);
-    const float rstd = rsqrtf(var + p.in_eps);
+    const double s0 = p.in_stats[((size_t)b * CIN + c) * 2 + 0];
+    const double s1 = p.in_stats[((size_t)b * CIN + c) * 2 + 1];
+    const double inv_len = 1.0 / (double)p.L_in;
+    const double mean = s0 * inv_len;
+    const double var = fmax(s1 * inv_len - mean * mean, 0.0);  // biased variance (InstanceNorm1d)
+    const float rstd = (float)(1.0 / sqrt(var + (double)p.in_eps));
     sScale[c] = rstd;
-    sShift[c] = -mean * rstd;
+    sShift[c] = (float)(-mean) * rstd;
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -167,11 +181,13 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs
         const int u = id / CH;
         const int i = i0 + u;
         uint4 o = y[k];
+        uint4 olo = make_uint4(0u, 0u, 0u, 0u);
         if (PRO != PRO_NONE) {
           if (i >= 0 && i < p.L_in) {  // zero padding applies to the *activated* signal
             uint32_t* yy = reinterpret_cast<uint32_t*>(&y[k]);
             uint32_t* rr = reinterpret_cast<uint32_t*>(&r[k]);
             uint32_t* oo = reinterpret_cast<uint32_t*>(&o);
+            uint32_t* ol = reinterpret_cast<uint32_t*>(&olo);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               float2 v = unpack_h2(yy[q]);
@@ -183,12 +199,18 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs
                 a1 = gelu_fast(a1 + rv.y);
               }
               oo[q] = pack_h2(a0, a1);
+              if (SPLIT) {
+                const float2 hi = unpack_h2(oo[q]);
+                ol[q] = pack_h2(a0 - hi.x, a1 - hi.y);
+              }
             }
           }
         }
         const int phase = u & (stride - 1);
         const int row = u >> p.stride_log2;
-        *reinterpret_cast<uint4*>(sA + ((size_t)(phase * CH + cch) * Rp + row) * 16) = o;
+        const size_t soff = ((size_t)(phase * CH + cch) * Rp + row) * 16;
+        *reinterpret_cast<uint4*>(sA + soff) = o;
+        if (SPLIT) *reinterpret_cast<uint4*>(sAlo + soff) = olo;
       }
     }
   }
@@ -204,10 +226,18 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs
       const uint4* src = reinterpret_cast<const uint4*>(p.w) + (size_t)t_begin * CH * COUT;
       uint4* dst = reinterpret_cast<uint4*>(sB);
       for (int k = tid; k < n16; k += kConvThreads) dst[k] = __ldg(src + k);
+      if (SPLIT) {
+        uint4* dlo = reinterpret_cast<uint4*>(sBlo);
+        for (int k = tid; k < n16; k += kConvThreads) dlo[k] = __ldg(src + (size_t)TAPS * CH * COUT + k);
+      }
       if (HAS_DS && g == 0) {
         const uint4* srcd = reinterpret_cast<const uint4*>(p.w_ds);
         uint4* dstd = dst + (size_t)GT * CH * COUT;
         for (int k = tid; k < CH * COUT; k += kConvThreads) dstd[k] = __ldg(srcd + k);
+        if (SPLIT) {
+          uint4* dlo = reinterpret_cast<uint4*>(sBlo) + (size_t)GT * CH * COUT;
+          for (int k = tid; k < CH * COUT; k += kConvThreads) dlo[k] = __ldg(srcd + (size_t)CH * COUT + k);
+        }
       }
     }
     fence_proxy_async_smem();
@@ -217,6 +247,10 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs
       tc_fence_after_sync();
       const uint32_t a_base = smem_u32(sA);
       const uint32_t b_base = smem_u32(sB);
+      const uint32_t a_lo_base = smem_u32(sAlo);
+      const uint32_t b_lo_base = smem_u32(sBlo);
+      (void)a_lo_base;
+      (void)b_lo_base;
       const uint32_t lbo_a = (uint32_t)Rp * 16;
       constexpr uint32_t lbo_b = COUT * 16;
 #pragma unroll 1
@@ -227,10 +261,15 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs
           const int rowoff = (uoff >> p.stride_log2) + j * 128;
 #pragma unroll
           for (int kk = 0; kk < KSTEPS; ++kk) {
-            const uint32_t a_addr = a_base + ((uint32_t)(phase * CH + 2 * kk) * Rp + rowoff) * 16;
-            const uint32_t b_addr = b_base + (uint32_t)((t - t_begin) * CH + 2 * kk) * COUT * 16;
-            umma_f16(tmem_base + j * COUT, umma_smem_desc(a_addr, lbo_a, 128), umma_smem_desc(b_addr, lbo_b, 128),
-                     IDESC, (t > 0 || kk > 0) ? 1u : 0u);
+            const uint32_t a_off = ((uint32_t)(phase * CH + 2 * kk) * Rp + rowoff) * 16;
+            const uint32_t b_off = (uint32_t)((t - t_begin) * CH + 2 * kk) * COUT * 16;
+            const uint64_t da = umma_smem_desc(a_base + a_off, lbo_a, 128);
+            const uint64_t db = umma_smem_desc(b_base + b_off, lbo_b, 128);
+            umma_f16(tmem_base + j * COUT, da, db, IDESC, (t > 0 || kk > 0) ? 1u : 0u);
+            if (SPLIT) {
+              umma_f16(tmem_base + j * COUT, umma_smem_desc(a_lo_base + a_off, lbo_a, 128), db, IDESC, 1u);
+              umma_f16(tmem_base + j * COUT, da, umma_smem_desc(b_lo_base + b_off, lbo_b, 128), IDESC, 1u);
+            }
           }
         }
         if (HAS_DS && g == 0) {
@@ -239,10 +278,15 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs
           const int rowoff = p.pad + j * 128;
 #pragma unroll
           for (int kk = 0; kk < KSTEPS; ++kk) {
-            const uint32_t a_addr = a_base + ((uint32_t)(2 * kk) * Rp + rowoff) * 16;
-            const uint32_t b_addr = b_base + (uint32_t)(GT * CH + 2 * kk) * COUT * 16;
-            umma_f16(tmem_base + 128 + j * COUT, umma_smem_desc(a_addr, lbo_a, 128),
-                     umma_smem_desc(b_addr, lbo_b, 128), IDESC, kk > 0 ? 1u : 0u);
+            const uint32_t a_off = ((uint32_t)(2 * kk) * Rp + rowoff) * 16;
+            const uint32_t b_off = (uint32_t)(GT * CH + 2 * kk) * COUT * 16;
+            const uint64_t da = umma_smem_desc(a_base + a_off, lbo_a, 128);
+            const uint64_t db = umma_smem_desc(b_base + b_off, lbo_b, 128);
+            umma_f16(tmem_base + 128 + j * COUT, da, db, IDESC, kk > 0 ? 1u : 0u);
+            if (SPLIT) {
+              umma_f16(tmem_base + 128 + j * COUT, umma_smem_desc(a_lo_base + a_off, lbo_a, 128), db, IDESC, 1u);
+              umma_f16(tmem_base + 128 + j * COUT, da, umma_smem_desc(b_lo_base + b_off, lbo_b, 128), IDESC, 1u);
+            }
           }
         }
       }
@@ -259,11 +303,6 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs
   const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
 
   if (EPI == EPI_STATS) {
-    if (tid < COUT) {
-      sSum[tid] = 0.0f;
-      sSq[tid] = 0.0f;
-    }
-    __syncthreads();
     act_t* outb = p.out + (size_t)b * p.L_out * COUT;
     constexpr int UNITS = MT * (COUT / 16);  // == 8
 #pragma unroll 1
@@ -290,10 +329,10 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs
       }
       butterfly16(v, lane);
       butterfly16(sq, lane);
-      if ((lane & 1) == 0) {
-        const int c = cg * 16 + butterfly16_channel(lane);
-        atomicAdd(&sSum[c], v[0]);
-        atomicAdd(&sSq[c], sq[0]);
+      if ((lane & 1) == 0) {  // one slot per (warp, unit, channel): no atomics, fixed summation order below
+        const int slot = (warp * 4 + (unit >> 1)) * 16 + butterfly16_channel(lane);
+        sPartSum[slot] = v[0];
+        sPartSq[slot] = sq[0];
       }
     }
     if (HAS_DS) {
@@ -317,8 +356,21 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs
     }
     __syncthreads();
     if (tid < COUT) {
-      atomicAdd(&p.out_stats[((size_t)b * COUT + tid) * 2 + 0], sSum[tid]);
-      atomicAdd(&p.out_stats[((size_t)b * COUT + tid) * 2 + 1], sSq[tid]);
+      // channel tid lives in units (j, cg = tid / 16), j = 0..MT-1; each unit was reduced by 4 warps (quads).
+      float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+      for (int j = 0; j < MT; ++j) {
+        const int unit = j * (COUT / 16) + (tid >> 4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int slot = (((unit & 1) * 4 + q) * 4 + (unit >> 1)) * 16 + (tid & 15);
+          s0 += sPartSum[slot];
+          s1 += sPartSq[slot];
+        }
+      }
+      // fp64 atomics: the cross-CTA summation order no longer changes the fp32 result (run-to-run determinism)
+      atomicAdd(&p.out_stats[((size_t)b * COUT + tid) * 2 + 0], (double)s0);
+      atomicAdd(&p.out_stats[((size_t)b * COUT + tid) * 2 + 1], (double)s1);
     }
   } else if (EPI == EPI_BIAS_GELU) {
     act_t* outb = p.out + (size_t)b * p.L_out * COUT;
@@ -428,9 +480,10 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs
 // Host-side launcher.  Returns cudaError_t of the launch.
 template <int CIN, int COUT, int TAPS, int GT, int PRO, int EPI, bool HAS_DS>
 inline cudaError_t launch_conv_igemm(const ConvArgs& a, int B, cudaStream_t stream) {
-  auto kern = conv_igemm_kernel<CIN, COUT, TAPS, GT, PRO, EPI, HAS_DS>;
+  constexpr bool SPLIT = ConvSplit<CIN, COUT>::value && EPI == EPI_STATS;
+  auto kern = conv_igemm_kernel<CIN, COUT, TAPS, GT, PRO, EPI, HAS_DS, SPLIT>;
   const int stride = 1 << a.stride_log2;
-  const size_t smem = conv_smem_bytes<CIN, COUT, GT, HAS_DS>(stride, TAPS, a.dil);
+  const size_t smem = conv_smem_bytes<CIN, COUT, GT, HAS_DS, SPLIT>(stride, TAPS, a.dil);
   static size_t configured = 0;  // per instantiation
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -19,7 +19,7 @@ struct FirstConvArgs {
   const float* w_ds;    // [16]     (downsample.weight[:, 0, 0])
   act_t* y1;            // [B, T, 16]
   act_t* r0;            // [B, T/2, 16]
-  float* stats;         // [B, 16, 2]  zeroed by caller
+  double* stats;        // [B, 16, 2]  zeroed by caller (fp64 accumulators)
   uint8_t* row_mask;    // [B]
   int T;
 };
@@ -36,14 +36,10 @@ __global__ void __launch_bounds__(kFirstConvThreads) first_conv_kernel(const Fir
   if (masked) return;
 
   __shared__ float sw[16 * 3 + 16];
-  __shared__ float sSum[16], sSq[16];
+  __shared__ float sSum[8][16], sSq[8][16];  // per-warp partials, summed in fixed order
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid < 48) sw[tid] = __ldg(p.w + tid);
   if (tid >= 64 && tid < 80) sw[48 + tid - 64] = __ldg(p.w_ds + tid - 64);
-  if (tid >= 96 && tid < 112) {
-    sSum[tid - 96] = 0.0f;
-    sSq[tid - 96] = 0.0f;
-  }
   __syncthreads();
 
   float acc[16], acc2[16];
@@ -84,13 +80,19 @@ __global__ void __launch_bounds__(kFirstConvThreads) first_conv_kernel(const Fir
   butterfly16(acc2, lane);
   if ((lane & 1) == 0) {
     const int c = butterfly16_channel(lane);
-    atomicAdd(&sSum[c], acc[0]);
-    atomicAdd(&sSq[c], acc2[0]);
+    sSum[tid >> 5][c] = acc[0];
+    sSq[tid >> 5][c] = acc2[0];
   }
   __syncthreads();
   if (tid < 16) {
-    atomicAdd(&p.stats[((size_t)b * 16 + tid) * 2 + 0], sSum[tid]);
-    atomicAdd(&p.stats[((size_t)b * 16 + tid) * 2 + 1], sSq[tid]);
+    float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kFirstConvThreads / 32; ++w) {
+      s0 += sSum[w][tid];
+      s1 += sSq[w][tid];
+    }
+    atomicAdd(&p.stats[((size_t)b * 16 + tid) * 2 + 0], (double)s0);
+    atomicAdd(&p.stats[((size_t)b * 16 + tid) * 2 + 1], (double)s1);
   }
 }
 

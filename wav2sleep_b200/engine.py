@@ -44,10 +44,13 @@ class _PackedEncoder:
             w = f32(w)
             if taps_major:
                 cout, cin = w.shape[0], w.shape[1] // taps
+                split = 0
             else:
                 cout, cin, taps = w.shape
-            out = torch.empty(taps * cin * cout, dtype=torch.float16, device=device)
-            _lib.check(lib.w2s_pack_conv_weight(w.data_ptr(), cout, cin, taps, taps_major, out.data_ptr(), st))
+                split = lib.w2s_conv_uses_split(cin, cout)
+            nbytes = lib.w2s_packed_conv_weight_bytes(cout, cin, taps, split)
+            out = torch.empty(nbytes // 2, dtype=torch.float16, device=device)
+            _lib.check(lib.w2s_pack_conv_weight(w.data_ptr(), cout, cin, taps, taps_major, split, out.data_ptr(), st))
             self.keep.append(out)
             return out.data_ptr()
 
@@ -132,7 +135,7 @@ class ForwardEngine:
                 w = f32(layer.conv.weight)
                 cout, cin, taps = w.shape
                 out = torch.empty(w.numel(), dtype=torch.float16, device=device)
-                _lib.check(lib.w2s_pack_conv_weight(w.data_ptr(), cout, cin, taps, 0, out.data_ptr(), st))
+                _lib.check(lib.w2s_pack_conv_weight(w.data_ptr(), cout, cin, taps, 0, 0, out.data_ptr(), st))
                 self.keep.append(out)
                 sd.w[b][k] = out.data_ptr()
                 sd.ln_w[b][k] = f32(layer.norm.weight.reshape(-1)).data_ptr()
