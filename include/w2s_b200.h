@@ -83,6 +83,9 @@ typedef struct w2s_conv_call {
 } w2s_conv_call;
 
 int w2s_conv1d_fwd(const w2s_conv_call* call, void* stream);
+/* Kernel selection for the encoder convs (testing / A-B measurement): 0 = auto (persistent warp-specialised
+ * streaming kernel, conv_stream.cuh), 1 = tile-per-CTA kernel only (conv_igemm.cuh).  Same results either way. */
+int w2s_set_conv_impl(int impl);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Stage 1: signal encoder.  Replaces SignalEncoders.forward for one signal (models/wav2sleep.py:146-161)

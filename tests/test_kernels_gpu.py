@@ -83,9 +83,18 @@ ENC_CASES = [
 ]
 
 
+@pytest.fixture(params=[0, 1], ids=["stream", "tile"])
+def conv_impl(request):
+    """Run with the persistent streaming kernel (default) and with the tile-per-CTA kernel."""
+    lib = _lib.load()
+    lib.w2s_set_conv_impl(request.param)
+    yield request.param
+    lib.w2s_set_conv_impl(0)
+
+
 @pytest.mark.parametrize("cin,cout,stride,has_ds,L", ENC_CASES)
-def test_encoder_conv_layer(cuda_device, cin, cout, stride, has_ds, L):
-    """conv_igemm_kernel, EPI_STATS: prologue norm+GELU(+res), k3 conv (tcgen05), fp16 store, sums, fused 1x1."""
+def test_encoder_conv_layer(cuda_device, conv_impl, cin, cout, stride, has_ds, L):
+    """EPI_STATS conv kernels: prologue norm+GELU(+res), k3 conv (tcgen05), fp16 store, sums, fused 1x1."""
     torch.manual_seed(cin * 1000 + cout + stride)
     B = 2
     dev = cuda_device
@@ -117,6 +126,44 @@ def test_encoder_conv_layer(cuda_device, cin, cout, stride, has_ds, L):
         refd = G.conv_ref(a, wd, stride=2, pad=0, split=split)
         assert refd.shape == out_ds.shape
         assert rel_err(out_ds, refd) < 4e-3
+
+
+@pytest.mark.parametrize("cin,cout,stride,has_ds,B,L", [
+    (16, 16, 1, 0, 5, 40000), (16, 16, 2, 0, 3, 70000), (16, 32, 1, 1, 4, 33000), (32, 32, 2, 0, 7, 9000),
+    (64, 64, 1, 0, 9, 5000), (128, 128, 2, 0, 6, 3000), (128, 128, 1, 1, 5, 2000), (64, 128, 1, 1, 20, 1000),
+])
+def test_encoder_conv_many_tiles_with_mask(cuda_device, conv_impl, cin, cout, stride, has_ds, B, L):
+    """Persistent CTAs walk tile ranges that cross sample boundaries; one sample in the middle is masked out."""
+    torch.manual_seed(B * L + cin)
+    dev = cuda_device
+    y = (torch.randn(B, L, cin, device=dev) + 0.2).half()
+    r = torch.randn(B, L, cin, device=dev).half() if has_ds else None
+    w = torch.randn(cout, cin, 3, device=dev) / (3 * cin) ** 0.5
+    wd = torch.randn(cout, cin, 1, device=dev) / cin ** 0.5 if has_ds else None
+    L_out = (L - 1) // stride + 1
+    out = torch.zeros(B, L_out, cout, dtype=torch.float16, device=dev)
+    out_ds = torch.zeros(B, L_out // 2, cout, dtype=torch.float16, device=dev) if has_ds else None
+    stats = torch.zeros(B, cout, 2, device=dev, dtype=torch.float64)
+    mask = torch.zeros(B, dtype=torch.uint8, device=dev)
+    mask[B // 2] = 1
+    split = G.uses_split(cin, cout)
+    G.run_conv(cin=cin, cout=cout, taps=3, stride=stride, dilation=1, pad=1,
+               prologue=_lib.PRO_NORM_RES if has_ds else _lib.PRO_NORM, epilogue=_lib.EPI_STATS, has_ds=has_ds,
+               B=B, L_in=L, L_out=L_out, **{"in": y}, in_res=r, in_stats=G.sums(y), w=G.pack_conv(w, split=split),
+               w_ds=G.pack_conv(wd, split=split) if has_ds else None, out=out, out_ds=out_ds, out_stats=stats,
+               row_mask=mask, in_eps=1e-2)
+    live = [b for b in range(B) if b != B // 2]
+    a = G.prologue_ref(y, r)
+    ref = G.conv_ref(a, w, stride=stride, split=split)
+    assert out[B // 2].abs().max().item() == 0 and stats[B // 2].abs().max().item() == 0
+    assert rel_err(out[live], ref[live]) < (1e-3 if split else 4e-3)
+    st = stats.float()
+    assert torch.allclose(st[live][..., 0], ref[live].sum(1), rtol=2e-3, atol=0.05 * L ** 0.5)
+    assert torch.allclose(st[live][..., 1], (ref[live] * ref[live]).sum(1), rtol=2e-3, atol=1e-2)
+    if has_ds:
+        refd = G.conv_ref(a, wd, stride=2, pad=0, split=split)
+        assert out_ds[B // 2].abs().max().item() == 0
+        assert rel_err(out_ds[live], refd[live]) < (1e-3 if split else 4e-3)
 
 
 def test_encoder_conv_row_mask_skips_sample(cuda_device):

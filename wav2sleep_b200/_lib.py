@@ -113,6 +113,7 @@ SYMBOLS = {
     "w2s_conv_uses_split": (C.c_int, [C.c_int, C.c_int]),
     "w2s_pack_linear_frag": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "w2s_conv1d_fwd": (C.c_int, [C.POINTER(ConvCall), C.c_void_p]),
+    "w2s_set_conv_impl": (C.c_int, [C.c_int]),
     "w2s_encoder_workspace_bytes": (C.c_size_t, [C.POINTER(EncoderDesc), C.c_int, C.c_int64, C.c_int]),
     "w2s_encoder_fwd": (C.c_int, [C.POINTER(EncoderDesc), C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_size_t,
                                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "conv_igemm.cuh"
+#include "conv_stream.cuh"
 #include "epoch_mixer.cuh"
 #include "first_conv.cuh"
 
@@ -48,6 +49,7 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // launch accounting + optional per-launch CUDA-event profile (bench.py reads it; off by default)
 // ------------------------------------------------------------------------------------------------
 std::atomic<long long> g_launches{0};
+std::atomic<int> g_conv_impl{0};  // 0 = auto (persistent streaming kernel where built), 1 = tile-per-CTA kernel only
 struct ProfRec {
   std::string label;
   cudaEvent_t e0, e1;
@@ -190,6 +192,35 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
                        (c.epilogue == W2S_EPI_LN_GELU_RES ? (double)c.B * c.L_out * c.cout * 2.0 : 0.0);
   const double fl = 2.0 * c.B * (double)c.L_out * c.cout * c.cin * (c.taps + (c.has_ds ? 0.5 : 0.0));
   LaunchScope scope(st, label, in_b + out_b, fl);
+  if (c.epilogue == W2S_EPI_STATS && c.taps == 3 && c.dilation == 1 && c.pad == 1 && g_conv_impl.load() == 0 &&
+      ((c.stride == 1 && c.L_out == c.L_in) || (c.stride == 2 && c.L_out == (c.L_in + 1) / 2))) {
+    const int sms = sm_count();
+#define W2S_STREAM(CIN, COUT, STRIDE, PRO, DS, MT, NR, NA)                                                  \
+  if (!found && c.cin == CIN && c.cout == COUT && c.stride == STRIDE && c.prologue == PRO && (c.has_ds != 0) == DS) { \
+    found = true;                                                                                           \
+    e = launch_conv_stream<CIN, COUT, STRIDE, PRO, DS, MT, NR, NA>(a, c.B, sms, st);                        \
+  }
+    W2S_STREAM(16, 16, 1, PRO_NORM, false, 4, 3, 2)
+    W2S_STREAM(16, 16, 2, PRO_NORM, false, 2, 3, 2)
+    W2S_STREAM(16, 16, 1, PRO_NORM_RES, true, 4, 3, 2)
+    W2S_STREAM(16, 32, 1, PRO_NORM_RES, true, 4, 3, 2)
+    W2S_STREAM(32, 32, 1, PRO_NORM, false, 2, 3, 2)
+    W2S_STREAM(32, 32, 2, PRO_NORM, false, 1, 3, 2)
+    W2S_STREAM(32, 32, 1, PRO_NORM_RES, true, 2, 3, 2)
+    W2S_STREAM(32, 64, 1, PRO_NORM_RES, true, 2, 3, 2)
+    W2S_STREAM(64, 64, 1, PRO_NORM, false, 2, 3, 2)
+    W2S_STREAM(64, 64, 2, PRO_NORM, false, 1, 3, 2)
+    W2S_STREAM(64, 64, 1, PRO_NORM_RES, true, 1, 3, 2)
+    W2S_STREAM(64, 128, 1, PRO_NORM_RES, true, 1, 3, 2)
+    W2S_STREAM(128, 128, 1, PRO_NORM, false, 1, 3, 1)
+    W2S_STREAM(128, 128, 2, PRO_NORM, false, 1, 1, 1)
+    W2S_STREAM(128, 128, 1, PRO_NORM_RES, true, 1, 1, 1)
+#undef W2S_STREAM
+    if (found) {
+      if (e != cudaSuccess) return cuda_fail(e, "conv_stream launch");
+      return 0;
+    }
+  }
 #define W2S_CASE(CIN, COUT, TAPS, GT, PRO, EPI, DS)                                                       \
   if (!found && c.cin == CIN && c.cout == COUT && c.taps == TAPS && c.prologue == PRO && c.epilogue == EPI && \
       (c.has_ds != 0) == DS) {                                                                            \
@@ -529,6 +560,12 @@ int w2s_seqmixer_head_fwd(const w2s_seq_desc* d, const void* x, int B, int S, vo
     }
     block_in = cur;
   }
+  return 0;
+}
+
+int w2s_set_conv_impl(int impl) {
+  if (impl != 0 && impl != 1) return fail("set_conv_impl: %d", impl);
+  g_conv_impl.store(impl);
   return 0;
 }
 

@@ -1,0 +1,435 @@
+// Persistent, warp-specialised streaming version of the encoder conv (k=3, pad=1, stride 1|2, EPI_STATS).
+//
+// Same math and memory formats as conv_igemm.cuh, different execution structure.  The tile-per-CTA kernel is
+// latency bound on the big C=16/32 layers (load -> transform -> MMA -> epilogue run back to back in every CTA);
+// here one CTA per SM walks a contiguous range of tiles and the four stages run concurrently on different tiles:
+//
+//   warp 0 (1 lane)  : producer   - one cp.async.bulk (TMA, 1-D) per tile: the tile's input rows are one
+//                                   contiguous byte range of the channels-last tensor -> raw ring in smem
+//   warps 6..13      : transform  - raw fp16 -> InstanceNorm (whole-night stats of the producer layer) -> GELU
+//                                   [-> + residual branch -> GELU] -> fp16 (hi [+ lo]) in UMMA chunk-major layout
+//   warp 1 (1 lane)  : MMA issuer - tcgen05.mma per 128-row sub-tile and tap into a double-buffered TMEM stage
+//   warps 2..5       : epilogue   - tcgen05.ld, fp16 store, sum / sum-of-squares kept in registers across tiles and
+//                                   flushed with fp64 atomics only when the sample changes
+// Stages hand over through mbarriers (raw full/empty, A full/empty, TMEM full/empty); weights are loaded once.
+#pragma once
+#include "conv_igemm.cuh"
+
+namespace w2s {
+
+constexpr int kStreamTransformWarps = 8;
+constexpr int kStreamThreads = 32 * (2 + 4 + kStreamTransformWarps);  // 448
+constexpr int kStreamFirstTransformWarp = 6;
+
+W2S_DEVINL void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+W2S_DEVINL void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA engine), completion counted in bytes on an mbarrier.
+W2S_DEVINL void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, bool SPLIT, int MT, int NR, int NA>
+struct StreamCfg {
+  static constexpr int CH = CIN / 8;
+  static constexpr int POS = 128 * MT;
+  static constexpr int R = (POS - 1) * STRIDE + 3;            // input rows per tile (with halo)
+  static constexpr int RP = (R + STRIDE - 1) / STRIDE;        // rows per stride phase
+  static constexpr int RAW_ONE = (R * CIN * 2 + 127) / 128 * 128;
+  static constexpr int RAW_BYTES = RAW_ONE * (PRO == PRO_NORM_RES ? 2 : 1);
+  static constexpr int A_ONE = STRIDE * CH * RP * 16;
+  static constexpr int A_BYTES = A_ONE * (SPLIT ? 2 : 1);
+  static constexpr int B_ONE = (3 + (HAS_DS ? 1 : 0)) * CH * COUT * 16;
+  static constexpr int B_BYTES = B_ONE * (SPLIT ? 2 : 1);
+  static constexpr int STAGE_COLS = MT * COUT * (HAS_DS ? 2 : 1);
+  static constexpr int TMEM_COLS = (2 * STAGE_COLS <= 32) ? 32 : (2 * STAGE_COLS <= 64) ? 64 : (2 * STAGE_COLS <= 128) ? 128 : (2 * STAGE_COLS <= 256) ? 256 : 512;
+  static constexpr int CTL_BYTES = 256;
+  static constexpr int SMEM_BYTES = NR * RAW_BYTES + NA * A_BYTES + B_BYTES + CTL_BYTES;
+  static_assert(2 * STAGE_COLS <= 512, "TMEM budget");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+  static_assert((kStreamTransformWarps * 32) % CH == 0, "fixed channel chunk per transform thread");
+};
+
+template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, bool SPLIT, int MT, int NR, int NA>
+__global__ void __launch_bounds__(kStreamThreads, 1)
+conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
+  using Cfg = StreamCfg<CIN, COUT, STRIDE, PRO, HAS_DS, SPLIT, MT, NR, NA>;
+  constexpr int CH = Cfg::CH, POS = Cfg::POS, R = Cfg::R, RP = Cfg::RP;
+  constexpr int KSTEPS = CIN / 16;
+  constexpr int NCG = COUT / 16;
+  constexpr uint32_t IDESC = umma_idesc_f16(128, COUT, false);
+  constexpr bool REG_STATS = (COUT <= 32);  // per-thread accumulators across tiles; else per-tile butterfly
+
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sRaw = smem;
+  uint8_t* sA = sRaw + NR * Cfg::RAW_BYTES;
+  uint8_t* sB = sA + NA * Cfg::A_BYTES;
+  uint8_t* sCtl = sB + Cfg::B_BYTES;
+  uint64_t* raw_full = reinterpret_cast<uint64_t*>(sCtl);
+  uint64_t* raw_empty = raw_full + NR;
+  uint64_t* a_full = raw_empty + NR;
+  uint64_t* a_empty = a_full + NA;
+  uint64_t* t_full = a_empty + NA;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile_begin = (int)((long long)blockIdx.x * total_tiles / gridDim.x);
+  const int tile_end = (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x);
+
+  // ---------------- one-time setup ----------------
+  if (warp == 0) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (tid == 32) {
+    for (int s = 0; s < NR; ++s) {
+      mbar_init(&raw_full[s], 1);
+      mbar_init(&raw_empty[s], kStreamTransformWarps);
+    }
+    for (int s = 0; s < NA; ++s) {
+      mbar_init(&a_full[s], kStreamTransformWarps);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&t_full[s], 1);
+      mbar_init(&t_empty[s], 4);
+    }
+    fence_mbar_init();
+  }
+  {  // weights -> smem (hi [, lo] blocks; ds after the taps), once per CTA
+    constexpr int n16 = 3 * CH * COUT;
+    const uint4* src = reinterpret_cast<const uint4*>(p.w);
+    uint4* dst = reinterpret_cast<uint4*>(sB);
+    for (int k = tid; k < n16; k += kStreamThreads) dst[k] = __ldg(src + k);
+    if (SPLIT) {
+      uint4* dlo = reinterpret_cast<uint4*>(sB + Cfg::B_ONE);
+      for (int k = tid; k < n16; k += kStreamThreads) dlo[k] = __ldg(src + n16 + k);
+    }
+    if (HAS_DS) {
+      const uint4* srcd = reinterpret_cast<const uint4*>(p.w_ds);
+      for (int k = tid; k < CH * COUT; k += kStreamThreads) dst[n16 + k] = __ldg(srcd + k);
+      if (SPLIT) {
+        uint4* dlo = reinterpret_cast<uint4*>(sB + Cfg::B_ONE);
+        for (int k = tid; k < CH * COUT; k += kStreamThreads) dlo[n16 + k] = __ldg(srcd + CH * COUT + k);
+      }
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ======================================================================================================
+  if (warp == 0) {
+    // ---------------- producer ----------------
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int b = tile / tiles_per_sample;
+        if (p.row_mask != nullptr && p.row_mask[b]) continue;
+        const int o0 = (tile - b * tiles_per_sample) * POS;
+        const int i0 = o0 * STRIDE - 1;
+        const int lo = i0 < 0 ? 0 : i0;
+        const int hi = (i0 + R < p.L_in) ? i0 + R : p.L_in;
+        const uint32_t nbytes = (uint32_t)(hi - lo) * CIN * 2;
+        mbar_wait(&raw_empty[s], ph ^ 1);
+        uint8_t* dst = sRaw + s * Cfg::RAW_BYTES + (size_t)(lo - i0) * CIN * 2;
+        const size_t goff = ((size_t)b * p.L_in + lo) * CIN;
+        mbar_arrive_expect_tx(&raw_full[s], nbytes * (PRO == PRO_NORM_RES ? 2u : 1u));
+        bulk_g2s(dst, p.in + goff, nbytes, &raw_full[s]);
+        if (PRO == PRO_NORM_RES) bulk_g2s(dst + Cfg::RAW_ONE, p.in_res + goff, nbytes, &raw_full[s]);
+        if (++s == NR) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      int as = 0, ts = 0;
+      uint32_t aph = 0, tph = 0;
+      const uint32_t b_base = smem_u32(sB);
+      constexpr uint32_t lbo_a = RP * 16, lbo_b = COUT * 16;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int b = tile / tiles_per_sample;
+        if (p.row_mask != nullptr && p.row_mask[b]) continue;
+        mbar_wait(&a_full[as], aph);
+        mbar_wait(&t_empty[ts], tph ^ 1);
+        tc_fence_after_sync();
+        const uint32_t a_base = smem_u32(sA + as * Cfg::A_BYTES);
+        const uint32_t d_base = tmem_base + ts * Cfg::STAGE_COLS;
+#pragma unroll 1
+        for (int j = 0; j < MT; ++j) {
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+            const int phase = t & (STRIDE - 1);
+            const int rowoff = t / STRIDE + j * 128;
+#pragma unroll
+            for (int kk = 0; kk < KSTEPS; ++kk) {
+              const uint32_t a_off = ((uint32_t)(phase * CH + 2 * kk) * RP + rowoff) * 16;
+              const uint32_t b_off = (uint32_t)(t * CH + 2 * kk) * COUT * 16;
+              const uint64_t da = umma_smem_desc(a_base + a_off, lbo_a, 128);
+              const uint64_t db = umma_smem_desc(b_base + b_off, lbo_b, 128);
+              umma_f16(d_base + j * COUT, da, db, IDESC, (t > 0 || kk > 0) ? 1u : 0u);
+              if (SPLIT) {
+                umma_f16(d_base + j * COUT, umma_smem_desc(a_base + Cfg::A_ONE + a_off, lbo_a, 128), db, IDESC, 1u);
+                umma_f16(d_base + j * COUT, da, umma_smem_desc(b_base + Cfg::B_ONE + b_off, lbo_b, 128), IDESC, 1u);
+              }
+            }
+          }
+          if (HAS_DS) {  // 1x1 stride-2 residual branch on the centre tap rows (STRIDE == 1 here)
+            const int rowoff = 1 + j * 128;
+#pragma unroll
+            for (int kk = 0; kk < KSTEPS; ++kk) {
+              const uint32_t a_off = ((uint32_t)(2 * kk) * RP + rowoff) * 16;
+              const uint32_t b_off = (uint32_t)(3 * CH + 2 * kk) * COUT * 16;
+              const uint64_t da = umma_smem_desc(a_base + a_off, lbo_a, 128);
+              const uint64_t db = umma_smem_desc(b_base + b_off, lbo_b, 128);
+              umma_f16(d_base + (MT + j) * COUT, da, db, IDESC, kk > 0 ? 1u : 0u);
+              if (SPLIT) {
+                umma_f16(d_base + (MT + j) * COUT, umma_smem_desc(a_base + Cfg::A_ONE + a_off, lbo_a, 128), db, IDESC, 1u);
+                umma_f16(d_base + (MT + j) * COUT, da, umma_smem_desc(b_base + Cfg::B_ONE + b_off, lbo_b, 128), IDESC, 1u);
+              }
+            }
+          }
+        }
+        umma_commit(&a_empty[as]);  // A stage reusable once these MMAs have read it
+        umma_commit(&t_full[ts]);   // accumulators ready for the epilogue
+        if (++as == NA) {
+          as = 0;
+          aph ^= 1;
+        }
+        if (++ts == 2) {
+          ts = 0;
+          tph ^= 1;
+        }
+      }
+    }
+  } else if (warp < kStreamFirstTransformWarp) {
+    // ---------------- epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) ----------------
+    const int quad = warp & 3;
+    const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
+    int ts = 0;
+    uint32_t tph = 0;
+    int cur_b = -1;
+    constexpr int NACC = REG_STATS ? NCG * 16 : NCG;
+    float acc[NACC], acc2[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = acc2[k] = 0.0f;
+
+    auto flush = [&](int b) {
+      if (b < 0) return;
+#pragma unroll
+      for (int cg = 0; cg < NCG; ++cg) {
+        float s0, s1;
+        if (REG_STATS) {
+          butterfly16(&acc[cg * 16], lane);
+          butterfly16(&acc2[cg * 16], lane);
+          s0 = acc[cg * 16];
+          s1 = acc2[cg * 16];
+        } else {
+          s0 = acc[cg];
+          s1 = acc2[cg];
+        }
+        if ((lane & 1) == 0) {
+          const int c = cg * 16 + butterfly16_channel(lane);
+          atomicAdd(&p.out_stats[((size_t)b * COUT + c) * 2 + 0], (double)s0);
+          atomicAdd(&p.out_stats[((size_t)b * COUT + c) * 2 + 1], (double)s1);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) acc[k] = acc2[k] = 0.0f;
+    };
+
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const int b = tile / tiles_per_sample;
+      if (p.row_mask != nullptr && p.row_mask[b]) continue;
+      if (b != cur_b) {
+        flush(cur_b);
+        cur_b = b;
+      }
+      const int o0 = (tile - b * tiles_per_sample) * POS;
+      mbar_wait(&t_full[ts], tph);
+      tc_fence_after_sync();
+      const uint32_t d_base = tmem_base + ts * Cfg::STAGE_COLS + t_lane;
+      act_t* outb = p.out + (size_t)b * p.L_out * COUT;
+#pragma unroll
+      for (int cg = 0; cg < NCG; ++cg) {
+        float ps[16], pq[16];
+        if (!REG_STATS) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) ps[k] = pq[k] = 0.0f;
+        }
+#pragma unroll 1
+        for (int j = 0; j < MT; ++j) {
+          float v[16];
+          tmem_ld16(d_base + j * COUT + cg * 16, v);
+          const int o = o0 + j * 128 + quad * 32 + lane;
+          if (o < p.L_out) {
+            uint4* dst = reinterpret_cast<uint4*>(outb + (size_t)o * COUT + cg * 16);
+            dst[0] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+            dst[1] = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              if (REG_STATS) {
+                acc[cg * 16 + k] += v[k];
+                acc2[cg * 16 + k] = fmaf(v[k], v[k], acc2[cg * 16 + k]);
+              } else {
+                ps[k] += v[k];
+                pq[k] = fmaf(v[k], v[k], pq[k]);
+              }
+            }
+          }
+        }
+        if (!REG_STATS) {
+          butterfly16(ps, lane);
+          butterfly16(pq, lane);
+          acc[cg] += ps[0];
+          acc2[cg] += pq[0];
+        }
+      }
+      if (HAS_DS) {
+        act_t* dsb = p.out_ds + (size_t)b * (p.L_out >> 1) * COUT;
+#pragma unroll 1
+        for (int j = 0; j < MT; ++j) {
+          const int o = o0 + j * 128 + quad * 32 + lane;
+#pragma unroll
+          for (int cg = 0; cg < NCG; ++cg) {
+            float v[16];
+            tmem_ld16(d_base + (MT + j) * COUT + cg * 16, v);
+            if (o < p.L_out && (o & 1) == 0) {
+              uint4* dst = reinterpret_cast<uint4*>(dsb + (size_t)(o >> 1) * COUT + cg * 16);
+              dst[0] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+              dst[1] = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[ts]);
+      if (++ts == 2) {
+        ts = 0;
+        tph ^= 1;
+      }
+    }
+    flush(cur_b);
+  } else {
+    // ---------------- transform warps ----------------
+    const int tt = tid - kStreamFirstTransformWarp * 32;  // 0..255
+    constexpr int NTT = kStreamTransformWarps * 32;
+    const int cch = tt & (CH - 1);
+    int rs = 0, as = 0;
+    uint32_t rph = 0, aph = 0;
+    int cur_b = -1;
+    float sc[8], sh[8];
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const int b = tile / tiles_per_sample;
+      if (p.row_mask != nullptr && p.row_mask[b]) continue;
+      if (b != cur_b) {
+        cur_b = b;
+        const double inv_len = 1.0 / (double)p.L_in;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int c = cch * 8 + k;
+          const double s0 = p.in_stats[((size_t)b * CIN + c) * 2 + 0];
+          const double s1 = p.in_stats[((size_t)b * CIN + c) * 2 + 1];
+          const double mean = s0 * inv_len;
+          const double var = fmax(s1 * inv_len - mean * mean, 0.0);
+          const float rstd = (float)(1.0 / sqrt(var + (double)p.in_eps));
+          sc[k] = rstd;
+          sh[k] = (float)(-mean) * rstd;
+        }
+      }
+      const int o0 = (tile - b * tiles_per_sample) * POS;
+      const int i0 = o0 * STRIDE - 1;
+      mbar_wait(&raw_full[rs], rph);
+      mbar_wait(&a_empty[as], aph ^ 1);
+      const uint8_t* raw = sRaw + rs * Cfg::RAW_BYTES;
+      uint8_t* adst = sA + as * Cfg::A_BYTES;
+#pragma unroll 2
+      for (int id = tt; id < R * CH; id += NTT) {
+        const int u = id / CH;
+        const int i = i0 + u;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u), olo = make_uint4(0u, 0u, 0u, 0u);
+        if (i >= 0 && i < p.L_in) {
+          const uint4 y = *reinterpret_cast<const uint4*>(raw + (size_t)id * 16);
+          uint4 r = make_uint4(0u, 0u, 0u, 0u);
+          if (PRO == PRO_NORM_RES) r = *reinterpret_cast<const uint4*>(raw + Cfg::RAW_ONE + (size_t)id * 16);
+          const uint32_t* yy = reinterpret_cast<const uint32_t*>(&y);
+          const uint32_t* rr = reinterpret_cast<const uint32_t*>(&r);
+          uint32_t* oo = reinterpret_cast<uint32_t*>(&o);
+          uint32_t* ol = reinterpret_cast<uint32_t*>(&olo);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 v = unpack_h2(yy[q]);
+            float a0 = gelu_fast(fmaf(v.x, sc[2 * q], sh[2 * q]));
+            float a1 = gelu_fast(fmaf(v.y, sc[2 * q + 1], sh[2 * q + 1]));
+            if (PRO == PRO_NORM_RES) {
+              const float2 rv = unpack_h2(rr[q]);
+              a0 = gelu_fast(a0 + rv.x);
+              a1 = gelu_fast(a1 + rv.y);
+            }
+            oo[q] = pack_h2(a0, a1);
+            if (SPLIT) {
+              const float2 hi = unpack_h2(oo[q]);
+              ol[q] = pack_h2(a0 - hi.x, a1 - hi.y);
+            }
+          }
+        }
+        const int phase = u & (STRIDE - 1);
+        const int row = u / STRIDE;
+        const size_t soff = ((size_t)(phase * CH + cch) * RP + row) * 16;
+        *reinterpret_cast<uint4*>(adst + soff) = o;
+        if (SPLIT) *reinterpret_cast<uint4*>(adst + Cfg::A_ONE + soff) = olo;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&a_full[as]);
+        mbar_arrive(&raw_empty[rs]);
+      }
+      if (++rs == NR) {
+        rs = 0;
+        rph ^= 1;
+      }
+      if (++as == NA) {
+        as = 0;
+        aph ^= 1;
+      }
+    }
+  }
+
+  // ---------------- teardown ----------------
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, int MT, int NR, int NA>
+inline cudaError_t launch_conv_stream(const ConvArgs& a, int B, int sm_count, cudaStream_t stream) {
+  constexpr bool SPLIT = ConvSplit<CIN, COUT>::value;
+  using Cfg = StreamCfg<CIN, COUT, STRIDE, PRO, HAS_DS, SPLIT, MT, NR, NA>;
+  auto kern = conv_stream_kernel<CIN, COUT, STRIDE, PRO, HAS_DS, SPLIT, MT, NR, NA>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int tiles_per_sample = (a.L_out + Cfg::POS - 1) / Cfg::POS;
+  const long long total = (long long)tiles_per_sample * B;
+  if (total > 0x7fffffffLL) return cudaErrorInvalidValue;
+  const int grid = total < sm_count ? (int)total : sm_count;
+  kern<<<grid, kStreamThreads, Cfg::SMEM_BYTES, stream>>>(a, tiles_per_sample, (int)total);
+  return cudaGetLastError();
+}
+
+}  // namespace w2s
