@@ -195,26 +195,27 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
   if (c.epilogue == W2S_EPI_STATS && c.taps == 3 && c.dilation == 1 && c.pad == 1 && g_conv_impl.load() == 0 &&
       ((c.stride == 1 && c.L_out == c.L_in) || (c.stride == 2 && c.L_out == (c.L_in + 1) / 2))) {
     const int sms = sm_count();
-#define W2S_STREAM(CIN, COUT, STRIDE, PRO, DS, MT, NR, NA)                                                  \
+#define W2S_STREAM(CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW)                                             \
   if (!found && c.cin == CIN && c.cout == COUT && c.stride == STRIDE && c.prologue == PRO && (c.has_ds != 0) == DS) { \
     found = true;                                                                                           \
-    e = launch_conv_stream<CIN, COUT, STRIDE, PRO, DS, MT, NR, NA>(a, c.B, sms, st);                        \
+    e = launch_conv_stream<CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW>(a, c.B, sms, st);                   \
   }
-    W2S_STREAM(16, 16, 1, PRO_NORM, false, 4, 3, 2)
-    W2S_STREAM(16, 16, 2, PRO_NORM, false, 2, 3, 2)
-    W2S_STREAM(16, 16, 1, PRO_NORM_RES, true, 4, 3, 2)
-    W2S_STREAM(16, 32, 1, PRO_NORM_RES, true, 4, 3, 2)
-    W2S_STREAM(32, 32, 1, PRO_NORM, false, 2, 3, 2)
-    W2S_STREAM(32, 32, 2, PRO_NORM, false, 1, 3, 2)
-    W2S_STREAM(32, 32, 1, PRO_NORM_RES, true, 2, 3, 2)
-    W2S_STREAM(32, 64, 1, PRO_NORM_RES, true, 2, 3, 2)
-    W2S_STREAM(64, 64, 1, PRO_NORM, false, 2, 3, 2)
-    W2S_STREAM(64, 64, 2, PRO_NORM, false, 1, 3, 2)
-    W2S_STREAM(64, 64, 1, PRO_NORM_RES, true, 1, 3, 2)
-    W2S_STREAM(64, 128, 1, PRO_NORM_RES, true, 1, 3, 2)
-    W2S_STREAM(128, 128, 1, PRO_NORM, false, 1, 3, 1)
-    W2S_STREAM(128, 128, 2, PRO_NORM, false, 1, 1, 1)
-    W2S_STREAM(128, 128, 1, PRO_NORM_RES, true, 1, 1, 1)
+    //          cin cout s  prologue      ds    MT NR NA NTW
+    W2S_STREAM(16, 16, 1, PRO_NORM, false, 4, 3, 2, 14)
+    W2S_STREAM(16, 16, 2, PRO_NORM, false, 2, 3, 2, 14)
+    W2S_STREAM(16, 16, 1, PRO_NORM_RES, true, 4, 3, 2, 14)
+    W2S_STREAM(16, 32, 1, PRO_NORM_RES, true, 4, 3, 2, 10)
+    W2S_STREAM(32, 32, 1, PRO_NORM, false, 2, 3, 2, 10)
+    W2S_STREAM(32, 32, 2, PRO_NORM, false, 1, 3, 2, 10)
+    W2S_STREAM(32, 32, 1, PRO_NORM_RES, true, 2, 3, 2, 10)
+    W2S_STREAM(32, 64, 1, PRO_NORM_RES, true, 2, 3, 2, 14)
+    W2S_STREAM(64, 64, 1, PRO_NORM, false, 2, 3, 2, 14)
+    W2S_STREAM(64, 64, 2, PRO_NORM, false, 1, 3, 2, 14)
+    W2S_STREAM(64, 64, 1, PRO_NORM_RES, true, 1, 3, 2, 14)
+    W2S_STREAM(64, 128, 1, PRO_NORM_RES, true, 1, 3, 2, 14)
+    W2S_STREAM(128, 128, 1, PRO_NORM, false, 1, 3, 1, 14)
+    W2S_STREAM(128, 128, 2, PRO_NORM, false, 1, 1, 1, 14)
+    W2S_STREAM(128, 128, 1, PRO_NORM_RES, true, 1, 1, 1, 14)
 #undef W2S_STREAM
     if (found) {
       if (e != cudaSuccess) return cuda_fail(e, "conv_stream launch");

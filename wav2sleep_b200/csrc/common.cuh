@@ -140,6 +140,32 @@ W2S_DEVINL float gelu_fast(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xc * q));
   return __fdividef(x, 1.0f + e);
 }
+// Two elements at once on the packed-fp32 pipe (FFMA2/FMUL2/FADD2, sm_100): ~half the issue slots of gelu_fast.
+// Clamping t = x^2 (not x) keeps the exponent monotone for |x| > 5: u = x * q(25), |u| >= 21.7, Phi saturates.
+W2S_DEVINL float2 gelu_fast2(float2 x) {
+  float2 t = __fmul2_rn(x, x);
+  t.x = fminf(t.x, 25.0f);
+  t.y = fminf(t.y, 25.0f);
+  float2 q = __ffma2_rn(t, make_float2(1.01448193e-3f, 1.01448193e-3f), make_float2(-0.10677673f, -0.10677673f));
+  q = __ffma2_rn(q, t, make_float2(-2.30112048f, -2.30112048f));
+  const float2 u = __fmul2_rn(x, q);
+  float2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(u.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(u.y));
+  const float2 d = __fadd2_rn(e, make_float2(1.0f, 1.0f));
+  float2 r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(d.y));
+  return __fmul2_rn(x, r);
+}
+W2S_DEVINL uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+W2S_DEVINL void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 // Exact-erf GELU for low-volume epilogues.
 W2S_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 

@@ -6,7 +6,7 @@
 //
 //   warp 0 (1 lane)  : producer   - one cp.async.bulk (TMA, 1-D) per tile: the tile's input rows are one
 //                                   contiguous byte range of the channels-last tensor -> raw ring in smem
-//   warps 6..13      : transform  - raw fp16 -> InstanceNorm (whole-night stats of the producer layer) -> GELU
+//   warps 6..6+NTW-1 : transform  - raw fp16 -> InstanceNorm (whole-night stats of the producer layer) -> GELU
 //                                   [-> + residual branch -> GELU] -> fp16 (hi [+ lo]) in UMMA chunk-major layout
 //   warp 1 (1 lane)  : MMA issuer - tcgen05.mma per 128-row sub-tile and tap into a double-buffered TMEM stage
 //   warps 2..5       : epilogue   - tcgen05.ld, fp16 store, sum / sum-of-squares kept in registers across tiles and
@@ -17,9 +17,8 @@
 
 namespace w2s {
 
-constexpr int kStreamTransformWarps = 8;
-constexpr int kStreamThreads = 32 * (2 + 4 + kStreamTransformWarps);  // 448
-constexpr int kStreamFirstTransformWarp = 6;
+constexpr int kStreamFirstTransformWarp = 6;  // warp 0 producer, 1 MMA, 2..5 epilogue, 6.. transform
+constexpr int stream_threads(int ntw) { return 32 * (kStreamFirstTransformWarp + ntw); }
 
 W2S_DEVINL void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -35,12 +34,23 @@ W2S_DEVINL void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, u
                : "memory");
 }
 
-template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, bool SPLIT, int MT, int NR, int NA>
+// Region stride (rows of 16 B) of the chunk-major A staging, padded so that the 8 lanes of a quarter-warp, which
+// write min(8, CH*STRIDE) different (phase, chunk) regions, hit disjoint shared-memory banks.
+constexpr int stream_rpad(int rp, int ch, int stride) {
+  const int nreg = ch * stride < 8 ? ch * stride : 8;
+  const int q = 8 / nreg;  // consecutive rows per region per quarter-warp
+  int r = rp;
+  while (nreg > 1 && (r % 8) != q && !(q == 1 && (r % 2) == 1)) ++r;
+  return r;
+}
+
+template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, bool SPLIT, int MT, int NR, int NA, int NTW>
 struct StreamCfg {
   static constexpr int CH = CIN / 8;
   static constexpr int POS = 128 * MT;
   static constexpr int R = (POS - 1) * STRIDE + 3;            // input rows per tile (with halo)
-  static constexpr int RP = (R + STRIDE - 1) / STRIDE;        // rows per stride phase
+  static constexpr int RP = stream_rpad((R + STRIDE - 1) / STRIDE, CH, STRIDE);  // rows per stride phase (padded)
+  static constexpr int THREADS = stream_threads(NTW);
   static constexpr int RAW_ONE = (R * CIN * 2 + 127) / 128 * 128;
   static constexpr int RAW_BYTES = RAW_ONE * (PRO == PRO_NORM_RES ? 2 : 1);
   static constexpr int A_ONE = STRIDE * CH * RP * 16;
@@ -53,13 +63,15 @@ struct StreamCfg {
   static constexpr int SMEM_BYTES = NR * RAW_BYTES + NA * A_BYTES + B_BYTES + CTL_BYTES;
   static_assert(2 * STAGE_COLS <= 512, "TMEM budget");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-  static_assert((kStreamTransformWarps * 32) % CH == 0, "fixed channel chunk per transform thread");
+  static_assert((NTW * 32) % CH == 0, "fixed channel chunk per transform thread");
 };
 
-template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, bool SPLIT, int MT, int NR, int NA>
-__global__ void __launch_bounds__(kStreamThreads, 1)
+template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, bool SPLIT, int MT, int NR, int NA, int NTW>
+__global__ void __launch_bounds__(stream_threads(NTW), 1)
 conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
-  using Cfg = StreamCfg<CIN, COUT, STRIDE, PRO, HAS_DS, SPLIT, MT, NR, NA>;
+  using Cfg = StreamCfg<CIN, COUT, STRIDE, PRO, HAS_DS, SPLIT, MT, NR, NA, NTW>;
+  constexpr int kStreamThreads = Cfg::THREADS;
+  constexpr int kStreamTransformWarps = NTW;
   constexpr int CH = Cfg::CH, POS = Cfg::POS, R = Cfg::R, RP = Cfg::RP;
   constexpr int KSTEPS = CIN / 16;
   constexpr int NCG = COUT / 16;
@@ -277,14 +289,16 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
             dst[0] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
             dst[1] = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              if (REG_STATS) {
-                acc[cg * 16 + k] += v[k];
-                acc2[cg * 16 + k] = fmaf(v[k], v[k], acc2[cg * 16 + k]);
-              } else {
-                ps[k] += v[k];
-                pq[k] = fmaf(v[k], v[k], pq[k]);
-              }
+            for (int k = 0; k < 16; k += 2) {  // packed fp32x2: one FADD2 + one FFMA2 per channel pair
+              const float2 vv = make_float2(v[k], v[k + 1]);
+              float* s = REG_STATS ? &acc[cg * 16 + k] : &ps[k];
+              float* q = REG_STATS ? &acc2[cg * 16 + k] : &pq[k];
+              const float2 ns = __fadd2_rn(make_float2(s[0], s[1]), vv);
+              const float2 nq = __ffma2_rn(vv, vv, make_float2(q[0], q[1]));
+              s[0] = ns.x;
+              s[1] = ns.y;
+              q[0] = nq.x;
+              q[1] = nq.y;
             }
           }
         }
@@ -329,7 +343,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
     int rs = 0, as = 0;
     uint32_t rph = 0, aph = 0;
     int cur_b = -1;
-    float sc[8], sh[8];
+    float2 sc[4], sh[4];  // per-channel scale / shift of this thread's 8 channels, as fp32x2 pairs
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       const int b = tile / tiles_per_sample;
       if (p.row_mask != nullptr && p.row_mask[b]) continue;
@@ -344,51 +358,56 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
           const double mean = s0 * inv_len;
           const double var = fmax(s1 * inv_len - mean * mean, 0.0);
           const float rstd = (float)(1.0 / sqrt(var + (double)p.in_eps));
-          sc[k] = rstd;
-          sh[k] = (float)(-mean) * rstd;
+          if (k & 1) {
+            sc[k >> 1].y = rstd;
+            sh[k >> 1].y = (float)(-mean) * rstd;
+          } else {
+            sc[k >> 1].x = rstd;
+            sh[k >> 1].x = (float)(-mean) * rstd;
+          }
         }
       }
       const int o0 = (tile - b * tiles_per_sample) * POS;
       const int i0 = o0 * STRIDE - 1;
       mbar_wait(&raw_full[rs], rph);
       mbar_wait(&a_empty[as], aph ^ 1);
-      const uint8_t* raw = sRaw + rs * Cfg::RAW_BYTES;
-      uint8_t* adst = sA + as * Cfg::A_BYTES;
-#pragma unroll 2
-      for (int id = tt; id < R * CH; id += NTT) {
+      const uint32_t raw = smem_u32(sRaw + rs * Cfg::RAW_BYTES);
+      const uint32_t adst = smem_u32(sA + as * Cfg::A_BYTES) + (uint32_t)cch * RP * 16;
+      const bool interior = (i0 >= 0) && (i0 + R <= p.L_in);  // no zero-padding rows in this tile
+      auto chunk = [&](int id, bool valid) {
         const int u = id / CH;
-        const int i = i0 + u;
         uint4 o = make_uint4(0u, 0u, 0u, 0u), olo = make_uint4(0u, 0u, 0u, 0u);
-        if (i >= 0 && i < p.L_in) {
-          const uint4 y = *reinterpret_cast<const uint4*>(raw + (size_t)id * 16);
+        if (valid) {
+          const uint4 y = lds128(raw + (uint32_t)id * 16);
           uint4 r = make_uint4(0u, 0u, 0u, 0u);
-          if (PRO == PRO_NORM_RES) r = *reinterpret_cast<const uint4*>(raw + Cfg::RAW_ONE + (size_t)id * 16);
+          if (PRO == PRO_NORM_RES) r = lds128(raw + Cfg::RAW_ONE + (uint32_t)id * 16);
           const uint32_t* yy = reinterpret_cast<const uint32_t*>(&y);
           const uint32_t* rr = reinterpret_cast<const uint32_t*>(&r);
           uint32_t* oo = reinterpret_cast<uint32_t*>(&o);
           uint32_t* ol = reinterpret_cast<uint32_t*>(&olo);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float2 v = unpack_h2(yy[q]);
-            float a0 = gelu_fast(fmaf(v.x, sc[2 * q], sh[2 * q]));
-            float a1 = gelu_fast(fmaf(v.y, sc[2 * q + 1], sh[2 * q + 1]));
-            if (PRO == PRO_NORM_RES) {
-              const float2 rv = unpack_h2(rr[q]);
-              a0 = gelu_fast(a0 + rv.x);
-              a1 = gelu_fast(a1 + rv.y);
-            }
-            oo[q] = pack_h2(a0, a1);
+            float2 a = gelu_fast2(__ffma2_rn(unpack_h2(yy[q]), sc[q], sh[q]));
+            if (PRO == PRO_NORM_RES) a = gelu_fast2(__fadd2_rn(a, unpack_h2(rr[q])));
+            oo[q] = pack_h2(a.x, a.y);
             if (SPLIT) {
-              const float2 hi = unpack_h2(oo[q]);
-              ol[q] = pack_h2(a0 - hi.x, a1 - hi.y);
+              const float2 lo = __ffma2_rn(unpack_h2(oo[q]), make_float2(-1.0f, -1.0f), a);
+              ol[q] = pack_h2(lo.x, lo.y);
             }
           }
         }
-        const int phase = u & (STRIDE - 1);
-        const int row = u / STRIDE;
-        const size_t soff = ((size_t)(phase * CH + cch) * RP + row) * 16;
-        *reinterpret_cast<uint4*>(adst + soff) = o;
-        if (SPLIT) *reinterpret_cast<uint4*>(adst + Cfg::A_ONE + soff) = olo;
+        const uint32_t soff = (uint32_t)((u & (STRIDE - 1)) * CH * RP + u / STRIDE) * 16;
+        sts128(adst + soff, o);
+        if (SPLIT) sts128(adst + Cfg::A_ONE + soff, olo);
+      };
+      if (interior) {
+#pragma unroll 2
+        for (int id = tt; id < R * CH; id += NTT) chunk(id, true);
+      } else {
+        for (int id = tt; id < R * CH; id += NTT) {
+          const int i = i0 + id / CH;
+          chunk(id, i >= 0 && i < p.L_in);
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -413,11 +432,11 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   if (warp == 0) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, int MT, int NR, int NA>
+template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, int MT, int NR, int NA, int NTW>
 inline cudaError_t launch_conv_stream(const ConvArgs& a, int B, int sm_count, cudaStream_t stream) {
   constexpr bool SPLIT = ConvSplit<CIN, COUT>::value;
-  using Cfg = StreamCfg<CIN, COUT, STRIDE, PRO, HAS_DS, SPLIT, MT, NR, NA>;
-  auto kern = conv_stream_kernel<CIN, COUT, STRIDE, PRO, HAS_DS, SPLIT, MT, NR, NA>;
+  using Cfg = StreamCfg<CIN, COUT, STRIDE, PRO, HAS_DS, SPLIT, MT, NR, NA, NTW>;
+  auto kern = conv_stream_kernel<CIN, COUT, STRIDE, PRO, HAS_DS, SPLIT, MT, NR, NA, NTW>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -428,7 +447,7 @@ inline cudaError_t launch_conv_stream(const ConvArgs& a, int B, int sm_count, cu
   const long long total = (long long)tiles_per_sample * B;
   if (total > 0x7fffffffLL) return cudaErrorInvalidValue;
   const int grid = total < sm_count ? (int)total : sm_count;
-  kern<<<grid, kStreamThreads, Cfg::SMEM_BYTES, stream>>>(a, tiles_per_sample, (int)total);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a, tiles_per_sample, (int)total);
   return cudaGetLastError();
 }
 
