@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -172,6 +173,7 @@ ConvArgs to_args(const w2s_conv_call& c) {
   a.pad = c.pad;
   a.in_eps = c.in_eps;
   a.ln_eps = c.ln_eps;
+  { const char* dbg = getenv("W2S_DEBUG_FLAGS"); a.debug_flags = dbg ? atoi(dbg) : 0; }
   return a;
 }
 

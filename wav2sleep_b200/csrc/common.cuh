@@ -47,6 +47,18 @@ W2S_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a fully converged warp (warp-uniform code keeps operands in uniform registers, so single-thread
+// instructions such as tcgen05.mma / cp.async.bulk need no per-lane waterfall loop).
+W2S_DEVINL bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------------------------
 // fences
 // ----------------------------------------------------------------------------------------------

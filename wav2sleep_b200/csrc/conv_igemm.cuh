@@ -52,6 +52,7 @@ struct ConvArgs {
   int dil, pad;
   float in_eps;           // InstanceNorm eps (1e-2)
   float ln_eps;           // ConvLayerNorm eps (1e-5)
+  int debug_flags;        // profiling experiments only (0 in production): 1 skip lo MMAs, 2 skip all MMAs, 4 skip GELU
 };
 
 constexpr int kConvThreads = 256;

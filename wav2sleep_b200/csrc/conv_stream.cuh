@@ -134,12 +134,12 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   // ======================================================================================================
   if (warp == 0) {
-    // ---------------- producer ----------------
-    if (lane == 0) {
+    // ---------------- producer (whole warp runs the loop; one elected lane issues) ----------------
+    {
       int s = 0;
       uint32_t ph = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
@@ -153,9 +153,12 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
         mbar_wait(&raw_empty[s], ph ^ 1);
         uint8_t* dst = sRaw + s * Cfg::RAW_BYTES + (size_t)(lo - i0) * CIN * 2;
         const size_t goff = ((size_t)b * p.L_in + lo) * CIN;
-        mbar_arrive_expect_tx(&raw_full[s], nbytes * (PRO == PRO_NORM_RES ? 2u : 1u));
-        bulk_g2s(dst, p.in + goff, nbytes, &raw_full[s]);
-        if (PRO == PRO_NORM_RES) bulk_g2s(dst + Cfg::RAW_ONE, p.in_res + goff, nbytes, &raw_full[s]);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&raw_full[s], nbytes * (PRO == PRO_NORM_RES ? 2u : 1u));
+          bulk_g2s(dst, p.in + goff, nbytes, &raw_full[s]);
+          if (PRO == PRO_NORM_RES) bulk_g2s(dst + Cfg::RAW_ONE, p.in_res + goff, nbytes, &raw_full[s]);
+        }
+        __syncwarp();
         if (++s == NR) {
           s = 0;
           ph ^= 1;
@@ -163,8 +166,8 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
       }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    // ---------------- MMA issuer (warp-uniform loop; one elected lane issues) ----------------
+    {
       int as = 0, ts = 0;
       uint32_t aph = 0, tph = 0;
       const uint32_t b_base = smem_u32(sB);
@@ -177,7 +180,8 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
         tc_fence_after_sync();
         const uint32_t a_base = smem_u32(sA + as * Cfg::A_BYTES);
         const uint32_t d_base = tmem_base + ts * Cfg::STAGE_COLS;
-#pragma unroll 1
+        if (elect_one()) {
+#pragma unroll
         for (int j = 0; j < MT; ++j) {
 #pragma unroll
           for (int t = 0; t < 3; ++t) {
@@ -189,8 +193,8 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
               const uint32_t b_off = (uint32_t)(t * CH + 2 * kk) * COUT * 16;
               const uint64_t da = umma_smem_desc(a_base + a_off, lbo_a, 128);
               const uint64_t db = umma_smem_desc(b_base + b_off, lbo_b, 128);
-              umma_f16(d_base + j * COUT, da, db, IDESC, (t > 0 || kk > 0) ? 1u : 0u);
-              if (SPLIT) {
+              if (!(p.debug_flags & 2)) umma_f16(d_base + j * COUT, da, db, IDESC, (t > 0 || kk > 0) ? 1u : 0u);
+              if (SPLIT && !(p.debug_flags & 3)) {
                 umma_f16(d_base + j * COUT, umma_smem_desc(a_base + Cfg::A_ONE + a_off, lbo_a, 128), db, IDESC, 1u);
                 umma_f16(d_base + j * COUT, da, umma_smem_desc(b_base + Cfg::B_ONE + b_off, lbo_b, 128), IDESC, 1u);
               }
@@ -214,6 +218,8 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
         }
         umma_commit(&a_empty[as]);  // A stage reusable once these MMAs have read it
         umma_commit(&t_full[ts]);   // accumulators ready for the epilogue
+        }
+        __syncwarp();
         if (++as == NA) {
           as = 0;
           aph ^= 1;
@@ -387,7 +393,8 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
           uint32_t* ol = reinterpret_cast<uint32_t*>(&olo);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            float2 a = gelu_fast2(__ffma2_rn(unpack_h2(yy[q]), sc[q], sh[q]));
+            float2 a = __ffma2_rn(unpack_h2(yy[q]), sc[q], sh[q]);
+            if (!(p.debug_flags & 4)) a = gelu_fast2(a);
             if (PRO == PRO_NORM_RES) a = gelu_fast2(__fadd2_rn(a, unpack_h2(rr[q])));
             oo[q] = pack_h2(a.x, a.y);
             if (SPLIT) {
