@@ -203,8 +203,8 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
     e = launch_conv_stream<CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW>(a, c.B, sms, st);                   \
   }
     //          cin cout s  prologue      ds    MT NR NA NTW
-    W2S_STREAM(16, 16, 1, PRO_NORM, false, 4, 3, 2, 14)
-    W2S_STREAM(16, 16, 2, PRO_NORM, false, 2, 3, 2, 14)
+    W2S_STREAM(16, 16, 1, PRO_NORM, false, 4, 3, 2, 18)
+    W2S_STREAM(16, 16, 2, PRO_NORM, false, 2, 3, 2, 18)
     W2S_STREAM(16, 16, 1, PRO_NORM_RES, true, 4, 3, 2, 14)
     W2S_STREAM(16, 32, 1, PRO_NORM_RES, true, 4, 3, 2, 10)
     W2S_STREAM(32, 32, 1, PRO_NORM, false, 2, 3, 2, 10)
