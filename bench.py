@@ -270,13 +270,19 @@ def run_cuda(args):
     kernels = []
     for label, (ms, by, fl, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
         kernels.append({"kernel": label, "launches_per_step": n // 2, "share": ms / total_ms,
-                        "avg_ms": ms / n, "algo_GBps": by / ms * 1e-6 if ms > 0 else None,
+                        "avg_ms": ms / n, "algo_bytes": by / n, "algo_GBps": by / ms * 1e-6 if ms > 0 else None,
                         "algo_TFLOPs": fl / ms * 1e-9 if ms > 0 else None})
     roofline = None
     if kernels:
         k = kernels[0]
+        # DRAM traffic per launch of that kernel from the committed `ncu --set full` capture (profiles/), if any
+        traffic = None
+        tf = ROOT / "profiles" / "traffic.json"
+        if tf.exists():
+            traffic = json.loads(tf.read_text()).get(k["kernel"], {}).get("dram_bytes_per_launch")
         roofline = {"bound": "hbm", "achieved": k["algo_GBps"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": k["algo_GBps"] / hbm_peak, "traffic": None, "kernel": k["kernel"],
+                    "frac": k["algo_GBps"] / hbm_peak, "traffic": traffic, "kernel": k["kernel"],
+                    "algo_bytes_per_launch": k["algo_bytes"],
                     "share_of_step": k["share"], "avg_launch_ms": k["avg_ms"], "peak_source": peak_src,
                     "whole_step": {"algo_GBps": sum(a[1] for a in agg.values()) / total_ms * 1e-6,
                                    "algo_TFLOPs": sum(a[2] for a in agg.values()) / total_ms * 1e-9,

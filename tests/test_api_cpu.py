@@ -1,0 +1,77 @@
+"""CPU tests of the host-side API: reference artefact loading and the N>1 sharding path (gloo, world_size 2)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import yaml
+
+from wav2sleep_b200 import api, build_default
+
+CARDIO = {"ABD": "ABD", "THX": "THX", "ECG": "ECG", "PPG": "PPG"}
+
+
+def test_instantiate_reference_targets_matches_build_default():
+    torch.manual_seed(0)
+    a = api.instantiate(api.default_config(CARDIO, 4))
+    b = build_default(CARDIO, 4, seed=0)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa) == list(sb)
+    assert all(torch.equal(sa[k], sb[k]) for k in sa)
+    with pytest.raises(ValueError):
+        api.instantiate({"_target_": "os.system", "command": "true"})
+
+
+def test_load_model_reads_reference_artefacts(tmp_path):
+    ref = build_default(CARDIO, 4, seed=3)
+    (tmp_path / "config.yaml").write_text(yaml.safe_dump(api.default_config(CARDIO, 4), sort_keys=False))
+    torch.save(ref.state_dict(), tmp_path / "state_dict.pth")
+    m = api.load_model(str(tmp_path), device="cpu")
+    assert not m.training and m.valid_signals == list(CARDIO) and m.num_classes == 4
+    assert all(torch.equal(v, ref.state_dict()[k]) for k, v in m.state_dict().items())
+    with pytest.raises(FileNotFoundError):
+        api.load_model(str(tmp_path / "missing"))
+
+
+@pytest.mark.parametrize("n,world", [(10, 3), (2, 4), (16, 8), (0, 2)])
+def test_shard_range_partitions(n, world):
+    parts = [list(api.shard_range(n, r, world)) for r in range(world)]
+    assert sum(parts, []) == list(range(n))
+    assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def _worker(rank, world, port, n_items, epochs, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    calls = []
+
+    def fake_predict(indices):  # stands in for model.predict on this rank's GPU
+        calls.append(list(indices))
+        return torch.tensor([[i * 100 + e for e in range(epochs)] for i in indices], dtype=torch.int64).reshape(-1, epochs)
+
+    out = api.predict_sharded(fake_predict, n_items, epochs)
+    q.put((rank, calls, out))
+    dist.destroy_process_group()
+
+
+def test_predict_sharded_gloo_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    n_items, epochs, world = 5, 7, 2
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_items, epochs, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect = torch.tensor([[i * 100 + e for e in range(epochs)] for i in range(n_items)])
+    assert res[0][1] == [[0, 1, 2]] and res[1][1] == [[3, 4]]  # disjoint contiguous shards
+    for _, _, out in res:
+        assert torch.equal(out, expect)  # every rank sees all predictions, in recording order

@@ -186,8 +186,8 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
   cudaError_t e = cudaErrorInvalidValue;
   bool found = false;
   char label[96];
-  snprintf(label, sizeof(label), "conv_igemm c%d->%d k%d s%d d%d pro%d epi%d%s", c.cin, c.cout, c.taps, c.stride,
-           c.dilation, c.prologue, c.epilogue, c.has_ds ? " +ds" : "");
+  snprintf(label, sizeof(label), "conv c%d->%d k%d s%d d%d pro%d epi%d%s B%d L%d", c.cin, c.cout, c.taps, c.stride,
+           c.dilation, c.prologue, c.epilogue, c.has_ds ? " +ds" : "", c.B, c.L_in);
   // algorithmic traffic: every input element read once (+ residual), every output written once; fp16
   const double in_b = (double)c.B * c.L_in * c.cin * 2.0 * (c.prologue == W2S_PRO_NORM_RES ? 2.0 : 1.0);
   const double out_b = (double)c.B * c.L_out * c.cout * 2.0 * (c.has_ds ? 1.5 : 1.0) +
@@ -411,7 +411,9 @@ int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T,
       fa.row_mask = row_mask;
       fa.T = L;
       {
-        LaunchScope scope(st, "first_conv c1->16 k3", (double)B * L * (4.0 + 32.0 + 16.0), 2.0 * B * (double)L * 16 * 3.5);
+        char fl_label[64];
+        snprintf(fl_label, sizeof(fl_label), "first_conv c1->16 k3 B%d L%d", B, L);
+        LaunchScope scope(st, fl_label, (double)B * L * (4.0 + 32.0 + 16.0), 2.0 * B * (double)L * 16 * 3.5);
         ce = launch_first_conv(fa, B, st);
       }
       if (ce != cudaSuccess) return cuda_fail(ce, "first_conv launch");
