@@ -56,7 +56,7 @@ int w2s_pack_linear_frag(const float* w, int n, int k, void* out_fp16, void* str
  * Replaces ConvLayer1D.forward (models/blocks.py:173-186) + the consumer-side InstanceNorm/GELU of its input.
  * ------------------------------------------------------------------------------------------------------- */
 enum { W2S_PRO_NONE = 0, W2S_PRO_NORM = 1, W2S_PRO_NORM_RES = 2 };
-enum { W2S_EPI_STATS = 0, W2S_EPI_BIAS_GELU = 1, W2S_EPI_LN_GELU = 2, W2S_EPI_LN_GELU_RES = 3 };
+enum { W2S_EPI_STATS = 0, W2S_EPI_BIAS_GELU = 1, W2S_EPI_LN_GELU = 2, W2S_EPI_LN_GELU_RES = 3, W2S_EPI_PLAIN = 4 };
 
 typedef struct w2s_conv_call {
   int32_t cin, cout, taps, stride, dilation, pad;
@@ -80,6 +80,9 @@ typedef struct w2s_conv_call {
   float* logits;          /* [B, L_out, n_classes] */
   int32_t n_classes;
   float in_eps, ln_eps;
+  /* W2S_EPI_PLAIN: out = acc (+ bias) (+ res), written to row o*out_stride + out_offset of a sample of out_rows
+   * rows (0, 0, 0 = dense: stride 1, offset 0, out_rows = L_out); res uses the same indexing. */
+  int32_t out_stride, out_offset, out_rows;
 } w2s_conv_call;
 
 int w2s_conv1d_fwd(const w2s_conv_call* call, void* stream);
@@ -108,6 +111,10 @@ typedef struct w2s_encoder_desc {
 /* keep_activations = 0: inference, tensors rotate through a few slots; 1: every layer output is kept
  * (layout = w2s_encoder_layout) for a backward pass. */
 size_t w2s_encoder_workspace_bytes(const w2s_encoder_desc* d, int B, int64_t T, int keep_activations);
+
+/* Byte offsets of the tensors kept by keep_activations = 1, 7 per block: sum/sumsq of conv1, conv2, conv3 outputs
+ * (fp64 [B, C, 2] each), y1 [B, L, C], r [B, L/2, C], y2 [B, L, C], y3 [B, L/2, C] (fp16).  offsets: host int64[7*n_blocks]. */
+int w2s_encoder_layout(const w2s_encoder_desc* d, int B, int64_t T, int64_t* offsets);
 
 /* x: fp32 [B, T] raw (z-scored) signal, rows of -inf = missing signal (data/dataset.py:170-173).
  * z_out: fp16 [B, T / samples_per_epoch, feature_dim]; rows of masked samples are left untouched.
@@ -168,6 +175,60 @@ size_t w2s_seqmixer_workspace_bytes(const w2s_seq_desc* d, int B, int S, int kee
  * logits: fp32 [B, S, n_classes]. */
 int w2s_seqmixer_head_fwd(const w2s_seq_desc* d, const void* x, int B, int S, void* workspace, size_t workspace_bytes,
                           int keep_activations, void* feat_out, float* logits, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Training path: kernel-level entry points; wav2sleep_b200/training.py strings them
+ * together into forward-with-saved-activations, backward, loss and optimizer step.  All tensors fp16 channels-last
+ * unless noted; gradients of parameters are fp32 and ACCUMULATED (+=) into caller-zeroed buffers.
+ * ------------------------------------------------------------------------------------------------------- */
+/* C[m*ldc_m + n*ldc_n] += scale * sum_{b,l} X[b,l,m] * Y[b, l*y_stride + y_offset, n]   (weight gradients of
+ * nn.Linear / one tap of nn.Conv1d).  Built for (M,N) in {16,32,64,128}x{16,32,64,128} pairs used by the model. */
+int w2s_gemm_tn(const void* X, const void* Y, float* C, int M, int N, int B, int LX, int LY, int y_stride, int y_offset,
+                long long ldc_m, long long ldc_n, float scale, const uint8_t* row_mask, void* stream);
+/* a = GELU(InstanceNorm(y)) [then GELU(a + r)]: re-materialises the activated input of a conv (models/blocks.py:57-71). */
+int w2s_enc_act_fwd(const void* y, const void* r, const double* stats, void* a, const uint8_t* row_mask, int B, int L, int C,
+                    float eps, void* stream);
+/* backward through GELU (and the block's residual add + GELU when r != NULL); writes d(x_hat), dr and accumulates the
+ * two whole-night reductions of the InstanceNorm backward into sums[B, C, 2] (fp64, caller-zeroed). */
+int w2s_enc_act_bwd(const void* dout, const void* y, const void* r, const double* stats, void* dxh, void* dr, double* sums,
+                    const uint8_t* row_mask, int B, int L, int C, float eps, void* stream);
+/* dy = rstd * (dxh - mean(dxh) - x_hat * mean(dxh * x_hat)); upsample = 1 writes row 2l of a zeroed [B, 2L, C] tensor. */
+int w2s_enc_norm_bwd(const void* dxh, const void* y, const double* stats, const double* sums, void* dy,
+                     const uint8_t* row_mask, int B, int L, int C, int upsample, float eps, void* stream);
+/* weight gradients of the Cin = 1 layers of block 0 (conv1 [16,1,3] and downsample [16,1,1]). */
+int w2s_first_conv_wgrad(const float* x, const void* dy1, const void* dr, float* dw1, float* dwds, const uint8_t* row_mask,
+                         int B, int T, void* stream);
+/* LayerNorm over 128 features per row (+GELU, + residual add + GELU): nn.LayerNorm / ConvLayerNorm (models/utils.py:9-23). */
+int w2s_row_ln_fwd(const void* x, const void* res, const float* g, const float* b, void* out, long long rows, int gelu,
+                   float eps, void* stream);
+int w2s_row_ln_bwd(const void* x, const void* res, const float* g, const float* b, const void* dout, const void* dadd,
+                   void* dx, void* ds, float* dg, float* db, long long rows, int gelu, float eps, void* stream);
+int w2s_gelu_fwd(const void* pre, void* out, long long n, void* stream);
+int w2s_gelu_bwd(const void* pre, const void* dout, void* din, long long n, void* stream);
+/* out[c] += sum over rows r of x[(r*row_stride + row_offset), c]  (bias gradients), C <= 128. */
+int w2s_colsum(const void* x, float* out, long long rows, int C, int row_stride, int row_offset, const uint8_t* row_mask,
+               long long rows_per_sample, void* stream);
+/* 8-head attention over the D <= 5 tokens of each epoch; q,k,v,o: [N, D, 128]; key_mask [N, D] (1 = masked key). */
+int w2s_attn_fwd(const void* q, const void* k, const void* v, void* o, const uint8_t* key_mask, int N, int D, void* stream);
+int w2s_attn_bwd(const void* q, const void* k, const void* v, const void* dout, void* dq, void* dk, void* dv,
+                 const uint8_t* key_mask, int N, int D, void* stream);
+/* token tensor [N, 1+n_sig, 128] = [cls, z_0[n], ...] (zeros + key mask for missing signals) and its backward. */
+int w2s_tokens_fwd(const void* const* z, const uint8_t* const* row_mask, const float* cls, void* tokens, uint8_t* key_mask,
+                   int N, int S, int n_sig, void* stream);
+int w2s_tokens_bwd(const void* dtokens, void* const* dz, const uint8_t* const* row_mask, float* dcls, int N, int S, int n_sig,
+                   void* stream);
+/* out[n] = in[n*stride + offset] (scatter = 0) or out[n*stride + offset] = in[n] (scatter = 1); rows of 128 fp16. */
+int w2s_rows_gather(const void* in, void* out, long long n_rows, int stride, int offset, int scatter, void* stream);
+/* classifier forward, CrossEntropyLoss(mean, ignore_index) forward+backward, classifier backward. */
+int w2s_head_fwd(const void* feat, const float* w, const float* b, float* logits, long long N, int C, void* stream);
+int w2s_ce_fwd_bwd(const float* logits, const long long* labels, long long N, int C, long long ignore_index, double* scratch2,
+                   float* loss, float* dlogits, void* stream);
+int w2s_head_bwd(const void* feat, const float* w, const float* dlogits, void* dfeat, float* dw, float* db, long long N, int C,
+                 void* stream);
+/* out += sum g^2 (fp64); fused global-norm clip (torch clip_grad_norm_) + AdamW step on flat fp32 buffers. */
+int w2s_sumsq(const float* g, long long n, double* out, void* stream);
+int w2s_adamw_step(float* p, const float* g, float* m, float* v, long long n, const double* gnorm_sq, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, float max_norm, float grad_scale, long long step, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Measurement hooks (bench.py).  Not part of the data path.

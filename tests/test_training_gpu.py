@@ -1,0 +1,140 @@
+"""-m gpu: training path.  Gradients of every parameter against torch autograd over the CPU oracle (fp32), plus the
+building blocks (gemm_tn, cross entropy, clip + AdamW) against torch.
+
+Tolerances: activations and activation gradients are stored in fp16 and the whole-night InstanceNorm backward couples
+millions of positions, so parameter gradients are compared by relative L2 error (<= 5e-2) and cosine similarity
+(>= 0.998) per tensor; dropout is p = 0 on both sides."""
+import ctypes as C
+
+import pytest
+import torch
+
+import gpu_utils as G
+from conftest import make_inputs
+from oracle import wav2sleep_oracle as oracle
+from wav2sleep_b200 import _lib, build_default
+
+pytestmark = pytest.mark.gpu
+CARDIO = {"ABD": "ABD", "THX": "THX", "ECG": "ECG", "PPG": "PPG"}
+
+
+@pytest.mark.parametrize("M,N,L,ys,yo", [(16, 16, 1000, 1, -1), (32, 16, 777, 1, 1), (128, 128, 300, 1, 0),
+                                         (128, 64, 260, 4, 2), (64, 64, 500, 2, 0)])
+def test_gemm_tn(cuda_device, M, N, L, ys, yo):
+    lib = _lib.load()
+    torch.manual_seed(M + N + L)
+    B = 3
+    LY = L * ys + 3
+    X = torch.randn(B, L, M, device=cuda_device).half()
+    Y = torch.randn(B, LY, N, device=cuda_device).half()
+    mask = torch.tensor([0, 1, 0], dtype=torch.uint8, device=cuda_device)
+    Cm = torch.zeros(M, N, device=cuda_device)
+    _lib.check(lib.w2s_gemm_tn(X.data_ptr(), Y.data_ptr(), Cm.data_ptr(), M, N, B, L, LY, ys, yo, N, 1, 1.0,
+                               mask.data_ptr(), G.stream()))
+    torch.cuda.synchronize()
+    ref = torch.zeros(M, N, device=cuda_device)
+    for b in (0, 2):
+        idx = torch.arange(L, device=cuda_device) * ys + yo
+        ok = (idx >= 0) & (idx < LY)
+        ref += X[b][ok].float().t() @ Y[b][idx[ok]].float()
+    assert (Cm - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+
+
+def test_ce_and_adamw_match_torch(cuda_device):
+    lib = _lib.load()
+    torch.manual_seed(0)
+    N, Cn = 5000, 4
+    logits = torch.randn(N, Cn, device=cuda_device)
+    labels = torch.randint(0, Cn, (N,), device=cuda_device)
+    labels[::7] = -1
+    scratch = torch.zeros(2, dtype=torch.float64, device=cuda_device)
+    loss = torch.zeros(1, device=cuda_device)
+    dlog = torch.empty_like(logits)
+    _lib.check(lib.w2s_ce_fwd_bwd(logits.data_ptr(), labels.data_ptr(), N, Cn, -1, scratch.data_ptr(), loss.data_ptr(),
+                                  dlog.data_ptr(), G.stream()))
+    lt = logits.clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lt, labels, ignore_index=-1)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-5
+    assert (dlog - lt.grad).abs().max().item() < 1e-7
+    # clip + AdamW, 3 steps
+    n = 100_003
+    p0 = torch.randn(n, device=cuda_device)
+    p_ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([p_ref], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
+    p, mom, var = p0.clone(), torch.zeros(n, device=cuda_device), torch.zeros(n, device=cuda_device)
+    nsq = torch.zeros(1, dtype=torch.float64, device=cuda_device)
+    for step in range(1, 4):
+        g = torch.randn(n, device=cuda_device) * 0.05
+        p_ref.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_([p_ref], 1.0)
+        opt.step()
+        nsq.zero_()
+        _lib.check(lib.w2s_sumsq(g.data_ptr(), n, nsq.data_ptr(), G.stream()))
+        _lib.check(lib.w2s_adamw_step(p.data_ptr(), g.data_ptr(), mom.data_ptr(), var.data_ptr(), n, nsq.data_ptr(), 1e-3,
+                                      0.9, 0.999, 1e-8, 1e-4, 1.0, 1.0, step, G.stream()))
+    torch.cuda.synchronize()
+    assert (p - p_ref.detach()).abs().max().item() < 2e-6
+
+
+def _grad_report(model, grads_ref):
+    rows = []
+    for name, p in model.named_parameters():
+        g, r = p.grad.detach().float().cpu(), grads_ref[name]
+        rn = r.norm().item()
+        rel = (g - r).norm().item() / max(rn, 1e-12)
+        cos = torch.nn.functional.cosine_similarity(g.flatten(), r.flatten(), dim=0).item() if rn > 0 else 1.0
+        rows.append((name, rn, rel, cos))
+    return rows
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_parameter_gradients_match_oracle_autograd(cuda_device, masked):
+    torch.manual_seed(0)
+    B, S = 2, 24
+    model = build_default(CARDIO, 4, seed=0)
+    x = make_inputs(CARDIO, B, S, masked=[("ABD", 0), ("PPG", 1)] if masked else [], seed=5)
+    labels = torch.randint(0, 4, (B, S))
+    labels[0, ::5] = -1
+    # oracle gradients (fp32 CPU autograd)
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    lo = oracle.forward_with_grad(x, params, oracle.cardio_config())
+    loss_ref = torch.nn.functional.cross_entropy(lo.view(-1, 4), labels.view(-1), ignore_index=-1)
+    loss_ref.backward()
+    grads_ref = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in params.items()}
+    # CUDA path
+    model = model.to(cuda_device).train()
+    logits = model({k: v.to(cuda_device) for k, v in x.items()})
+    assert logits.requires_grad
+    loss = torch.nn.functional.cross_entropy(logits.view(-1, 4), labels.to(cuda_device).view(-1), ignore_index=-1)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - loss_ref.item()) < 5e-3
+    rows = _grad_report(model, grads_ref)
+    worst = sorted(rows, key=lambda r: -r[2])[:8]
+    for name, rn, rel, cos in worst:
+        print(f"{name:70s} |g_ref| {rn:.3e} rel {rel:.3e} cos {cos:.5f}")
+    for name, rn, rel, cos in rows:
+        if rn == 0.0:  # parameters of fully masked encoders get exact zero gradients
+            assert model.get_parameter(name).grad.abs().max().item() == 0.0, name
+            continue
+        assert rel < 5e-2 and cos > 0.998, (name, rn, rel, cos)
+
+
+def test_training_reduces_loss(cuda_device):
+    """A few clip + AdamW steps on one fixed batch through the public training API lower the loss."""
+    from wav2sleep_b200.optim import FusedAdamW
+    torch.manual_seed(0)
+    model = build_default({"ECG": "ECG", "ABD": "ABD"}, 4, seed=0).to(cuda_device).train()
+    x = {k: v.to(cuda_device) for k, v in make_inputs({"ECG": "ECG", "ABD": "ABD"}, 2, 16, seed=9).items()}
+    y = torch.randint(0, 4, (2, 16), device=cuda_device)
+    opt = FusedAdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, max_grad_norm=1.0)
+    losses = []
+    for _ in range(8):
+        opt.zero_grad()
+        loss = torch.nn.functional.cross_entropy(model(x).view(-1, 4), y.view(-1))
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    print(losses)
+    assert losses[-1] < losses[0] - 0.05

@@ -25,7 +25,7 @@ MAX_DILATIONS = 8
 ABI_VERSION = 1
 
 PRO_NONE, PRO_NORM, PRO_NORM_RES = 0, 1, 2
-EPI_STATS, EPI_BIAS_GELU, EPI_LN_GELU, EPI_LN_GELU_RES = 0, 1, 2, 3
+EPI_STATS, EPI_BIAS_GELU, EPI_LN_GELU, EPI_LN_GELU_RES, EPI_PLAIN = 0, 1, 2, 3, 4
 
 
 def nvcc_path() -> str:
@@ -67,6 +67,7 @@ class ConvCall(C.Structure):
         ("row_mask", C.c_void_p), ("bias", C.c_void_p), ("ln_w", C.c_void_p), ("ln_b", C.c_void_p),
         ("res", C.c_void_p), ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("logits", C.c_void_p),
         ("n_classes", C.c_int32), ("in_eps", C.c_float), ("ln_eps", C.c_float),
+        ("out_stride", C.c_int32), ("out_offset", C.c_int32), ("out_rows", C.c_int32),
     ]
 
 
@@ -115,6 +116,7 @@ SYMBOLS = {
     "w2s_conv1d_fwd": (C.c_int, [C.POINTER(ConvCall), C.c_void_p]),
     "w2s_set_conv_impl": (C.c_int, [C.c_int]),
     "w2s_encoder_workspace_bytes": (C.c_size_t, [C.POINTER(EncoderDesc), C.c_int, C.c_int64, C.c_int]),
+    "w2s_encoder_layout": (C.c_int, [C.POINTER(EncoderDesc), C.c_int, C.c_int64, C.POINTER(C.c_int64)]),
     "w2s_encoder_fwd": (C.c_int, [C.POINTER(EncoderDesc), C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_size_t,
                                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "w2s_epoch_mixer_fwd": (C.c_int, [C.POINTER(MixerDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int,
@@ -123,6 +125,31 @@ SYMBOLS = {
     "w2s_seqmixer_head_fwd": (C.c_int, [C.POINTER(SeqDesc), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "w2s_argmax": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "w2s_gemm_tn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                              C.c_longlong, C.c_longlong, C.c_float, C.c_void_p, C.c_void_p]),
+    "w2s_enc_act_fwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "w2s_enc_act_bwd": (C.c_int, [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "w2s_enc_norm_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "w2s_first_conv_wgrad": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p]),
+    "w2s_row_ln_fwd": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_int, C.c_float, C.c_void_p]),
+    "w2s_row_ln_bwd": (C.c_int, [C.c_void_p] * 10 + [C.c_longlong, C.c_int, C.c_float, C.c_void_p]),
+    "w2s_gelu_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "w2s_gelu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "w2s_colsum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong,
+                             C.c_void_p]),
+    "w2s_attn_fwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_void_p]),
+    "w2s_attn_bwd": (C.c_int, [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_void_p]),
+    "w2s_tokens_fwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                 C.c_int, C.c_int, C.c_void_p]),
+    "w2s_tokens_bwd": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int,
+                                 C.c_int, C.c_void_p]),
+    "w2s_rows_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "w2s_head_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
+    "w2s_ce_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
+    "w2s_head_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_longlong, C.c_int, C.c_void_p]),
+    "w2s_sumsq": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "w2s_adamw_step": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_void_p] + [C.c_float] * 7 + [C.c_longlong, C.c_void_p]),
     "w2s_launch_count": (C.c_longlong, []),
     "w2s_profile_enable": (C.c_int, [C.c_int]),
     "w2s_profile_count": (C.c_int, []),

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <cstdlib>
 #include <mutex>
@@ -15,6 +16,8 @@
 #include "conv_stream.cuh"
 #include "epoch_mixer.cuh"
 #include "first_conv.cuh"
+#include "gemm_tn.cuh"
+#include "train_kernels.cuh"
 
 using namespace w2s;
 
@@ -173,6 +176,9 @@ ConvArgs to_args(const w2s_conv_call& c) {
   a.pad = c.pad;
   a.in_eps = c.in_eps;
   a.ln_eps = c.ln_eps;
+  a.out_stride = c.out_stride > 0 ? c.out_stride : 1;
+  a.out_offset = c.out_offset;
+  a.out_rows = c.out_rows > 0 ? c.out_rows : c.L_out;
   { const char* dbg = getenv("W2S_DEBUG_FLAGS"); a.debug_flags = dbg ? atoi(dbg) : 0; }
   return a;
 }
@@ -249,6 +255,23 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
   // sequence mixer dilated convs
   W2S_CASE(128, 128, 7, 4, PRO_NONE, EPI_LN_GELU, false)
   W2S_CASE(128, 128, 7, 4, PRO_NONE, EPI_LN_GELU_RES, false)
+  // training path: plain GEMMs (taps 1 / 4) and data-gradient convolutions (input already materialised)
+  W2S_CASE(128, 128, 1, 1, PRO_NONE, EPI_PLAIN, false)
+  W2S_CASE(128, 128, 4, 2, PRO_NONE, EPI_PLAIN, false)
+  W2S_CASE(128, 128, 7, 4, PRO_NONE, EPI_PLAIN, false)
+  W2S_CASE(128, 64, 1, 1, PRO_NONE, EPI_PLAIN, false)
+  W2S_CASE(16, 16, 3, 3, PRO_NONE, EPI_PLAIN, false)
+  W2S_CASE(32, 16, 3, 3, PRO_NONE, EPI_PLAIN, false)
+  W2S_CASE(32, 32, 3, 3, PRO_NONE, EPI_PLAIN, false)
+  W2S_CASE(64, 32, 3, 3, PRO_NONE, EPI_PLAIN, false)
+  W2S_CASE(64, 64, 3, 3, PRO_NONE, EPI_PLAIN, false)
+  W2S_CASE(128, 64, 3, 3, PRO_NONE, EPI_PLAIN, false)
+  W2S_CASE(128, 128, 3, 3, PRO_NONE, EPI_PLAIN, false)
+  W2S_CASE(16, 16, 1, 1, PRO_NONE, EPI_PLAIN, false)
+  W2S_CASE(32, 16, 1, 1, PRO_NONE, EPI_PLAIN, false)
+  W2S_CASE(32, 32, 1, 1, PRO_NONE, EPI_PLAIN, false)
+  W2S_CASE(64, 32, 1, 1, PRO_NONE, EPI_PLAIN, false)
+  W2S_CASE(64, 64, 1, 1, PRO_NONE, EPI_PLAIN, false)
 #undef W2S_CASE
   if (!found)
     return fail("conv1d: no kernel for cin=%d cout=%d taps=%d pro=%d epi=%d ds=%d", c.cin, c.cout, c.taps, c.prologue,
@@ -343,6 +366,28 @@ size_t w2s_encoder_workspace_bytes(const w2s_encoder_desc* d, int B, int64_t T, 
     L /= 2;
   }
   return stats + act;
+}
+
+int w2s_encoder_layout(const w2s_encoder_desc* d, int B, int64_t T, int64_t* offsets) {
+  // keep_activations = 1 layout: per block 7 byte offsets into the workspace: stats1, stats2, stats3, y1, r, y2, y3
+  if (check_encoder_desc(d) != 0 || offsets == nullptr || B <= 0 || T <= 0) return fail("encoder_layout: bad arguments");
+  const size_t stats_bytes = align_up(enc_stats_count(d, B) * sizeof(double), 256);
+  size_t st = 0, act = stats_bytes;
+  int64_t L = T;
+  for (int i = 0; i < d->n_blocks; ++i) {
+    const size_t c = d->channels[i], e = sizeof(__half);
+    int64_t* o = offsets + 7 * i;
+    for (int k = 0; k < 3; ++k) {
+      o[k] = (int64_t)st;
+      st += (size_t)B * c * 2 * sizeof(double);
+    }
+    o[3] = (int64_t)act; act += align_up((size_t)B * L * c * e, 256);        // y1
+    o[4] = (int64_t)act; act += align_up((size_t)B * (L / 2) * c * e, 256);  // r
+    o[5] = (int64_t)act; act += align_up((size_t)B * L * c * e, 256);        // y2
+    o[6] = (int64_t)act; act += align_up((size_t)B * (L / 2) * c * e, 256);  // y3
+    L /= 2;
+  }
+  return 0;
 }
 
 int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T, void* workspace, size_t ws_bytes,
@@ -566,6 +611,249 @@ int w2s_seqmixer_head_fwd(const w2s_seq_desc* d, const void* x, int B, int S, vo
     block_in = cur;
   }
   return 0;
+}
+
+// ================================================================================================
+// training path: kernel-level entry points (orchestrated by wav2sleep_b200/training.py)
+// ================================================================================================
+#define W2S_LAUNCH_CHECK(what)                                       \
+  do {                                                               \
+    cudaError_t e__ = cudaGetLastError();                            \
+    if (e__ != cudaSuccess) return cuda_fail(e__, what);             \
+    return 0;                                                        \
+  } while (0)
+
+static int ew_grid(long long work_items, int threads = 256) {
+  long long g = (work_items + threads - 1) / threads;
+  const long long cap = 8LL * sm_count();
+  if (g > cap) g = cap;
+  return g < 1 ? 1 : (int)g;
+}
+
+int w2s_gemm_tn(const void* X, const void* Y, float* Cm, int M, int N, int B, int LX, int LY, int y_stride, int y_offset,
+                long long ldc_m, long long ldc_n, float scale, const uint8_t* row_mask, void* stream) {
+  if (!X || !Y || !Cm || B <= 0 || LX <= 0 || LY <= 0) return fail("gemm_tn: bad arguments");
+  GemmTNArgs a;
+  a.X = (const act_t*)X; a.Y = (const act_t*)Y; a.C = Cm; a.row_mask = row_mask;
+  a.B = B; a.LX = LX; a.LY = LY; a.y_stride = y_stride; a.y_offset = y_offset;
+  a.ldc_m = ldc_m; a.ldc_n = ldc_n; a.scale = scale;
+  cudaStream_t st = (cudaStream_t)stream;
+  char label[64];
+  snprintf(label, sizeof(label), "gemm_tn %dx%d B%d L%d", M, N, B, LX);
+  LaunchScope scope(st, label, (double)B * LX * (M + N) * 2.0, 2.0 * B * (double)LX * M * N);
+  cudaError_t e = cudaErrorInvalidValue;
+#define W2S_TN(MM, NN) if (M == MM && N == NN) e = launch_gemm_tn<MM, NN>(a, sm_count(), st);
+  W2S_TN(16, 16) W2S_TN(32, 16) W2S_TN(32, 32) W2S_TN(64, 32) W2S_TN(64, 64) W2S_TN(128, 64) W2S_TN(128, 128)
+#undef W2S_TN
+  if (e == cudaErrorInvalidValue) return fail("gemm_tn: no kernel for M=%d N=%d", M, N);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "gemm_tn launch");
+}
+
+int w2s_enc_act_fwd(const void* y, const void* r, const double* stats, void* a, const uint8_t* row_mask, int B, int L,
+                    int Cc, float eps, void* stream) {
+  if (!y || !stats || !a || Cc % 8) return fail("enc_act_fwd: bad arguments");
+  EncActArgs p{(const act_t*)y, (const act_t*)r, stats, (act_t*)a, row_mask, B, L, Cc, eps};
+  LaunchScope scope((cudaStream_t)stream, "enc_act_fwd", (double)B * L * Cc * (r ? 6.0 : 4.0), 0);
+  dim3 grid(ew_grid((long long)L * (Cc / 8)) / (B > 1 ? 1 : 1), B);
+  enc_act_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  W2S_LAUNCH_CHECK("enc_act_fwd");
+}
+
+int w2s_enc_act_bwd(const void* dout, const void* y, const void* r, const double* stats, void* dxh, void* dr, double* sums,
+                    const uint8_t* row_mask, int B, int L, int Cc, float eps, void* stream) {
+  if (!dout || !y || !stats || !dxh || !sums || Cc % 8 || 256 % (Cc / 8)) return fail("enc_act_bwd: bad arguments");
+  if (r && !dr) return fail("enc_act_bwd: dr missing");
+  EncActBwdArgs p{(const act_t*)dout, (const act_t*)y, (const act_t*)r, stats, (act_t*)dxh, (act_t*)dr, sums, row_mask,
+                  B, L, Cc, eps};
+  LaunchScope scope((cudaStream_t)stream, "enc_act_bwd", (double)B * L * Cc * (r ? 10.0 : 6.0), 0);
+  const int rows_per_block = 256 / (Cc / 8);
+  int gx = (L + rows_per_block * 8 - 1) / (rows_per_block * 8);
+  if (gx > 4 * sm_count()) gx = 4 * sm_count();
+  dim3 grid(gx < 1 ? 1 : gx, B);
+  enc_act_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  W2S_LAUNCH_CHECK("enc_act_bwd");
+}
+
+int w2s_enc_norm_bwd(const void* dxh, const void* y, const double* stats, const double* sums, void* dy,
+                     const uint8_t* row_mask, int B, int L, int Cc, int upsample, float eps, void* stream) {
+  if (!dxh || !y || !stats || !sums || !dy || Cc % 8) return fail("enc_norm_bwd: bad arguments");
+  EncNormBwdArgs p{(const act_t*)dxh, (const act_t*)y, stats, sums, (act_t*)dy, row_mask, B, L, Cc, upsample, eps};
+  LaunchScope scope((cudaStream_t)stream, "enc_norm_bwd", (double)B * L * Cc * 6.0, 0);
+  dim3 grid(ew_grid((long long)L * (Cc / 8)), B);
+  enc_norm_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  W2S_LAUNCH_CHECK("enc_norm_bwd");
+}
+
+int w2s_first_conv_wgrad(const float* x, const void* dy1, const void* dr, float* dw1, float* dwds, const uint8_t* row_mask,
+                         int B, int T, void* stream) {
+  if (!x || !dy1 || !dr || !dw1 || !dwds) return fail("first_conv_wgrad: bad arguments");
+  FirstWgradArgs p{x, (const act_t*)dy1, (const act_t*)dr, dw1, dwds, row_mask, B, T};
+  LaunchScope scope((cudaStream_t)stream, "first_conv_wgrad", (double)B * T * (4.0 + 32.0 + 16.0), 0);
+  int gx = (T + 256 * 16 - 1) / (256 * 16);
+  dim3 grid(gx < 1 ? 1 : gx, B);
+  first_conv_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  W2S_LAUNCH_CHECK("first_conv_wgrad");
+}
+
+int w2s_row_ln_fwd(const void* x, const void* res, const float* g, const float* b, void* out, long long rows, int gelu,
+                   float eps, void* stream) {
+  if (!x || !g || !b || !out || rows <= 0) return fail("row_ln_fwd: bad arguments");
+  RowLnArgs p;
+  memset(&p, 0, sizeof(p));
+  p.x = (const act_t*)x; p.res = (const act_t*)res; p.g = g; p.b = b; p.out = (act_t*)out; p.rows = rows; p.gelu = gelu;
+  p.eps = eps;
+  LaunchScope scope((cudaStream_t)stream, "row_ln_fwd", (double)rows * 128 * (res ? 6.0 : 4.0), 0);
+  row_ln_fwd_kernel<<<ew_grid(rows * 32), 256, 0, (cudaStream_t)stream>>>(p);
+  W2S_LAUNCH_CHECK("row_ln_fwd");
+}
+
+int w2s_row_ln_bwd(const void* x, const void* res, const float* g, const float* b, const void* dout, const void* dadd,
+                   void* dx, void* ds, float* dg, float* db, long long rows, int gelu, float eps, void* stream) {
+  if (!x || !g || !b || !dout || !dx || !dg || !db || rows <= 0) return fail("row_ln_bwd: bad arguments");
+  RowLnArgs p;
+  memset(&p, 0, sizeof(p));
+  p.x = (const act_t*)x; p.res = (const act_t*)res; p.g = g; p.b = b; p.out = (act_t*)dx; p.dout = (const act_t*)dout;
+  p.dadd = (const act_t*)dadd; p.ds = (act_t*)ds; p.dg = dg; p.db = db; p.rows = rows; p.gelu = gelu; p.eps = eps;
+  LaunchScope scope((cudaStream_t)stream, "row_ln_bwd", (double)rows * 128 * 8.0, 0);
+  int gx = ew_grid(rows * 32);
+  if (gx > 2 * sm_count()) gx = 2 * sm_count();
+  row_ln_bwd_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>(p);
+  W2S_LAUNCH_CHECK("row_ln_bwd");
+}
+
+int w2s_gelu_fwd(const void* pre, void* out, long long n, void* stream) {
+  if (!pre || !out || n <= 0 || n % 8) return fail("gelu_fwd: bad arguments");
+  LaunchScope scope((cudaStream_t)stream, "gelu_fwd", (double)n * 4.0, 0);
+  gelu_fwd_kernel<<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>((const act_t*)pre, (act_t*)out, n / 8);
+  W2S_LAUNCH_CHECK("gelu_fwd");
+}
+int w2s_gelu_bwd(const void* pre, const void* dout, void* din, long long n, void* stream) {
+  if (!pre || !dout || !din || n <= 0 || n % 8) return fail("gelu_bwd: bad arguments");
+  LaunchScope scope((cudaStream_t)stream, "gelu_bwd", (double)n * 6.0, 0);
+  gelu_bwd_kernel<<<ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>((const act_t*)pre, (const act_t*)dout, (act_t*)din, n / 8);
+  W2S_LAUNCH_CHECK("gelu_bwd");
+}
+
+int w2s_colsum(const void* x, float* out, long long rows, int Cc, int row_stride, int row_offset, const uint8_t* row_mask,
+               long long rows_per_sample, void* stream) {
+  if (!x || !out || rows <= 0 || Cc % 8 || Cc > 128 || 256 % (Cc / 8)) return fail("colsum: bad arguments");
+  LaunchScope scope((cudaStream_t)stream, "colsum", (double)rows * Cc * 2.0, 0);
+  int gx = ew_grid(rows * (Cc / 8));
+  if (gx > 2 * sm_count()) gx = 2 * sm_count();
+  colsum_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>((const act_t*)x, out, rows, Cc, row_stride > 0 ? row_stride : 1,
+                                                      row_offset, row_mask, rows_per_sample > 0 ? rows_per_sample : rows);
+  W2S_LAUNCH_CHECK("colsum");
+}
+
+int w2s_attn_fwd(const void* q, const void* k, const void* v, void* o, const uint8_t* key_mask, int N, int D, void* stream) {
+  if (!q || !k || !v || !o || N <= 0 || D < 1 || D > 5) return fail("attn_fwd: bad arguments");
+  AttnArgs p;
+  memset(&p, 0, sizeof(p));
+  p.q = (const act_t*)q; p.k = (const act_t*)k; p.v = (const act_t*)v; p.o = (act_t*)o; p.key_mask = key_mask; p.N = N; p.D = D;
+  LaunchScope scope((cudaStream_t)stream, "attn_fwd", (double)N * D * 128 * 8.0, 0);
+  attn_kernel<false><<<(N * 8 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p);
+  W2S_LAUNCH_CHECK("attn_fwd");
+}
+int w2s_attn_bwd(const void* q, const void* k, const void* v, const void* dout, void* dq, void* dk, void* dv,
+                 const uint8_t* key_mask, int N, int D, void* stream) {
+  if (!q || !k || !v || !dout || !dq || !dk || !dv || N <= 0 || D < 1 || D > 5) return fail("attn_bwd: bad arguments");
+  AttnArgs p;
+  memset(&p, 0, sizeof(p));
+  p.q = (const act_t*)q; p.k = (const act_t*)k; p.v = (const act_t*)v; p.dout = (const act_t*)dout;
+  p.dq = (act_t*)dq; p.dk = (act_t*)dk; p.dv = (act_t*)dv; p.key_mask = key_mask; p.N = N; p.D = D;
+  LaunchScope scope((cudaStream_t)stream, "attn_bwd", (double)N * D * 128 * 14.0, 0);
+  attn_kernel<true><<<(N * 8 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p);
+  W2S_LAUNCH_CHECK("attn_bwd");
+}
+
+int w2s_tokens_fwd(const void* const* z, const uint8_t* const* row_mask, const float* cls, void* tokens, uint8_t* key_mask,
+                   int N, int S, int n_sig, void* stream) {
+  if (!z || !cls || !tokens || !key_mask || n_sig < 1 || n_sig > 4) return fail("tokens_fwd: bad arguments");
+  TokenArgs p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < n_sig; ++i) { p.z[i] = (const act_t*)z[i]; p.row_mask[i] = row_mask ? row_mask[i] : nullptr; }
+  p.cls = cls; p.tokens = (act_t*)tokens; p.key_mask = key_mask; p.N = N; p.S = S; p.n_sig = n_sig;
+  LaunchScope scope((cudaStream_t)stream, "tokens_fwd", (double)N * (n_sig + 1) * 128 * 4.0, 0);
+  tokens_fwd_kernel<<<ew_grid((long long)N * (n_sig + 1) * 16), 256, 0, (cudaStream_t)stream>>>(p);
+  W2S_LAUNCH_CHECK("tokens_fwd");
+}
+int w2s_tokens_bwd(const void* dtokens, void* const* dz, const uint8_t* const* row_mask, float* dcls, int N, int S, int n_sig,
+                   void* stream) {
+  if (!dtokens || !dz || !dcls || n_sig < 1 || n_sig > 4) return fail("tokens_bwd: bad arguments");
+  TokenArgs p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < n_sig; ++i) { p.dz[i] = (act_t*)dz[i]; p.row_mask[i] = row_mask ? row_mask[i] : nullptr; }
+  p.dtokens = (const act_t*)dtokens; p.dcls = dcls; p.N = N; p.S = S; p.n_sig = n_sig;
+  LaunchScope scope((cudaStream_t)stream, "tokens_bwd", (double)N * (n_sig + 1) * 128 * 4.0, 0);
+  int gx = ew_grid((long long)N * (n_sig + 1) * 16);
+  if (gx > 2 * sm_count()) gx = 2 * sm_count();
+  tokens_bwd_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>(p);
+  W2S_LAUNCH_CHECK("tokens_bwd");
+}
+int w2s_rows_gather(const void* in, void* out, long long n_rows, int stride, int offset, int scatter, void* stream) {
+  if (!in || !out || n_rows <= 0 || stride < 1) return fail("rows_gather: bad arguments");
+  LaunchScope scope((cudaStream_t)stream, "rows_gather", (double)n_rows * 128 * 4.0, 0);
+  rows_gather_kernel<<<ew_grid(n_rows * 16), 256, 0, (cudaStream_t)stream>>>((const act_t*)in, (act_t*)out, n_rows, stride,
+                                                                          offset, scatter);
+  W2S_LAUNCH_CHECK("rows_gather");
+}
+
+int w2s_head_fwd(const void* feat, const float* w, const float* b, float* logits, long long N, int Cc, void* stream) {
+  if (!feat || !w || !b || !logits || N <= 0 || Cc < 1 || Cc > 8) return fail("head_fwd: bad arguments");
+  HeadArgs p;
+  memset(&p, 0, sizeof(p));
+  p.feat = (const act_t*)feat; p.w = w; p.b = b; p.logits = logits; p.N = N; p.C = Cc;
+  LaunchScope scope((cudaStream_t)stream, "head_fwd", (double)N * 128 * 2.0, 0);
+  head_fwd_kernel<<<ew_grid(N * 32), 256, 0, (cudaStream_t)stream>>>(p);
+  W2S_LAUNCH_CHECK("head_fwd");
+}
+int w2s_ce_fwd_bwd(const float* logits, const long long* labels, long long N, int Cc, long long ignore_index, double* scratch2,
+                   float* loss, float* dlogits, void* stream) {
+  if (!logits || !labels || !scratch2 || !loss || !dlogits || N <= 0 || Cc < 1 || Cc > 8) return fail("ce_fwd_bwd: bad arguments");
+  HeadArgs p;
+  memset(&p, 0, sizeof(p));
+  p.logits = (float*)logits; p.labels = labels; p.loss_sum = scratch2; p.count = scratch2 + 1; p.loss = loss; p.N = N; p.C = Cc;
+  p.ignore_index = ignore_index;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(scratch2, 0, 2 * sizeof(double), st);
+  if (e != cudaSuccess) return cuda_fail(e, "ce memset");
+  LaunchScope scope(st, "ce_fwd_bwd", (double)N * Cc * 8.0, 0);
+  ce_loss_kernel<<<ew_grid(N), 256, 0, st>>>(p);
+  ce_grad_kernel<<<ew_grid(N), 256, 0, st>>>(p, dlogits);
+  W2S_LAUNCH_CHECK("ce_fwd_bwd");
+}
+int w2s_head_bwd(const void* feat, const float* w, const float* dlogits, void* dfeat, float* dw, float* db, long long N, int Cc,
+                 void* stream) {
+  if (!feat || !w || !dlogits || !dfeat || !dw || !db || N <= 0 || Cc < 1 || Cc > 8) return fail("head_bwd: bad arguments");
+  HeadArgs p;
+  memset(&p, 0, sizeof(p));
+  p.feat = (const act_t*)feat; p.w = w; p.dlogits = dlogits; p.dfeat = (act_t*)dfeat; p.dw = dw; p.db = db; p.N = N; p.C = Cc;
+  LaunchScope scope((cudaStream_t)stream, "head_bwd", (double)N * 128 * 4.0, 0);
+  int gx = ew_grid(N * 32);
+  if (gx > sm_count()) gx = sm_count();
+  head_bwd_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>(p);
+  W2S_LAUNCH_CHECK("head_bwd");
+}
+
+int w2s_sumsq(const float* g, long long n, double* out, void* stream) {
+  if (!g || !out || n <= 0) return fail("sumsq: bad arguments");
+  LaunchScope scope((cudaStream_t)stream, "sumsq", (double)n * 4.0, 0);
+  int gx = ew_grid(n);
+  if (gx > 2 * sm_count()) gx = 2 * sm_count();
+  sumsq_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>(g, n, out);
+  W2S_LAUNCH_CHECK("sumsq");
+}
+int w2s_adamw_step(float* p_, const float* g, float* m, float* v, long long n, const double* gnorm_sq, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, float max_norm, float grad_scale, long long step, void* stream) {
+  if (!p_ || !g || !m || !v || n <= 0 || step < 1) return fail("adamw_step: bad arguments");
+  AdamWArgs a;
+  a.p = p_; a.g = g; a.m = m; a.v = v; a.n = n; a.gnorm_sq = gnorm_sq; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
+  a.weight_decay = weight_decay; a.max_norm = max_norm; a.grad_scale = grad_scale;
+  a.bias_c1 = (float)(1.0 - pow((double)beta1, (double)step));
+  a.bias_c2 = (float)(1.0 - pow((double)beta2, (double)step));
+  LaunchScope scope((cudaStream_t)stream, "adamw_step", (double)n * 28.0, (double)n * 12.0);
+  adamw_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(a);
+  W2S_LAUNCH_CHECK("adamw_step");
 }
 
 int w2s_set_conv_impl(int impl) {

@@ -19,13 +19,15 @@
 //   EPI_BIAS_GELU : + bias, exact GELU, stores fp16
 //   EPI_LN_GELU   : LayerNorm over the 128 channels of the thread's row, affine, GELU
 //   EPI_LN_GELU_RES: ... + block input, GELU, optional fused classifier head
+//   EPI_PLAIN     : (+ bias) (+ residual tensor) -> fp16, output rows at o*out_stride + out_offset (plain GEMMs and
+//                   data-gradient convolutions of the training path)
 #pragma once
 #include "common.cuh"
 
 namespace w2s {
 
 enum : int { PRO_NONE = 0, PRO_NORM = 1, PRO_NORM_RES = 2 };
-enum : int { EPI_STATS = 0, EPI_BIAS_GELU = 1, EPI_LN_GELU = 2, EPI_LN_GELU_RES = 3 };
+enum : int { EPI_STATS = 0, EPI_BIAS_GELU = 1, EPI_LN_GELU = 2, EPI_LN_GELU_RES = 3, EPI_PLAIN = 4 };
 
 struct ConvArgs {
   // input side
@@ -52,6 +54,9 @@ struct ConvArgs {
   int dil, pad;
   float in_eps;           // InstanceNorm eps (1e-2)
   float ln_eps;           // ConvLayerNorm eps (1e-5)
+  int out_stride;         // EPI_PLAIN: output row = o * out_stride + out_offset inside a sample of out_rows rows
+  int out_offset;
+  int out_rows;
   int debug_flags;        // profiling experiments only (0 in production): 1 skip lo MMAs, 2 skip all MMAs, 4 skip GELU
 };
 
@@ -89,7 +94,7 @@ template <int CIN, int COUT, int TAPS, int GT /*taps resident per weight group*/
 __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs p) {
   static_assert(!SPLIT || (GT == TAPS && PRO != PRO_NONE), "split operands: single weight group, computed prologue");
   static_assert(CIN % 16 == 0 && COUT % 16 == 0 && COUT <= 128, "UMMA shape");
-  static_assert(EPI == EPI_STATS || COUT == 128, "row-wise epilogues need the full channel dim in one tile");
+  static_assert(EPI == EPI_STATS || EPI == EPI_PLAIN || COUT == 128, "row-wise epilogues need the full channel dim in one tile");
   constexpr int CH = CIN / 8;                 // 16-byte chunks per input row
   constexpr int MT = ConvTile<COUT>::MT;
   constexpr int POS = ConvTile<COUT>::POS;
@@ -372,6 +377,37 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs
       // fp64 atomics: the cross-CTA summation order no longer changes the fp32 result (run-to-run determinism)
       atomicAdd(&p.out_stats[((size_t)b * COUT + tid) * 2 + 0], (double)s0);
       atomicAdd(&p.out_stats[((size_t)b * COUT + tid) * 2 + 1], (double)s1);
+    }
+  } else if (EPI == EPI_PLAIN) {
+    constexpr int UNITS = MT * (COUT / 16);
+#pragma unroll 1
+    for (int unit = wg; unit < UNITS; unit += 2) {
+      const int j = unit / (COUT / 16);
+      const int cg = unit % (COUT / 16);
+      float v[16];
+      tmem_ld16(tmem_base + t_lane + j * COUT + cg * 16, v);
+      const int o = o0 + j * 128 + quad * 32 + lane;
+      if (o < p.L_out) {
+        const size_t off = ((size_t)b * p.out_rows + (size_t)o * p.out_stride + p.out_offset) * COUT + cg * 16;
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] += __ldg(p.bias + cg * 16 + k);
+        }
+        if (p.res != nullptr) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.res + off);
+          uint4 rz[2] = {__ldg(rp), __ldg(rp + 1)};
+          const uint32_t* rr = reinterpret_cast<const uint32_t*>(rz);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float2 r2 = unpack_h2(rr[k]);
+            v[2 * k] += r2.x;
+            v[2 * k + 1] += r2.y;
+          }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(p.out + off);
+        dst[0] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+        dst[1] = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+      }
     }
   } else if (EPI == EPI_BIAS_GELU) {
     act_t* outb = p.out + (size_t)b * p.L_out * COUT;

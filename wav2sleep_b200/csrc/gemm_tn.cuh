@@ -1,0 +1,164 @@
+// Weight-gradient GEMM of the training path:  C[M, N] += sum over rows r of X[r, :]^T (x) Y[map(r), :]
+//
+// X = output-side gradient rows [B, LX, M] (fp16, channels-last), Y = input-side activation rows [B, LY, N];
+// map(r) = l * y_stride + y_offset inside the same sample (rows outside [0, LY) contribute zero: conv padding).
+// This is dW of every Linear (y_stride 1, y_offset 0) and of every conv tap (reference autograd of
+// nn.Conv1d / nn.Linear: blocks.py:154-163, wav2sleep.py:230,286-296,41): the reduction runs over positions
+// (up to 2e7 rows) while M, N <= 128, so it is a streaming, HBM-bound kernel.  Warp-level mma.sync.m16n8k16 with
+// both operands transposed on load (ldmatrix.trans from row-major [row][channel] tiles); each CTA reduces a
+// contiguous row range into registers and finishes with fp32 atomics into C (stride-addressed, so C can be a
+// tap slice of a [Cout, Cin, taps] conv weight gradient).
+#pragma once
+#include "common.cuh"
+
+namespace w2s {
+
+struct GemmTNArgs {
+  const act_t* X;   // [B, LX, M]
+  const act_t* Y;   // [B, LY, N]
+  float* C;         // element (m, n) at C[m * ldc_m + n * ldc_n]
+  const uint8_t* row_mask;  // [B] or null
+  int B, LX, LY;
+  int y_stride, y_offset;
+  long long ldc_m, ldc_n;
+  float scale;      // multiplies the contribution (1.0)
+};
+
+constexpr int kGemmTNThreads = 256;
+constexpr int kGemmTNRows = 128;  // rows per smem tile
+
+template <int M, int N>
+struct GemmTNCfg {
+  static constexpr int MW = M < 64 ? M : 64;       // warp tile
+  static constexpr int NW = N < 32 ? N : 32;
+  static constexpr int WARPS_MN = (M / MW) * (N / NW);
+  static constexpr int KG = 8 / WARPS_MN;          // warps that split the rows of a tile
+  static constexpr int LDX = M + 8, LDY = N + 8;   // padded smem row strides (halfs)
+  static constexpr int MT = MW / 16, NT = NW / 8;
+  static_assert(WARPS_MN <= 8 && 8 % WARPS_MN == 0, "warp layout");
+  static_assert(kGemmTNRows % (16 * KG) == 0, "row tile vs k-groups");
+};
+
+W2S_DEVINL void ldmatrix_x4_trans(uint32_t (&r)[4], const __half* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+W2S_DEVINL void ldmatrix_x2_trans(uint32_t (&r)[2], const __half* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];"
+               : "=r"(r[0]), "=r"(r[1])
+               : "r"(smem_u32(p)));
+}
+W2S_DEVINL void mma_16816_f16(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int M, int N>
+__global__ void __launch_bounds__(kGemmTNThreads) gemm_tn_kernel(const GemmTNArgs p) {
+  using Cfg = GemmTNCfg<M, N>;
+  constexpr int LDX = Cfg::LDX, LDY = Cfg::LDY, MT = Cfg::MT, NT = Cfg::NT, KG = Cfg::KG;
+  extern __shared__ __align__(16) uint8_t gemm_tn_smem[];
+  __half* sX = reinterpret_cast<__half*>(gemm_tn_smem);
+  __half* sY = sX + kGemmTNRows * LDX;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wmn = warp % Cfg::WARPS_MN, kg = warp / Cfg::WARPS_MN;
+  const int m0 = (wmn / (N / Cfg::NW)) * Cfg::MW;
+  const int n0 = (wmn % (N / Cfg::NW)) * Cfg::NW;
+
+  float acc[MT][NT][4];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.0f;
+
+  const long long total = (long long)p.B * p.LX;
+  const long long tiles = (total + kGemmTNRows - 1) / kGemmTNRows;
+  const long long t_begin = tiles * blockIdx.x / gridDim.x, t_end = tiles * (blockIdx.x + 1) / gridDim.x;
+
+  for (long long tile = t_begin; tile < t_end; ++tile) {
+    const long long r0 = tile * kGemmTNRows;
+    __syncthreads();
+    // ---- stage X rows and mapped Y rows (zero where out of range / masked) ----
+    for (int id = tid; id < kGemmTNRows * (M / 8); id += kGemmTNThreads) {
+      const int k = id / (M / 8), c = id % (M / 8);
+      const long long r = r0 + k;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (r < total) {
+        const int b = (int)(r / p.LX);
+        if (p.row_mask == nullptr || !p.row_mask[b]) v = __ldg(reinterpret_cast<const uint4*>(p.X + r * M) + c);
+      }
+      *reinterpret_cast<uint4*>(sX + k * LDX + c * 8) = v;
+    }
+    for (int id = tid; id < kGemmTNRows * (N / 8); id += kGemmTNThreads) {
+      const int k = id / (N / 8), c = id % (N / 8);
+      const long long r = r0 + k;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (r < total) {
+        const int b = (int)(r / p.LX);
+        const int l = (int)(r - (long long)b * p.LX);
+        const int ly = l * p.y_stride + p.y_offset;
+        if (ly >= 0 && ly < p.LY && (p.row_mask == nullptr || !p.row_mask[b]))
+          v = __ldg(reinterpret_cast<const uint4*>(p.Y + ((long long)b * p.LY + ly) * N) + c);
+      }
+      *reinterpret_cast<uint4*>(sY + k * LDY + c * 8) = v;
+    }
+    __syncthreads();
+    // ---- each k-group of warps takes its share of the 128 rows ----
+    constexpr int KSTEPS = kGemmTNRows / 16 / KG;
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+      const int k0 = (kg * KSTEPS + ks) * 16;
+      uint32_t a[MT][4];
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+        ldmatrix_x4_trans(a[i], sX + (k0 + (lane >> 4) * 8 + (lane & 7)) * LDX + m0 + i * 16 + ((lane >> 3) & 1) * 8);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        uint32_t bf[2];
+        ldmatrix_x2_trans(bf, sY + (k0 + ((lane >> 3) & 1) * 8 + (lane & 7)) * LDY + n0 + j * 8);
+#pragma unroll
+        for (int i = 0; i < MT; ++i) mma_16816_f16(acc[i][j], a[i], bf);
+      }
+    }
+  }
+  // ---- accumulate into C ----
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int m = m0 + i * 16 + (lane >> 2);
+      const int n = n0 + j * 8 + (lane & 3) * 2;
+      float* c0 = p.C + m * p.ldc_m + n * p.ldc_n;
+      atomicAdd(c0, acc[i][j][0] * p.scale);
+      atomicAdd(c0 + p.ldc_n, acc[i][j][1] * p.scale);
+      atomicAdd(c0 + 8 * p.ldc_m, acc[i][j][2] * p.scale);
+      atomicAdd(c0 + 8 * p.ldc_m + p.ldc_n, acc[i][j][3] * p.scale);
+    }
+}
+
+template <int M, int N>
+inline cudaError_t launch_gemm_tn(const GemmTNArgs& a, int sm_count, cudaStream_t stream) {
+  const long long tiles = ((long long)a.B * a.LX + kGemmTNRows - 1) / kGemmTNRows;
+  long long grid = 2LL * sm_count;
+  if (grid > tiles) grid = tiles;
+  if (grid < 1) grid = 1;
+  using Cfg = GemmTNCfg<M, N>;
+  constexpr int smem = kGemmTNRows * (Cfg::LDX + Cfg::LDY) * 2;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<M, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  gemm_tn_kernel<M, N><<<(int)grid, kGemmTNThreads, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace w2s

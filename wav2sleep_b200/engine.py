@@ -80,7 +80,8 @@ class ForwardEngine:
 
     # ------------------------------------------------------------------ weights
     def _params_key(self, device):
-        return (str(device),) + tuple((p.data_ptr(), p._version) for p in self.model.parameters())
+        from . import optim  # WEIGHTS_EPOCH: in-place updates by the fused optimizer do not bump tensor versions
+        return (str(device), optim.WEIGHTS_EPOCH) + tuple((p.data_ptr(), p._version) for p in self.model.parameters())
 
     def _ensure_packed(self, device):
         key = self._params_key(device)
@@ -196,9 +197,6 @@ class ForwardEngine:
 
     @torch.no_grad()
     def forward(self, x: dict[str, Tensor]) -> Tensor:
-        if self.model.training and torch.is_grad_enabled():
-            raise NotImplementedError("wav2sleep_b200: backward kernels are not built yet; call under "
-                                      "model.eval() / torch.no_grad() (DESIGN.md, scope)")
         B, S, device = self._check_inputs(x)
         lib = self.lib
         with torch.cuda.device(device):

@@ -220,13 +220,21 @@ class Wav2Sleep(nn.Module):
         return list(self.signal_encoders.signal_map.keys())
 
     def _get_engine(self):
-        from .engine import ForwardEngine  # deferred: loads the CUDA library
+        from .training import TrainEngine  # deferred: loads the CUDA library
         if self._engine is None:
-            object.__setattr__(self, "_engine", ForwardEngine(self))
+            object.__setattr__(self, "_engine", TrainEngine(self))
         return self._engine
 
+    _get_train_engine = _get_engine
+
     def forward(self, x: dict[str, Tensor]) -> Tensor:
-        """dict of [B, S * samples_per_epoch] fp32 (rows of -inf = missing signal) -> logits [B, S, num_classes]."""
+        """dict of [B, S * samples_per_epoch] fp32 (rows of -inf = missing signal) -> logits [B, S, num_classes].
+
+        Under ``train()`` with grad enabled the logits carry a grad_fn whose backward runs the CUDA backward pass
+        (dropout is treated as p = 0, see training.py); otherwise the fused inference kernels run."""
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .training import forward_with_grad
+            return forward_with_grad(self, x)
         return self._get_engine().forward(x)
 
     def predict(self, x: dict[str, Tensor]) -> Tensor:

@@ -1,0 +1,482 @@
+"""Training path: forward with saved activations, backward, for ``Wav2Sleep``.
+
+Replaces what the reference gets from autograd over ``Wav2Sleep.forward`` (trainer/main.py:161-163 ->
+``loss.backward()``).  Every FLOP runs in ``libw2s_b200.so``; this file is the host-side schedule (which kernel on which
+buffer), written in Python like the reference's training code is.  Encoders reuse the streaming tcgen05 kernels with
+``keep_activations=1``; epoch mixer and sequence mixer run un-fused in training (tcgen05 implicit-GEMM kernel with a
+plain epilogue + row-wise kernels) so that every intermediate needed by the backward is materialised once.  Data
+gradients are tcgen05 convolutions with flipped/transposed weights, weight gradients are the streaming ``gemm_tn``
+kernel, everything else is element-/row-wise.
+
+Limits of this round: dropout is treated as p = 0 (the reference's gradient can only be reproduced without it,
+SURVEY H6); fp16 storage of activations and activation gradients, fp32 parameter gradients.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import ConvCall, EPI_PLAIN, PRO_NONE
+from .engine import ForwardEngine, _stream
+
+F16 = torch.float16
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class TrainEngine(ForwardEngine):
+    """Adds forward_train / backward to the inference engine (shares the packed forward weights)."""
+
+    def __init__(self, model):
+        super().__init__(model)
+        self._train_key = None
+        self.saved = None
+        self.bucket_hooks = []  # callables(name) fired as gradient buckets become final (data-parallel overlap)
+        self.direct = set()
+
+    # ------------------------------------------------------------------ weight packing for the backward
+    def _pack(self, w: Tensor, taps_major=0, taps=None) -> Tensor:
+        """fp32 [cout, cin, taps] (or [cout, taps*cin] with taps_major) -> fp16 UMMA layout (no hi/lo split)."""
+        lib, st = self.lib, _stream()
+        w = w.detach().to(torch.float32).contiguous()
+        if taps_major:
+            cout, cin = w.shape[0], w.shape[1] // taps
+        else:
+            cout, cin, taps = w.shape
+        out = torch.empty(taps * cin * cout, dtype=F16, device=w.device)
+        _lib.check(lib.w2s_pack_conv_weight(w.data_ptr(), cout, cin, taps, taps_major, 0, out.data_ptr(), st))
+        self._tk.append(w)
+        return out
+
+    def _ensure_train_packed(self, device):
+        self._ensure_packed(device)
+        if self._train_key == self._weights_key:
+            return
+        m = self.model
+        self._tk: list[Tensor] = []
+        flipT = lambda w: w.flip(2).permute(1, 0, 2)  # conv weight for the data gradient (transposed conv)
+        self.tw = {"enc": {}, "mix": [], "seq": []}
+        for name, enc in m.signal_encoders.encoders.items():
+            e = {"conv": [], "ds": [], "lin_fwd": None, "lin_dgrad": []}
+            for i, blk in enumerate(enc.cnn):
+                e["conv"].append([
+                    self._pack(flipT(blk.conv1.conv.weight)) if i > 0 else None,
+                    self._pack(flipT(blk.conv2.conv.weight)),
+                    self._pack(flipT(blk.conv3.conv.weight)),
+                ])
+                e["ds"].append(self._pack(blk.downsample.weight.permute(1, 0, 2)) if i > 0 else None)
+            Cl = enc.channels[-1]
+            e["lin_fwd"] = self._pack(enc.linear.weight, taps_major=1, taps=4)
+            e["lin_dgrad"] = [self._pack(enc.linear.weight[:, t * Cl:(t + 1) * Cl].t().unsqueeze(-1)) for t in range(4)]
+            self.tw["enc"][name] = e
+        for layer in m.epoch_mixer.transformer_encoder.layers:
+            Win, W1, W2 = layer.self_attn.in_proj_weight, layer.linear1.weight, layer.linear2.weight
+            Wo = layer.self_attn.out_proj.weight
+            self.tw["mix"].append({
+                "qkv": [self._pack(Win[j * 128:(j + 1) * 128].unsqueeze(-1)) for j in range(3)],
+                "qkv_T": [self._pack(Win[j * 128:(j + 1) * 128].t().unsqueeze(-1)) for j in range(3)],
+                "o": self._pack(Wo.unsqueeze(-1)), "o_T": self._pack(Wo.t().unsqueeze(-1)),
+                "ff1": [self._pack(W1[j * 128:(j + 1) * 128].unsqueeze(-1)) for j in range(4)],
+                "ff1_T": self._pack(W1.view(4, 128, 128).permute(2, 1, 0)),          # taps=4 conv for d(h2)
+                "ff2": self._pack(W2, taps_major=1, taps=4),
+                "ff2_T": [self._pack(W2[:, j * 128:(j + 1) * 128].t().unsqueeze(-1)) for j in range(4)],
+            })
+        for blk in m.sequence_mixer.dilated_convs:
+            self.tw["seq"].append([{"fwd": self._pack(l.conv.weight), "T": self._pack(flipT(l.conv.weight))}
+                                   for l in blk.conv_layers])
+        self._train_key = self._weights_key
+
+    # ------------------------------------------------------------------ kernel helpers
+    def conv(self, inp, w, cin, cout, taps, B, L_in, L_out, out, stride=1, dil=1, pad=0, bias=None, res=None,
+             out_stride=0, out_offset=0, out_rows=0, row_mask=None):
+        c = ConvCall()
+        c.cin, c.cout, c.taps, c.stride, c.dilation, c.pad = cin, cout, taps, stride, dil, pad
+        c.prologue, c.epilogue, c.has_ds = PRO_NONE, EPI_PLAIN, 0
+        c.B, c.L_in, c.L_out = B, L_in, L_out
+        c.in_, c.w, c.out = inp.data_ptr(), w.data_ptr(), out.data_ptr()
+        c.bias = bias.data_ptr() if bias is not None else None
+        c.res = res.data_ptr() if res is not None else None
+        c.row_mask = row_mask.data_ptr() if row_mask is not None else None
+        c.out_stride, c.out_offset, c.out_rows = out_stride, out_offset, out_rows
+        _lib.check(self.lib.w2s_conv1d_fwd(C.byref(c), _stream()))
+
+    def gemm_tn(self, X, Y, Cbuf, M, N, B, LX, LY, ldc_m, ldc_n, y_stride=1, y_offset=0, row_mask=None, c_off=0):
+        _lib.check(self.lib.w2s_gemm_tn(X.data_ptr(), Y.data_ptr(), Cbuf.data_ptr() + 4 * c_off, M, N, B, LX, LY, y_stride,
+                                        y_offset, ldc_m, ldc_n, 1.0, _p(row_mask), _stream()))
+
+    def ln_fwd(self, x, g, b, rows, gelu, eps, res=None):
+        out = torch.empty_like(x)
+        _lib.check(self.lib.w2s_row_ln_fwd(x.data_ptr(), _p(res), g.data_ptr(), b.data_ptr(), out.data_ptr(), rows, gelu,
+                                           eps, _stream()))
+        return out
+
+    def ln_bwd(self, x, g, b, dout, dg, db, rows, gelu, eps, res=None, dadd=None, want_ds=False):
+        dx = torch.empty_like(x)
+        ds = torch.empty_like(x) if want_ds else None
+        _lib.check(self.lib.w2s_row_ln_bwd(x.data_ptr(), _p(res), g.data_ptr(), b.data_ptr(), dout.data_ptr(), _p(dadd),
+                                           dx.data_ptr(), _p(ds), dg.data_ptr(), db.data_ptr(), rows, gelu, eps,
+                                           _stream()))
+        return dx, ds
+
+    def colsum(self, x, out, rows, Cc, row_stride=1, row_offset=0, row_mask=None, rows_per_sample=0, out_off=0):
+        _lib.check(self.lib.w2s_colsum(x.data_ptr(), out.data_ptr() + 4 * out_off, rows, Cc, row_stride, row_offset,
+                                       _p(row_mask), rows_per_sample, _stream()))
+
+    # ------------------------------------------------------------------ gradients storage
+    def _grad(self, p: Tensor) -> Tensor:
+        """fp32 gradient buffer of a parameter, zeroed at the start of every backward, accumulated by the kernels."""
+        g = self.grads.get(id(p))
+        if g is None:
+            if p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous():
+                g = p.grad  # accumulate straight into the (flat-buffer) gradient: no copy, no autograd hand-over
+                self.direct.add(id(p))
+            else:
+                g = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.contiguous_format)
+            self.grads[id(p)] = g
+        return g
+
+    # ================================================================== forward (training)
+    @torch.no_grad()
+    def forward_train(self, x: dict[str, Tensor]) -> Tensor:
+        B, S, device = self._check_inputs(x)
+        lib, m = self.lib, self.model
+        with torch.cuda.device(device):
+            self._ensure_train_packed(device)
+            st = _stream()
+            names = sorted(x.keys())
+            N = B * S
+            sv = {"B": B, "S": S, "names": names, "enc": {}, "device": device}
+            # ---- encoders (streaming kernels, every layer output kept) ----
+            for n in names:
+                enc = m.signal_encoders.get_encoder(n)
+                pe = self.enc[m.signal_encoders.signal_map[n]]
+                xs = x[n].detach().to(torch.float32).contiguous()
+                T = xs.size(1)
+                ws_bytes = lib.w2s_encoder_workspace_bytes(C.byref(pe.desc), B, T, 1)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+                mask = torch.zeros(B, dtype=torch.uint8, device=device)
+                z_unused = torch.empty(B, S, 128, dtype=F16, device=device)
+                _lib.check(lib.w2s_encoder_fwd(C.byref(pe.desc), xs.data_ptr(), B, T, ws.data_ptr(), ws_bytes, 1,
+                                               z_unused.data_ptr(), mask.data_ptr(), st), ValueError)
+                nb = len(enc.channels)
+                offs = (C.c_int64 * (7 * nb))()
+                _lib.check(lib.w2s_encoder_layout(C.byref(pe.desc), B, T, offs))
+                e = {"x": xs, "ws": ws, "mask": mask, "T": T, "blocks": [], "enc": enc,
+                     "tw": self.tw["enc"][m.signal_encoders.signal_map[n]]}
+                L = T
+                for i, c in enumerate(enc.channels):
+                    o = offs[7 * i:7 * i + 7]
+                    view = lambda off, rows, ch: ws[off: off + B * rows * ch * 2].view(F16).view(B, rows, ch)
+                    stat = lambda off, ch: ws[off: off + B * ch * 16].view(torch.float64).view(B, ch, 2)
+                    e["blocks"].append({"C": c, "L": L, "s1": stat(o[0], c), "s2": stat(o[1], c), "s3": stat(o[2], c),
+                                        "y1": view(o[3], L, c), "r": view(o[4], L // 2, c), "y2": view(o[5], L, c),
+                                        "y3": view(o[6], L // 2, c)})
+                    L //= 2
+                # time-distributed linear on the re-materialised activated block output
+                last = e["blocks"][-1]
+                Cl, L4 = last["C"], last["L"] // 2  # L4 = 4 * S
+                a_last = torch.empty(B, L4, Cl, dtype=F16, device=device)
+                _lib.check(lib.w2s_enc_act_fwd(last["y3"].data_ptr(), last["r"].data_ptr(), last["s3"].data_ptr(),
+                                               a_last.data_ptr(), mask.data_ptr(), B, L4, Cl, enc.norm_eps, st))
+                z_pre = torch.zeros(B, S, 128, dtype=F16, device=device)
+                bl = self._f32(enc.linear.bias)
+                self.conv(a_last, e["tw"]["lin_fwd"], Cl, 128, 4, B, L4, S, z_pre, stride=4, bias=bl, row_mask=mask)
+                z = torch.zeros(B, S, 128, dtype=F16, device=device)
+                _lib.check(lib.w2s_gelu_fwd(z_pre.data_ptr(), z.data_ptr(), z.numel(), st))
+                e.update(a_last=a_last, z_pre=z_pre, z=z)
+                sv["enc"][n] = e
+            # ---- epoch mixer (un-fused) ----
+            mix = m.epoch_mixer
+            D = len(names) + 1
+            T_tok = N * D
+            zs = (C.c_void_p * len(names))(*[sv["enc"][n]["z"].data_ptr() for n in names])
+            ms = (C.c_void_p * len(names))(*[sv["enc"][n]["mask"].data_ptr() for n in names])
+            tokens = torch.empty(T_tok, 128, dtype=F16, device=device)
+            key_mask = torch.empty(T_tok, dtype=torch.uint8, device=device)
+            cls = self._f32(mix.register_tokens[0, 0, :, 0])
+            _lib.check(lib.w2s_tokens_fwd(zs, ms, cls.data_ptr(), tokens.data_ptr(), key_mask.data_ptr(), N, S, len(names), st))
+            sv.update(D=D, key_mask=key_mask, layers=[])
+            xcur = tokens
+            for l, layer in enumerate(mix.transformer_encoder.layers):
+                tw = self.tw["mix"][l]
+                eps = layer.norm1.eps
+                f = self._f32
+                h1 = self.ln_fwd(xcur, f(layer.norm1.weight), f(layer.norm1.bias), T_tok, 0, eps)
+                qkv = []
+                bin_ = f(layer.self_attn.in_proj_bias)
+                for j in range(3):
+                    o = torch.empty(T_tok, 128, dtype=F16, device=device)
+                    self.conv(h1, tw["qkv"][j], 128, 128, 1, 1, T_tok, T_tok, o, bias=bin_[j * 128:(j + 1) * 128])
+                    qkv.append(o)
+                ao = torch.empty(T_tok, 128, dtype=F16, device=device)
+                _lib.check(lib.w2s_attn_fwd(qkv[0].data_ptr(), qkv[1].data_ptr(), qkv[2].data_ptr(), ao.data_ptr(),
+                                            key_mask.data_ptr(), N, D, st))
+                x_mid = torch.empty(T_tok, 128, dtype=F16, device=device)
+                self.conv(ao, tw["o"], 128, 128, 1, 1, T_tok, T_tok, x_mid, bias=f(layer.self_attn.out_proj.bias), res=xcur)
+                h2 = self.ln_fwd(x_mid, f(layer.norm2.weight), f(layer.norm2.bias), T_tok, 0, eps)
+                hpre = torch.empty(4 * T_tok, 128, dtype=F16, device=device)  # [T, 512] row-major
+                b1 = f(layer.linear1.bias)
+                for j in range(4):
+                    self.conv(h2, tw["ff1"][j], 128, 128, 1, 1, T_tok, T_tok, hpre, bias=b1[j * 128:(j + 1) * 128],
+                              out_stride=4, out_offset=j, out_rows=4 * T_tok)
+                hact = torch.empty_like(hpre)
+                _lib.check(lib.w2s_gelu_fwd(hpre.data_ptr(), hact.data_ptr(), hpre.numel(), st))
+                x_out = torch.empty(T_tok, 128, dtype=F16, device=device)
+                self.conv(hact, tw["ff2"], 128, 128, 4, 1, 4 * T_tok, T_tok, x_out, stride=4, bias=f(layer.linear2.bias),
+                          res=x_mid)
+                sv["layers"].append(dict(x=xcur, h1=h1, q=qkv[0], k=qkv[1], v=qkv[2], ao=ao, x_mid=x_mid, h2=h2, hpre=hpre,
+                                         hact=hact))
+                xcur = x_out
+            mixed = torch.empty(N, 128, dtype=F16, device=device)
+            _lib.check(lib.w2s_rows_gather(xcur.data_ptr(), mixed.data_ptr(), N, D, 0, 0, st))
+            # ---- sequence mixer (un-fused) + classifier ----
+            sv["seq"] = []
+            blk_in = mixed
+            for bi, blk in enumerate(m.sequence_mixer.dilated_convs):
+                cur = blk_in
+                rec = {"in": blk_in, "layers": []}
+                nl = len(blk.conv_layers)
+                for k, layer in enumerate(blk.conv_layers):
+                    d = blk.dilations[k]
+                    c = torch.empty(B, S, 128, dtype=F16, device=device)
+                    self.conv(cur, self.tw["seq"][bi][k]["fwd"], 128, 128, 7, B, S, S, c, dil=d, pad=3 * d)
+                    g_, b_ = self._f32(layer.norm.weight.reshape(-1)), self._f32(layer.norm.bias.reshape(-1))
+                    y = self.ln_fwd(c.view(N, 128), g_, b_, N, 1, layer.norm.eps,
+                                    res=blk_in.view(N, 128) if k == nl - 1 else None).view(B, S, 128)
+                    rec["layers"].append({"in": cur, "c": c, "g": g_, "b": b_, "eps": layer.norm.eps, "d": d})
+                    cur = y
+                sv["seq"].append(rec)
+                blk_in = cur
+            feat = blk_in
+            logits = torch.empty(B, S, m.num_classes, dtype=torch.float32, device=device)
+            wc, bc = self._f32(m.classifier.weight), self._f32(m.classifier.bias)
+            _lib.check(lib.w2s_head_fwd(feat.data_ptr(), wc.data_ptr(), bc.data_ptr(), logits.data_ptr(), N, m.num_classes, st))
+            sv.update(feat=feat, wc=wc)
+            self.saved = sv
+        return logits
+
+    def _f32(self, t: Tensor) -> Tensor:
+        t = t.detach()
+        return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
+
+    # ================================================================== backward
+    @torch.no_grad()
+    def backward(self, dlogits: Tensor) -> dict[int, Tensor]:
+        """Back-propagates d(loss)/d(logits) through the saved forward; returns {id(param): fp32 grad}."""
+        sv, lib, m = self.saved, self.lib, self.model
+        if sv is None:
+            raise RuntimeError("backward called without a preceding forward_train")
+        B, S, device = sv["B"], sv["S"], sv["device"]
+        N = B * S
+        self.grads = {}
+        self.direct = set()
+        with torch.cuda.device(device):
+            st = _stream()
+            G = self._grad
+            dlogits = dlogits.detach().to(torch.float32).contiguous()
+            # ---- classifier ----
+            dfeat = torch.empty(N, 128, dtype=F16, device=device)
+            _lib.check(lib.w2s_head_bwd(sv["feat"].data_ptr(), sv["wc"].data_ptr(), dlogits.data_ptr(), dfeat.data_ptr(),
+                                        G(m.classifier.weight).data_ptr(), G(m.classifier.bias).data_ptr(), N,
+                                        m.num_classes, st))
+            # ---- sequence mixer ----
+            dout = dfeat
+            for bi in reversed(range(len(sv["seq"]))):
+                rec, blk = sv["seq"][bi], m.sequence_mixer.dilated_convs[bi]
+                nl = len(rec["layers"])
+                ds = None
+                for k in reversed(range(nl)):
+                    lr, layer = rec["layers"][k], blk.conv_layers[k]
+                    dg, db = G(layer.norm.weight).view(-1), G(layer.norm.bias).view(-1)
+                    last = k == nl - 1
+                    dc, ds_k = self.ln_bwd(lr["c"].view(N, 128), lr["g"], lr["b"], dout, dg, db, N, 1, lr["eps"],
+                                           res=rec["in"].view(N, 128) if last else None, want_ds=last)
+                    if last:
+                        ds = ds_k
+                    d = lr["d"]
+                    dW = G(layer.conv.weight)
+                    for t in range(7):
+                        self.gemm_tn(dc, lr["in"], dW, 128, 128, B, S, S, 128 * 7, 7, y_stride=1, y_offset=(t - 3) * d, c_off=t)
+                    din = torch.empty(N, 128, dtype=F16, device=device)
+                    self.conv(dc, self.tw["seq"][bi][k]["T"], 128, 128, 7, B, S, S, din, dil=d, pad=3 * d,
+                              res=ds if k == 0 else None)
+                    dout = din
+            dmix = dout  # [N, 128]
+            # ---- epoch mixer ----
+            D, key_mask = sv["D"], sv["key_mask"]
+            T_tok = N * D
+            dx = torch.zeros(T_tok, 128, dtype=F16, device=device)
+            _lib.check(lib.w2s_rows_gather(dmix.data_ptr(), dx.data_ptr(), N, D, 0, 1, st))
+            mix = m.epoch_mixer
+            for l in reversed(range(len(sv["layers"]))):
+                L_, layer, tw = sv["layers"][l], mix.transformer_encoder.layers[l], self.tw["mix"][l]
+                eps = layer.norm1.eps
+                f = self._f32
+                # FFN
+                dW2, dW1 = G(layer.linear2.weight), G(layer.linear1.weight)
+                d_hact = torch.empty(4 * T_tok, 128, dtype=F16, device=device)
+                for j in range(4):
+                    self.conv(dx, tw["ff2_T"][j], 128, 128, 1, 1, T_tok, T_tok, d_hact, out_stride=4, out_offset=j,
+                              out_rows=4 * T_tok)
+                    self.gemm_tn(dx, L_["hact"], dW2, 128, 128, 1, T_tok, 4 * T_tok, 512, 1, y_stride=4, y_offset=j, c_off=j * 128)
+                self.colsum(dx, G(layer.linear2.bias), T_tok, 128)
+                d_hpre = torch.empty_like(d_hact)
+                _lib.check(lib.w2s_gelu_bwd(L_["hpre"].data_ptr(), d_hact.data_ptr(), d_hpre.data_ptr(), d_hact.numel(), st))
+                for j in range(4):
+                    # dW1[j*128 + n, m] += sum_o h2[o, m] * d_hpre[4o + j, n]   (transposed addressing of C)
+                    self.gemm_tn(L_["h2"], d_hpre, dW1, 128, 128, 1, T_tok, 4 * T_tok, 1, 128, y_stride=4, y_offset=j,
+                                 c_off=j * 128 * 128)
+                    self.colsum(d_hpre, G(layer.linear1.bias), T_tok, 128, row_stride=4, row_offset=j, out_off=j * 128)
+                d_h2 = torch.empty(T_tok, 128, dtype=F16, device=device)
+                self.conv(d_hpre, tw["ff1_T"], 128, 128, 4, 1, 4 * T_tok, T_tok, d_h2, stride=4)
+                dx_mid, _ = self.ln_bwd(L_["x_mid"], f(layer.norm2.weight), f(layer.norm2.bias), d_h2, G(layer.norm2.weight),
+                                        G(layer.norm2.bias), T_tok, 0, eps, dadd=dx)
+                # attention
+                d_ao = torch.empty(T_tok, 128, dtype=F16, device=device)
+                self.conv(dx_mid, tw["o_T"], 128, 128, 1, 1, T_tok, T_tok, d_ao)
+                self.gemm_tn(dx_mid, L_["ao"], G(layer.self_attn.out_proj.weight), 128, 128, 1, T_tok, T_tok, 128, 1)
+                self.colsum(dx_mid, G(layer.self_attn.out_proj.bias), T_tok, 128)
+                dq, dk, dv = (torch.empty(T_tok, 128, dtype=F16, device=device) for _ in range(3))
+                _lib.check(lib.w2s_attn_bwd(L_["q"].data_ptr(), L_["k"].data_ptr(), L_["v"].data_ptr(), d_ao.data_ptr(),
+                                            dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), key_mask.data_ptr(), N, D, st))
+                dWin, dbin = G(layer.self_attn.in_proj_weight), G(layer.self_attn.in_proj_bias)
+                d_h1 = None
+                for j, dj in enumerate((dq, dk, dv)):
+                    self.gemm_tn(dj, L_["h1"], dWin, 128, 128, 1, T_tok, T_tok, 128, 1, c_off=j * 128 * 128)
+                    self.colsum(dj, dbin, T_tok, 128, out_off=j * 128)
+                    nxt = torch.empty(T_tok, 128, dtype=F16, device=device)
+                    self.conv(dj, tw["qkv_T"][j], 128, 128, 1, 1, T_tok, T_tok, nxt, res=d_h1)
+                    d_h1 = nxt
+                dx, _ = self.ln_bwd(L_["x"], f(layer.norm1.weight), f(layer.norm1.bias), d_h1, G(layer.norm1.weight),
+                                    G(layer.norm1.bias), T_tok, 0, eps, dadd=dx_mid)
+            names = sv["names"]
+            dz = {n: torch.zeros(B, S, 128, dtype=F16, device=device) for n in names}
+            dzs = (C.c_void_p * len(names))(*[dz[n].data_ptr() for n in names])
+            ms = (C.c_void_p * len(names))(*[sv["enc"][n]["mask"].data_ptr() for n in names])
+            dcls = torch.zeros(128, dtype=torch.float32, device=device)
+            _lib.check(lib.w2s_tokens_bwd(dx.data_ptr(), dzs, ms, dcls.data_ptr(), N, S, len(names), st))
+            G(mix.register_tokens).view(-1).add_(dcls)  # register_tokens is [1, 1, 128, 1]
+            # ---- encoders ----
+            for hook in self.bucket_hooks:
+                hook("tail")  # classifier + sequence mixer + epoch mixer gradients are final
+            for n in names:
+                self._encoder_backward(sv["enc"][n], dz[n], B, S)
+            for hook in self.bucket_hooks:
+                hook("encoders")
+            self.saved = None
+        return self.grads
+
+    def _encoder_backward(self, e, dz, B, S):
+        lib, st, G = self.lib, _stream(), self._grad
+        enc, mask, tw, device = e["enc"], e["mask"], e["tw"], dz.device
+        eps = enc.norm_eps
+        blocks = e["blocks"]
+        last = blocks[-1]
+        Cl, L4 = last["C"], last["L"] // 2
+        new = lambda *shape: torch.empty(*shape, dtype=F16, device=device)
+        zeros64 = lambda c: torch.zeros(B, c, 2, dtype=torch.float64, device=device)
+        # linear + GELU
+        d_zpre = new(B, S, 128)
+        _lib.check(lib.w2s_gelu_bwd(e["z_pre"].data_ptr(), dz.data_ptr(), d_zpre.data_ptr(), dz.numel(), st))
+        dWl = G(enc.linear.weight)
+        d_a = new(B, L4, Cl)
+        for t in range(4):
+            self.gemm_tn(d_zpre, e["a_last"], dWl, 128, Cl, B, S, L4, 4 * Cl, 1, y_stride=4, y_offset=t, row_mask=mask,
+                         c_off=t * Cl)
+            self.conv(d_zpre, tw["lin_dgrad"][t], 128, Cl, 1, B, S, S, d_a, out_stride=4, out_offset=t, out_rows=L4,
+                      row_mask=mask)
+        self.colsum(d_zpre, G(enc.linear.bias), B * S, 128, row_mask=mask, rows_per_sample=S)
+        dout = d_a  # gradient wrt the activated output of the last block, [B, L/2, C]
+        for i in reversed(range(len(blocks))):
+            bk, blk = blocks[i], enc.cnn[i]
+            Cc, L = bk["C"], bk["L"]
+            Lh = L // 2
+            # ---- conv3 (stride 2) + block output ----
+            dxh, dr, sums = new(B, Lh, Cc), new(B, Lh, Cc), zeros64(Cc)
+            _lib.check(lib.w2s_enc_act_bwd(dout.data_ptr(), bk["y3"].data_ptr(), bk["r"].data_ptr(), bk["s3"].data_ptr(),
+                                           dxh.data_ptr(), dr.data_ptr(), sums.data_ptr(), mask.data_ptr(), B, Lh, Cc, eps, st))
+            dy_up = torch.zeros(B, L, Cc, dtype=F16, device=device)
+            _lib.check(lib.w2s_enc_norm_bwd(dxh.data_ptr(), bk["y3"].data_ptr(), bk["s3"].data_ptr(), sums.data_ptr(),
+                                            dy_up.data_ptr(), mask.data_ptr(), B, Lh, Cc, 1, eps, st))
+            a2 = new(B, L, Cc)
+            _lib.check(lib.w2s_enc_act_fwd(bk["y2"].data_ptr(), None, bk["s2"].data_ptr(), a2.data_ptr(), mask.data_ptr(),
+                                           B, L, Cc, eps, st))
+            dW = G(blk.conv3.conv.weight)
+            for t in range(3):
+                self.gemm_tn(dy_up, a2, dW, Cc, Cc, B, L, L, Cc * 3, 3, y_offset=t - 1, row_mask=mask, c_off=t)
+            d_a2 = new(B, L, Cc)
+            self.conv(dy_up, tw["conv"][i][2], Cc, Cc, 3, B, L, L, d_a2, pad=1, row_mask=mask)
+            del dy_up, a2, dxh
+            # ---- conv2 ----
+            dxh, sums = new(B, L, Cc), zeros64(Cc)
+            _lib.check(lib.w2s_enc_act_bwd(d_a2.data_ptr(), bk["y2"].data_ptr(), None, bk["s2"].data_ptr(), dxh.data_ptr(),
+                                           None, sums.data_ptr(), mask.data_ptr(), B, L, Cc, eps, st))
+            dy2 = d_a2  # reuse
+            _lib.check(lib.w2s_enc_norm_bwd(dxh.data_ptr(), bk["y2"].data_ptr(), bk["s2"].data_ptr(), sums.data_ptr(),
+                                            dy2.data_ptr(), mask.data_ptr(), B, L, Cc, 0, eps, st))
+            a1 = dxh  # reuse as a1 buffer after dy2 is written? no: dxh is read above only; safe to overwrite now
+            _lib.check(lib.w2s_enc_act_fwd(bk["y1"].data_ptr(), None, bk["s1"].data_ptr(), a1.data_ptr(), mask.data_ptr(),
+                                           B, L, Cc, eps, st))
+            dW = G(blk.conv2.conv.weight)
+            for t in range(3):
+                self.gemm_tn(dy2, a1, dW, Cc, Cc, B, L, L, Cc * 3, 3, y_offset=t - 1, row_mask=mask, c_off=t)
+            d_a1 = new(B, L, Cc)
+            self.conv(dy2, tw["conv"][i][1], Cc, Cc, 3, B, L, L, d_a1, pad=1, row_mask=mask)
+            # ---- conv1 (+ 1x1 stride-2 residual branch) ----
+            dxh, sums = a1, zeros64(Cc)
+            _lib.check(lib.w2s_enc_act_bwd(d_a1.data_ptr(), bk["y1"].data_ptr(), None, bk["s1"].data_ptr(), dxh.data_ptr(),
+                                           None, sums.data_ptr(), mask.data_ptr(), B, L, Cc, eps, st))
+            dy1 = d_a1
+            _lib.check(lib.w2s_enc_norm_bwd(dxh.data_ptr(), bk["y1"].data_ptr(), bk["s1"].data_ptr(), sums.data_ptr(),
+                                            dy1.data_ptr(), mask.data_ptr(), B, L, Cc, 0, eps, st))
+            if i == 0:
+                _lib.check(lib.w2s_first_conv_wgrad(e["x"].data_ptr(), dy1.data_ptr(), dr.data_ptr(),
+                                                    G(blk.conv1.conv.weight).data_ptr(), G(blk.downsample.weight).data_ptr(),
+                                                    mask.data_ptr(), B, L, st))
+                break
+            pb = blocks[i - 1]
+            Ci = pb["C"]
+            a_in = new(B, L, Ci)
+            _lib.check(lib.w2s_enc_act_fwd(pb["y3"].data_ptr(), pb["r"].data_ptr(), pb["s3"].data_ptr(), a_in.data_ptr(),
+                                           mask.data_ptr(), B, L, Ci, eps, st))
+            dW = G(blk.conv1.conv.weight)
+            for t in range(3):
+                self.gemm_tn(dy1, a_in, dW, Cc, Ci, B, L, L, Ci * 3, 3, y_offset=t - 1, row_mask=mask, c_off=t)
+            self.gemm_tn(dr, a_in, G(blk.downsample.weight), Cc, Ci, B, Lh, L, Ci, 1, y_stride=2, y_offset=0, row_mask=mask)
+            tmp = torch.zeros(B, L, Ci, dtype=F16, device=device)
+            self.conv(dr, tw["ds"][i], Cc, Ci, 1, B, Lh, Lh, tmp, out_stride=2, out_offset=0, out_rows=L, row_mask=mask)
+            d_in = new(B, L, Ci)
+            self.conv(dy1, tw["conv"][i][0], Cc, Ci, 3, B, L, L, d_in, pad=1, res=tmp, row_mask=mask)
+            dout = d_in
+            del tmp, a_in, dy1, dy2, dxh, d_a1, d_a2
+
+
+class _TrainFn(torch.autograd.Function):
+    """autograd bridge: ``logits = model(x)`` in train mode gets a grad_fn whose backward runs the CUDA backward."""
+
+    @staticmethod
+    def forward(ctx, engine, x, *params):
+        ctx.engine = engine
+        ctx.params = params
+        return engine.forward_train(x)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        grads = ctx.engine.backward(dlogits)
+        out = []
+        for p in ctx.params:
+            g = grads.get(id(p))
+            direct = id(p) in ctx.engine.direct  # already accumulated into p.grad by the kernels
+            out.append(None if (g is None or direct) else g.to(p.dtype).view_as(p))
+        return (None, None, *out)
+
+
+def forward_with_grad(model, x: dict[str, Tensor]) -> Tensor:
+    eng = model._get_train_engine()
+    params = tuple(p for p in model.parameters() if p.requires_grad)
+    return _TrainFn.apply(eng, x, *params)
