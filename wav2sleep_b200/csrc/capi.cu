@@ -258,6 +258,7 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
   // training path: plain GEMMs (taps 1 / 4) and data-gradient convolutions (input already materialised)
   W2S_CASE(128, 128, 1, 1, PRO_NONE, EPI_PLAIN, false)
   W2S_CASE(128, 128, 4, 2, PRO_NONE, EPI_PLAIN, false)
+  W2S_CASE(64, 128, 4, 4, PRO_NONE, EPI_PLAIN, false)
   W2S_CASE(128, 128, 7, 4, PRO_NONE, EPI_PLAIN, false)
   W2S_CASE(128, 64, 1, 1, PRO_NONE, EPI_PLAIN, false)
   W2S_CASE(16, 16, 3, 3, PRO_NONE, EPI_PLAIN, false)
