@@ -252,6 +252,10 @@ def run_cuda(args):
             prof = collect_profile(lib)
             lib.w2s_profile_enable(0)
 
+    train = None
+    if not args.no_train:
+        train = time_train_step(model, dev, world, rank, barrier, max_over_ranks, lib)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -307,10 +311,48 @@ def run_cuda(args):
         "roofline": roofline,
         "kernels": kernels[:8],
         "cpu_baseline": cpu,
+        "train": train,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_train_step(model, dev, world, rank, barrier, max_over_ranks, lib, steps=5, warmup=3):
+    """Secondary metric (BASELINE.json "train step ms", configs[3]): cardio training step at 16 nights per GPU =
+    polarity flip + config masker + forward (activations kept) + CE + backward + bucketed gradient all-reduce + fused
+    clip + AdamW.  Dropout is p = 0 (DESIGN.md)."""
+    from wav2sleep_b200.optim import FusedAdamW
+    from wav2sleep_b200.trainer import SignalMasker, SleepLightningModule
+    torch.manual_seed(1234 + rank)
+    masker = SignalMasker({"ABD": 0.7, "THX": 0.7, "ECG": 0.5, "PPG": 0.1}, backups=["ECG", "PPG"])
+    pl = SleepLightningModule(model, optimizer=lambda ps: FusedAdamW(ps, lr=1e-3, weight_decay=1e-4, max_grad_norm=1.0),
+                              num_classes=4, masker=masker)
+    pl.setup_training()
+    src = {k: v.to(dev) for k, v in make_night_batch(BATCH, seed=7 + rank).items()}
+    y = torch.randint(0, 4, (BATCH, S_EPOCHS), device=dev)
+    y[torch.rand(BATCH, S_EPOCHS, device=dev) < 0.05] = -1
+
+    def one():
+        x = {k: v.clone() for k, v in src.items()}
+        return pl.fit_step((x, y))
+
+    for _ in range(warmup):
+        one()
+    barrier()
+    l0 = lib.w2s_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = one()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    model.eval()
+    return {"ms_per_step": ms, "nights_per_gpu": BATCH, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "last_loss": float(loss), "gpu_launches_per_step": int((lib.w2s_launch_count() - l0) / steps),
+            "masker": "config cardiorespiratory/all.yaml (ABD .7, THX .7, ECG .5, PPG .1; backups ECG, PPG)",
+            "dropout": 0.0, "optimizer": "fused clip(1.0) + AdamW(lr 1e-3, wd 1e-4)"}
 
 
 def main():
@@ -320,6 +362,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary train-step timing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else max(args.warmup, 1)
     if args.impl == "reference":

@@ -1,0 +1,96 @@
+"""CPU tests of the training harness host logic: masker semantics, LR schedule, bucketed gradient all-reduce (gloo x2)."""
+import math
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from wav2sleep_b200.optim import ExpWarmUpScheduler
+from wav2sleep_b200.trainer import GradReducer, SignalMasker, confusion_matrix, invert_signals
+
+
+def test_masker_keeps_at_least_one_signal_and_respects_backups():
+    torch.manual_seed(0)
+    masker = SignalMasker({"ABD": 0.7, "THX": 0.7, "ECG": 0.5, "PPG": 0.1}, backups=["ECG", "PPG"])
+    drops = {k: 0 for k in ("ABD", "THX", "ECG", "PPG")}
+    n = 0
+    for _ in range(50):
+        x = {k: torch.randn(16, 8) for k in drops}
+        x["PPG"][3] = float("-inf")  # PPG missing for sample 3 before masking
+        masker(x)
+        miss = torch.stack([torch.isinf(v[:, 0]) for v in x.values()], -1)
+        assert not miss.all(-1).any()          # every sample keeps >= 1 signal
+        assert miss[3, 3]                       # an unavailable signal stays unavailable
+        assert all(torch.isinf(v).all(-1).eq(torch.isinf(v[:, 0])).all() for v in x.values())  # whole rows
+        for i, k in enumerate(drops):
+            drops[k] += miss[:, i].sum().item()
+        n += 16
+    assert 0.6 < drops["ABD"] / n < 0.8 and 0.4 < drops["ECG"] / n < 0.6 and drops["PPG"] / n < 0.25
+    with pytest.raises(ValueError):
+        SignalMasker({"ECG": 0.5})({"ECG": torch.full((2, 4), float("-inf"))})
+
+
+def test_invert_signals_and_confusion_matrix():
+    torch.manual_seed(1)
+    x = {"ECG": torch.ones(64, 5)}
+    invert_signals(x)
+    assert set(x["ECG"][:, 0].tolist()) == {1.0, -1.0} and (x["ECG"].abs() == 1).all()
+    logits = torch.tensor([[2.0, 0, 0], [0, 3.0, 0], [0, 0, 1.0], [5.0, 0, 0]])
+    cm = confusion_matrix(logits, torch.tensor([0, 1, 1, -1]), 3)
+    assert cm.tolist() == [[1, 0, 0], [0, 1, 1], [0, 0, 0]]
+
+
+def test_exp_warmup_scheduler_matches_reference_formula():
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([p], lr=1.0)
+    sched = ExpWarmUpScheduler(opt, lr_max=1e-3, warmup_steps=10, tau=100.0)
+    lrs = []
+    for _ in range(30):
+        lrs.append(opt.param_groups[0]["lr"])
+        opt.step()
+        sched.step()
+    # values printed by the reference's own ExpWarmUpScheduler (trainer/scheduler.py) for these settings: the LR of
+    # optimizer step k (0-based) uses step = k + 1
+    assert lrs[:3] == pytest.approx([1e-4, 2e-4, 3e-4], abs=1e-15) and lrs[9] == pytest.approx(1e-3, abs=1e-15)
+    assert lrs[10] == pytest.approx(0.000990049833749168, abs=1e-15)
+    for k, lr in enumerate(lrs):
+        step = k + 1
+        want = 1e-3 * step / 10 if step <= 10 else 1e-3 * math.exp(-(step - 10) / 100.0)
+        assert abs(lr - want) < 1e-12, (step, lr, want)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    flat = torch.arange(10, dtype=torch.float32) * (rank + 1)
+    red = GradReducer(flat, {"encoders": (0, 6), "tail": (6, 10)}, use_stream=False)
+    red("tail")       # fired first by the backward
+    after_tail = flat.clone()
+    red("encoders")
+    red.wait()
+    q.put((rank, after_tail, flat.clone()))
+    dist.destroy_process_group()
+
+
+def test_grad_reducer_buckets_gloo_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    base = torch.arange(10, dtype=torch.float32)
+    for rank, after_tail, final in res:
+        assert torch.equal(after_tail[6:], base[6:] * 3)            # tail bucket summed over ranks (1x + 2x)
+        assert torch.equal(after_tail[:6], base[:6] * (rank + 1))   # encoder bucket still local
+        assert torch.equal(final, base * 3)

@@ -140,3 +140,32 @@ def test_training_reduces_loss(cuda_device):
         losses.append(loss.item())
     print(losses)
     assert losses[-1] < losses[0] - 0.05
+
+
+def test_lightning_shaped_module_fit_with_masker(cuda_device):
+    """SleepLightningModule-shaped harness: polarity flip + SignalMasker + CE + backward + fused clip/AdamW + scheduler."""
+    from wav2sleep_b200.optim import ExpWarmUpScheduler, FusedAdamW
+    from wav2sleep_b200.trainer import SignalMasker, SleepLightningModule
+    torch.manual_seed(0)
+    model = build_default(CARDIO, 4, seed=0).to(cuda_device)
+    masker = SignalMasker({"ABD": 0.7, "THX": 0.7, "ECG": 0.5, "PPG": 0.1}, backups=["ECG", "PPG"])
+    pl = SleepLightningModule(model, optimizer=lambda ps: FusedAdamW(ps, lr=1e-3, weight_decay=1e-4, max_grad_norm=1.0),
+                              scheduler=lambda o: ExpWarmUpScheduler(o, lr_max=1e-3, warmup_steps=4, tau=1e4),
+                              num_classes=4, masker=masker)
+    y = torch.randint(0, 4, (4, 8), device=cuda_device)
+    y[0, :2] = -1
+
+    def batches():
+        while True:
+            x = {k: v.to(cuda_device) for k, v in make_inputs(CARDIO, 4, 8, seed=3).items()}
+            yield x, y
+
+    losses = pl.fit(batches(), max_steps=12)
+    print(losses)
+    assert all(l == l for l in losses) and min(losses[-4:]) < losses[0]
+    assert int(pl.cmats["train"].sum()) == 12 * (4 * 8 - 2)
+    # inference after training uses the updated weights (operand copies are re-packed)
+    model.eval()
+    with torch.no_grad():
+        out = model({k: v.to(cuda_device) for k, v in make_inputs(CARDIO, 4, 8, seed=3).items()})
+    assert torch.isfinite(out).all()

@@ -1,0 +1,221 @@
+"""Training harness with the shape of the reference's ``SleepLightningModule`` (trainer/main.py:62-297), without
+Lightning (not installed here): same constructor keywords and the same ``forward`` / ``reshape_for_loss`` /
+``on_after_batch_transfer`` / ``_step`` / ``training_step`` / ``configure_optimizers`` methods, so a Lightning
+``Trainer`` (or the small ``fit`` loop below) can drive it.  The forward/backward it drives is the CUDA path
+(model.py -> training.py); the optimizer is the fused clip + AdamW (optim.py).
+
+Data parallelism: one process per GPU, replicated parameters, ONE exchange per step - the SUM
+all-reduce of the flat gradient buffer over NCCL/NVLink.  It is issued in two buckets from hooks inside the backward
+(``tail`` = classifier + sequence mixer + epoch mixer as soon as they are final, then ``encoders``) on a side stream, so
+the first bucket overlaps the encoder backward, which is >90 % of the step.
+"""
+from __future__ import annotations
+
+from typing import Callable, Iterable, Optional
+
+import torch
+import torch.distributed as dist
+from torch import Tensor, nn
+
+from .optim import ExpWarmUpScheduler, FusedAdamW
+
+TRAIN, VAL, TEST = "train", "val", "test"
+
+
+class SignalMasker:
+    """Stochastic modality dropout (reference trainer/masker.py:5-51): per sample keep signal i with prob 1 - p_i; if
+    nothing is left, draw one of the available backup signals; dropped signals become rows of -inf, in place."""
+
+    def __init__(self, dropouts: dict[str, float], backups: list[str] | None = None):
+        self.channel_dropouts = dropouts
+        self.backup_channels = backups
+
+    def __call__(self, signals: dict[str, Tensor]) -> dict[str, Tensor]:
+        names = list(signals.keys())
+        dev = signals[names[0]].device
+        missing = torch.stack([torch.isinf(signals[n][:, 0]) for n in names], dim=-1)  # [B, C] True = unavailable
+        if missing.all(dim=-1).any():
+            raise ValueError("Found batch element with all signals unavailable.")
+        p = torch.tensor([self.channel_dropouts.get(n, 0.0) for n in names], device=dev)
+        if ((p < 0) | (p > 1)).any():
+            raise ValueError("dropout probabilities must be in [0, 1]")
+        if (p == 1).all():
+            raise ValueError("Dropout probability equal to 1 for all channels.")
+        B = missing.size(0)
+        keep = torch.rand(B, len(names), device=dev) >= p  # Bernoulli(1 - p)
+        if self.backup_channels is not None:
+            w = torch.stack([(~missing[:, i]).float() if n in self.backup_channels else torch.zeros(B, device=dev)
+                             for i, n in enumerate(names)], dim=-1)
+        else:
+            w = (~missing).float() * (1 - p)
+        if (w == 0).all(dim=-1).any():
+            raise ValueError("No backup channels for stochastic sampling were available")
+        backup = torch.nn.functional.one_hot(torch.multinomial(w, 1).squeeze(-1), len(names)).bool()
+        none_left = (missing | ~keep).all(dim=-1)
+        keep[none_left] = backup[none_left]
+        for i, n in enumerate(names):
+            signals[n][~keep[:, i]] = float("-inf")
+        return signals
+
+
+def invert_signals(signals: dict[str, Tensor]) -> dict[str, Tensor]:
+    """Random polarity flip per (sample, signal), p = 0.5 (reference trainer/main.py:342-353)."""
+    for name, x in signals.items():
+        flip = 2 * torch.randint(0, 2, (x.size(0), 1), dtype=x.dtype, device=x.device) - 1
+        signals[name] = x.mul_(flip)
+    return signals
+
+
+def confusion_matrix(logits_NC: Tensor, y_N: Tensor, num_classes: int, ignore_index: int = -1) -> Tensor:
+    pred = logits_NC.argmax(-1)
+    ok = y_N != ignore_index
+    idx = y_N[ok].long() * num_classes + pred[ok]
+    return torch.bincount(idx, minlength=num_classes * num_classes).view(num_classes, num_classes)
+
+
+def sum_if_distributed(t: Tensor) -> Tensor:
+    """reference trainer/main.py:41-46 (kept in torch: off the performance path)."""
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+class GradReducer:
+    """Bucketed SUM all-reduce of a flat gradient buffer, fired from the backward's bucket hooks."""
+
+    def __init__(self, flat_grad: Tensor, segments: dict[str, tuple[int, int]], process_group=None, use_stream=True):
+        self.flat_grad, self.segments, self.group = flat_grad, segments, process_group
+        self.use_stream = use_stream and flat_grad.is_cuda
+        self.comm = torch.cuda.Stream(device=flat_grad.device) if self.use_stream else None
+        self.done = []
+        self.fired = []
+
+    @property
+    def world_size(self) -> int:
+        return dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+
+    def __call__(self, bucket: str) -> None:
+        self.fired.append(bucket)
+        if self.world_size == 1 or bucket not in self.segments:
+            return
+        a, b = self.segments[bucket]
+        seg = self.flat_grad[a:b]
+        if self.use_stream:
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(seg.device))
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(ready)
+                dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.group)
+                ev = torch.cuda.Event()
+                ev.record(self.comm)
+            self.done.append(ev)
+        else:
+            dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.group)
+
+    def wait(self) -> None:
+        """Make the current stream wait for every bucket issued since the last call (before the optimizer step)."""
+        for ev in self.done:
+            torch.cuda.current_stream().wait_event(ev)
+        self.done.clear()
+        self.fired.clear()
+
+
+class SleepLightningModule(nn.Module):
+    def __init__(self, model, criterion=None, optimizer: Optional[Callable] = None, aux_metrics=None,
+                 scheduler: Optional[Callable] = None, debug_level=2, on_step: bool = False, on_epoch: bool = True,
+                 num_classes: int = 4, masker: SignalMasker | None = None, flip_polarity: bool = True,
+                 causal: bool = False):
+        super().__init__()
+        self.model = model
+        self.num_classes = num_classes
+        self.criterion = criterion if criterion is not None else nn.CrossEntropyLoss(ignore_index=-1)
+        self.optimizer = optimizer if optimizer is not None else (
+            lambda params: FusedAdamW(params, lr=1e-3, weight_decay=1e-4, max_grad_norm=1.0))
+        self.scheduler = scheduler
+        self.masker = masker
+        self.flip_polarity = flip_polarity
+        self.causal = causal
+        self.unified = len(model.signal_encoders) > 1
+        self.cmats = {m: torch.zeros(num_classes, num_classes, dtype=torch.long) for m in (TRAIN, VAL, TEST)}
+        self._opt = self._sched = self._reducer = None
+
+    def forward(self, x: dict[str, Tensor], y: Tensor | None = None) -> Tensor:
+        return self.model(x)
+
+    def reshape_for_loss(self, outputs: Tensor, labels: Tensor):
+        return outputs.view(-1, outputs.size(-1)), labels.view(-1)
+
+    def on_after_batch_transfer(self, batch, dataloader_idx: int = 0, training: bool = True):
+        x, y = batch
+        if training:
+            if self.flip_polarity:
+                invert_signals(x)
+            if self.unified and self.masker is not None:
+                self.masker(x)
+        return x, y
+
+    def _step(self, batch, mode: str, dataloader_idx: int = 0, signals=None) -> Tensor:
+        x, y = batch
+        if signals is not None:
+            x = {s: x[s] for s in signals}
+        logits = self(x, y)
+        logits_NC, y_N = self.reshape_for_loss(logits, y)
+        loss = self.criterion(logits_NC, y_N.long())
+        with torch.no_grad():
+            cm = sum_if_distributed(confusion_matrix(logits_NC.detach(), y_N, self.num_classes))
+            self.cmats[mode] = self.cmats[mode].to(cm.device) + cm
+        return loss
+
+    def training_step(self, batch, batch_idx: int = 0) -> Tensor:
+        return self._step(batch, TRAIN)
+
+    def validation_step(self, batch, batch_idx: int = 0, dataloader_idx: int = 0) -> Tensor:
+        with torch.no_grad():
+            return self._step(batch, VAL, dataloader_idx)
+
+    def configure_optimizers(self) -> dict:
+        optimizer = self.optimizer(self.model.parameters())
+        out = {"optimizer": optimizer}
+        if self.scheduler is not None:
+            out["lr_scheduler"] = {"scheduler": self.scheduler(optimizer), "interval": "step", "frequency": 1,
+                                   "strict": True}
+        return out
+
+    # ---- Lightning-free driver (what Lightning's loop + DDP strategy would do) ----
+    def setup_training(self, process_group=None) -> None:
+        cfg = self.configure_optimizers()
+        self._opt = cfg["optimizer"]
+        self._sched = cfg.get("lr_scheduler", {}).get("scheduler")
+        if isinstance(self._opt, FusedAdamW):
+            enc = list(self.model.signal_encoders.parameters())
+            enc_ids = {id(p) for p in enc}
+            tail = [p for p in self.model.parameters() if id(p) not in enc_ids]
+            segs = {"encoders": self._opt.segment(enc), "tail": self._opt.segment(tail)}
+            self._reducer = GradReducer(self._opt.flat_grad, segs, process_group)
+            self._opt.grad_scale = 1.0 / self._reducer.world_size
+            eng = self.model._get_train_engine()
+            eng.bucket_hooks = [self._reducer]
+
+    def fit_step(self, batch) -> Tensor:
+        """One optimisation step: transforms -> forward -> loss -> backward (+ overlapped all-reduce) -> clip + AdamW."""
+        if self._opt is None:
+            self.setup_training()
+        self.model.train()
+        batch = self.on_after_batch_transfer(batch, training=True)
+        self._opt.zero_grad()
+        loss = self.training_step(batch)
+        loss.backward()
+        if self._reducer is not None:
+            self._reducer.wait()
+        self._opt.step()
+        if self._sched is not None:
+            self._sched.step()
+        return loss.detach()
+
+    def fit(self, batches: Iterable, max_steps: int | None = None) -> list[float]:
+        losses = []
+        for i, batch in enumerate(batches):
+            if max_steps is not None and i >= max_steps:
+                break
+            losses.append(float(self.fit_step(batch)))
+        return losses
