@@ -29,7 +29,7 @@ def test_gemm_tn(cuda_device, M, N, L, ys, yo):
     Y = torch.randn(B, LY, N, device=cuda_device).half()
     mask = torch.tensor([0, 1, 0], dtype=torch.uint8, device=cuda_device)
     Cm = torch.zeros(M, N, device=cuda_device)
-    _lib.check(lib.w2s_gemm_tn(X.data_ptr(), Y.data_ptr(), Cm.data_ptr(), M, N, B, L, LY, ys, yo, N, 1, 1.0,
+    _lib.check(lib.w2s_gemm_tn(X.data_ptr(), Y.data_ptr(), Cm.data_ptr(), M, N, 1, B, L, LY, ys, yo, N, 1, 0, 1.0,
                                mask.data_ptr(), G.stream()))
     torch.cuda.synchronize()
     ref = torch.zeros(M, N, device=cuda_device)
@@ -38,6 +38,25 @@ def test_gemm_tn(cuda_device, M, N, L, ys, yo):
         ok = (idx >= 0) & (idx < LY)
         ref += X[b][ok].float().t() @ Y[b][idx[ok]].float()
     assert (Cm - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("M,N,L", [(16, 16, 1000), (32, 16, 333), (32, 32, 700), (64, 64, 260)])
+def test_gemm_tn_conv_taps(cuda_device, M, N, L):
+    """taps = 3: conv weight gradient dW[m, n, t] in one pass (fused kernel for small tiles, per-tap passes otherwise)."""
+    lib = _lib.load()
+    torch.manual_seed(M * N + L)
+    B = 2
+    X = torch.randn(B, L, M, device=cuda_device).half()
+    Y = torch.randn(B, L, N, device=cuda_device).half()
+    dW = torch.zeros(M, N, 3, device=cuda_device)
+    _lib.check(lib.w2s_gemm_tn(X.data_ptr(), Y.data_ptr(), dW.data_ptr(), M, N, 3, B, L, L, 1, -1, N * 3, 3, 1, 1.0, None,
+                               G.stream()))
+    torch.cuda.synchronize()
+    # reference: gradient of conv1d(k=3, pad=1) wrt its weight
+    w = torch.zeros(M, N, 3, device=cuda_device, requires_grad=True)
+    out = torch.nn.functional.conv1d(Y.float().transpose(1, 2), w, padding=1)
+    out.backward(X.float().transpose(1, 2))
+    assert (dW - w.grad).abs().max().item() < 2e-3 * w.grad.abs().max().item()
 
 
 def test_ce_and_adamw_match_torch(cuda_device):

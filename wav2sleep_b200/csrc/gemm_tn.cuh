@@ -16,16 +16,16 @@ namespace w2s {
 struct GemmTNArgs {
   const act_t* X;   // [B, LX, M]
   const act_t* Y;   // [B, LY, N]
-  float* C;         // element (m, n) at C[m * ldc_m + n * ldc_n]
+  float* C;         // element (m, n) of tap t at C[m * ldc_m + n * ldc_n + t * ldc_t]
   const uint8_t* row_mask;  // [B] or null
   int B, LX, LY;
-  int y_stride, y_offset;
-  long long ldc_m, ldc_n;
+  int y_stride, y_offset;   // Y row of X row l, tap t:  l * y_stride + y_offset + t
+  long long ldc_m, ldc_n, ldc_t;
   float scale;      // multiplies the contribution (1.0)
 };
 
 constexpr int kGemmTNThreads = 256;
-constexpr int kGemmTNRows = 128;  // rows per smem tile
+constexpr int kGemmTNRows = 128;  // X rows per smem tile (tiles never straddle two samples)
 
 template <int M, int N>
 struct GemmTNCfg {
@@ -57,60 +57,58 @@ W2S_DEVINL void mma_16816_f16(float (&c)[4], const uint32_t (&a)[4], const uint3
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-template <int M, int N>
+// TAPS > 1: the taps of a convolution (consecutive Y rows, y_stride must be 1) are reduced in one pass over X and a
+// haloed Y tile: X and Y are read once instead of TAPS times.
+template <int M, int N, int TAPS>
 __global__ void __launch_bounds__(kGemmTNThreads) gemm_tn_kernel(const GemmTNArgs p) {
   using Cfg = GemmTNCfg<M, N>;
   constexpr int LDX = Cfg::LDX, LDY = Cfg::LDY, MT = Cfg::MT, NT = Cfg::NT, KG = Cfg::KG;
   extern __shared__ __align__(16) uint8_t gemm_tn_smem[];
   __half* sX = reinterpret_cast<__half*>(gemm_tn_smem);
   __half* sY = sX + kGemmTNRows * LDX;
+  const int y_rows = (kGemmTNRows - 1) * p.y_stride + TAPS;  // staged Y rows per tile
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wmn = warp % Cfg::WARPS_MN, kg = warp / Cfg::WARPS_MN;
   const int m0 = (wmn / (N / Cfg::NW)) * Cfg::MW;
   const int n0 = (wmn % (N / Cfg::NW)) * Cfg::NW;
 
-  float acc[MT][NT][4];
+  float acc[TAPS][MT][NT][4];
 #pragma unroll
-  for (int i = 0; i < MT; ++i)
+  for (int t = 0; t < TAPS; ++t)
 #pragma unroll
-    for (int j = 0; j < NT; ++j)
+    for (int i = 0; i < MT; ++i)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.0f;
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[t][i][j][q] = 0.0f;
 
-  const long long total = (long long)p.B * p.LX;
-  const long long tiles = (total + kGemmTNRows - 1) / kGemmTNRows;
+  const int tiles_per_sample = (p.LX + kGemmTNRows - 1) / kGemmTNRows;
+  const long long tiles = (long long)tiles_per_sample * p.B;
   const long long t_begin = tiles * blockIdx.x / gridDim.x, t_end = tiles * (blockIdx.x + 1) / gridDim.x;
 
   for (long long tile = t_begin; tile < t_end; ++tile) {
-    const long long r0 = tile * kGemmTNRows;
+    const int b = (int)(tile / tiles_per_sample);
+    if (p.row_mask != nullptr && p.row_mask[b]) continue;  // uniform over the CTA
+    const int l0 = (int)(tile - (long long)b * tiles_per_sample) * kGemmTNRows;
+    const act_t* Xb = p.X + ((size_t)b * p.LX) * M;
+    const act_t* Yb = p.Y + ((size_t)b * p.LY) * N;
+    const int ybase = l0 * p.y_stride + p.y_offset;
     __syncthreads();
-    // ---- stage X rows and mapped Y rows (zero where out of range / masked) ----
     for (int id = tid; id < kGemmTNRows * (M / 8); id += kGemmTNThreads) {
       const int k = id / (M / 8), c = id % (M / 8);
-      const long long r = r0 + k;
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (r < total) {
-        const int b = (int)(r / p.LX);
-        if (p.row_mask == nullptr || !p.row_mask[b]) v = __ldg(reinterpret_cast<const uint4*>(p.X + r * M) + c);
-      }
+      if (l0 + k < p.LX) v = __ldg(reinterpret_cast<const uint4*>(Xb + (size_t)(l0 + k) * M) + c);
       *reinterpret_cast<uint4*>(sX + k * LDX + c * 8) = v;
     }
-    for (int id = tid; id < kGemmTNRows * (N / 8); id += kGemmTNThreads) {
+    for (int id = tid; id < y_rows * (N / 8); id += kGemmTNThreads) {
       const int k = id / (N / 8), c = id % (N / 8);
-      const long long r = r0 + k;
+      const int ly = ybase + k;
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (r < total) {
-        const int b = (int)(r / p.LX);
-        const int l = (int)(r - (long long)b * p.LX);
-        const int ly = l * p.y_stride + p.y_offset;
-        if (ly >= 0 && ly < p.LY && (p.row_mask == nullptr || !p.row_mask[b]))
-          v = __ldg(reinterpret_cast<const uint4*>(p.Y + ((long long)b * p.LY + ly) * N) + c);
-      }
+      if (ly >= 0 && ly < p.LY) v = __ldg(reinterpret_cast<const uint4*>(Yb + (size_t)ly * N) + c);
       *reinterpret_cast<uint4*>(sY + k * LDY + c * 8) = v;
     }
     __syncthreads();
-    // ---- each k-group of warps takes its share of the 128 rows ----
     constexpr int KSTEPS = kGemmTNRows / 16 / KG;
 #pragma unroll
     for (int ks = 0; ks < KSTEPS; ++ks) {
@@ -120,44 +118,51 @@ __global__ void __launch_bounds__(kGemmTNThreads) gemm_tn_kernel(const GemmTNArg
       for (int i = 0; i < MT; ++i)
         ldmatrix_x4_trans(a[i], sX + (k0 + (lane >> 4) * 8 + (lane & 7)) * LDX + m0 + i * 16 + ((lane >> 3) & 1) * 8);
 #pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        uint32_t bf[2];
-        ldmatrix_x2_trans(bf, sY + (k0 + ((lane >> 3) & 1) * 8 + (lane & 7)) * LDY + n0 + j * 8);
+      for (int t = 0; t < TAPS; ++t) {
 #pragma unroll
-        for (int i = 0; i < MT; ++i) mma_16816_f16(acc[i][j], a[i], bf);
+        for (int j = 0; j < NT; ++j) {
+          uint32_t bf[2];
+          const int yrow = (k0 + ((lane >> 3) & 1) * 8 + (lane & 7)) * p.y_stride + t;
+          ldmatrix_x2_trans(bf, sY + yrow * LDY + n0 + j * 8);
+#pragma unroll
+          for (int i = 0; i < MT; ++i) mma_16816_f16(acc[t][i][j], a[i], bf);
+        }
       }
     }
   }
   // ---- accumulate into C ----
 #pragma unroll
-  for (int i = 0; i < MT; ++i)
+  for (int t = 0; t < TAPS; ++t)
 #pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      const int m = m0 + i * 16 + (lane >> 2);
-      const int n = n0 + j * 8 + (lane & 3) * 2;
-      float* c0 = p.C + m * p.ldc_m + n * p.ldc_n;
-      atomicAdd(c0, acc[i][j][0] * p.scale);
-      atomicAdd(c0 + p.ldc_n, acc[i][j][1] * p.scale);
-      atomicAdd(c0 + 8 * p.ldc_m, acc[i][j][2] * p.scale);
-      atomicAdd(c0 + 8 * p.ldc_m + p.ldc_n, acc[i][j][3] * p.scale);
-    }
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int m = m0 + i * 16 + (lane >> 2);
+        const int n = n0 + j * 8 + (lane & 3) * 2;
+        float* c0 = p.C + m * p.ldc_m + n * p.ldc_n + t * p.ldc_t;
+        atomicAdd(c0, acc[t][i][j][0] * p.scale);
+        atomicAdd(c0 + p.ldc_n, acc[t][i][j][1] * p.scale);
+        atomicAdd(c0 + 8 * p.ldc_m, acc[t][i][j][2] * p.scale);
+        atomicAdd(c0 + 8 * p.ldc_m + p.ldc_n, acc[t][i][j][3] * p.scale);
+      }
 }
 
-template <int M, int N>
+template <int M, int N, int TAPS>
 inline cudaError_t launch_gemm_tn(const GemmTNArgs& a, int sm_count, cudaStream_t stream) {
-  const long long tiles = ((long long)a.B * a.LX + kGemmTNRows - 1) / kGemmTNRows;
+  const long long tiles = (long long)((a.LX + kGemmTNRows - 1) / kGemmTNRows) * a.B;
   long long grid = 2LL * sm_count;
   if (grid > tiles) grid = tiles;
   if (grid < 1) grid = 1;
   using Cfg = GemmTNCfg<M, N>;
-  constexpr int smem = kGemmTNRows * (Cfg::LDX + Cfg::LDY) * 2;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<M, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int y_rows = (kGemmTNRows - 1) * a.y_stride + TAPS;
+  const int smem = (kGemmTNRows * Cfg::LDX + y_rows * Cfg::LDY) * 2;
+  static int configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<M, N, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured = smem;
   }
-  gemm_tn_kernel<M, N><<<(int)grid, kGemmTNThreads, smem, stream>>>(a);
+  gemm_tn_kernel<M, N, TAPS><<<(int)grid, kGemmTNThreads, smem, stream>>>(a);
   return cudaGetLastError();
 }
 

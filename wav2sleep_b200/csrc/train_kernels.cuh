@@ -16,6 +16,25 @@ W2S_DEVINL float gelu_grad(float x) {  // d/dx [x Phi(x)] = Phi(x) + x phi(x)
   const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
+// tanh-form GELU and derivative (same fitted exponent as the forward prologue, one MUFU.TANH): used on the whole-night
+// encoder tensors where erff/expf would make the element-wise kernels compute bound.
+W2S_DEVINL float gelu_tanh(float x) {
+  const float t = fminf(x * x, 25.0f);
+  const float q = fmaf(fmaf(t, -3.5159264e-4f, 0.037005995f), t, 0.79750759f);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(x * q));
+  const float h = 0.5f * x;
+  return fmaf(h, th, h);
+}
+W2S_DEVINL float gelu_grad_tanh(float x) {
+  const float x2 = x * x;
+  const float t = fminf(x2, 25.0f);
+  const float q = fmaf(fmaf(t, -3.5159264e-4f, 0.037005995f), t, 0.79750759f);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(x * q));
+  const float dq = x2 < 25.0f ? 2.0f * x2 * fmaf(t, -7.0318528e-4f, 0.037005995f) : 0.0f;  // x * dq/dx
+  return 0.5f * (1.0f + th) + 0.5f * x * (1.0f - th * th) * (q + dq);
+}
 W2S_DEVINL void unpack8(const uint4& u, float* v) {
   const uint32_t* w = reinterpret_cast<const uint32_t*>(&u);
 #pragma unroll
@@ -48,21 +67,21 @@ __global__ void __launch_bounds__(256) enc_act_fwd_kernel(const EncActArgs p) {
   const int b = blockIdx.y;
   if (p.row_mask && p.row_mask[b]) return;
   const int CH = p.C / 8;
-  const size_t n = (size_t)p.L * CH;
+  const int n = p.L * CH;  // < 2^31 (L <= 2^27 rows)
   // the grid stride (gridDim.x * 256) is a multiple of CH, so a thread always sees the same channel chunk
-  const int c8 = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) % CH);
+  const int c8 = (int)((blockIdx.x * blockDim.x + threadIdx.x) % CH);
   float mean[8], rstd[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) in_consts(p.stats, b, p.C, c8 * 8 + k, p.L, p.eps, mean[k], rstd[k]);
-  for (size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x; id < n; id += (size_t)gridDim.x * blockDim.x) {
-    const size_t off = ((size_t)b * p.L) * p.C + id * 8;
+  for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
+    const size_t off = ((size_t)b * p.L) * p.C + (size_t)id * 8;
     float v[8], rr[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(p.y + off)), v);
     if (p.r) unpack8(__ldg(reinterpret_cast<const uint4*>(p.r + off)), rr);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float a = gelu_erf((v[k] - mean[k]) * rstd[k]);
-      if (p.r) a = gelu_erf(a + rr[k]);
+      float a = gelu_tanh((v[k] - mean[k]) * rstd[k]);
+      if (p.r) a = gelu_tanh(a + rr[k]);
       v[k] = a;
     }
     *reinterpret_cast<uint4*>(p.a + off) = pack8(v);
@@ -104,10 +123,10 @@ __global__ void __launch_bounds__(256) enc_act_bwd_kernel(const EncActBwdArgs p)
       const float xh = (v[k] - mean[k]) * rstd[k];
       float g = d[k];
       if (p.r) {
-        g *= gelu_grad(gelu_erf(xh) + rr[k]);
+        g *= gelu_grad_tanh(gelu_tanh(xh) + rr[k]);
         rr[k] = g;  // dr
       }
-      g *= gelu_grad(xh);
+      g *= gelu_grad_tanh(xh);
       d[k] = g;
       s0[k] += g;
       s1[k] = fmaf(g, xh, s1[k]);
@@ -144,9 +163,10 @@ __global__ void __launch_bounds__(256) enc_norm_bwd_kernel(const EncNormBwdArgs 
   const int b = blockIdx.y;
   if (p.row_mask && p.row_mask[b]) return;
   const int CH = p.C / 8;
-  const size_t n = (size_t)p.L * CH;
+  const int n = p.L * CH;
+  const int ch_shift = 31 - __clz(CH);  // CH is a power of two
   const float invL = 1.0f / (float)p.L;
-  const int c8 = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) % CH);  // fixed per thread (see above)
+  const int c8 = (int)((blockIdx.x * blockDim.x + threadIdx.x) % CH);  // fixed per thread (see above)
   float mean[8], rstd[8], m1[8], m2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -155,8 +175,8 @@ __global__ void __launch_bounds__(256) enc_norm_bwd_kernel(const EncNormBwdArgs 
     m1[k] = (float)p.sums[((size_t)b * p.C + c) * 2] * invL;
     m2[k] = (float)p.sums[((size_t)b * p.C + c) * 2 + 1] * invL;
   }
-  for (size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x; id < n; id += (size_t)gridDim.x * blockDim.x) {
-    const size_t l = id / CH;
+  for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
+    const size_t l = (size_t)(id >> ch_shift);
     const size_t off = ((size_t)b * p.L + l) * p.C + c8 * 8;
     float d[8], v[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(p.dxh + off)), d);

@@ -105,9 +105,10 @@ class TrainEngine(ForwardEngine):
         c.out_stride, c.out_offset, c.out_rows = out_stride, out_offset, out_rows
         _lib.check(self.lib.w2s_conv1d_fwd(C.byref(c), _stream()))
 
-    def gemm_tn(self, X, Y, Cbuf, M, N, B, LX, LY, ldc_m, ldc_n, y_stride=1, y_offset=0, row_mask=None, c_off=0):
-        _lib.check(self.lib.w2s_gemm_tn(X.data_ptr(), Y.data_ptr(), Cbuf.data_ptr() + 4 * c_off, M, N, B, LX, LY, y_stride,
-                                        y_offset, ldc_m, ldc_n, 1.0, _p(row_mask), _stream()))
+    def gemm_tn(self, X, Y, Cbuf, M, N, B, LX, LY, ldc_m, ldc_n, y_stride=1, y_offset=0, row_mask=None, c_off=0, taps=1,
+                ldc_t=0):
+        _lib.check(self.lib.w2s_gemm_tn(X.data_ptr(), Y.data_ptr(), Cbuf.data_ptr() + 4 * c_off, M, N, taps, B, LX, LY,
+                                        y_stride, y_offset, ldc_m, ldc_n, ldc_t, 1.0, _p(row_mask), _stream()))
 
     def ln_fwd(self, x, g, b, rows, gelu, eps, res=None):
         out = torch.empty_like(x)
@@ -407,8 +408,7 @@ class TrainEngine(ForwardEngine):
             _lib.check(lib.w2s_enc_act_fwd(bk["y2"].data_ptr(), None, bk["s2"].data_ptr(), a2.data_ptr(), mask.data_ptr(),
                                            B, L, Cc, eps, st))
             dW = G(blk.conv3.conv.weight)
-            for t in range(3):
-                self.gemm_tn(dy_up, a2, dW, Cc, Cc, B, L, L, Cc * 3, 3, y_offset=t - 1, row_mask=mask, c_off=t)
+            self.gemm_tn(dy_up, a2, dW, Cc, Cc, B, L, L, Cc * 3, 3, y_offset=-1, row_mask=mask, taps=3, ldc_t=1)
             d_a2 = new(B, L, Cc)
             self.conv(dy_up, tw["conv"][i][2], Cc, Cc, 3, B, L, L, d_a2, pad=1, row_mask=mask)
             del dy_up, a2, dxh
@@ -423,8 +423,7 @@ class TrainEngine(ForwardEngine):
             _lib.check(lib.w2s_enc_act_fwd(bk["y1"].data_ptr(), None, bk["s1"].data_ptr(), a1.data_ptr(), mask.data_ptr(),
                                            B, L, Cc, eps, st))
             dW = G(blk.conv2.conv.weight)
-            for t in range(3):
-                self.gemm_tn(dy2, a1, dW, Cc, Cc, B, L, L, Cc * 3, 3, y_offset=t - 1, row_mask=mask, c_off=t)
+            self.gemm_tn(dy2, a1, dW, Cc, Cc, B, L, L, Cc * 3, 3, y_offset=-1, row_mask=mask, taps=3, ldc_t=1)
             d_a1 = new(B, L, Cc)
             self.conv(dy2, tw["conv"][i][1], Cc, Cc, 3, B, L, L, d_a1, pad=1, row_mask=mask)
             # ---- conv1 (+ 1x1 stride-2 residual branch) ----
@@ -445,8 +444,7 @@ class TrainEngine(ForwardEngine):
             _lib.check(lib.w2s_enc_act_fwd(pb["y3"].data_ptr(), pb["r"].data_ptr(), pb["s3"].data_ptr(), a_in.data_ptr(),
                                            mask.data_ptr(), B, L, Ci, eps, st))
             dW = G(blk.conv1.conv.weight)
-            for t in range(3):
-                self.gemm_tn(dy1, a_in, dW, Cc, Ci, B, L, L, Ci * 3, 3, y_offset=t - 1, row_mask=mask, c_off=t)
+            self.gemm_tn(dy1, a_in, dW, Cc, Ci, B, L, L, Ci * 3, 3, y_offset=-1, row_mask=mask, taps=3, ldc_t=1)
             self.gemm_tn(dr, a_in, G(blk.downsample.weight), Cc, Ci, B, Lh, L, Ci, 1, y_stride=2, y_offset=0, row_mask=mask)
             tmp = torch.zeros(B, L, Ci, dtype=F16, device=device)
             self.conv(dr, tw["ds"][i], Cc, Ci, 1, B, Lh, Lh, tmp, out_stride=2, out_offset=0, out_rows=L, row_mask=mask)
