@@ -161,6 +161,7 @@ def run_cuda(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/w2s_nccl_%h_%p.log")  # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     hbm_peak, tf_peak, peak_src = measured_peaks()

@@ -25,7 +25,9 @@ struct GemmTNArgs {
 };
 
 constexpr int kGemmTNThreads = 256;
-constexpr int kGemmTNRows = 128;  // X rows per smem tile (tiles never straddle two samples)
+// X rows per smem tile (tiles never straddle two samples): long tiles for narrow operands, so that every staging
+// round moves >= 16 KB per CTA and the per-tile synchronisation is amortised.
+constexpr int gemm_tn_rows(int m, int n) { return (m + n) <= 32 ? 512 : 128; }
 
 template <int M, int N>
 struct GemmTNCfg {
@@ -35,8 +37,9 @@ struct GemmTNCfg {
   static constexpr int KG = 8 / WARPS_MN;          // warps that split the rows of a tile
   static constexpr int LDX = M + 8, LDY = N + 8;   // padded smem row strides (halfs)
   static constexpr int MT = MW / 16, NT = NW / 8;
+  static constexpr int ROWS = gemm_tn_rows(M, N);
   static_assert(WARPS_MN <= 8 && 8 % WARPS_MN == 0, "warp layout");
-  static_assert(kGemmTNRows % (16 * KG) == 0, "row tile vs k-groups");
+  static_assert(ROWS % (16 * KG) == 0, "row tile vs k-groups");
 };
 
 W2S_DEVINL void ldmatrix_x4_trans(uint32_t (&r)[4], const __half* p) {
@@ -63,6 +66,7 @@ template <int M, int N, int TAPS>
 __global__ void __launch_bounds__(kGemmTNThreads) gemm_tn_kernel(const GemmTNArgs p) {
   using Cfg = GemmTNCfg<M, N>;
   constexpr int LDX = Cfg::LDX, LDY = Cfg::LDY, MT = Cfg::MT, NT = Cfg::NT, KG = Cfg::KG;
+  constexpr int kGemmTNRows = Cfg::ROWS;
   extern __shared__ __align__(16) uint8_t gemm_tn_smem[];
   __half* sX = reinterpret_cast<__half*>(gemm_tn_smem);
   __half* sY = sX + kGemmTNRows * LDX;
@@ -149,11 +153,12 @@ __global__ void __launch_bounds__(kGemmTNThreads) gemm_tn_kernel(const GemmTNArg
 
 template <int M, int N, int TAPS>
 inline cudaError_t launch_gemm_tn(const GemmTNArgs& a, int sm_count, cudaStream_t stream) {
+  using Cfg = GemmTNCfg<M, N>;
+  constexpr int kGemmTNRows = Cfg::ROWS;
   const long long tiles = (long long)((a.LX + kGemmTNRows - 1) / kGemmTNRows) * a.B;
-  long long grid = 2LL * sm_count;
+  long long grid = 4LL * sm_count;
   if (grid > tiles) grid = tiles;
   if (grid < 1) grid = 1;
-  using Cfg = GemmTNCfg<M, N>;
   const int y_rows = (kGemmTNRows - 1) * a.y_stride + TAPS;
   const int smem = (kGemmTNRows * Cfg::LDX + y_rows * Cfg::LDY) * 2;
   static int configured = 0;
