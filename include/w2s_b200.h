@@ -181,12 +181,13 @@ int w2s_seqmixer_head_fwd(const w2s_seq_desc* d, const void* x, int B, int S, vo
  * together into forward-with-saved-activations, backward, loss and optimizer step.  All tensors fp16 channels-last
  * unless noted; gradients of parameters are fp32 and ACCUMULATED (+=) into caller-zeroed buffers.
  * ------------------------------------------------------------------------------------------------------- */
-/* C[m*ldc_m + n*ldc_n + t*ldc_t] += scale * sum_{b,l} X[b,l,m] * Y[b, l*y_stride + y_offset + t, n], t < taps
- * (weight gradients of nn.Linear (taps 1) / of the taps of nn.Conv1d (taps 3: X and Y are read once for all taps)).
+/* C[m*ldc_m + n*ldc_n + t*ldc_t] += scale * sum_{b,l} X[b,l,m] * Y[b, l*y_stride + y_offset + t*tap_stride, n], t < taps
+ * (weight gradients of nn.Linear (taps 1) and of all taps of an nn.Conv1d in one launch; for taps = 3, unit tap stride
+ * and M, N <= 32, X and Y are read once for all taps).
  * Built for the (M,N) pairs of the model: (16,16) (32,16) (32,32) (64,32) (64,64) (128,64) (128,128). */
-int w2s_gemm_tn(const void* X, const void* Y, float* C, int M, int N, int taps, int B, int LX, int LY, int y_stride,
-                int y_offset, long long ldc_m, long long ldc_n, long long ldc_t, float scale, const uint8_t* row_mask,
-                void* stream);
+int w2s_gemm_tn(const void* X, const void* Y, float* C, int M, int N, int taps, int tap_stride, int B, int LX, int LY,
+                int y_stride, int y_offset, long long ldc_m, long long ldc_n, long long ldc_t, float scale,
+                const uint8_t* row_mask, void* stream);
 /* a = GELU(InstanceNorm(y)) [then GELU(a + r)]: re-materialises the activated input of a conv (models/blocks.py:57-71). */
 int w2s_enc_act_fwd(const void* y, const void* r, const double* stats, void* a, const uint8_t* row_mask, int B, int L, int C,
                     float eps, void* stream);

@@ -29,7 +29,7 @@ def test_gemm_tn(cuda_device, M, N, L, ys, yo):
     Y = torch.randn(B, LY, N, device=cuda_device).half()
     mask = torch.tensor([0, 1, 0], dtype=torch.uint8, device=cuda_device)
     Cm = torch.zeros(M, N, device=cuda_device)
-    _lib.check(lib.w2s_gemm_tn(X.data_ptr(), Y.data_ptr(), Cm.data_ptr(), M, N, 1, B, L, LY, ys, yo, N, 1, 0, 1.0,
+    _lib.check(lib.w2s_gemm_tn(X.data_ptr(), Y.data_ptr(), Cm.data_ptr(), M, N, 1, 1, B, L, LY, ys, yo, N, 1, 0, 1.0,
                                mask.data_ptr(), G.stream()))
     torch.cuda.synchronize()
     ref = torch.zeros(M, N, device=cuda_device)
@@ -49,7 +49,7 @@ def test_gemm_tn_conv_taps(cuda_device, M, N, L):
     X = torch.randn(B, L, M, device=cuda_device).half()
     Y = torch.randn(B, L, N, device=cuda_device).half()
     dW = torch.zeros(M, N, 3, device=cuda_device)
-    _lib.check(lib.w2s_gemm_tn(X.data_ptr(), Y.data_ptr(), dW.data_ptr(), M, N, 3, B, L, L, 1, -1, N * 3, 3, 1, 1.0, None,
+    _lib.check(lib.w2s_gemm_tn(X.data_ptr(), Y.data_ptr(), dW.data_ptr(), M, N, 3, 1, B, L, L, 1, -1, N * 3, 3, 1, 1.0, None,
                                G.stream()))
     torch.cuda.synchronize()
     # reference: gradient of conv1d(k=3, pad=1) wrt its weight

@@ -126,7 +126,8 @@ SYMBOLS = {
                                         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "w2s_argmax": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "w2s_gemm_tn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                              C.c_int, C.c_longlong, C.c_longlong, C.c_longlong, C.c_float, C.c_void_p, C.c_void_p]),
+                              C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_longlong, C.c_float, C.c_void_p,
+                              C.c_void_p]),
     "w2s_enc_act_fwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "w2s_enc_act_bwd": (C.c_int, [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "w2s_enc_norm_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),

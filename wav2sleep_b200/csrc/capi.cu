@@ -631,30 +631,24 @@ static int ew_grid(long long work_items, int threads = 256) {
   return g < 1 ? 1 : (int)g;
 }
 
-int w2s_gemm_tn(const void* X, const void* Y, float* Cm, int M, int N, int taps, int B, int LX, int LY, int y_stride,
-                int y_offset, long long ldc_m, long long ldc_n, long long ldc_t, float scale, const uint8_t* row_mask,
-                void* stream) {
-  if (!X || !Y || !Cm || B <= 0 || LX <= 0 || LY <= 0 || y_stride < 1) return fail("gemm_tn: bad arguments");
-  if (taps != 1 && taps != 3) return fail("gemm_tn: taps=%d (1 or 3)", taps);
-  if (taps == 3 && (y_stride != 1 || M > 32 || N > 32)) {
-    // shapes without a fused-tap kernel: one pass per tap
-    for (int t = 0; t < 3; ++t) {
-      const int rc = w2s_gemm_tn(X, Y, Cm + t * ldc_t, M, N, 1, B, LX, LY, y_stride, y_offset + t, ldc_m, ldc_n, 0, scale,
-                                 row_mask, stream);
-      if (rc != 0) return rc;
-    }
-    return 0;
-  }
+int w2s_gemm_tn(const void* X, const void* Y, float* Cm, int M, int N, int taps, int tap_stride, int B, int LX, int LY,
+                int y_stride, int y_offset, long long ldc_m, long long ldc_n, long long ldc_t, float scale,
+                const uint8_t* row_mask, void* stream) {
+  if (!X || !Y || !Cm || B <= 0 || LX <= 0 || LY <= 0 || y_stride < 1 || taps < 1 || taps > 16) return fail("gemm_tn: bad arguments");
+  // taps == 3 with unit tap stride on narrow operands: fused kernel (X and Y read once); else one grid slice per tap
+  const bool fused = (taps == 3 && tap_stride == 1 && y_stride == 1 && M <= 32 && N <= 32);
   GemmTNArgs a;
   a.X = (const act_t*)X; a.Y = (const act_t*)Y; a.C = Cm; a.row_mask = row_mask;
   a.B = B; a.LX = LX; a.LY = LY; a.y_stride = y_stride; a.y_offset = y_offset;
   a.ldc_m = ldc_m; a.ldc_n = ldc_n; a.ldc_t = ldc_t; a.scale = scale;
+  a.grid_taps = fused ? 1 : taps; a.tap_stride = tap_stride;
   cudaStream_t st = (cudaStream_t)stream;
   char label[64];
   snprintf(label, sizeof(label), "gemm_tn %dx%d t%d B%d L%d", M, N, taps, B, LX);
+  const int ktaps = fused ? 3 : 1;
   LaunchScope scope(st, label, (double)B * LX * (M + N) * 2.0, 2.0 * B * (double)LX * M * N * taps);
   cudaError_t e = cudaErrorInvalidValue;
-#define W2S_TN(MM, NN, TT) if (M == MM && N == NN && taps == TT) e = launch_gemm_tn<MM, NN, TT>(a, sm_count(), st);
+#define W2S_TN(MM, NN, TT) if (M == MM && N == NN && ktaps == TT) e = launch_gemm_tn<MM, NN, TT>(a, sm_count(), st);
   W2S_TN(16, 16, 1) W2S_TN(32, 16, 1) W2S_TN(32, 32, 1) W2S_TN(64, 32, 1) W2S_TN(64, 64, 1) W2S_TN(128, 64, 1)
   W2S_TN(128, 128, 1) W2S_TN(16, 16, 3) W2S_TN(32, 16, 3) W2S_TN(32, 32, 3)
 #undef W2S_TN

@@ -20,6 +20,7 @@ struct GemmTNArgs {
   const uint8_t* row_mask;  // [B] or null
   int B, LX, LY;
   int y_stride, y_offset;   // Y row of X row l, tap t:  l * y_stride + y_offset + t
+  int grid_taps, tap_stride;  // TAPS == 1 kernels: blockIdx.y = tap, Y offset += tap * tap_stride, C += tap * ldc_t
   long long ldc_m, ldc_n, ldc_t;
   float scale;      // multiplies the contribution (1.0)
 };
@@ -97,20 +98,55 @@ __global__ void __launch_bounds__(kGemmTNThreads) gemm_tn_kernel(const GemmTNArg
     const int l0 = (int)(tile - (long long)b * tiles_per_sample) * kGemmTNRows;
     const act_t* Xb = p.X + ((size_t)b * p.LX) * M;
     const act_t* Yb = p.Y + ((size_t)b * p.LY) * N;
-    const int ybase = l0 * p.y_stride + p.y_offset;
+    const int ybase = l0 * p.y_stride + p.y_offset + (int)blockIdx.y * p.tap_stride;
     __syncthreads();
-    for (int id = tid; id < kGemmTNRows * (M / 8); id += kGemmTNThreads) {
-      const int k = id / (M / 8), c = id % (M / 8);
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (l0 + k < p.LX) v = __ldg(reinterpret_cast<const uint4*>(Xb + (size_t)(l0 + k) * M) + c);
-      *reinterpret_cast<uint4*>(sX + k * LDX + c * 8) = v;
-    }
-    for (int id = tid; id < y_rows * (N / 8); id += kGemmTNThreads) {
-      const int k = id / (N / 8), c = id % (N / 8);
-      const int ly = ybase + k;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (ly >= 0 && ly < p.LY) v = __ldg(reinterpret_cast<const uint4*>(Yb + (size_t)ly * N) + c);
-      *reinterpret_cast<uint4*>(sY + k * LDY + c * 8) = v;
+    {  // all loads of the tile are issued before the first shared-memory store (memory-level parallelism)
+      constexpr int XN = kGemmTNRows * (M / 8) / kGemmTNThreads;
+      static_assert(kGemmTNRows * (M / 8) % kGemmTNThreads == 0, "X staging");
+      uint4 xv[XN];
+#pragma unroll
+      for (int i = 0; i < XN; ++i) {
+        const int id = tid + i * kGemmTNThreads;
+        const int k = id / (M / 8), c = id % (M / 8);
+        xv[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (l0 + k < p.LX) xv[i] = __ldg(reinterpret_cast<const uint4*>(Xb + (size_t)(l0 + k) * M) + c);
+      }
+      constexpr int YN = (kGemmTNRows * (N / 8) + kGemmTNThreads - 1) / kGemmTNThreads;  // y_stride == 1 part
+      const int y_total = y_rows * (N / 8);
+      if (p.y_stride == 1) {
+        uint4 yv[YN + 1];
+#pragma unroll
+        for (int i = 0; i < YN + 1; ++i) {
+          const int id = tid + i * kGemmTNThreads;
+          const int k = id / (N / 8), c = id % (N / 8);
+          const int ly = ybase + k;
+          yv[i] = make_uint4(0u, 0u, 0u, 0u);
+          if (id < y_total && ly >= 0 && ly < p.LY) yv[i] = __ldg(reinterpret_cast<const uint4*>(Yb + (size_t)ly * N) + c);
+        }
+#pragma unroll
+        for (int i = 0; i < XN; ++i) {
+          const int id = tid + i * kGemmTNThreads;
+          *reinterpret_cast<uint4*>(sX + (id / (M / 8)) * LDX + (id % (M / 8)) * 8) = xv[i];
+        }
+#pragma unroll
+        for (int i = 0; i < YN + 1; ++i) {
+          const int id = tid + i * kGemmTNThreads;
+          if (id < y_total) *reinterpret_cast<uint4*>(sY + (id / (N / 8)) * LDY + (id % (N / 8)) * 8) = yv[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < XN; ++i) {
+          const int id = tid + i * kGemmTNThreads;
+          *reinterpret_cast<uint4*>(sX + (id / (M / 8)) * LDX + (id % (M / 8)) * 8) = xv[i];
+        }
+        for (int id = tid; id < y_total; id += kGemmTNThreads) {
+          const int k = id / (N / 8), c = id % (N / 8);
+          const int ly = ybase + k;
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (ly >= 0 && ly < p.LY) v = __ldg(reinterpret_cast<const uint4*>(Yb + (size_t)ly * N) + c);
+          *reinterpret_cast<uint4*>(sY + k * LDY + c * 8) = v;
+        }
+      }
     }
     __syncthreads();
     constexpr int KSTEPS = kGemmTNRows / 16 / KG;
@@ -135,20 +171,48 @@ __global__ void __launch_bounds__(kGemmTNThreads) gemm_tn_kernel(const GemmTNArg
     }
   }
   // ---- accumulate into C ----
+  // k-group partials are first combined in shared memory (the staging buffers are free now), so that C sees one
+  // atomic per element and CTA instead of one per warp: C is tiny (<= 48 KB) and contended by every CTA.
+  if (KG > 1) {
+    float* sC = reinterpret_cast<float*>(gemm_tn_smem);
+    __syncthreads();
+    for (int i = tid; i < M * N * TAPS; i += kGemmTNThreads) sC[i] = 0.0f;
+    __syncthreads();
 #pragma unroll
-  for (int t = 0; t < TAPS; ++t)
+    for (int t = 0; t < TAPS; ++t)
 #pragma unroll
-    for (int i = 0; i < MT; ++i)
+      for (int i = 0; i < MT; ++i)
 #pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        const int m = m0 + i * 16 + (lane >> 2);
-        const int n = n0 + j * 8 + (lane & 3) * 2;
-        float* c0 = p.C + m * p.ldc_m + n * p.ldc_n + t * p.ldc_t;
-        atomicAdd(c0, acc[t][i][j][0] * p.scale);
-        atomicAdd(c0 + p.ldc_n, acc[t][i][j][1] * p.scale);
-        atomicAdd(c0 + 8 * p.ldc_m, acc[t][i][j][2] * p.scale);
-        atomicAdd(c0 + 8 * p.ldc_m + p.ldc_n, acc[t][i][j][3] * p.scale);
-      }
+        for (int j = 0; j < NT; ++j) {
+          const int m = m0 + i * 16 + (lane >> 2);
+          const int n = n0 + j * 8 + (lane & 3) * 2;
+          float* c0 = sC + (t * M + m) * N + n;
+          atomicAdd(c0, acc[t][i][j][0]);
+          atomicAdd(c0 + 1, acc[t][i][j][1]);
+          atomicAdd(c0 + 8 * N, acc[t][i][j][2]);
+          atomicAdd(c0 + 8 * N + 1, acc[t][i][j][3]);
+        }
+    __syncthreads();
+    for (int i = tid; i < M * N * TAPS; i += kGemmTNThreads) {
+      const int t = i / (M * N), m = (i / N) % M, n = i % N;
+      atomicAdd(p.C + m * p.ldc_m + n * p.ldc_n + (t + (int)blockIdx.y) * p.ldc_t, sC[i] * p.scale);
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t)
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const int m = m0 + i * 16 + (lane >> 2);
+          const int n = n0 + j * 8 + (lane & 3) * 2;
+          float* c0 = p.C + m * p.ldc_m + n * p.ldc_n + (t + (int)blockIdx.y) * p.ldc_t;
+          atomicAdd(c0, acc[t][i][j][0] * p.scale);
+          atomicAdd(c0 + p.ldc_n, acc[t][i][j][1] * p.scale);
+          atomicAdd(c0 + 8 * p.ldc_m, acc[t][i][j][2] * p.scale);
+          atomicAdd(c0 + 8 * p.ldc_m + p.ldc_n, acc[t][i][j][3] * p.scale);
+        }
+  }
 }
 
 template <int M, int N, int TAPS>
@@ -156,18 +220,21 @@ inline cudaError_t launch_gemm_tn(const GemmTNArgs& a, int sm_count, cudaStream_
   using Cfg = GemmTNCfg<M, N>;
   constexpr int kGemmTNRows = Cfg::ROWS;
   const long long tiles = (long long)((a.LX + kGemmTNRows - 1) / kGemmTNRows) * a.B;
+  // every CTA ends with M*N*TAPS atomics into the same small C: give each CTA enough tiles to amortise them
+  constexpr int kMinTiles = (M * N >= 64 * 64) ? 8 : 2;
   long long grid = 4LL * sm_count;
-  if (grid > tiles) grid = tiles;
+  if (grid > tiles / kMinTiles) grid = tiles / kMinTiles;
   if (grid < 1) grid = 1;
   const int y_rows = (kGemmTNRows - 1) * a.y_stride + TAPS;
-  const int smem = (kGemmTNRows * Cfg::LDX + y_rows * Cfg::LDY) * 2;
+  int smem = (kGemmTNRows * Cfg::LDX + y_rows * Cfg::LDY) * 2;
+  if (Cfg::KG > 1 && smem < M * N * TAPS * 4) smem = M * N * TAPS * 4;
   static int configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<M, N, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  gemm_tn_kernel<M, N, TAPS><<<(int)grid, kGemmTNThreads, smem, stream>>>(a);
+  gemm_tn_kernel<M, N, TAPS><<<dim3((unsigned)grid, TAPS == 1 && a.grid_taps > 1 ? a.grid_taps : 1), kGemmTNThreads, smem, stream>>>(a);
   return cudaGetLastError();
 }
 

@@ -56,6 +56,24 @@ W2S_DEVINL void in_consts(const double* stats, int b, int C, int c, int L, float
   rstd = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+// Block-wide InstanceNorm constants: the fp64 division / square root is done once per (block, channel) by the first C
+// threads and shared through smem (doing it per thread made the element-wise kernels fp64-bound).
+// sm: [4][128] floats = mean, rstd, m1, m2
+W2S_DEVINL void block_in_consts(float* sm, const double* stats, const double* sums, int b, int C, int L, float eps) {
+  if ((int)threadIdx.x < C) {
+    float mean, rstd;
+    in_consts(stats, b, C, threadIdx.x, L, eps, mean, rstd);
+    sm[threadIdx.x] = mean;
+    sm[128 + threadIdx.x] = rstd;
+    if (sums != nullptr) {
+      const float invL = 1.0f / (float)L;
+      sm[256 + threadIdx.x] = (float)sums[((size_t)b * C + threadIdx.x) * 2] * invL;
+      sm[384 + threadIdx.x] = (float)sums[((size_t)b * C + threadIdx.x) * 2 + 1] * invL;
+    }
+  }
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // A. a = GELU(IN(y)) [ -> GELU(a + r) ]   (re-materialise an activated tensor for wgrad)
 // ------------------------------------------------------------------------------------------------------------
@@ -70,9 +88,14 @@ __global__ void __launch_bounds__(256) enc_act_fwd_kernel(const EncActArgs p) {
   const int n = p.L * CH;  // < 2^31 (L <= 2^27 rows)
   // the grid stride (gridDim.x * 256) is a multiple of CH, so a thread always sees the same channel chunk
   const int c8 = (int)((blockIdx.x * blockDim.x + threadIdx.x) % CH);
+  __shared__ float sm[512];
+  block_in_consts(sm, p.stats, nullptr, b, p.C, p.L, p.eps);
   float mean[8], rstd[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) in_consts(p.stats, b, p.C, c8 * 8 + k, p.L, p.eps, mean[k], rstd[k]);
+  for (int k = 0; k < 8; ++k) {
+    mean[k] = sm[c8 * 8 + k];
+    rstd[k] = sm[128 + c8 * 8 + k];
+  }
   for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
     const size_t off = ((size_t)b * p.L) * p.C + (size_t)id * 8;
     float v[8], rr[8];
@@ -106,10 +129,13 @@ __global__ void __launch_bounds__(256) enc_act_bwd_kernel(const EncActBwdArgs p)
   // each thread keeps one channel chunk (blockDim.x % CH == 0) and strides over rows
   const int c8 = threadIdx.x % CH;
   const int rows_per_iter = blockDim.x / CH;
+  __shared__ float sm[512];
+  block_in_consts(sm, p.stats, nullptr, b, p.C, p.L, p.eps);
   float mean[8], rstd[8], s0[8], s1[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    in_consts(p.stats, b, p.C, c8 * 8 + k, p.L, p.eps, mean[k], rstd[k]);
+    mean[k] = sm[c8 * 8 + k];
+    rstd[k] = sm[128 + c8 * 8 + k];
     s0[k] = s1[k] = 0.0f;
   }
   for (int l = blockIdx.x * rows_per_iter + threadIdx.x / CH; l < p.L; l += gridDim.x * rows_per_iter) {
@@ -167,13 +193,17 @@ __global__ void __launch_bounds__(256) enc_norm_bwd_kernel(const EncNormBwdArgs 
   const int ch_shift = 31 - __clz(CH);  // CH is a power of two
   const float invL = 1.0f / (float)p.L;
   const int c8 = (int)((blockIdx.x * blockDim.x + threadIdx.x) % CH);  // fixed per thread (see above)
+  __shared__ float sm[512];
+  block_in_consts(sm, p.stats, p.sums, b, p.C, p.L, p.eps);
+  (void)invL;
   float mean[8], rstd[8], m1[8], m2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int c = c8 * 8 + k;
-    in_consts(p.stats, b, p.C, c, p.L, p.eps, mean[k], rstd[k]);
-    m1[k] = (float)p.sums[((size_t)b * p.C + c) * 2] * invL;
-    m2[k] = (float)p.sums[((size_t)b * p.C + c) * 2 + 1] * invL;
+    mean[k] = sm[c];
+    rstd[k] = sm[128 + c];
+    m1[k] = sm[256 + c];
+    m2[k] = sm[384 + c];
   }
   for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
     const size_t l = (size_t)(id >> ch_shift);

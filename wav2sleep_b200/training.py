@@ -106,9 +106,9 @@ class TrainEngine(ForwardEngine):
         _lib.check(self.lib.w2s_conv1d_fwd(C.byref(c), _stream()))
 
     def gemm_tn(self, X, Y, Cbuf, M, N, B, LX, LY, ldc_m, ldc_n, y_stride=1, y_offset=0, row_mask=None, c_off=0, taps=1,
-                ldc_t=0):
-        _lib.check(self.lib.w2s_gemm_tn(X.data_ptr(), Y.data_ptr(), Cbuf.data_ptr() + 4 * c_off, M, N, taps, B, LX, LY,
-                                        y_stride, y_offset, ldc_m, ldc_n, ldc_t, 1.0, _p(row_mask), _stream()))
+                ldc_t=0, tap_stride=1):
+        _lib.check(self.lib.w2s_gemm_tn(X.data_ptr(), Y.data_ptr(), Cbuf.data_ptr() + 4 * c_off, M, N, taps, tap_stride, B,
+                                        LX, LY, y_stride, y_offset, ldc_m, ldc_n, ldc_t, 1.0, _p(row_mask), _stream()))
 
     def ln_fwd(self, x, g, b, rows, gelu, eps, res=None):
         out = torch.empty_like(x)
@@ -301,8 +301,7 @@ class TrainEngine(ForwardEngine):
                         ds = ds_k
                     d = lr["d"]
                     dW = G(layer.conv.weight)
-                    for t in range(7):
-                        self.gemm_tn(dc, lr["in"], dW, 128, 128, B, S, S, 128 * 7, 7, y_stride=1, y_offset=(t - 3) * d, c_off=t)
+                    self.gemm_tn(dc, lr["in"], dW, 128, 128, B, S, S, 128 * 7, 7, y_offset=-3 * d, taps=7, tap_stride=d, ldc_t=1)
                     din = torch.empty(N, 128, dtype=F16, device=device)
                     self.conv(dc, self.tw["seq"][bi][k]["T"], 128, 128, 7, B, S, S, din, dil=d, pad=3 * d,
                               res=ds if k == 0 else None)
