@@ -55,7 +55,7 @@ int w2s_pack_linear_frag(const float* w, int n, int k, void* out_fp16, void* str
  * One generic implicit-GEMM conv layer (kernel-level entry, used by the tests and by the stage calls below).
  * Replaces ConvLayer1D.forward (models/blocks.py:173-186) + the consumer-side InstanceNorm/GELU of its input.
  * ------------------------------------------------------------------------------------------------------- */
-enum { W2S_PRO_NONE = 0, W2S_PRO_NORM = 1, W2S_PRO_NORM_RES = 2 };
+enum { W2S_PRO_NONE = 0, W2S_PRO_NORM = 1, W2S_PRO_NORM_RES = 2, W2S_PRO_FIR = 3, W2S_PRO_NORM_RES_X = 4 };
 enum { W2S_EPI_STATS = 0, W2S_EPI_BIAS_GELU = 1, W2S_EPI_LN_GELU = 2, W2S_EPI_LN_GELU_RES = 3, W2S_EPI_PLAIN = 4 };
 
 typedef struct w2s_conv_call {
@@ -83,6 +83,12 @@ typedef struct w2s_conv_call {
   /* W2S_EPI_PLAIN: out = acc (+ bias) (+ res), written to row o*out_stride + out_offset of a sample of out_rows
    * rows (0, 0, 0 = dense: stride 1, offset 0, out_rows = L_out); res uses the same indexing. */
   int32_t out_stride, out_offset, out_rows;
+  /* block-0 fusion (W2S_PRO_FIR: the input is conv1(x) recomputed from the raw signal; W2S_PRO_NORM_RES_X: the residual
+   * branch is w_first_ds * x[2i]); x_raw fp32 [B, T_raw], w_first fp32 [16,3], w_first_ds fp32 [16]. */
+  const float* x_raw;
+  const float* w_first;
+  const float* w_first_ds;
+  int32_t T_raw;
 } w2s_conv_call;
 
 int w2s_conv1d_fwd(const w2s_conv_call* call, void* stream);

@@ -56,12 +56,11 @@ def test_first_conv(cuda_device, B, T):
                                    mask.data_ptr(), G.stream()))
     torch.cuda.synchronize()
     assert mask.tolist() == [0] + ([1] if B > 1 else []) + [0] * max(0, B - 2)
-    n_stats = sum(3 * B * c * 2 for c in enc.channels)
-    stats_bytes = (n_stats * 8 + 255) // 256 * 256
-    y1 = ws[stats_bytes: stats_bytes + B * T * 16 * 2].view(torch.float16).view(B, T, 16)
-    off_r = stats_bytes + (B * T * 16 * 2 + 255) // 256 * 256
-    r0 = ws[off_r: off_r + B * (T // 2) * 16 * 2].view(torch.float16).view(B, T // 2, 16)
-    s1 = ws[: B * 16 * 2 * 8].view(torch.float64).view(B, 16, 2).float()
+    offs = (C.c_int64 * (7 * len(enc.channels)))()
+    _lib.check(lib.w2s_encoder_layout(C.byref(pe.desc), B, T, offs))
+    s1 = ws[offs[0]: offs[0] + B * 16 * 2 * 8].view(torch.float64).view(B, 16, 2).float()
+    y1 = ws[offs[3]: offs[3] + B * T * 16 * 2].view(torch.float16).view(B, T, 16)
+    r0 = ws[offs[4]: offs[4] + B * (T // 2) * 16 * 2].view(torch.float16).view(B, T // 2, 16)
     w1 = enc.cnn[0].conv1.conv.weight
     wd = enc.cnn[0].downsample.weight
     live = [b for b in range(B) if not (B > 1 and b == 1)]

@@ -24,7 +24,7 @@ MAX_SEQ_BLOCKS = 4
 MAX_DILATIONS = 8
 ABI_VERSION = 1
 
-PRO_NONE, PRO_NORM, PRO_NORM_RES = 0, 1, 2
+PRO_NONE, PRO_NORM, PRO_NORM_RES, PRO_FIR, PRO_NORM_RES_X = 0, 1, 2, 3, 4
 EPI_STATS, EPI_BIAS_GELU, EPI_LN_GELU, EPI_LN_GELU_RES, EPI_PLAIN = 0, 1, 2, 3, 4
 
 
@@ -68,6 +68,7 @@ class ConvCall(C.Structure):
         ("res", C.c_void_p), ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("logits", C.c_void_p),
         ("n_classes", C.c_int32), ("in_eps", C.c_float), ("ln_eps", C.c_float),
         ("out_stride", C.c_int32), ("out_offset", C.c_int32), ("out_rows", C.c_int32),
+        ("x_raw", C.c_void_p), ("w_first", C.c_void_p), ("w_first_ds", C.c_void_p), ("T_raw", C.c_int32),
     ]
 
 

@@ -176,6 +176,7 @@ ConvArgs to_args(const w2s_conv_call& c) {
   a.pad = c.pad;
   a.in_eps = c.in_eps;
   a.ln_eps = c.ln_eps;
+  a.x_raw = c.x_raw; a.w_first = c.w_first; a.w_first_ds = c.w_first_ds; a.T_raw = c.T_raw;
   a.out_stride = c.out_stride > 0 ? c.out_stride : 1;
   a.out_offset = c.out_offset;
   a.out_rows = c.out_rows > 0 ? c.out_rows : c.L_out;
@@ -195,7 +196,9 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
   snprintf(label, sizeof(label), "conv c%d->%d k%d s%d d%d pro%d epi%d%s B%d L%d", c.cin, c.cout, c.taps, c.stride,
            c.dilation, c.prologue, c.epilogue, c.has_ds ? " +ds" : "", c.B, c.L_in);
   // algorithmic traffic: every input element read once (+ residual), every output written once; fp16
-  const double in_b = (double)c.B * c.L_in * c.cin * 2.0 * (c.prologue == W2S_PRO_NORM_RES ? 2.0 : 1.0);
+  const double in_b = c.prologue == W2S_PRO_FIR ? (double)c.B * c.L_in * 4.0
+                      : (double)c.B * c.L_in * c.cin * 2.0 * (c.prologue == W2S_PRO_NORM_RES ? 2.0 : 1.0) +
+                            (c.prologue == W2S_PRO_NORM_RES_X ? (double)c.B * c.L_in * 8.0 : 0.0);
   const double out_b = (double)c.B * c.L_out * c.cout * 2.0 * (c.has_ds ? 1.5 : 1.0) +
                        (c.epilogue == W2S_EPI_LN_GELU_RES ? (double)c.B * c.L_out * c.cout * 2.0 : 0.0);
   const double fl = 2.0 * c.B * (double)c.L_out * c.cout * c.cin * (c.taps + (c.has_ds ? 0.5 : 0.0));
@@ -209,6 +212,8 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
     e = launch_conv_stream<CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW>(a, c.B, sms, st);                   \
   }
     //          cin cout s  prologue      ds    MT NR NA NTW
+    W2S_STREAM(16, 16, 1, PRO_FIR, false, 4, 3, 2, 18)
+    W2S_STREAM(16, 16, 1, PRO_NORM_RES_X, true, 4, 3, 2, 14)
     W2S_STREAM(16, 16, 1, PRO_NORM, false, 4, 3, 2, 18)
     W2S_STREAM(16, 16, 2, PRO_NORM, false, 2, 3, 2, 18)
     W2S_STREAM(16, 16, 1, PRO_NORM_RES, true, 4, 3, 2, 14)
@@ -304,11 +309,13 @@ struct Slots {
 
 constexpr int kEncSlots = 5;
 
-size_t enc_stats_count(const w2s_encoder_desc* d, int B) {  // number of fp64 accumulators
+size_t enc_layer_stats_count(const w2s_encoder_desc* d, int B) {  // fp64 sum / sumsq accumulators of all conv layers
   size_t n = 0;
   for (int i = 0; i < d->n_blocks; ++i) n += (size_t)3 * B * d->channels[i] * 2;
   return n;
 }
+// + 4 doubles per sample for the raw-signal sums of the block-0 fusion (S0, R0, R1, R2)
+size_t enc_stats_count(const w2s_encoder_desc* d, int B) { return enc_layer_stats_count(d, B) + (size_t)4 * B; }
 
 int check_encoder_desc(const w2s_encoder_desc* d) {
   if (d == nullptr) return fail("encoder: null descriptor");
@@ -446,7 +453,26 @@ int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T,
     double* s2 = next_stats(c);
     double* s3 = next_stats(c);
     if (y1 == nullptr || r == nullptr) return fail("encoder: slot allocator exhausted");
-    if (i == 0) {
+    const bool fuse0 = !keep && d->n_blocks >= 2 && d->channels[1] == 16;  // block-0 fusion (inference only)
+    if (i == 0 && fuse0) {
+      // conv1 of block 0 is recomputed inside conv2's prologue; only its statistics are needed up front
+      release(y1);
+      release(r);
+      y1 = nullptr;
+      r = nullptr;
+      double* xs = stats + enc_layer_stats_count(d, B);  // zeroed with the rest of the statistics region
+      XStatsArgs xa;
+      xa.x = x; xa.xs = xs; xa.row_mask = row_mask; xa.T = L;
+      {
+        LaunchScope scope(st, "x_stats", (double)B * L * 4.0, (double)B * L * 8.0);
+        int gx = (L / 16 + 255) / 256;
+        if (gx > 4 * sm_count()) gx = 4 * sm_count();
+        x_stats_kernel<<<dim3(gx < 1 ? 1 : gx, B), 256, 0, st>>>(xa);
+        x_stats_finalize_kernel<<<(B * 16 + 127) / 128, 128, 0, st>>>(x, xs, d->w_first, row_mask, s1, B, L);
+      }
+      ce = cudaGetLastError();
+      if (ce != cudaSuccess) return cuda_fail(ce, "x_stats launch");
+    } else if (i == 0) {
       FirstConvArgs fa;
       fa.x = x;
       fa.w = d->w_first;
@@ -468,6 +494,10 @@ int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T,
       memset(&cc, 0, sizeof(cc));
       cc.cin = prev_c; cc.cout = c; cc.taps = 3; cc.stride = 1; cc.dilation = 1; cc.pad = 1;
       cc.prologue = W2S_PRO_NORM_RES; cc.epilogue = W2S_EPI_STATS; cc.has_ds = 1;
+      if (i == 1 && fuse0) {  // residual branch of block 0 recomputed from the raw signal
+        cc.prologue = W2S_PRO_NORM_RES_X;
+        cc.x_raw = x; cc.w_first_ds = d->w_first_ds; cc.T_raw = (int)T;
+      }
       cc.B = B; cc.L_in = L; cc.L_out = L;
       cc.in = prev_y3; cc.in_res = prev_r; cc.in_stats = prev_s3;
       cc.w = d->w_conv[i][0]; cc.w_ds = d->w_ds[i];
@@ -483,6 +513,10 @@ int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T,
       memset(&cc, 0, sizeof(cc));
       cc.cin = c; cc.cout = c; cc.taps = 3; cc.stride = 1; cc.dilation = 1; cc.pad = 1;
       cc.prologue = W2S_PRO_NORM; cc.epilogue = W2S_EPI_STATS;
+      if (i == 0 && fuse0) {
+        cc.prologue = W2S_PRO_FIR;
+        cc.x_raw = x; cc.w_first = d->w_first; cc.T_raw = (int)T;
+      }
       cc.B = B; cc.L_in = L; cc.L_out = L;
       cc.in = y1; cc.in_stats = s1; cc.w = d->w_conv[i][1];
       cc.out = y2; cc.out_stats = s2; cc.row_mask = row_mask; cc.in_eps = d->norm_eps;

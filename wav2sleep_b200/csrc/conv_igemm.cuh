@@ -26,7 +26,7 @@
 
 namespace w2s {
 
-enum : int { PRO_NONE = 0, PRO_NORM = 1, PRO_NORM_RES = 2 };
+enum : int { PRO_NONE = 0, PRO_NORM = 1, PRO_NORM_RES = 2, PRO_FIR = 3, PRO_NORM_RES_X = 4 };
 enum : int { EPI_STATS = 0, EPI_BIAS_GELU = 1, EPI_LN_GELU = 2, EPI_LN_GELU_RES = 3, EPI_PLAIN = 4 };
 
 struct ConvArgs {
@@ -57,6 +57,11 @@ struct ConvArgs {
   int out_stride;         // EPI_PLAIN: output row = o * out_stride + out_offset inside a sample of out_rows rows
   int out_offset;
   int out_rows;
+  // streaming kernel, block-0 fusion (PRO_FIR / PRO_NORM_RES_X): the raw signal and the Cin = 1 weights of block 0
+  const float* x_raw;     // [B, T_raw] fp32
+  const float* w_first;   // [16, 3]
+  const float* w_first_ds;  // [16]
+  int T_raw;
   int debug_flags;        // profiling experiments only (0 in production): 1 skip lo MMAs, 2 skip all MMAs, 4 skip GELU
 };
 

@@ -51,8 +51,11 @@ struct StreamCfg {
   static constexpr int R = (POS - 1) * STRIDE + 3;            // input rows per tile (with halo)
   static constexpr int RP = stream_rpad((R + STRIDE - 1) / STRIDE, CH, STRIDE);  // rows per stride phase (padded)
   static constexpr int THREADS = stream_threads(NTW);
-  static constexpr int RAW_ONE = (R * CIN * 2 + 127) / 128 * 128;
-  static constexpr int RAW_BYTES = RAW_ONE * (PRO == PRO_NORM_RES ? 2 : 1);
+  // raw ring entry: [y rows (fp16)] [residual rows (fp16) | raw-signal floats for the block-0 fusion modes]
+  static constexpr int XN = (PRO == PRO_FIR) ? R + 12 : (PRO == PRO_NORM_RES_X) ? 2 * R + 12 : 0;  // staged x floats
+  static constexpr int RAW_ONE = (PRO == PRO_FIR) ? 0 : (R * CIN * 2 + 127) / 128 * 128;
+  static constexpr int RAW_X = (XN * 4 + 127) / 128 * 128;
+  static constexpr int RAW_BYTES = RAW_ONE * (PRO == PRO_NORM_RES ? 2 : 1) + RAW_X;
   static constexpr int A_ONE = STRIDE * CH * RP * 16;
   static constexpr int A_BYTES = A_ONE * (SPLIT ? 2 : 1);
   static constexpr int B_ONE = (3 + (HAS_DS ? 1 : 0)) * CH * COUT * 16;
@@ -149,14 +152,25 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
         const int i0 = o0 * STRIDE - 1;
         const int lo = i0 < 0 ? 0 : i0;
         const int hi = (i0 + R < p.L_in) ? i0 + R : p.L_in;
-        const uint32_t nbytes = (uint32_t)(hi - lo) * CIN * 2;
+        const uint32_t nbytes = (PRO == PRO_FIR) ? 0u : (uint32_t)(hi - lo) * CIN * 2;
+        // raw-signal window of the block-0 fusion modes: x[xs0, xs0 + Cfg::XN) clipped to the sample, 16-B aligned
+        //   PRO_FIR        : conv1 needs x[i - 1 .. i + 1] for the staged rows i = i0 .. i0 + R - 1
+        //   PRO_NORM_RES_X : the residual branch needs x[2 i]
+        const int xs0 = (PRO == PRO_FIR) ? ((i0 - 1) & ~3) : ((2 * i0) & ~3);  // floor to a multiple of 4 (also < 0)
+        const int xlo = xs0 < 0 ? 0 : xs0;
+        int xhi = xs0 + Cfg::XN;
+        xhi = (xhi > p.T_raw ? p.T_raw : xhi) & ~3;
+        const uint32_t xbytes = (Cfg::XN > 0 && xhi > xlo) ? (uint32_t)(xhi - xlo) * 4 : 0u;
         mbar_wait(&raw_empty[s], ph ^ 1);
         uint8_t* dst = sRaw + s * Cfg::RAW_BYTES + (size_t)(lo - i0) * CIN * 2;
         const size_t goff = ((size_t)b * p.L_in + lo) * CIN;
         if (elect_one()) {
-          mbar_arrive_expect_tx(&raw_full[s], nbytes * (PRO == PRO_NORM_RES ? 2u : 1u));
-          bulk_g2s(dst, p.in + goff, nbytes, &raw_full[s]);
+          mbar_arrive_expect_tx(&raw_full[s], nbytes * (PRO == PRO_NORM_RES ? 2u : 1u) + xbytes);
+          if (PRO != PRO_FIR) bulk_g2s(dst, p.in + goff, nbytes, &raw_full[s]);
           if (PRO == PRO_NORM_RES) bulk_g2s(dst + Cfg::RAW_ONE, p.in_res + goff, nbytes, &raw_full[s]);
+          if (Cfg::XN > 0 && xbytes > 0)
+            bulk_g2s(sRaw + s * Cfg::RAW_BYTES + Cfg::RAW_ONE + (size_t)(xlo - xs0) * 4,
+                     p.x_raw + (size_t)b * p.T_raw + xlo, xbytes, &raw_full[s]);
         }
         __syncwarp();
         if (++s == NR) {
@@ -350,6 +364,20 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
     uint32_t rph = 0, aph = 0;
     int cur_b = -1;
     float2 sc[4], sh[4];  // per-channel scale / shift of this thread's 8 channels, as fp32x2 pairs
+    float2 fws[4][3];     // PRO_FIR: conv1 taps pre-multiplied by the per-sample InstanceNorm scale
+    float2 fw[4][3];      // block-0 fusion modes: conv1 taps (PRO_FIR) / downsample weight in [.][0] (PRO_NORM_RES_X)
+    if (PRO == PRO_FIR || PRO == PRO_NORM_RES_X) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = cch * 8 + 2 * q;
+        if (PRO == PRO_FIR) {
+#pragma unroll
+          for (int t = 0; t < 3; ++t) fw[q][t] = make_float2(__ldg(p.w_first + c * 3 + t), __ldg(p.w_first + (c + 1) * 3 + t));
+        } else {
+          fw[q][0] = make_float2(__ldg(p.w_first_ds + c), __ldg(p.w_first_ds + c + 1));
+        }
+      }
+    }
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       const int b = tile / tiles_per_sample;
       if (p.row_mask != nullptr && p.row_mask[b]) continue;
@@ -372,6 +400,12 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
             sh[k >> 1].x = (float)(-mean) * rstd;
           }
         }
+        if (PRO == PRO_FIR) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int t = 0; t < 3; ++t) fws[q][t] = __fmul2_rn(fw[q][t], sc[q]);
+        }
       }
       const int o0 = (tile - b * tiles_per_sample) * POS;
       const int i0 = o0 * STRIDE - 1;
@@ -380,22 +414,50 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
       const uint32_t raw = smem_u32(sRaw + rs * Cfg::RAW_BYTES);
       const uint32_t adst = smem_u32(sA + as * Cfg::A_BYTES) + (uint32_t)cch * RP * 16;
       const bool interior = (i0 >= 0) && (i0 + R <= p.L_in);  // no zero-padding rows in this tile
+      const int xs0 = (PRO == PRO_FIR) ? ((i0 - 1) & ~3) : ((2 * i0) & ~3);
+      const float* xraw = reinterpret_cast<const float*>(sRaw + rs * Cfg::RAW_BYTES + Cfg::RAW_ONE);  // staged x window
+      const bool x_interior = xs0 >= 0 && xs0 + Cfg::XN <= p.T_raw;  // whole x window inside the sample
+      auto xat = [&](int j) -> float {  // x[j] of this sample with conv1's zero padding and the -inf -> 0 rule
+        if (!x_interior && (j < 0 || j >= p.T_raw)) return 0.0f;
+        const float v = xraw[j - xs0];
+        return isinf(v) ? 0.0f : v;
+      };
       auto chunk = [&](int id, bool valid) {
         const int u = id / CH;
         uint4 o = make_uint4(0u, 0u, 0u, 0u), olo = make_uint4(0u, 0u, 0u, 0u);
         if (valid) {
-          const uint4 y = lds128(raw + (uint32_t)id * 16);
+          uint4 y = make_uint4(0u, 0u, 0u, 0u);
+          if (PRO != PRO_FIR) y = lds128(raw + (uint32_t)id * 16);
           uint4 r = make_uint4(0u, 0u, 0u, 0u);
           if (PRO == PRO_NORM_RES) r = lds128(raw + Cfg::RAW_ONE + (uint32_t)id * 16);
+          float xm = 0.0f, x0 = 0.0f, xp = 0.0f;
+          if (PRO == PRO_FIR) {
+            xm = xat(i0 + u - 1);
+            x0 = xat(i0 + u);
+            xp = xat(i0 + u + 1);
+          } else if (PRO == PRO_NORM_RES_X) {
+            x0 = xat(2 * (i0 + u));
+          }
           const uint32_t* yy = reinterpret_cast<const uint32_t*>(&y);
           const uint32_t* rr = reinterpret_cast<const uint32_t*>(&r);
           uint32_t* oo = reinterpret_cast<uint32_t*>(&o);
           uint32_t* ol = reinterpret_cast<uint32_t*>(&olo);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            float2 a = __ffma2_rn(unpack_h2(yy[q]), sc[q], sh[q]);
+            float2 yv;
+            float2 a;
+            if (PRO == PRO_FIR) {
+              // conv1 of block 0 recomputed in fp32 (never stored, never rounded); the InstanceNorm scale is folded
+              // into the taps (fws = w * rstd), the shift is the FMA addend: 3 packed FMAs give x_hat directly
+              a = __ffma2_rn(fws[q][2], make_float2(xp, xp),
+                             __ffma2_rn(fws[q][1], make_float2(x0, x0), __ffma2_rn(fws[q][0], make_float2(xm, xm), sh[q])));
+            } else {
+              yv = unpack_h2(yy[q]);
+              a = __ffma2_rn(yv, sc[q], sh[q]);
+            }
             if (!(p.debug_flags & 4)) a = gelu_fast2(a);
             if (PRO == PRO_NORM_RES) a = gelu_fast2(__fadd2_rn(a, unpack_h2(rr[q])));
+            if (PRO == PRO_NORM_RES_X) a = gelu_fast2(__ffma2_rn(fw[q][0], make_float2(x0, x0), a));
             oo[q] = pack_h2(a.x, a.y);
             if (SPLIT) {
               const float2 lo = __ffma2_rn(unpack_h2(oo[q]), make_float2(-1.0f, -1.0f), a);
