@@ -53,6 +53,18 @@ def test_forward_matches_oracle(cuda_device, smap, ncls, B, S):
     #                       checked on full nights in test_full_night_argmax
 
 
+@pytest.mark.parametrize("smap,ncls,B,S", [(CARDIO, 4, 1, 1), (CARDIO, 4, 5, 3), (EOG, 5, 3, 1), ({"ECG": "UNI"}, 4, 2, 2)])
+def test_forward_tiny_and_ragged_shapes(cuda_device, smap, ncls, B, S):
+    """Edge sizes: a single epoch (every layer shorter than one tile), odd batch sizes, shared encoder name."""
+    model = build_default(smap, ncls, seed=1)
+    x = make_inputs(smap, B, S, seed=13)
+    cfg = oracle.OracleConfig(signal_map=smap, num_classes=ncls)
+    ref = oracle.forward(x, model.state_dict(), cfg)
+    out = run_cuda(model, x, cuda_device)
+    assert out.shape == (B, S, ncls)
+    assert (out - ref).abs().max().item() < TOL
+
+
 def test_full_night_argmax(cuda_device):
     """Config-1 shape (one 10-h cardio night, S=1200) plus a second night: argmax agreement >= 99.9 %."""
     model = build_default(CARDIO, 4, seed=0)

@@ -23,6 +23,7 @@ ap.add_argument("--L", type=int, default=1228800)
 ap.add_argument("--ds", action="store_true")
 ap.add_argument("--impl", type=int, default=0)
 ap.add_argument("--iters", type=int, default=5)
+ap.add_argument("--fir", action="store_true", help="block-0 fusion prologue (input = raw signal, conv1 recomputed)")
 a = ap.parse_args()
 
 dev = torch.device("cuda:0")
@@ -43,6 +44,12 @@ kw = dict(cin=a.cin, cout=a.cout, taps=3, stride=a.stride, dilation=1, pad=1,
           L_in=a.L, L_out=L_out, in_res=r, in_stats=G.sums(y), w=G.pack_conv(w, split=split),
           w_ds=G.pack_conv(wd, split=split) if a.ds else None, out=out, out_ds=out_ds, out_stats=stats, in_eps=1e-2)
 kw["in"] = y
+if a.fir:
+    x = torch.randn(a.B, a.L, device=dev)
+    w1 = torch.randn(16, 3, device=dev) / 1.7
+    y1 = torch.nn.functional.conv1d(x[:, None], w1[:, None], padding=1).transpose(1, 2).contiguous()
+    kw.update(prologue=_lib.PRO_FIR, x_raw=x, w_first=w1.contiguous(), T_raw=a.L,
+              in_stats=torch.stack([y1.double().sum(1), (y1.double() ** 2).sum(1)], -1).contiguous())
 G.run_conv(**kw)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ts = []

@@ -70,7 +70,7 @@ struct StreamCfg {
 };
 
 template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, bool SPLIT, int MT, int NR, int NA, int NTW>
-__global__ void __launch_bounds__(stream_threads(NTW), 1)
+__global__ void __launch_bounds__(stream_threads(NTW), (stream_threads(NTW) <= 384 ? 2 : 1))
 conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   using Cfg = StreamCfg<CIN, COUT, STRIDE, PRO, HAS_DS, SPLIT, MT, NR, NA, NTW>;
   constexpr int kStreamThreads = Cfg::THREADS;
@@ -366,16 +366,11 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
     float2 sc[4], sh[4];  // per-channel scale / shift of this thread's 8 channels, as fp32x2 pairs
     float2 fws[4][3];     // PRO_FIR: conv1 taps pre-multiplied by the per-sample InstanceNorm scale
     float2 fw[4][3];      // block-0 fusion modes: conv1 taps (PRO_FIR) / downsample weight in [.][0] (PRO_NORM_RES_X)
-    if (PRO == PRO_FIR || PRO == PRO_NORM_RES_X) {
+    if (PRO == PRO_NORM_RES_X) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int c = cch * 8 + 2 * q;
-        if (PRO == PRO_FIR) {
-#pragma unroll
-          for (int t = 0; t < 3; ++t) fw[q][t] = make_float2(__ldg(p.w_first + c * 3 + t), __ldg(p.w_first + (c + 1) * 3 + t));
-        } else {
-          fw[q][0] = make_float2(__ldg(p.w_first_ds + c), __ldg(p.w_first_ds + c + 1));
-        }
+        fw[q][0] = make_float2(__ldg(p.w_first_ds + c), __ldg(p.w_first_ds + c + 1));
       }
     }
     for (int tile = tile_begin; tile < tile_end; ++tile) {
@@ -400,11 +395,14 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
             sh[k >> 1].x = (float)(-mean) * rstd;
           }
         }
-        if (PRO == PRO_FIR) {
+        if (PRO == PRO_FIR) {  // taps re-read (L1/L2 hits) on a sample change instead of living in registers
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
+          for (int q = 0; q < 4; ++q) {
+            const int c = cch * 8 + 2 * q;
 #pragma unroll
-            for (int t = 0; t < 3; ++t) fws[q][t] = __fmul2_rn(fw[q][t], sc[q]);
+            for (int t = 0; t < 3; ++t)
+              fws[q][t] = __fmul2_rn(make_float2(__ldg(p.w_first + c * 3 + t), __ldg(p.w_first + (c + 1) * 3 + t)), sc[q]);
+          }
         }
       }
       const int o0 = (tile - b * tiles_per_sample) * POS;
@@ -515,7 +513,8 @@ inline cudaError_t launch_conv_stream(const ConvArgs& a, int B, int sm_count, cu
   const int tiles_per_sample = (a.L_out + Cfg::POS - 1) / Cfg::POS;
   const long long total = (long long)tiles_per_sample * B;
   if (total > 0x7fffffffLL) return cudaErrorInvalidValue;
-  const int grid = total < sm_count ? (int)total : sm_count;
+  const int ctas = sm_count * (Cfg::THREADS <= 384 ? 2 : 1);  // small CTAs run two per SM
+  const int grid = total < ctas ? (int)total : ctas;
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a, tiles_per_sample, (int)total);
   return cudaGetLastError();
 }
