@@ -111,6 +111,28 @@ def test_masked_equals_absent_and_batch_independence(cuda_device):
     assert (full[1:2] - one).abs().max().item() < 2e-3  # fp32 atomic-order noise through fp16 re-rounding
 
 
+def test_cuda_graph_replay_matches_eager(cuda_device):
+    """Small batches replay one captured CUDA graph from the second call on; results must equal the eager launches,
+    follow new inputs and survive a weight update (re-capture)."""
+    model = build_default(CARDIO, 4, seed=0).to(cuda_device).eval()
+    eng = model._get_engine()
+    xa = {k: v.to(cuda_device) for k, v in make_inputs(CARDIO, 1, 6, seed=1).items()}
+    xb = {k: v.to(cuda_device) for k, v in make_inputs(CARDIO, 1, 6, seed=2).items()}
+    with torch.inference_mode():
+        eng.use_graph = False
+        ea, eb = model(xa).clone(), model(xb).clone()
+        eng.use_graph = True
+        model(xa)            # eager warm-up call
+        ga = model(xa)       # captured + replayed
+        gb = model(xb)       # replayed with new inputs
+        assert eng.replayed_launches > 0
+        assert torch.equal(ga, ea) and torch.equal(gb, eb)
+        with torch.no_grad():
+            model.classifier.bias.add_(1.0)
+        gc = model(xa)
+        assert torch.allclose(gc, ea + 1.0, atol=1e-6)
+
+
 def test_predict_is_argmax(cuda_device):
     model = build_default(EOG, 5, seed=0).to(cuda_device).eval()
     x = {k: v.to(cuda_device) for k, v in make_inputs(EOG, 2, 6, seed=5).items()}

@@ -77,6 +77,8 @@ class ForwardEngine:
         self.lib = _lib.load()
         self._weights_key = None
         self._ws: dict = {}
+        self.use_graph = True          # CUDA-graph replay of small-batch forwards (see forward)
+        self.replayed_launches = 0     # kernels launched through graph replays (not seen by w2s_launch_count)
 
     # ------------------------------------------------------------------ weights
     def _params_key(self, device):
@@ -195,31 +197,54 @@ class ForwardEngine:
             raise ValueError("empty batch")
         return B, S, device
 
+    def _launch(self, buf, xs: dict[str, Tensor], names, B: int, S: int, logits: Tensor) -> None:
+        """Enqueue the three stage calls on the current stream (also what gets captured into a CUDA graph)."""
+        lib, st = self.lib, _stream()
+        for n in names:
+            pe = self.enc[self.model.signal_encoders.signal_map[n]]
+            _lib.check(lib.w2s_encoder_fwd(C.byref(pe.desc), xs[n].data_ptr(), B, xs[n].size(1), buf["enc_ws"].data_ptr(),
+                                           buf["enc_ws"].numel(), 0, buf["z"][n].data_ptr(), buf["mask"][n].data_ptr(), st),
+                       ValueError)
+        zs = (C.c_void_p * len(names))(*[buf["z"][n].data_ptr() for n in names])
+        ms = (C.c_void_p * len(names))(*[buf["mask"][n].data_ptr() for n in names])
+        _lib.check(lib.w2s_epoch_mixer_fwd(C.byref(self.mixer_desc), zs, ms, len(names), B, S, buf["mix"].data_ptr(), st))
+        _lib.check(lib.w2s_seqmixer_head_fwd(C.byref(self.seq_desc), buf["mix"].data_ptr(), B, S, buf["seq_ws"].data_ptr(),
+                                             buf["seq_ws"].numel(), 0, None, logits.data_ptr(), st))
+
+    # Small batches are launch-latency bound (~100 launches for ~2 ms of GPU work at B = 1): from the second call with
+    # the same shape on, the whole forward is replayed from one CUDA graph over static input / output buffers.
+    GRAPH_MAX_INPUT_BYTES = 32 << 20
+
     @torch.no_grad()
     def forward(self, x: dict[str, Tensor]) -> Tensor:
         B, S, device = self._check_inputs(x)
-        lib = self.lib
         with torch.cuda.device(device):
             self._ensure_packed(device)
             names = sorted(x.keys())  # token order of the mixer, wav2sleep.py:311
             buf = self._buffers(device, names, B, S)
-            st = _stream()
+            xs = {}
             for n in names:
-                pe = self.enc[self.model.signal_encoders.signal_map[n]]
-                xs = x[n].detach()
-                if xs.dtype != torch.float32 or not xs.is_contiguous():
-                    xs = xs.to(torch.float32).contiguous()
-                _lib.check(lib.w2s_encoder_fwd(C.byref(pe.desc), xs.data_ptr(), B, xs.size(1), buf["enc_ws"].data_ptr(),
-                                               buf["enc_ws"].numel(), 0, buf["z"][n].data_ptr(),
-                                               buf["mask"][n].data_ptr(), st), ValueError)
-            zs = (C.c_void_p * len(names))(*[buf["z"][n].data_ptr() for n in names])
-            ms = (C.c_void_p * len(names))(*[buf["mask"][n].data_ptr() for n in names])
-            _lib.check(lib.w2s_epoch_mixer_fwd(C.byref(self.mixer_desc), zs, ms, len(names), B, S,
-                                               buf["mix"].data_ptr(), st))
+                t = x[n].detach()
+                xs[n] = t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
+            in_bytes = sum(t.numel() * 4 for t in xs.values())
+            if (self.use_graph and in_bytes <= self.GRAPH_MAX_INPUT_BYTES and buf.get("calls", 0) >= 1
+                    and not torch.cuda.is_current_stream_capturing()):
+                if buf.get("graph") is None or buf.get("graph_wkey") != self._weights_key:
+                    buf["xin"] = {n: torch.empty_like(xs[n]) for n in names}
+                    buf["logits"] = torch.empty(B, S, self.model.num_classes, dtype=torch.float32, device=device)
+                    l0 = self.lib.w2s_launch_count()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._launch(buf, buf["xin"], names, B, S, buf["logits"])
+                    buf.update(graph=g, graph_wkey=self._weights_key, graph_launches=self.lib.w2s_launch_count() - l0)
+                for n in names:
+                    buf["xin"][n].copy_(xs[n], non_blocking=True)
+                buf["graph"].replay()
+                self.replayed_launches += buf["graph_launches"]
+                return buf["logits"].clone()
+            buf["calls"] = buf.get("calls", 0) + 1
             logits = torch.empty(B, S, self.model.num_classes, dtype=torch.float32, device=device)
-            _lib.check(lib.w2s_seqmixer_head_fwd(C.byref(self.seq_desc), buf["mix"].data_ptr(), B, S,
-                                                 buf["seq_ws"].data_ptr(), buf["seq_ws"].numel(), 0, None,
-                                                 logits.data_ptr(), st))
+            self._launch(buf, xs, names, B, S, logits)
         return logits
 
     @torch.no_grad()
