@@ -240,6 +240,21 @@ int w2s_adamw_step(float* p, const float* g, float* m, float* v, long long n, co
                    float beta2, float eps, float weight_decay, float max_norm, float grad_scale, long long step, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * fp32 check mode: straightforward fp32 CUDA-core restatement of every op (fp32 channels-last tensors, PyTorch weight
+ * layouts, exact erf GELU, fp64 statistics).  wav2sleep_b200/check.py strings these into a forward whose logits agree
+ * with the reference to <= 1e-4 (north-star fp32 gate).  A second GPU implementation for validation, never a fallback.
+ * ------------------------------------------------------------------------------------------------------- */
+/* generic conv / linear: mode 0 input as is, 1 GELU(InstanceNorm(in)), 2 GELU(GELU(InstanceNorm(in)) + in_res), 3 raw
+ * signal (inf -> 0); w [cout, cin, taps] (taps_major: [cout, taps*cin]); optional bias, residual `add`, output GELU. */
+int w2s_chk_conv(const float* in, const float* in_res, const double* in_stats, const float* w, const float* bias,
+                 const float* add, float* out, const uint8_t* row_mask, int B, int L_in, int L_out, int cin, int cout, int taps,
+                 int stride, int dil, int pad, int mode, int taps_major, int gelu_out, float eps, void* stream);
+int w2s_chk_stats(const float* x, double* stats, const uint8_t* row_mask, int B, int L, int C, void* stream);
+int w2s_chk_rowln(const float* x, const float* res, const float* g, const float* b, float* out, long long rows, int gelu,
+                  float eps, void* stream);
+int w2s_chk_attn(const float* q, const float* k, const float* v, float* o, const uint8_t* key_mask, int N, int D, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Measurement hooks (bench.py).  Not part of the data path.
  * ------------------------------------------------------------------------------------------------------- */
 /* Number of kernels this library has launched in this process (monotonic). */

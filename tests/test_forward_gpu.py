@@ -111,6 +111,23 @@ def test_masked_equals_absent_and_batch_independence(cuda_device):
     assert (full[1:2] - one).abs().max().item() < 2e-3  # fp32 atomic-order noise through fp16 re-rounding
 
 
+@pytest.mark.parametrize("smap,ncls,B,S,masked", [(CARDIO, 4, 2, 24, [("ABD", 0), ("ECG", 1)]), (EOG, 5, 1, 12, [])])
+def test_fp32_check_mode_within_1e4(cuda_device, smap, ncls, B, S, masked):
+    """North-star fp32 gate: the fp32 check mode (plain fp32 CUDA-core kernels, fp32 storage) reproduces the reference
+    logits to <= 1e-4 max-abs and the same argmax on every epoch."""
+    from wav2sleep_b200.check import forward_fp32
+    model = build_default(smap, ncls, seed=0)
+    x = make_inputs(smap, B, S, masked=masked, seed=21)
+    ref = oracle.forward(x, model.state_dict(), oracle.OracleConfig(signal_map=smap, num_classes=ncls))
+    model = model.to(cuda_device).eval()
+    out = forward_fp32(model, {k: v.to(cuda_device) for k, v in x.items()}).float().cpu()
+    err = (out - ref).abs().max().item()
+    print(f"fp32 check mode max-abs {err:.3e}")
+    assert out.shape == ref.shape
+    assert err < 1e-4
+    assert (out.argmax(-1) == ref.argmax(-1)).all()
+
+
 def test_cuda_graph_replay_matches_eager(cuda_device):
     """Small batches replay one captured CUDA graph from the second call on; results must equal the eager launches,
     follow new inputs and survive a weight update (re-capture)."""

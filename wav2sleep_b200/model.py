@@ -241,6 +241,12 @@ class Wav2Sleep(nn.Module):
         """Most likely class per epoch, int64 [B, S]  (argmax kernel on the logits)."""
         return self._get_engine().predict(x)
 
+    def forward_fp32_check(self, x: dict[str, Tensor]) -> Tensor:
+        """The same forward through the un-fused fp32 CUDA-core check kernels (check.py): slow, <= 1e-4 from the
+        reference's fp32 logits.  A validation aid, not an inference path."""
+        from .check import forward_fp32
+        return forward_fp32(self, x)
+
 
 def build_default(signal_map: dict[str, str], num_classes: int, seed: int | None = None) -> Wav2Sleep:
     """The model of scripts/config/model/wav2sleep.yaml + main.yaml (feature_dim 128, non-causal)."""
