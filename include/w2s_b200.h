@@ -89,6 +89,9 @@ typedef struct w2s_conv_call {
   const float* w_first;
   const float* w_first_ds;
   int32_t T_raw;
+  /* wide storage (encoder EPI_STATS convs with cin, cout <= 64 only): in / in_res, resp. out / out_ds, are fp32
+   * instead of fp16 tensors of the same shape. */
+  int32_t in_wide, out_wide;
 } w2s_conv_call;
 
 int w2s_conv1d_fwd(const w2s_conv_call* call, void* stream);
@@ -112,6 +115,10 @@ typedef struct w2s_encoder_desc {
   const void* w_ds[W2S_MAX_BLOCKS];         /* packed fp16 downsample ([0] unused) */
   const void* w_lin;                        /* packed fp16 linear.weight as taps=4 */
   const float* b_lin;                       /* fp32 [feature_dim] */
+  /* inference only: the conv outputs of the first wide_blocks blocks are stored as fp32 instead of fp16 (allowed for
+   * blocks with <= 32 channels: 2 or 4, < n_blocks).  0 = all fp16.  Deep stacks (EOG, 10 blocks) need it to meet the parity
+   * gates; it doubles the bytes of those layers. */
+  int32_t wide_blocks;
 } w2s_encoder_desc;
 
 /* keep_activations = 0: inference, tensors rotate through a few slots; 1: every layer output is kept

@@ -78,6 +78,14 @@ def summarize_launches(csvf: Path, out: Path, last=102):
 OUT.mkdir(exist_ok=True)
 g = ROOT / "gpurun_out"
 if (g / "launches.csv").exists():
-    summarize_launches(g / "launches.csv", OUT / f"{tag}_launch_list_bench_step.txt")
+    last = 102
+    log = g / "ncu_bench.log"
+    if log.exists():  # one step's launch count as bench.py itself counted it
+        import json
+        for line in log.read_text().splitlines():
+            if line.startswith("{") and "gpu_launches" in line:
+                d = json.loads(line)
+                last = d["gpu_launches"] // max(d["steps"], 1)
+    summarize_launches(g / "launches.csv", OUT / f"{tag}_launch_list_bench_step.txt", last=last)
 for rep in sorted(g.glob("prof_*.ncu-rep")):
     summarize_report(rep, OUT / f"{tag}_{rep.stem}.txt")

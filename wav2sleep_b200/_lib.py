@@ -69,6 +69,7 @@ class ConvCall(C.Structure):
         ("n_classes", C.c_int32), ("in_eps", C.c_float), ("ln_eps", C.c_float),
         ("out_stride", C.c_int32), ("out_offset", C.c_int32), ("out_rows", C.c_int32),
         ("x_raw", C.c_void_p), ("w_first", C.c_void_p), ("w_first_ds", C.c_void_p), ("T_raw", C.c_int32),
+        ("in_wide", C.c_int32), ("out_wide", C.c_int32),
     ]
 
 
@@ -79,6 +80,7 @@ class EncoderDesc(C.Structure):
         ("w_first", C.c_void_p), ("w_first_ds", C.c_void_p),
         ("w_conv", (C.c_void_p * 3) * MAX_BLOCKS), ("w_ds", C.c_void_p * MAX_BLOCKS),
         ("w_lin", C.c_void_p), ("b_lin", C.c_void_p),
+        ("wide_blocks", C.c_int32),
     ]
 
 

@@ -190,28 +190,35 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
   if (ilog2_exact(c.stride) < 0 || c.stride > 4) return fail("conv1d: stride %d unsupported", c.stride);
   if (c.B > 65535) return fail("conv1d: B=%d exceeds grid.y", c.B);
   if (c.n_classes > 8) return fail("conv1d: n_classes=%d > 8", c.n_classes);
+  if ((c.in_wide || c.out_wide) && (c.epilogue != W2S_EPI_STATS || g_conv_impl.load() != 0))
+    return fail("conv1d: wide storage is only built for the streaming encoder kernels");
   const ConvArgs a = to_args(c);
   cudaError_t e = cudaErrorInvalidValue;
   bool found = false;
   char label[96];
-  snprintf(label, sizeof(label), "conv c%d->%d k%d s%d d%d pro%d epi%d%s B%d L%d", c.cin, c.cout, c.taps, c.stride,
-           c.dilation, c.prologue, c.epilogue, c.has_ds ? " +ds" : "", c.B, c.L_in);
+  snprintf(label, sizeof(label), "conv c%d->%d k%d s%d d%d pro%d epi%d%s%s B%d L%d", c.cin, c.cout, c.taps, c.stride,
+           c.dilation, c.prologue, c.epilogue, c.has_ds ? " +ds" : "",
+           c.in_wide ? (c.out_wide ? " w32/32" : " w32/16") : (c.out_wide ? " w16/32" : ""), c.B, c.L_in);
+  const double ein = c.in_wide ? 4.0 : 2.0, eout = c.out_wide ? 4.0 : 2.0;
   // algorithmic traffic: every input element read once (+ residual), every output written once; fp16
   const double in_b = c.prologue == W2S_PRO_FIR ? (double)c.B * c.L_in * 4.0
-                      : (double)c.B * c.L_in * c.cin * 2.0 * (c.prologue == W2S_PRO_NORM_RES ? 2.0 : 1.0) +
+                      : (double)c.B * c.L_in * c.cin * ein * (c.prologue == W2S_PRO_NORM_RES ? 2.0 : 1.0) +
                             (c.prologue == W2S_PRO_NORM_RES_X ? (double)c.B * c.L_in * 8.0 : 0.0);
-  const double out_b = (double)c.B * c.L_out * c.cout * 2.0 * (c.has_ds ? 1.5 : 1.0) +
+  const double out_b = (double)c.B * c.L_out * c.cout * eout * (c.has_ds ? 1.5 : 1.0) +
                        (c.epilogue == W2S_EPI_LN_GELU_RES ? (double)c.B * c.L_out * c.cout * 2.0 : 0.0);
   const double fl = 2.0 * c.B * (double)c.L_out * c.cout * c.cin * (c.taps + (c.has_ds ? 0.5 : 0.0));
   LaunchScope scope(st, label, in_b + out_b, fl);
   if (c.epilogue == W2S_EPI_STATS && c.taps == 3 && c.dilation == 1 && c.pad == 1 && g_conv_impl.load() == 0 &&
       ((c.stride == 1 && c.L_out == c.L_in) || (c.stride == 2 && c.L_out == (c.L_in + 1) / 2))) {
     const int sms = sm_count();
-#define W2S_STREAM(CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW)                                             \
-  if (!found && c.cin == CIN && c.cout == COUT && c.stride == STRIDE && c.prologue == PRO && (c.has_ds != 0) == DS) { \
+#define W2S_STREAMW(CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW, WIN, WOUT)                                 \
+  if (!found && c.cin == CIN && c.cout == COUT && c.stride == STRIDE && c.prologue == PRO && (c.has_ds != 0) == DS && \
+      (c.in_wide != 0) == WIN && (c.out_wide != 0) == WOUT) {                                               \
     found = true;                                                                                           \
-    e = launch_conv_stream<CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW>(a, c.B, sms, st);                   \
+    e = launch_conv_stream<CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW, WIN, WOUT>(a, c.B, sms, st);        \
   }
+#define W2S_STREAM(CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW) \
+  W2S_STREAMW(CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW, false, false)
     //          cin cout s  prologue      ds    MT NR NA NTW
     W2S_STREAM(16, 16, 1, PRO_FIR, false, 4, 3, 2, 18)
     W2S_STREAM(16, 16, 1, PRO_NORM_RES_X, true, 4, 3, 2, 14)
@@ -230,7 +237,22 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
     W2S_STREAM(128, 128, 1, PRO_NORM, false, 1, 3, 1, 14)
     W2S_STREAM(128, 128, 2, PRO_NORM, false, 1, 1, 1, 14)
     W2S_STREAM(128, 128, 1, PRO_NORM_RES, true, 1, 1, 1, 14)
+    // wide (fp32) storage of the leading <= 32-channel blocks            MT NR NA NTW  in     out
+    W2S_STREAMW(16, 16, 1, PRO_FIR, false, 4, 3, 2, 18, false, true)
+    W2S_STREAMW(16, 16, 1, PRO_NORM_RES_X, true, 4, 3, 2, 14, true, true)
+    W2S_STREAMW(16, 16, 1, PRO_NORM, false, 4, 3, 2, 18, true, true)
+    W2S_STREAMW(16, 16, 2, PRO_NORM, false, 2, 3, 2, 18, true, true)
+    W2S_STREAMW(16, 32, 1, PRO_NORM_RES, true, 4, 2, 2, 10, true, false)
+    W2S_STREAMW(16, 32, 1, PRO_NORM_RES, true, 4, 2, 2, 10, true, true)
+    W2S_STREAMW(32, 32, 1, PRO_NORM, false, 2, 3, 2, 10, true, true)
+    W2S_STREAMW(32, 32, 2, PRO_NORM, false, 1, 3, 2, 10, true, true)
+    W2S_STREAMW(32, 32, 1, PRO_NORM_RES, true, 2, 2, 2, 10, true, true)
+    W2S_STREAMW(32, 64, 1, PRO_NORM_RES, true, 2, 2, 2, 14, true, false)
 #undef W2S_STREAM
+#undef W2S_STREAMW
+    if (!found && (c.in_wide || c.out_wide))
+      return fail("conv1d: no wide-storage kernel for cin=%d cout=%d stride=%d prologue=%d in_wide=%d out_wide=%d", c.cin,
+                  c.cout, c.stride, c.prologue, c.in_wide, c.out_wide);
     if (found) {
       if (e != cudaSuccess) return cuda_fail(e, "conv_stream launch");
       return 0;
@@ -323,6 +345,10 @@ int check_encoder_desc(const w2s_encoder_desc* d) {
   if (d->n_blocks < 1 || d->n_blocks > W2S_MAX_BLOCKS) return fail("encoder: n_blocks=%d out of range", d->n_blocks);
   if (d->feature_dim != 128) return fail("encoder: feature_dim=%d (only 128 is built)", d->feature_dim);
   if (d->channels[0] != 16) return fail("encoder: initial_channels=%d (only 16 is built)", d->channels[0]);
+  if (d->wide_blocks < 0 || d->wide_blocks >= d->n_blocks || (d->wide_blocks > 0 && d->channels[d->wide_blocks - 1] > 32))
+    return fail("encoder: wide_blocks=%d must cover only leading blocks with <= 32 channels", d->wide_blocks);
+  if (d->wide_blocks > 0 && (d->n_blocks < 2 || d->channels[1] != 16)) return fail("encoder: wide_blocks needs the fused block 0");
+  if (d->wide_blocks & 1) return fail("encoder: wide_blocks=%d (only whole channel groups: 0, 2 or 4 are built)", d->wide_blocks);
   return 0;
 }
 
@@ -365,7 +391,7 @@ size_t w2s_encoder_workspace_bytes(const w2s_encoder_desc* d, int B, int64_t T, 
   if (check_encoder_desc(d) != 0 || B <= 0 || T <= 0) return 0;
   const size_t stats = align_up(enc_stats_count(d, B) * sizeof(double), 256);
   const size_t e = sizeof(__half);
-  if (!keep) return stats + (size_t)kEncSlots * align_up((size_t)B * T * 16 * e, 256);
+  if (!keep) return stats + (size_t)kEncSlots * align_up((size_t)B * T * 16 * (d->wide_blocks > 0 ? 4 : e), 256);
   size_t act = 0;
   int64_t L = T;
   for (int i = 0; i < d->n_blocks; ++i) {
@@ -420,7 +446,8 @@ int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T,
   Slots slots;
   memset(&slots, 0, sizeof(slots));
   slots.base = act_base;
-  slots.slot_bytes = align_up((size_t)B * T * 16 * sizeof(__half), 256);
+  slots.slot_bytes = align_up((size_t)B * T * 16 * (!keep && d->wide_blocks > 0 ? 4 : sizeof(__half)), 256);
+  auto wide = [&](int blk) { return !keep && blk >= 0 && blk < d->wide_blocks; };
   slots.n = kEncSlots;
   size_t bump = 0;
   auto alloc = [&](size_t bytes) -> void* {
@@ -503,6 +530,7 @@ int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T,
       cc.in = prev_y3; cc.in_res = prev_r; cc.in_stats = prev_s3;
       cc.w = d->w_conv[i][0]; cc.w_ds = d->w_ds[i];
       cc.out = y1; cc.out_ds = r; cc.out_stats = s1; cc.row_mask = row_mask; cc.in_eps = d->norm_eps;
+      cc.in_wide = wide(i - 1); cc.out_wide = wide(i);
       if (conv_dispatch(cc, st) != 0) return 1;
       release(prev_y3);
       release(prev_r);
@@ -521,6 +549,7 @@ int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T,
       cc.B = B; cc.L_in = L; cc.L_out = L;
       cc.in = y1; cc.in_stats = s1; cc.w = d->w_conv[i][1];
       cc.out = y2; cc.out_stats = s2; cc.row_mask = row_mask; cc.in_eps = d->norm_eps;
+      cc.in_wide = wide(i) && !(i == 0 && fuse0); cc.out_wide = wide(i);
       if (conv_dispatch(cc, st) != 0) return 1;
     }
     release(y1);
@@ -534,6 +563,7 @@ int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T,
       cc.B = B; cc.L_in = L; cc.L_out = L / 2;
       cc.in = y2; cc.in_stats = s2; cc.w = d->w_conv[i][2];
       cc.out = y3; cc.out_stats = s3; cc.row_mask = row_mask; cc.in_eps = d->norm_eps;
+      cc.in_wide = wide(i); cc.out_wide = wide(i);
       if (conv_dispatch(cc, st) != 0) return 1;
     }
     release(y2);

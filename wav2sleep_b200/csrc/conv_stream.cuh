@@ -34,6 +34,20 @@ W2S_DEVINL void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, u
                : "memory");
 }
 
+// 16 consecutive channels of one output row: fp16 (2 x 16 B) or, for wide storage, fp32 (4 x 16 B).
+template <bool WIDE>
+W2S_DEVINL void store16(uint8_t* base, size_t elem, const float (&v)[16]) {
+  if (WIDE) {
+    float4* dst = reinterpret_cast<float4*>(base + elem * 4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  } else {
+    uint4* dst = reinterpret_cast<uint4*>(base + elem * 2);
+    dst[0] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+    dst[1] = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+  }
+}
+
 // Region stride (rows of 16 B) of the chunk-major A staging, padded so that the 8 lanes of a quarter-warp, which
 // write min(8, CH*STRIDE) different (phase, chunk) regions, hit disjoint shared-memory banks.
 constexpr int stream_rpad(int rp, int ch, int stride) {
@@ -44,16 +58,20 @@ constexpr int stream_rpad(int rp, int ch, int stride) {
   return r;
 }
 
-template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, bool SPLIT, int MT, int NR, int NA, int NTW>
+// WIN / WOUT: the input (y and residual) / output (y and residual branch) tensors are stored as fp32 instead of fp16
+// ("wide" storage of the leading blocks of deep encoders, see DESIGN.md "Numerics").
+template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, bool SPLIT, int MT, int NR, int NA, int NTW,
+          bool WIN = false, bool WOUT = false>
 struct StreamCfg {
   static constexpr int CH = CIN / 8;
+  static constexpr int ESZ = WIN ? 4 : 2;  // bytes per stored input element
   static constexpr int POS = 128 * MT;
   static constexpr int R = (POS - 1) * STRIDE + 3;            // input rows per tile (with halo)
   static constexpr int RP = stream_rpad((R + STRIDE - 1) / STRIDE, CH, STRIDE);  // rows per stride phase (padded)
   static constexpr int THREADS = stream_threads(NTW);
   // raw ring entry: [y rows (fp16)] [residual rows (fp16) | raw-signal floats for the block-0 fusion modes]
   static constexpr int XN = (PRO == PRO_FIR) ? R + 12 : (PRO == PRO_NORM_RES_X) ? 2 * R + 12 : 0;  // staged x floats
-  static constexpr int RAW_ONE = (PRO == PRO_FIR) ? 0 : (R * CIN * 2 + 127) / 128 * 128;
+  static constexpr int RAW_ONE = (PRO == PRO_FIR) ? 0 : (R * CIN * ESZ + 127) / 128 * 128;
   static constexpr int RAW_X = (XN * 4 + 127) / 128 * 128;
   static constexpr int RAW_BYTES = RAW_ONE * (PRO == PRO_NORM_RES ? 2 : 1) + RAW_X;
   static constexpr int A_ONE = STRIDE * CH * RP * 16;
@@ -69,10 +87,11 @@ struct StreamCfg {
   static_assert((NTW * 32) % CH == 0, "fixed channel chunk per transform thread");
 };
 
-template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, bool SPLIT, int MT, int NR, int NA, int NTW>
+template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, bool SPLIT, int MT, int NR, int NA, int NTW, bool WIN, bool WOUT>
 __global__ void __launch_bounds__(stream_threads(NTW), (stream_threads(NTW) <= 384 ? 2 : 1))
 conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
-  using Cfg = StreamCfg<CIN, COUT, STRIDE, PRO, HAS_DS, SPLIT, MT, NR, NA, NTW>;
+  using Cfg = StreamCfg<CIN, COUT, STRIDE, PRO, HAS_DS, SPLIT, MT, NR, NA, NTW, WIN, WOUT>;
+  constexpr int ESZ = Cfg::ESZ;
   constexpr int kStreamThreads = Cfg::THREADS;
   constexpr int kStreamTransformWarps = NTW;
   constexpr int CH = Cfg::CH, POS = Cfg::POS, R = Cfg::R, RP = Cfg::RP;
@@ -152,7 +171,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
         const int i0 = o0 * STRIDE - 1;
         const int lo = i0 < 0 ? 0 : i0;
         const int hi = (i0 + R < p.L_in) ? i0 + R : p.L_in;
-        const uint32_t nbytes = (PRO == PRO_FIR) ? 0u : (uint32_t)(hi - lo) * CIN * 2;
+        const uint32_t nbytes = (PRO == PRO_FIR) ? 0u : (uint32_t)(hi - lo) * CIN * ESZ;
         // raw-signal window of the block-0 fusion modes: x[xs0, xs0 + Cfg::XN) clipped to the sample, 16-B aligned
         //   PRO_FIR        : conv1 needs x[i - 1 .. i + 1] for the staged rows i = i0 .. i0 + R - 1
         //   PRO_NORM_RES_X : the residual branch needs x[2 i]
@@ -162,12 +181,13 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
         xhi = (xhi > p.T_raw ? p.T_raw : xhi) & ~3;
         const uint32_t xbytes = (Cfg::XN > 0 && xhi > xlo) ? (uint32_t)(xhi - xlo) * 4 : 0u;
         mbar_wait(&raw_empty[s], ph ^ 1);
-        uint8_t* dst = sRaw + s * Cfg::RAW_BYTES + (size_t)(lo - i0) * CIN * 2;
-        const size_t goff = ((size_t)b * p.L_in + lo) * CIN;
+        uint8_t* dst = sRaw + s * Cfg::RAW_BYTES + (size_t)(lo - i0) * CIN * ESZ;
+        const size_t goff = ((size_t)b * p.L_in + lo) * CIN * ESZ;  // byte offset
         if (elect_one()) {
           mbar_arrive_expect_tx(&raw_full[s], nbytes * (PRO == PRO_NORM_RES ? 2u : 1u) + xbytes);
-          if (PRO != PRO_FIR) bulk_g2s(dst, p.in + goff, nbytes, &raw_full[s]);
-          if (PRO == PRO_NORM_RES) bulk_g2s(dst + Cfg::RAW_ONE, p.in_res + goff, nbytes, &raw_full[s]);
+          if (PRO != PRO_FIR) bulk_g2s(dst, reinterpret_cast<const uint8_t*>(p.in) + goff, nbytes, &raw_full[s]);
+          if (PRO == PRO_NORM_RES)
+            bulk_g2s(dst + Cfg::RAW_ONE, reinterpret_cast<const uint8_t*>(p.in_res) + goff, nbytes, &raw_full[s]);
           if (Cfg::XN > 0 && xbytes > 0)
             bulk_g2s(sRaw + s * Cfg::RAW_BYTES + Cfg::RAW_ONE + (size_t)(xlo - xs0) * 4,
                      p.x_raw + (size_t)b * p.T_raw + xlo, xbytes, &raw_full[s]);
@@ -291,7 +311,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
       mbar_wait(&t_full[ts], tph);
       tc_fence_after_sync();
       const uint32_t d_base = tmem_base + ts * Cfg::STAGE_COLS + t_lane;
-      act_t* outb = p.out + (size_t)b * p.L_out * COUT;
+      uint8_t* outb = reinterpret_cast<uint8_t*>(p.out) + (size_t)b * p.L_out * COUT * (WOUT ? 4 : 2);
 #pragma unroll
       for (int cg = 0; cg < NCG; ++cg) {
         float ps[16], pq[16];
@@ -305,9 +325,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
           tmem_ld16(d_base + j * COUT + cg * 16, v);
           const int o = o0 + j * 128 + quad * 32 + lane;
           if (o < p.L_out) {
-            uint4* dst = reinterpret_cast<uint4*>(outb + (size_t)o * COUT + cg * 16);
-            dst[0] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-            dst[1] = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+            store16<WOUT>(outb, (size_t)o * COUT + cg * 16, v);
 #pragma unroll
             for (int k = 0; k < 16; k += 2) {  // packed fp32x2: one FADD2 + one FFMA2 per channel pair
               const float2 vv = make_float2(v[k], v[k + 1]);
@@ -330,7 +348,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
         }
       }
       if (HAS_DS) {
-        act_t* dsb = p.out_ds + (size_t)b * (p.L_out >> 1) * COUT;
+        uint8_t* dsb = reinterpret_cast<uint8_t*>(p.out_ds) + (size_t)b * (p.L_out >> 1) * COUT * (WOUT ? 4 : 2);
 #pragma unroll 1
         for (int j = 0; j < MT; ++j) {
           const int o = o0 + j * 128 + quad * 32 + lane;
@@ -339,9 +357,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
             float v[16];
             tmem_ld16(d_base + (MT + j) * COUT + cg * 16, v);
             if (o < p.L_out && (o & 1) == 0) {
-              uint4* dst = reinterpret_cast<uint4*>(dsb + (size_t)(o >> 1) * COUT + cg * 16);
-              dst[0] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-              dst[1] = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+              store16<WOUT>(dsb, (size_t)(o >> 1) * COUT + cg * 16, v);
             }
           }
         }
@@ -424,10 +440,17 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
         const int u = id / CH;
         uint4 o = make_uint4(0u, 0u, 0u, 0u), olo = make_uint4(0u, 0u, 0u, 0u);
         if (valid) {
-          uint4 y = make_uint4(0u, 0u, 0u, 0u);
-          if (PRO != PRO_FIR) y = lds128(raw + (uint32_t)id * 16);
-          uint4 r = make_uint4(0u, 0u, 0u, 0u);
-          if (PRO == PRO_NORM_RES) r = lds128(raw + Cfg::RAW_ONE + (uint32_t)id * 16);
+          // 8 channels of one input row: one 16-B load (fp16) or two (wide fp32 storage)
+          uint4 y = make_uint4(0u, 0u, 0u, 0u), y2 = y;
+          if (PRO != PRO_FIR) {
+            y = lds128(raw + (uint32_t)id * (8 * ESZ));
+            if (WIN) y2 = lds128(raw + (uint32_t)id * 32 + 16);
+          }
+          uint4 r = make_uint4(0u, 0u, 0u, 0u), r2 = r;
+          if (PRO == PRO_NORM_RES) {
+            r = lds128(raw + Cfg::RAW_ONE + (uint32_t)id * (8 * ESZ));
+            if (WIN) r2 = lds128(raw + Cfg::RAW_ONE + (uint32_t)id * 32 + 16);
+          }
           float xm = 0.0f, x0 = 0.0f, xp = 0.0f;
           if (PRO == PRO_FIR) {
             xm = xat(i0 + u - 1);
@@ -436,8 +459,11 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
           } else if (PRO == PRO_NORM_RES_X) {
             x0 = xat(2 * (i0 + u));
           }
-          const uint32_t* yy = reinterpret_cast<const uint32_t*>(&y);
-          const uint32_t* rr = reinterpret_cast<const uint32_t*>(&r);
+          const uint32_t yy[8] = {y.x, y.y, y.z, y.w, y2.x, y2.y, y2.z, y2.w};
+          const uint32_t rr[8] = {r.x, r.y, r.z, r.w, r2.x, r2.y, r2.z, r2.w};
+          auto pair = [&](const uint32_t (&w)[8], int q) -> float2 {  // channels 2q, 2q+1 of the 8 as fp32
+            return WIN ? make_float2(__uint_as_float(w[2 * q]), __uint_as_float(w[2 * q + 1])) : unpack_h2(w[q]);
+          };
           uint32_t* oo = reinterpret_cast<uint32_t*>(&o);
           uint32_t* ol = reinterpret_cast<uint32_t*>(&olo);
 #pragma unroll
@@ -450,11 +476,11 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
               a = __ffma2_rn(fws[q][2], make_float2(xp, xp),
                              __ffma2_rn(fws[q][1], make_float2(x0, x0), __ffma2_rn(fws[q][0], make_float2(xm, xm), sh[q])));
             } else {
-              yv = unpack_h2(yy[q]);
+              yv = pair(yy, q);
               a = __ffma2_rn(yv, sc[q], sh[q]);
             }
             if (!(p.debug_flags & 4)) a = gelu_fast2(a);
-            if (PRO == PRO_NORM_RES) a = gelu_fast2(__fadd2_rn(a, unpack_h2(rr[q])));
+            if (PRO == PRO_NORM_RES) a = gelu_fast2(__fadd2_rn(a, pair(rr, q)));
             if (PRO == PRO_NORM_RES_X) a = gelu_fast2(__ffma2_rn(fw[q][0], make_float2(x0, x0), a));
             oo[q] = pack_h2(a.x, a.y);
             if (SPLIT) {
@@ -499,11 +525,11 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   if (warp == 0) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, int MT, int NR, int NA, int NTW>
+template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, int MT, int NR, int NA, int NTW, bool WIN = false, bool WOUT = false>
 inline cudaError_t launch_conv_stream(const ConvArgs& a, int B, int sm_count, cudaStream_t stream) {
   constexpr bool SPLIT = ConvSplit<CIN, COUT>::value;
-  using Cfg = StreamCfg<CIN, COUT, STRIDE, PRO, HAS_DS, SPLIT, MT, NR, NA, NTW>;
-  auto kern = conv_stream_kernel<CIN, COUT, STRIDE, PRO, HAS_DS, SPLIT, MT, NR, NA, NTW>;
+  using Cfg = StreamCfg<CIN, COUT, STRIDE, PRO, HAS_DS, SPLIT, MT, NR, NA, NTW, WIN, WOUT>;
+  auto kern = conv_stream_kernel<CIN, COUT, STRIDE, PRO, HAS_DS, SPLIT, MT, NR, NA, NTW, WIN, WOUT>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);

@@ -33,6 +33,7 @@ class _PackedEncoder:
             d.channels[i] = c
         d.feature_dim = enc.feature_dim
         d.norm_eps = enc.norm_eps
+        d.wide_blocks = int(getattr(enc, "wide_blocks", 0))
         st = _stream()
 
         def f32(t):
@@ -83,7 +84,9 @@ class ForwardEngine:
     # ------------------------------------------------------------------ weights
     def _params_key(self, device):
         from . import optim  # WEIGHTS_EPOCH: in-place updates by the fused optimizer do not bump tensor versions
-        return (str(device), optim.WEIGHTS_EPOCH) + tuple((p.data_ptr(), p._version) for p in self.model.parameters())
+        wide = tuple(int(getattr(e, "wide_blocks", 0)) for e in self.model.signal_encoders.encoders.values())
+        return (str(device), optim.WEIGHTS_EPOCH, wide) + tuple((p.data_ptr(), p._version)
+                                                                for p in self.model.parameters())
 
     def _ensure_packed(self, device):
         key = self._params_key(device)
@@ -147,6 +150,7 @@ class ForwardEngine:
         sd.head_b = f32(m.classifier.bias).data_ptr()
         self.seq_desc = sd
         self._weights_key = key
+        self._ws.clear()  # workspace sizes depend on the encoders' storage policy
 
     # ------------------------------------------------------------------ buffers
     def _buffers(self, device, names, B, S):

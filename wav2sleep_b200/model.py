@@ -95,6 +95,10 @@ class SignalEncoder(nn.Module):
         _require(1 <= num_blocks <= 12, f"samples_per_epoch={samples_per_epoch}")
         self.channels = [min(initial_channels * 2 ** (i // 2), max_channels) for i in range(num_blocks)]
         self.norm_eps = 1e-2  # models/wav2sleep.py:213-215
+        # Inference storage policy (not a reference argument): number of leading blocks whose conv outputs are kept as
+        # fp32 instead of fp16 (0, 2 or 4).  Stacks of >= 10 blocks (EOG) default to 4: their 16/32-channel layers
+        # otherwise push the logits to the edge of the 2e-2 parity gate (DESIGN.md "Numerics").
+        self.wide_blocks = 4 if num_blocks >= 10 else 0
         blocks, cin = [], input_dim
         for cout in self.channels:
             blocks.append(ConvBlock1D(cin, cout, norm_eps=self.norm_eps))
