@@ -224,10 +224,19 @@ int w2s_gelu_bwd(const void* pre, const void* dout, void* din, long long n, void
 /* out[c] += sum over rows r of x[(r*row_stride + row_offset), c]  (bias gradients), C <= 128. */
 int w2s_colsum(const void* x, float* out, long long rows, int C, int row_stride, int row_offset, const uint8_t* row_mask,
                long long rows_per_sample, void* stream);
-/* 8-head attention over the D <= 5 tokens of each epoch; q,k,v,o: [N, D, 128]; key_mask [N, D] (1 = masked key). */
-int w2s_attn_fwd(const void* q, const void* k, const void* v, void* o, const uint8_t* key_mask, int N, int D, void* stream);
+/* nn.Dropout of the training path (nn.TransformerEncoderLayer dropout / dropout1 / dropout2, DilatedConvBlock.dropout,
+ * models/blocks.py:111,123): out[i] = (keep(seed, site, i) ? x[i] / (1 - p) : 0) + (res ? res[i] : 0) over n fp16
+ * elements (n % 8 == 0).  keep() is a counter-based hash of (seed, site, i), so calling it again on a gradient with the
+ * same (seed, site) is the backward.  mask_out != NULL: only write the n keep decisions (0/1) there (test hook). */
+int w2s_dropout(const void* x, const void* res, void* out, uint8_t* mask_out, int64_t n, float p, uint64_t seed,
+                uint32_t site, void* stream);
+/* 8-head attention over the D <= 5 tokens of each epoch; q,k,v,o: [N, D, 128]; key_mask [N, D] (1 = masked key).
+ * drop_p > 0: dropout on the attention weights (as nn.MultiheadAttention in training), element index
+ * ((n * 8 + head) * D + query) * D + key of dropout site `site`. */
+int w2s_attn_fwd(const void* q, const void* k, const void* v, void* o, const uint8_t* key_mask, int N, int D, float drop_p,
+                 uint64_t seed, uint32_t site, void* stream);
 int w2s_attn_bwd(const void* q, const void* k, const void* v, const void* dout, void* dq, void* dk, void* dv,
-                 const uint8_t* key_mask, int N, int D, void* stream);
+                 const uint8_t* key_mask, int N, int D, float drop_p, uint64_t seed, uint32_t site, void* stream);
 /* token tensor [N, 1+n_sig, 128] = [cls, z_0[n], ...] (zeros + key mask for missing signals) and its backward. */
 int w2s_tokens_fwd(const void* const* z, const uint8_t* const* row_mask, const float* cls, void* tokens, uint8_t* key_mask,
                    int N, int S, int n_sig, void* stream);

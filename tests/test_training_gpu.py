@@ -3,7 +3,9 @@ building blocks (gemm_tn, cross entropy, clip + AdamW) against torch.
 
 Tolerances: activations and activation gradients are stored in fp16 and the whole-night InstanceNorm backward couples
 millions of positions, so parameter gradients are compared by relative L2 error (<= 1e-1; measured: median 1e-2,
-worst 6e-2 on the block-0 weights, 24 fp16 layers deep) and cosine similarity (>= 0.995) per tensor; dropout is p = 0 on both sides."""
+worst 6e-2 on the block-0 weights, 24 fp16 layers deep) and cosine similarity (>= 0.995) per tensor.  Dropout is
+tested both off (p = 0 on both sides) and on: the CUDA path's counter-based keep masks are dumped through the
+``w2s_dropout`` test hook and handed to the oracle, which applies exactly those masks in the reference's training graph."""
 import ctypes as C
 
 import pytest
@@ -107,17 +109,44 @@ def _grad_report(model, grads_ref):
     return rows
 
 
-@pytest.mark.parametrize("masked", [False, True])
-def test_parameter_gradients_match_oracle_autograd(cuda_device, masked):
+def _dropout_masks(model, eng, B, S, D, seed, device):
+    """The keep masks the CUDA training path will use for this seed, in the oracle's layout."""
+    N = B * S
+    p_mix, out = float(model.epoch_mixer.dropout), {"p_mix": float(model.epoch_mixer.dropout), "mix": [], "seq": []}
+    for l in range(model.epoch_mixer.num_layers):
+        mk = lambda site, n: eng.dropout_mask(n, 8 * l + site, p_mix, seed, device).cpu()
+        out["mix"].append({"attn": mk(0, (N * 8 * D * D + 7) // 8 * 8)[:N * 8 * D * D].view(N, 8, D, D),
+                           "sa": mk(1, N * D * 128).view(N, D, 128), "ff": mk(2, N * D * 512).view(N, D, 512),
+                           "out": mk(3, N * D * 128).view(N, D, 128)})
+    blocks = model.sequence_mixer.dilated_convs
+    out["p_seq"] = float(blocks[0].dropout.p)
+    for bi in range(len(blocks)):
+        out["seq"].append(eng.dropout_mask(N * 128, 64 + bi, out["p_seq"], seed, device).cpu().view(B, S, 128))
+    return out
+
+
+@pytest.mark.parametrize("masked,dropout", [(False, False), (True, False), (True, True)])
+def test_parameter_gradients_match_oracle_autograd(cuda_device, masked, dropout):
     torch.manual_seed(0)
     B, S = 2, 24
     model = build_default(CARDIO, 4, seed=0)
     x = make_inputs(CARDIO, B, S, masked=[("ABD", 0), ("PPG", 1)] if masked else [], seed=5)
     labels = torch.randint(0, 4, (B, S))
     labels[0, ::5] = -1
+    drop = None
+    if dropout:  # default config: p = 0.1 in both mixers; fixed step seed so that the masks can be dumped up front
+        eng = model._get_engine()
+        eng.dropout_seed = 1234567
+        drop = _dropout_masks(model, eng, B, S, len(CARDIO) + 1, eng.dropout_seed, cuda_device)
+        kept = drop["mix"][0]["ff"].float().mean().item()
+        assert abs(kept - 0.9) < 0.01, kept  # keep rate of the generator
+    else:
+        model.epoch_mixer.dropout = 0.0
+        for blk in model.sequence_mixer.dilated_convs:
+            blk.dropout.p = 0.0
     # oracle gradients (fp32 CPU autograd)
     params = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
-    lo = oracle.forward_with_grad(x, params, oracle.cardio_config())
+    lo = oracle.forward_with_grad(x, params, oracle.cardio_config(), dropout=drop)
     loss_ref = torch.nn.functional.cross_entropy(lo.view(-1, 4), labels.view(-1), ignore_index=-1)
     loss_ref.backward()
     grads_ref = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in params.items()}

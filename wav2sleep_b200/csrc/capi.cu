@@ -817,25 +817,43 @@ int w2s_colsum(const void* x, float* out, long long rows, int Cc, int row_stride
   W2S_LAUNCH_CHECK("colsum");
 }
 
-int w2s_attn_fwd(const void* q, const void* k, const void* v, void* o, const uint8_t* key_mask, int N, int D, void* stream) {
+int w2s_attn_fwd(const void* q, const void* k, const void* v, void* o, const uint8_t* key_mask, int N, int D, float drop_p,
+                 uint64_t seed, uint32_t site, void* stream) {
   if (!q || !k || !v || !o || N <= 0 || D < 1 || D > 5) return fail("attn_fwd: bad arguments");
+  if (!(drop_p >= 0.0f && drop_p < 1.0f)) return fail("attn_fwd: dropout p=%g outside [0, 1)", drop_p);
   AttnArgs p;
   memset(&p, 0, sizeof(p));
+  p.drop_p = drop_p; p.seed = seed; p.site = site;
   p.q = (const act_t*)q; p.k = (const act_t*)k; p.v = (const act_t*)v; p.o = (act_t*)o; p.key_mask = key_mask; p.N = N; p.D = D;
   LaunchScope scope((cudaStream_t)stream, "attn_fwd", (double)N * D * 128 * 8.0, 0);
   attn_kernel<false><<<(N * 8 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p);
   W2S_LAUNCH_CHECK("attn_fwd");
 }
 int w2s_attn_bwd(const void* q, const void* k, const void* v, const void* dout, void* dq, void* dk, void* dv,
-                 const uint8_t* key_mask, int N, int D, void* stream) {
+                 const uint8_t* key_mask, int N, int D, float drop_p, uint64_t seed, uint32_t site, void* stream) {
   if (!q || !k || !v || !dout || !dq || !dk || !dv || N <= 0 || D < 1 || D > 5) return fail("attn_bwd: bad arguments");
+  if (!(drop_p >= 0.0f && drop_p < 1.0f)) return fail("attn_bwd: dropout p=%g outside [0, 1)", drop_p);
   AttnArgs p;
   memset(&p, 0, sizeof(p));
+  p.drop_p = drop_p; p.seed = seed; p.site = site;
   p.q = (const act_t*)q; p.k = (const act_t*)k; p.v = (const act_t*)v; p.dout = (const act_t*)dout;
   p.dq = (act_t*)dq; p.dk = (act_t*)dk; p.dv = (act_t*)dv; p.key_mask = key_mask; p.N = N; p.D = D;
   LaunchScope scope((cudaStream_t)stream, "attn_bwd", (double)N * D * 128 * 14.0, 0);
   attn_kernel<true><<<(N * 8 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p);
   W2S_LAUNCH_CHECK("attn_bwd");
+}
+
+int w2s_dropout(const void* x, const void* res, void* out, uint8_t* mask_out, int64_t n, float p, uint64_t seed, uint32_t site,
+                void* stream) {
+  if (n <= 0 || n % 8 != 0 || n > 0xffffffffLL) return fail("dropout: n=%lld must be a positive multiple of 8", (long long)n);
+  if (!(p >= 0.0f && p < 1.0f)) return fail("dropout: p=%g outside [0, 1)", p);
+  if (mask_out == nullptr && (x == nullptr || out == nullptr)) return fail("dropout: null pointer");
+  DropArgs a;
+  a.x = (const act_t*)x; a.res = (const act_t*)res; a.out = (act_t*)out; a.mask_out = mask_out;
+  a.n = n; a.p = p; a.seed = seed; a.site = site;
+  LaunchScope scope((cudaStream_t)stream, "dropout", (double)n * (res ? 6.0 : 4.0), 0);
+  dropout_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  W2S_LAUNCH_CHECK("dropout");
 }
 
 int w2s_tokens_fwd(const void* const* z, const uint8_t* const* row_mask, const float* cls, void* tokens, uint8_t* key_mask,

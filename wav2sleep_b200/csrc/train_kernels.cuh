@@ -456,6 +456,42 @@ __global__ void __launch_bounds__(256) colsum_kernel(const act_t* x, float* out,
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// J0. dropout (nn.Dropout inside nn.TransformerEncoderLayer and DilatedConvBlock, training only).
+//     Counter-based: the keep decision of element idx of dropout site `site` is a pure function of (seed, site, idx),
+//     so the backward regenerates the mask instead of storing it.  out = keep ? x / (1 - p) : 0  (+ res).
+// ------------------------------------------------------------------------------------------------------------
+W2S_DEVINL bool drop_keep(unsigned long long seed, unsigned site, unsigned idx, float p) {
+  unsigned long long z = seed + (((unsigned long long)site << 32) | idx) * 0x9E3779B97F4A7C15ull;  // splitmix64
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (float)(unsigned)(z >> 40) * (1.0f / 16777216.0f) >= p;
+}
+struct DropArgs {
+  const act_t* x; const act_t* res; act_t* out; uint8_t* mask_out;
+  long long n; float p; unsigned long long seed; unsigned site;
+};
+__global__ void __launch_bounds__(256) dropout_kernel(const DropArgs a) {
+  const long long i8 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8;
+  if (i8 >= a.n) return;
+  const float scale = 1.0f / (1.0f - a.p);
+  if (a.mask_out) {  // test hook: dump the keep decisions
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a.mask_out[i8 + k] = drop_keep(a.seed, a.site, (unsigned)(i8 + k), a.p) ? 1 : 0;
+    return;
+  }
+  float v[8], r[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(a.x + i8)), v);
+  if (a.res) unpack8(__ldg(reinterpret_cast<const uint4*>(a.res + i8)), r);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    v[k] = drop_keep(a.seed, a.site, (unsigned)(i8 + k), a.p) ? v[k] * scale : 0.0f;
+    if (a.res) v[k] += r[k];
+  }
+  *reinterpret_cast<uint4*>(a.out + i8) = pack8(v);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // H. per-epoch multi-head attention over D <= 5 tokens (training path: separate Q, K, V tensors [N*D, 128])
 // ------------------------------------------------------------------------------------------------------------
 struct AttnArgs {
@@ -465,6 +501,7 @@ struct AttnArgs {
   act_t* dq; act_t* dk; act_t* dv;
   const uint8_t* key_mask;                          // [N, D] 1 = masked key (may be null)
   int N, D;
+  float drop_p; unsigned long long seed; unsigned site;  // dropout on the attention weights (index ((n*8+h)*D+i)*D+j)
 };
 template <bool BWD>
 __global__ void __launch_bounds__(128) attn_kernel(const AttnArgs p) {
@@ -499,6 +536,14 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnArgs p) {
     const float inv = 1.0f / den;
     for (int j = 0; j < D; ++j) P[i][j] *= inv;
   }
+  float M[5][5];  // dropout multiplier of each attention weight: 0 or 1 / (1 - p)
+  {
+    const float keep_scale = 1.0f / (1.0f - p.drop_p);
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j < D; ++j)
+        M[i][j] = (p.drop_p > 0.0f && !drop_keep(p.seed, p.site, (unsigned)((it * D + i) * D + j), p.drop_p)) ? 0.0f
+                  : (p.drop_p > 0.0f ? keep_scale : 1.0f);
+  }
   if (!BWD) {
     for (int i = 0; i < D; ++i) {
       float o[16];
@@ -506,7 +551,7 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnArgs p) {
       for (int c = 0; c < 16; ++c) o[c] = 0.0f;
       for (int j = 0; j < D; ++j)
 #pragma unroll
-        for (int c = 0; c < 16; ++c) o[c] = fmaf(P[i][j], v[j][c], o[c]);
+        for (int c = 0; c < 16; ++c) o[c] = fmaf(P[i][j] * M[i][j], v[j][c], o[c]);
       uint4* op = reinterpret_cast<uint4*>(p.o + base + (size_t)i * 128);
       op[0] = pack8(o);
       op[1] = pack8(o + 8);
@@ -526,8 +571,9 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnArgs p) {
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           d = fmaf(dO[c], v[j][c], d);
-          dv[j][c] = fmaf(P[i][j], dO[c], dv[j][c]);
+          dv[j][c] = fmaf(P[i][j] * M[i][j], dO[c], dv[j][c]);
         }
+        d *= M[i][j];
         dP[j] = d;
         dot = fmaf(P[i][j], d, dot);
       }

@@ -235,7 +235,7 @@ class Wav2Sleep(nn.Module):
         """dict of [B, S * samples_per_epoch] fp32 (rows of -inf = missing signal) -> logits [B, S, num_classes].
 
         Under ``train()`` with grad enabled the logits carry a grad_fn whose backward runs the CUDA backward pass
-        (dropout is treated as p = 0, see training.py); otherwise the fused inference kernels run."""
+        (dropout with counter-based masks, see training.py); otherwise the fused inference kernels run."""
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from .training import forward_with_grad
             return forward_with_grad(self, x)

@@ -8,8 +8,11 @@ plain epilogue + row-wise kernels) so that every intermediate needed by the back
 gradients are tcgen05 convolutions with flipped/transposed weights, weight gradients are the streaming ``gemm_tn``
 kernel, everything else is element-/row-wise.
 
-Limits of this round: dropout is treated as p = 0 (the reference's gradient can only be reproduced without it,
-SURVEY H6); fp16 storage of activations and activation gradients, fp32 parameter gradients.
+Dropout (epoch mixer p, sequence mixer p; the encoder ConvLayer1D dropout is p = 0 in the reference config) uses a
+counter-based generator: the keep decision of an element is a hash of (step seed, dropout site, element index), so the
+backward regenerates the masks instead of storing them, and a test can dump them (``w2s_dropout`` mask_out) to feed the
+oracle the very same masks.  The masks are therefore not the ones torch's Philox stream would draw - same distribution,
+different realisation.  Storage: fp16 activations and activation gradients, fp32 parameter gradients.
 """
 from __future__ import annotations
 
@@ -29,6 +32,11 @@ def _p(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _rank() -> int:
+    import torch.distributed as dist
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
 class TrainEngine(ForwardEngine):
     """Adds forward_train / backward to the inference engine (shares the packed forward weights)."""
 
@@ -38,6 +46,20 @@ class TrainEngine(ForwardEngine):
         self.saved = None
         self.bucket_hooks = []  # callables(name) fired as gradient buckets become final (data-parallel overlap)
         self.direct = set()
+        self.dropout_seed = None  # int: fixed seed for every step (tests); None: drawn from torch's CPU generator
+        self.last_dropout_seed = 0
+
+    # dropout sites: 8 * layer + {0 attention weights, 1 after self-attention, 2 FF hidden, 3 after FF}; 64 + seq block
+    def dropout(self, x: Tensor, site: int, p: float, seed: int, res: Tensor | None = None, out: Tensor | None = None):
+        out = torch.empty_like(x) if out is None else out
+        _lib.check(self.lib.w2s_dropout(x.data_ptr(), _p(res), out.data_ptr(), None, x.numel(), p, seed, site, _stream()))
+        return out
+
+    def dropout_mask(self, n: int, site: int, p: float, seed: int, device) -> Tensor:
+        """The keep decisions (uint8 0/1) of the first n elements of a dropout site (test hook)."""
+        m = torch.empty(n, dtype=torch.uint8, device=device)
+        _lib.check(self.lib.w2s_dropout(None, None, None, m.data_ptr(), n, p, seed, site, _stream()))
+        return m
 
     # ------------------------------------------------------------------ weight packing for the backward
     def _pack(self, w: Tensor, taps_major=0, taps=None) -> Tensor:
@@ -152,6 +174,13 @@ class TrainEngine(ForwardEngine):
             names = sorted(x.keys())
             N = B * S
             sv = {"B": B, "S": S, "names": names, "enc": {}, "device": device}
+            if self.dropout_seed is not None:
+                seed = int(self.dropout_seed)
+            else:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item()) ^ (0x5851F42D4C957F2D * (1 + _rank()) & (2 ** 62 - 1))
+            self.last_dropout_seed = seed
+            p_mix = float(m.epoch_mixer.dropout) if m.training else 0.0
+            sv.update(seed=seed, p_mix=p_mix)
             # ---- encoders (streaming kernels, every layer output kept) ----
             for n in names:
                 enc = m.signal_encoders.get_encoder(n)
@@ -216,9 +245,14 @@ class TrainEngine(ForwardEngine):
                     qkv.append(o)
                 ao = torch.empty(T_tok, 128, dtype=F16, device=device)
                 _lib.check(lib.w2s_attn_fwd(qkv[0].data_ptr(), qkv[1].data_ptr(), qkv[2].data_ptr(), ao.data_ptr(),
-                                            key_mask.data_ptr(), N, D, st))
+                                            key_mask.data_ptr(), N, D, p_mix, seed, 8 * l, st))
                 x_mid = torch.empty(T_tok, 128, dtype=F16, device=device)
-                self.conv(ao, tw["o"], 128, 128, 1, 1, T_tok, T_tok, x_mid, bias=f(layer.self_attn.out_proj.bias), res=xcur)
+                if p_mix > 0:  # x + dropout1(out_proj(attention))
+                    self.conv(ao, tw["o"], 128, 128, 1, 1, T_tok, T_tok, x_mid, bias=f(layer.self_attn.out_proj.bias))
+                    self.dropout(x_mid, 8 * l + 1, p_mix, seed, res=xcur, out=x_mid)
+                else:
+                    self.conv(ao, tw["o"], 128, 128, 1, 1, T_tok, T_tok, x_mid, bias=f(layer.self_attn.out_proj.bias),
+                              res=xcur)
                 h2 = self.ln_fwd(x_mid, f(layer.norm2.weight), f(layer.norm2.bias), T_tok, 0, eps)
                 hpre = torch.empty(4 * T_tok, 128, dtype=F16, device=device)  # [T, 512] row-major
                 b1 = f(layer.linear1.bias)
@@ -228,8 +262,13 @@ class TrainEngine(ForwardEngine):
                 hact = torch.empty_like(hpre)
                 _lib.check(lib.w2s_gelu_fwd(hpre.data_ptr(), hact.data_ptr(), hpre.numel(), st))
                 x_out = torch.empty(T_tok, 128, dtype=F16, device=device)
-                self.conv(hact, tw["ff2"], 128, 128, 4, 1, 4 * T_tok, T_tok, x_out, stride=4, bias=f(layer.linear2.bias),
-                          res=x_mid)
+                if p_mix > 0:  # x + dropout2(linear2(dropout(gelu(linear1(.)))))
+                    self.dropout(hact, 8 * l + 2, p_mix, seed, out=hact)
+                    self.conv(hact, tw["ff2"], 128, 128, 4, 1, 4 * T_tok, T_tok, x_out, stride=4, bias=f(layer.linear2.bias))
+                    self.dropout(x_out, 8 * l + 3, p_mix, seed, res=x_mid, out=x_out)
+                else:
+                    self.conv(hact, tw["ff2"], 128, 128, 4, 1, 4 * T_tok, T_tok, x_out, stride=4,
+                              bias=f(layer.linear2.bias), res=x_mid)
                 sv["layers"].append(dict(x=xcur, h1=h1, q=qkv[0], k=qkv[1], v=qkv[2], ao=ao, x_mid=x_mid, h2=h2, hpre=hpre,
                                          hact=hact))
                 xcur = x_out
@@ -247,9 +286,18 @@ class TrainEngine(ForwardEngine):
                     c = torch.empty(B, S, 128, dtype=F16, device=device)
                     self.conv(cur, self.tw["seq"][bi][k]["fwd"], 128, 128, 7, B, S, S, c, dil=d, pad=3 * d)
                     g_, b_ = self._f32(layer.norm.weight.reshape(-1)), self._f32(layer.norm.bias.reshape(-1))
-                    y = self.ln_fwd(c.view(N, 128), g_, b_, N, 1, layer.norm.eps,
-                                    res=blk_in.view(N, 128) if k == nl - 1 else None).view(B, S, 128)
-                    rec["layers"].append({"in": cur, "c": c, "g": g_, "b": b_, "eps": layer.norm.eps, "d": d})
+                    p_seq = float(blk.dropout.p) if m.training else 0.0
+                    lrec = {"in": cur, "c": c, "g": g_, "b": b_, "eps": layer.norm.eps, "d": d}
+                    if k == nl - 1 and p_seq > 0:  # gelu(dropout(layers(x)) + x), models/blocks.py:123-125
+                        y = self.ln_fwd(c.view(N, 128), g_, b_, N, 1, layer.norm.eps)
+                        t = self.dropout(y, 64 + bi, p_seq, seed, res=blk_in.view(N, 128), out=y)
+                        y = torch.empty(B, S, 128, dtype=F16, device=device)
+                        _lib.check(lib.w2s_gelu_fwd(t.data_ptr(), y.data_ptr(), t.numel(), st))
+                        lrec.update(t=t, p=p_seq)
+                    else:
+                        y = self.ln_fwd(c.view(N, 128), g_, b_, N, 1, layer.norm.eps,
+                                        res=blk_in.view(N, 128) if k == nl - 1 else None).view(B, S, 128)
+                    rec["layers"].append(lrec)
                     cur = y
                 sv["seq"].append(rec)
                 blk_in = cur
@@ -295,10 +343,16 @@ class TrainEngine(ForwardEngine):
                     lr, layer = rec["layers"][k], blk.conv_layers[k]
                     dg, db = G(layer.norm.weight).view(-1), G(layer.norm.bias).view(-1)
                     last = k == nl - 1
-                    dc, ds_k = self.ln_bwd(lr["c"].view(N, 128), lr["g"], lr["b"], dout, dg, db, N, 1, lr["eps"],
-                                           res=rec["in"].view(N, 128) if last else None, want_ds=last)
-                    if last:
-                        ds = ds_k
+                    if last and "t" in lr:  # dropout between the layers and the residual add
+                        ds = torch.empty(N, 128, dtype=F16, device=device)
+                        _lib.check(lib.w2s_gelu_bwd(lr["t"].data_ptr(), dout.data_ptr(), ds.data_ptr(), ds.numel(), st))
+                        dy = self.dropout(ds, 64 + bi, lr["p"], sv["seed"])
+                        dc, _ = self.ln_bwd(lr["c"].view(N, 128), lr["g"], lr["b"], dy, dg, db, N, 1, lr["eps"])
+                    else:
+                        dc, ds_k = self.ln_bwd(lr["c"].view(N, 128), lr["g"], lr["b"], dout, dg, db, N, 1, lr["eps"],
+                                               res=rec["in"].view(N, 128) if last else None, want_ds=last)
+                        if last:
+                            ds = ds_k
                     d = lr["d"]
                     dW = G(layer.conv.weight)
                     self.gemm_tn(dc, lr["in"], dW, 128, 128, B, S, S, 128 * 7, 7, y_offset=-3 * d, taps=7, tap_stride=d, ldc_t=1)
@@ -320,11 +374,15 @@ class TrainEngine(ForwardEngine):
                 # FFN
                 dW2, dW1 = G(layer.linear2.weight), G(layer.linear1.weight)
                 d_hact = torch.empty(4 * T_tok, 128, dtype=F16, device=device)
+                p_mix, seed = sv["p_mix"], sv["seed"]
+                g2 = self.dropout(dx, 8 * l + 3, p_mix, seed) if p_mix > 0 else dx  # gradient of the linear2 output
                 for j in range(4):
-                    self.conv(dx, tw["ff2_T"][j], 128, 128, 1, 1, T_tok, T_tok, d_hact, out_stride=4, out_offset=j,
+                    self.conv(g2, tw["ff2_T"][j], 128, 128, 1, 1, T_tok, T_tok, d_hact, out_stride=4, out_offset=j,
                               out_rows=4 * T_tok)
-                    self.gemm_tn(dx, L_["hact"], dW2, 128, 128, 1, T_tok, 4 * T_tok, 512, 1, y_stride=4, y_offset=j, c_off=j * 128)
-                self.colsum(dx, G(layer.linear2.bias), T_tok, 128)
+                    self.gemm_tn(g2, L_["hact"], dW2, 128, 128, 1, T_tok, 4 * T_tok, 512, 1, y_stride=4, y_offset=j, c_off=j * 128)
+                self.colsum(g2, G(layer.linear2.bias), T_tok, 128)
+                if p_mix > 0:
+                    self.dropout(d_hact, 8 * l + 2, p_mix, seed, out=d_hact)
                 d_hpre = torch.empty_like(d_hact)
                 _lib.check(lib.w2s_gelu_bwd(L_["hpre"].data_ptr(), d_hact.data_ptr(), d_hpre.data_ptr(), d_hact.numel(), st))
                 for j in range(4):
@@ -338,12 +396,14 @@ class TrainEngine(ForwardEngine):
                                         G(layer.norm2.bias), T_tok, 0, eps, dadd=dx)
                 # attention
                 d_ao = torch.empty(T_tok, 128, dtype=F16, device=device)
-                self.conv(dx_mid, tw["o_T"], 128, 128, 1, 1, T_tok, T_tok, d_ao)
-                self.gemm_tn(dx_mid, L_["ao"], G(layer.self_attn.out_proj.weight), 128, 128, 1, T_tok, T_tok, 128, 1)
-                self.colsum(dx_mid, G(layer.self_attn.out_proj.bias), T_tok, 128)
+                g1 = self.dropout(dx_mid, 8 * l + 1, p_mix, seed) if p_mix > 0 else dx_mid  # gradient of out_proj's output
+                self.conv(g1, tw["o_T"], 128, 128, 1, 1, T_tok, T_tok, d_ao)
+                self.gemm_tn(g1, L_["ao"], G(layer.self_attn.out_proj.weight), 128, 128, 1, T_tok, T_tok, 128, 1)
+                self.colsum(g1, G(layer.self_attn.out_proj.bias), T_tok, 128)
                 dq, dk, dv = (torch.empty(T_tok, 128, dtype=F16, device=device) for _ in range(3))
                 _lib.check(lib.w2s_attn_bwd(L_["q"].data_ptr(), L_["k"].data_ptr(), L_["v"].data_ptr(), d_ao.data_ptr(),
-                                            dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), key_mask.data_ptr(), N, D, st))
+                                            dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), key_mask.data_ptr(), N, D, p_mix,
+                                            seed, 8 * l, st))
                 dWin, dbin = G(layer.self_attn.in_proj_weight), G(layer.self_attn.in_proj_bias)
                 d_h1 = None
                 for j, dj in enumerate((dq, dk, dv)):
