@@ -71,3 +71,44 @@ def test_oracle_errors():
         oracle.forward({"ECG": torch.zeros(1, 1000)}, model.state_dict(), cfg)
     with pytest.raises(ValueError):
         oracle.epoch_mixer({}, model.state_dict(), cfg)
+
+
+def test_oracle_training_graph_matches_reference_with_dropout_masks():
+    """Train-mode pin (oracle/make_golden_train.py): the reference in train() with nn.Dropout patched to explicit keep
+    masks -> logits, loss and parameter gradients; the oracle's training graph with the same masks must reproduce them."""
+    from pathlib import Path
+    g = np.load(Path(__file__).parent / "golden" / "train_dropout_cardio.npz")
+    smap = {"ABD": "ABD", "THX": "THX", "ECG": "ECG", "PPG": "PPG"}
+    B, S = g["labels"].shape
+    model = build_default(smap, 4, seed=int(g["weights_seed"]))
+    x = make_inputs(smap, B, S, masked=[("ABD", 0), ("PPG", 1)], seed=int(g["input_seed"]))
+    masks = {}
+    for i, name in enumerate(g["mask_names"]):
+        shape = tuple(int(v) for v in g[f"mask_{i}_shape"])
+        n = int(np.prod(shape))
+        masks[str(name)] = torch.from_numpy(np.unpackbits(g[f"mask_{i}_bits"])[:n].reshape(shape).copy())
+    pre = "epoch_mixer.transformer_encoder.layers"
+    drop = {"p_mix": float(g["mask_p"][0]), "p_seq": float(g["mask_p"][-1]),
+            "mix": [{"sa": masks[f"{pre}.{l}.dropout1"], "ff": masks[f"{pre}.{l}.dropout"], "out": masks[f"{pre}.{l}.dropout2"]}
+                    for l in range(2)],
+            "seq": [masks[f"sequence_mixer.dilated_convs.{b}.dropout"].transpose(1, 2) for b in range(2)]}  # [B,F,S]->[B,S,F]
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    logits = oracle.forward_with_grad(x, params, oracle.cardio_config(), dropout=drop)
+    labels = torch.from_numpy(g["labels"])
+    loss = torch.nn.functional.cross_entropy(logits.reshape(-1, 4), labels.reshape(-1), ignore_index=-1)
+    loss.backward()
+    assert np.abs(logits.detach().numpy() - g["logits"]).max() < 1e-4
+    assert abs(loss.item() - float(g["loss"])) < 1e-5
+    for name, ref_norm in zip(g["grad_norm_names"], g["grad_norms"]):
+        gr = params[str(name)].grad
+        got = 0.0 if gr is None else gr.norm().item()
+        assert abs(got - ref_norm) <= 2e-3 * max(ref_norm, 1e-6) + 1e-7, (name, got, ref_norm)
+    for key in g.files:
+        if key.startswith("grad::"):
+            ref = torch.from_numpy(g[key])
+            got = params[key[6:]].grad
+            assert (got - ref).norm().item() <= 2e-3 * ref.norm().item() + 1e-7, key
+    # and the eval graph differs (the masks matter)
+    with torch.no_grad():
+        ev = oracle.forward_with_grad(x, params, oracle.cardio_config())
+    assert (ev - logits).abs().max().item() > 1e-2
