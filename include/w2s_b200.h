@@ -95,6 +95,10 @@ typedef struct w2s_conv_call {
 } w2s_conv_call;
 
 int w2s_conv1d_fwd(const w2s_conv_call* call, void* stream);
+/* Profiling aid: with W2S_DEBUG_FLAGS & 64 in the environment, CTA 0 of the streaming conv kernel records %globaltimer
+ * (ns) at its pipeline milestones and every CTA its entry / exit time; this copies the 16 milestone slots and
+ * (optionally) the [512][2] entry/exit table of the last launch to the host (synchronises). */
+int w2s_debug_timestamps(uint64_t* out16, uint64_t* cta1024);
 /* Kernel selection for the encoder convs (testing / A-B measurement): 0 = auto (persistent warp-specialised
  * streaming kernel, conv_stream.cuh), 1 = tile-per-CTA kernel only (conv_igemm.cuh).  Same results either way. */
 int w2s_set_conv_impl(int impl);

@@ -23,6 +23,7 @@ ap.add_argument("--L", type=int, default=1228800)
 ap.add_argument("--ds", action="store_true")
 ap.add_argument("--impl", type=int, default=0)
 ap.add_argument("--iters", type=int, default=5)
+ap.add_argument("--reps", type=int, default=1, help="launches between the two events")
 ap.add_argument("--fir", action="store_true", help="block-0 fusion prologue (input = raw signal, conv1 recomputed)")
 a = ap.parse_args()
 
@@ -55,10 +56,35 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 ts = []
 for _ in range(a.iters):
     e0.record()
-    G.run_conv(**kw)
+    for _ in range(a.reps):
+        G.run_conv(**kw)
     e1.record()
     torch.cuda.synchronize()
-    ts.append(e0.elapsed_time(e1))
+    ts.append(e0.elapsed_time(e1) / a.reps)
 byt = a.B * a.L * a.cin * 2 * (2 if a.ds else 1) + a.B * L_out * a.cout * 2 * (1.5 if a.ds else 1)
 ms = sorted(ts)[len(ts) // 2]
 print(f"cin={a.cin} cout={a.cout} s={a.stride} ds={a.ds} impl={a.impl}: {ms:.3f} ms  {byt / ms * 1e-6:.0f} GB/s algorithmic")
+
+import os
+if int(os.environ.get("W2S_DEBUG_FLAGS", "0")) & 64:
+    import ctypes
+    buf = (ctypes.c_uint64 * 16)()
+    torch.cuda.synchronize()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(); G.run_conv(**kw); t1.record(); torch.cuda.synchronize()
+    cta = (ctypes.c_uint64 * 1024)()
+    lib.w2s_debug_timestamps(buf, cta)
+    import numpy as np
+    ct = np.array(cta[:2 * 148], dtype=np.int64).reshape(148, 2)
+    t00 = ct[:, 0].min()
+    st, en = (ct[:, 0] - t00) / 1e3, (ct[:, 1] - t00) / 1e3
+    print("CTA entry (us): min %.1f med %.1f max %.1f | exit: min %.1f med %.1f max %.1f | duration: min %.1f med %.1f max %.1f"
+          % (st.min(), np.median(st), st.max(), en.min(), np.median(en), en.max(), (en - st).min(), np.median(en - st),
+             (en - st).max()))
+    order = np.argsort(en)
+    print("slowest CTAs:", [(int(i), round(float(en[i]), 1)) for i in order[-6:]], "fastest:", [(int(i), round(float(en[i]), 1)) for i in order[:4]])
+    names = ["entry", "tmem_alloc", "setup_done", "xform_start", "xform_raw_ready", "xform_first_done", "epi_first_full",
+             "epi_loop_done", "epi_flushed", "teardown_sync", "dealloc"]
+    base = buf[0]
+    print("event-timed %.1f us; CTA0 milestones (us since entry): " % (t0.elapsed_time(t1) * 1e3)
+          + ", ".join(f"{n}={(buf[i] - base) / 1e3:.1f}" for i, n in enumerate(names)))

@@ -382,6 +382,13 @@ int w2s_pack_linear_frag(const float* w, int n, int k, void* out, void* stream) 
   return e == cudaSuccess ? 0 : cuda_fail(e, "pack_frag");
 }
 
+int w2s_debug_timestamps(uint64_t* out16, uint64_t* cta1024) {
+  if (out16 == nullptr) return fail("debug_timestamps: null pointer");
+  cudaError_t e = cudaMemcpyFromSymbol(out16, g_stream_ts, 16 * sizeof(uint64_t));
+  if (e == cudaSuccess && cta1024 != nullptr) e = cudaMemcpyFromSymbol(cta1024, g_stream_cta_ts, 1024 * sizeof(uint64_t));
+  return e == cudaSuccess ? 0 : cuda_fail(e, "debug_timestamps");
+}
+
 int w2s_conv1d_fwd(const w2s_conv_call* call, void* stream) {
   if (call == nullptr) return fail("conv1d: null call");
   return conv_dispatch(*call, (cudaStream_t)stream);

@@ -17,6 +17,17 @@
 
 namespace w2s {
 
+// debug_flags & 64: CTA 0 records %globaltimer at its pipeline milestones (read back with w2s_debug_timestamps)
+__device__ unsigned long long g_stream_ts[16];
+__device__ unsigned long long g_stream_cta_ts[2 * 512];  // debug_flags & 64: entry / exit time of every CTA
+W2S_DEVINL void dbg_ts(const ConvArgs& p, int slot) {
+  if ((p.debug_flags & 64) && blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_stream_ts[slot] = t;
+  }
+}
+
 constexpr int kStreamFirstTransformWarp = 6;  // warp 0 producer, 1 MMA, 2..5 epilogue, 6.. transform
 constexpr int stream_threads(int ntw) { return 32 * (kStreamFirstTransformWarp + ntw); }
 
@@ -118,7 +129,14 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   const int tile_end = (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x);
 
   // ---------------- one-time setup ----------------
+  if (tid == 0) dbg_ts(p, 0);
+  if ((p.debug_flags & 64) && tid == 0 && blockIdx.x < 512) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_stream_cta_ts[2 * blockIdx.x] = t;
+  }
   if (warp == 0) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (tid == 0) dbg_ts(p, 1);
   if (tid == 32) {
     for (int s = 0; s < NR; ++s) {
       mbar_init(&raw_full[s], 1);
@@ -157,6 +175,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  if (tid == 0) dbg_ts(p, 2);
 
   // ======================================================================================================
   if (warp == 0) {
@@ -310,6 +329,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
       const int o0 = (tile - b * tiles_per_sample) * POS;
       mbar_wait(&t_full[ts], tph);
       tc_fence_after_sync();
+      if (warp == 2 && lane == 0 && tile == tile_begin) dbg_ts(p, 6);
       const uint32_t d_base = tmem_base + ts * Cfg::STAGE_COLS + t_lane;
       uint8_t* outb = reinterpret_cast<uint8_t*>(p.out) + (size_t)b * p.L_out * COUT * (WOUT ? 4 : 2);
 #pragma unroll
@@ -322,9 +342,10 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
 #pragma unroll 1
         for (int j = 0; j < MT; ++j) {
           float v[16];
+          if (p.debug_flags & 16) continue;
           tmem_ld16(d_base + j * COUT + cg * 16, v);
           const int o = o0 + j * 128 + quad * 32 + lane;
-          if (o < p.L_out) {
+          if (o < p.L_out && !((p.debug_flags & 8) && v[0] != 123.456f)) {
             store16<WOUT>(outb, (size_t)o * COUT + cg * 16, v);
 #pragma unroll
             for (int k = 0; k < 16; k += 2) {  // packed fp32x2: one FADD2 + one FFMA2 per channel pair
@@ -370,7 +391,9 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
         tph ^= 1;
       }
     }
+    if (warp == 2 && lane == 0) dbg_ts(p, 7);
     flush(cur_b);
+    if (warp == 2 && lane == 0) dbg_ts(p, 8);
   } else {
     // ---------------- transform warps ----------------
     const int tt = tid - kStreamFirstTransformWarp * 32;  // 0..255
@@ -402,7 +425,8 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
           const double s1 = p.in_stats[((size_t)b * CIN + c) * 2 + 1];
           const double mean = s0 * inv_len;
           const double var = fmax(s1 * inv_len - mean * mean, 0.0);
-          const float rstd = (float)(1.0 / sqrt(var + (double)p.in_eps));
+          // mean / variance need fp64 (sumsq / L - mean^2 cancels); the reciprocal square root does not
+          const float rstd = 1.0f / sqrtf((float)(var + (double)p.in_eps));
           if (k & 1) {
             sc[k >> 1].y = rstd;
             sh[k >> 1].y = (float)(-mean) * rstd;
@@ -423,8 +447,10 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
       }
       const int o0 = (tile - b * tiles_per_sample) * POS;
       const int i0 = o0 * STRIDE - 1;
+      if (tt == 0 && tile == tile_begin) dbg_ts(p, 3);
       mbar_wait(&raw_full[rs], rph);
       mbar_wait(&a_empty[as], aph ^ 1);
+      if (tt == 0 && tile == tile_begin) dbg_ts(p, 4);
       const uint32_t raw = smem_u32(sRaw + rs * Cfg::RAW_BYTES);
       const uint32_t adst = smem_u32(sA + as * Cfg::A_BYTES) + (uint32_t)cch * RP * 16;
       const bool interior = (i0 >= 0) && (i0 + R <= p.L_in);  // no zero-padding rows in this tile
@@ -493,7 +519,8 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
         sts128(adst + soff, o);
         if (SPLIT) sts128(adst + Cfg::A_ONE + soff, olo);
       };
-      if (interior) {
+      if (p.debug_flags & 32) {
+      } else if (interior) {
 #pragma unroll 2
         for (int id = tt; id < R * CH; id += NTT) chunk(id, true);
       } else {
@@ -504,6 +531,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
       }
       fence_proxy_async_smem();
       __syncwarp();
+      if (tt == 0 && tile == tile_begin) dbg_ts(p, 5);
       if (lane == 0) {
         mbar_arrive(&a_full[as]);
         mbar_arrive(&raw_empty[rs]);
@@ -522,7 +550,14 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   // ---------------- teardown ----------------
   tc_fence_before_sync();
   __syncthreads();
+  if (tid == 0) dbg_ts(p, 9);
   if (warp == 0) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (tid == 0) dbg_ts(p, 10);
+  if ((p.debug_flags & 64) && tid == 0 && blockIdx.x < 512) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_stream_cta_ts[2 * blockIdx.x + 1] = t;
+  }
 }
 
 template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, int MT, int NR, int NA, int NTW, bool WIN = false, bool WOUT = false>
