@@ -364,7 +364,7 @@ def time_train_step(model, dev, world, rank, barrier, max_over_ranks, lib, steps
     return {"ms_per_step": ms, "nights_per_gpu": BATCH, "n_gpus": world, "steps": steps, "warmup": warmup,
             "last_loss": float(loss), "gpu_launches_per_step": int((lib.w2s_launch_count() - l0) / steps),
             "masker": "config cardiorespiratory/all.yaml (ABD .7, THX .7, ECG .5, PPG .1; backups ECG, PPG)",
-            "dropout": 0.0, "optimizer": "fused clip(1.0) + AdamW(lr 1e-3, wd 1e-4)"}
+            "dropout": float(model.epoch_mixer.dropout), "optimizer": "fused clip(1.0) + AdamW(lr 1e-3, wd 1e-4)"}
 
 
 def main():
