@@ -95,6 +95,17 @@ typedef struct w2s_conv_call {
 } w2s_conv_call;
 
 int w2s_conv1d_fwd(const w2s_conv_call* call, void* stream);
+/* ---------------------------------------------------------------------------------------------------------
+ * Input staging.  Replaces ParquetDataset._zscore_normalize (data/dataset.py:76-87) and the -inf fill
+ * of missing signals (:170-173) for a batch of raw nights already copied to the device:
+ *   out[b] = (raw[b] - mean_b) / max(std_b, 1e-6)   (std unbiased as torch.std; nights holding a non-finite sample are
+ *   passed through unchanged; nights with present[b] == 0 become rows of -inf).
+ * raw: [B, T] of raw_dtype 0 = fp32, 1 = fp16, 2 = int16 (ADC counts); out: fp32 [B, T]; ws: [B, 3] doubles of scratch
+ * (zeroed by the call; holds sum, sumsq, non-finite flag afterwards); T % 4 == 0.
+ * ------------------------------------------------------------------------------------------------------- */
+int w2s_stage_zscore(const void* raw, int raw_dtype, float* out, const uint8_t* present, double* ws, int B, int64_t T,
+                     void* stream);
+
 /* Profiling aid: with W2S_DEBUG_FLAGS & 64 in the environment, CTA 0 of the streaming conv kernel records %globaltimer
  * (ns) at its pipeline milestones and every CTA its entry / exit time; this copies the 16 milestone slots and
  * (optionally) the [512][2] entry/exit table of the last launch to the host (synchronises). */

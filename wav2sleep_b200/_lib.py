@@ -141,6 +141,7 @@ SYMBOLS = {
     "w2s_gelu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "w2s_colsum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong,
                              C.c_void_p]),
+    "w2s_stage_zscore": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
     "w2s_debug_timestamps": (C.c_int, [C.c_void_p, C.c_void_p]),
     "w2s_dropout": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_float, C.c_uint64, C.c_uint32, C.c_void_p]),
     "w2s_attn_fwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_float, C.c_uint64, C.c_uint32, C.c_void_p]),

@@ -19,6 +19,7 @@
 #include "gemm_tn.cuh"
 #include "train_kernels.cuh"
 #include "check_fp32.cuh"
+#include "staging.cuh"
 
 using namespace w2s;
 
@@ -380,6 +381,36 @@ int w2s_pack_linear_frag(const float* w, int n, int k, void* out, void* stream) 
   pack_frag_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, n, k, (__half*)out);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "pack_frag");
+}
+
+int w2s_stage_zscore(const void* raw, int raw_dtype, float* out, const uint8_t* present, double* ws, int B, int64_t T,
+                     void* stream) {
+  if (raw == nullptr || out == nullptr || ws == nullptr) return fail("stage_zscore: null pointer");
+  if (B <= 0 || B > 65535 || T <= 0 || T % 4 != 0) return fail("stage_zscore: B=%d T=%lld (T must be a multiple of 4)", B, (long long)T);
+  if (raw_dtype < 0 || raw_dtype > 2) return fail("stage_zscore: raw_dtype=%d (0 fp32, 1 fp16, 2 int16)", raw_dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)B * 3 * sizeof(double), st);
+  if (e != cudaSuccess) return cuda_fail(e, "stage_zscore memset");
+  StageArgs a{raw, out, present, ws, (long long)T};
+  long long gx = (T / 4 + 255) / 256;
+  const long long cap = 8LL * sm_count() / B + 1;
+  if (gx > cap) gx = cap;
+  const dim3 grid((unsigned)gx, B);
+  const double esz = raw_dtype == 0 ? 4.0 : 2.0;
+  {
+    LaunchScope scope(st, "stage_stats", (double)B * T * esz, 0);
+    if (raw_dtype == 0) stage_stats_kernel<STAGE_F32><<<grid, 256, 0, st>>>(a);
+    else if (raw_dtype == 1) stage_stats_kernel<STAGE_F16><<<grid, 256, 0, st>>>(a);
+    else stage_stats_kernel<STAGE_I16><<<grid, 256, 0, st>>>(a);
+  }
+  {
+    LaunchScope scope(st, "stage_apply", (double)B * T * (esz + 4.0), 0);
+    if (raw_dtype == 0) stage_apply_kernel<STAGE_F32><<<grid, 256, 0, st>>>(a);
+    else if (raw_dtype == 1) stage_apply_kernel<STAGE_F16><<<grid, 256, 0, st>>>(a);
+    else stage_apply_kernel<STAGE_I16><<<grid, 256, 0, st>>>(a);
+  }
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "stage_zscore launch");
 }
 
 int w2s_debug_timestamps(uint64_t* out16, uint64_t* cta1024) {

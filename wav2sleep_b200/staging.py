@@ -1,0 +1,68 @@
+"""Input staging on the device.
+
+The reference z-scores every night on the CPU inside ``ParquetDataset.__getitem__`` (data/dataset.py:76-87) and fills
+missing signals with ``-inf`` (:170-173) before the batch is moved to the GPU.  Here the raw samples (fp32, fp16 or int16
+ADC counts) are copied as they are and normalised by ``w2s_stage_zscore`` on the device; with int16 transport the
+host->device bytes of a cardio night drop from 12.3 MB to 6.1 MB.
+"""
+from __future__ import annotations
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from .model import COLS_TO_SAMPLES_PER_EPOCH
+
+_DTYPES = {torch.float32: 0, torch.float16: 1, torch.int16: 2}
+
+
+def zscore_on_device(raw: Tensor, present: Tensor | None = None) -> Tensor:
+    """[B, T] raw nights on a CUDA device (fp32 / fp16 / int16) -> z-scored fp32 [B, T]; present[b] == False -> -inf row."""
+    if raw.dim() != 2:
+        raise ValueError(f"expected [B, T], got {tuple(raw.shape)}")
+    if not raw.is_cuda:
+        raise RuntimeError("zscore_on_device needs a CUDA tensor (there is no CPU fallback)")
+    if raw.dtype not in _DTYPES:
+        raise TypeError(f"raw dtype {raw.dtype} not supported (float32, float16, int16)")
+    lib = _lib.load()
+    raw = raw.contiguous()
+    B, T = raw.shape
+    out = torch.empty(B, T, dtype=torch.float32, device=raw.device)
+    ws = torch.empty(B, 3, dtype=torch.float64, device=raw.device)
+    pm = None
+    if present is not None:
+        pm = present.to(device=raw.device, dtype=torch.uint8).contiguous()
+        if pm.numel() != B:
+            raise ValueError("present must have one entry per night")
+    with torch.cuda.device(raw.device):
+        _lib.check(lib.w2s_stage_zscore(raw.data_ptr(), _DTYPES[raw.dtype], out.data_ptr(),
+                                        None if pm is None else pm.data_ptr(), ws.data_ptr(), B, T,
+                                        torch.cuda.current_stream().cuda_stream), ValueError)
+    return out
+
+
+def stage_batch(raw: dict[str, Tensor], device, n_epochs: int | None = None, columns=None) -> dict[str, Tensor]:
+    """Host (ideally pinned) raw batch {signal: [B, T_sig]} -> model inputs on ``device``.
+
+    Signals listed in ``columns`` but absent from ``raw`` become ``-inf`` tensors of the right length, like the
+    reference dataset does for missing parquet columns (``n_epochs`` inferred from the present signals)."""
+    out = {}
+    for name, t in raw.items():
+        if name not in COLS_TO_SAMPLES_PER_EPOCH:
+            raise ValueError(f"Column {name} unrecognised.")  # data/dataset.py:68-69
+        spe = COLS_TO_SAMPLES_PER_EPOCH[name]
+        if t.size(1) % spe:
+            raise ValueError(f"{name}: length {t.size(1)} is not a whole number of epochs")
+        ep = t.size(1) // spe
+        if n_epochs is None:
+            n_epochs = ep
+        elif ep != n_epochs:
+            raise ValueError(f"prev_inferred_recording_length_epochs={n_epochs} != inferred_recording_length_epochs={ep}")
+        out[name] = zscore_on_device(t.to(device, non_blocking=True))
+    if not out:
+        raise ValueError("No relevant columns found.")
+    B = next(iter(out.values())).size(0)
+    for name in columns or ():
+        if name not in out:
+            out[name] = torch.full((B, n_epochs * COLS_TO_SAMPLES_PER_EPOCH[name]), float("-inf"), device=device)
+    return out
