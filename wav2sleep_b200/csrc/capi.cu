@@ -221,14 +221,14 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
 #define W2S_STREAM(CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW) \
   W2S_STREAMW(CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW, false, false)
     //          cin cout s  prologue      ds    MT NR NA NTW
-    W2S_STREAM(16, 16, 1, PRO_FIR, false, 4, 3, 2, 18)
-    W2S_STREAM(16, 16, 1, PRO_NORM_RES_X, true, 4, 3, 2, 14)
-    W2S_STREAM(16, 16, 1, PRO_NORM, false, 4, 3, 2, 18)
-    W2S_STREAM(16, 16, 2, PRO_NORM, false, 2, 3, 2, 18)
+    W2S_STREAM(16, 16, 1, PRO_FIR, false, 8, 3, 2, 18)
+    W2S_STREAM(16, 16, 1, PRO_NORM_RES_X, true, 8, 2, 2, 14)
+    W2S_STREAM(16, 16, 1, PRO_NORM, false, 8, 2, 2, 18)
+    W2S_STREAM(16, 16, 2, PRO_NORM, false, 4, 2, 2, 18)
     W2S_STREAM(16, 16, 1, PRO_NORM_RES, true, 4, 3, 2, 14)
     W2S_STREAM(16, 32, 1, PRO_NORM_RES, true, 4, 3, 2, 10)
-    W2S_STREAM(32, 32, 1, PRO_NORM, false, 2, 3, 2, 10)
-    W2S_STREAM(32, 32, 2, PRO_NORM, false, 1, 3, 2, 10)
+    W2S_STREAM(32, 32, 1, PRO_NORM, false, 4, 2, 2, 10)
+    W2S_STREAM(32, 32, 2, PRO_NORM, false, 2, 2, 2, 10)
     W2S_STREAM(32, 32, 1, PRO_NORM_RES, true, 2, 3, 2, 10)
     W2S_STREAM(32, 64, 1, PRO_NORM_RES, true, 2, 3, 2, 14)
     W2S_STREAM(64, 64, 1, PRO_NORM, false, 2, 3, 2, 14)

@@ -6,7 +6,7 @@
 //
 //   warp 0 (1 lane)  : producer   - one cp.async.bulk (TMA, 1-D) per tile: the tile's input rows are one
 //                                   contiguous byte range of the channels-last tensor -> raw ring in smem
-//   warps 6..6+NTW-1 : transform  - raw fp16 -> InstanceNorm (whole-night stats of the producer layer) -> GELU
+//   warps 2+E..      : transform  - raw fp16 -> InstanceNorm (whole-night stats of the producer layer) -> GELU
 //                                   [-> + residual branch -> GELU] -> fp16 (hi [+ lo]) in UMMA chunk-major layout
 //   warp 1 (1 lane)  : MMA issuer - tcgen05.mma per 128-row sub-tile and tap into a double-buffered TMEM stage
 //   warps 2..5       : epilogue   - tcgen05.ld, fp16 store, sum / sum-of-squares kept in registers across tiles and
@@ -28,8 +28,31 @@ W2S_DEVINL void dbg_ts(const ConvArgs& p, int slot) {
   }
 }
 
-constexpr int kStreamFirstTransformWarp = 6;  // warp 0 producer, 1 MMA, 2..5 epilogue, 6.. transform
-constexpr int stream_threads(int ntw) { return 32 * (kStreamFirstTransformWarp + ntw); }
+// debug_flags & 64: cycles a role spends blocked in mbarrier waits (slot 11 producer, 12 MMA, 13 epilogue warp 2,
+// 14 transform warp 0, 15 = total cycles of the CTA), to see which stage the pipeline is waiting for.
+struct WaitClock {
+  long long acc = 0;
+  W2S_DEVINL void wait(const ConvArgs& p, uint64_t* bar, uint32_t parity) {
+    if (p.debug_flags & 64) {
+      const long long t0 = clock64();
+      mbar_wait(bar, parity);
+      acc += clock64() - t0;
+    } else {
+      mbar_wait(bar, parity);
+    }
+  }
+  W2S_DEVINL void publish(const ConvArgs& p, int slot) const {
+    if ((p.debug_flags & 64) && blockIdx.x == 0) g_stream_ts[slot] = (unsigned long long)acc;
+  }
+};
+
+// warp 0 producer, 1 MMA, 2..2+E-1 epilogue, then transform.  E = 4 or 8: with 8, two warps share each TMEM lane
+// quadrant (a warp may only read the quadrant warp_id % 4) and split the (column group, sub-tile) items.  Measured for
+// COUT >= 64, where the epilogue is the busiest stage (93 %): no gain - it is bound by the LSU wavefronts of its
+// row-per-lane stores (32 lines per STG), not by warp count - so E stays 4.
+constexpr int stream_epi_warps(int /*cout*/) { return 4; }
+constexpr int stream_first_transform_warp(int cout) { return 2 + stream_epi_warps(cout); }
+constexpr int stream_threads(int ntw, int cout) { return 32 * (stream_first_transform_warp(cout) + ntw); }
 
 W2S_DEVINL void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -79,7 +102,9 @@ struct StreamCfg {
   static constexpr int POS = 128 * MT;
   static constexpr int R = (POS - 1) * STRIDE + 3;            // input rows per tile (with halo)
   static constexpr int RP = stream_rpad((R + STRIDE - 1) / STRIDE, CH, STRIDE);  // rows per stride phase (padded)
-  static constexpr int THREADS = stream_threads(NTW);
+  static constexpr int THREADS = stream_threads(NTW, COUT);
+  static constexpr int EPI_WARPS = stream_epi_warps(COUT);
+  static constexpr int FIRST_TW = stream_first_transform_warp(COUT);
   // raw ring entry: [y rows (fp16)] [residual rows (fp16) | raw-signal floats for the block-0 fusion modes]
   static constexpr int XN = (PRO == PRO_FIR) ? R + 12 : (PRO == PRO_NORM_RES_X) ? 2 * R + 12 : 0;  // staged x floats
   static constexpr int RAW_ONE = (PRO == PRO_FIR) ? 0 : (R * CIN * ESZ + 127) / 128 * 128;
@@ -99,12 +124,14 @@ struct StreamCfg {
 };
 
 template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, bool SPLIT, int MT, int NR, int NA, int NTW, bool WIN, bool WOUT>
-__global__ void __launch_bounds__(stream_threads(NTW), (stream_threads(NTW) <= 384 ? 2 : 1))
+__global__ void __launch_bounds__(stream_threads(NTW, COUT), (stream_threads(NTW, COUT) <= 384 ? 2 : 1))
 conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   using Cfg = StreamCfg<CIN, COUT, STRIDE, PRO, HAS_DS, SPLIT, MT, NR, NA, NTW, WIN, WOUT>;
   constexpr int ESZ = Cfg::ESZ;
   constexpr int kStreamThreads = Cfg::THREADS;
   constexpr int kStreamTransformWarps = NTW;
+  constexpr int kStreamFirstTransformWarp = Cfg::FIRST_TW;
+  constexpr int EPI_SPLIT = Cfg::EPI_WARPS / 4;  // epilogue warps per TMEM lane quadrant
   constexpr int CH = Cfg::CH, POS = Cfg::POS, R = Cfg::R, RP = Cfg::RP;
   constexpr int KSTEPS = CIN / 16;
   constexpr int NCG = COUT / 16;
@@ -148,7 +175,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&t_full[s], 1);
-      mbar_init(&t_empty[s], 4);
+      mbar_init(&t_empty[s], Cfg::EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -183,6 +210,8 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
     {
       int s = 0;
       uint32_t ph = 0;
+      WaitClock wc;
+      const long long cta_t0 = clock64();
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         const int b = tile / tiles_per_sample;
         if (p.row_mask != nullptr && p.row_mask[b]) continue;
@@ -199,7 +228,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
         int xhi = xs0 + Cfg::XN;
         xhi = (xhi > p.T_raw ? p.T_raw : xhi) & ~3;
         const uint32_t xbytes = (Cfg::XN > 0 && xhi > xlo) ? (uint32_t)(xhi - xlo) * 4 : 0u;
-        mbar_wait(&raw_empty[s], ph ^ 1);
+        wc.wait(p, &raw_empty[s], ph ^ 1);
         uint8_t* dst = sRaw + s * Cfg::RAW_BYTES + (size_t)(lo - i0) * CIN * ESZ;
         const size_t goff = ((size_t)b * p.L_in + lo) * CIN * ESZ;  // byte offset
         if (elect_one()) {
@@ -217,19 +246,24 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
           ph ^= 1;
         }
       }
+      if (lane == 0) {
+        wc.publish(p, 11);
+        if ((p.debug_flags & 64) && blockIdx.x == 0) g_stream_ts[15] = (unsigned long long)(clock64() - cta_t0);
+      }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer (warp-uniform loop; one elected lane issues) ----------------
     {
       int as = 0, ts = 0;
       uint32_t aph = 0, tph = 0;
+      WaitClock wc;
       const uint32_t b_base = smem_u32(sB);
       constexpr uint32_t lbo_a = RP * 16, lbo_b = COUT * 16;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         const int b = tile / tiles_per_sample;
         if (p.row_mask != nullptr && p.row_mask[b]) continue;
-        mbar_wait(&a_full[as], aph);
-        mbar_wait(&t_empty[ts], tph ^ 1);
+        wc.wait(p, &a_full[as], aph);
+        wc.wait(p, &t_empty[ts], tph ^ 1);
         tc_fence_after_sync();
         const uint32_t a_base = smem_u32(sA + as * Cfg::A_BYTES);
         const uint32_t d_base = tmem_base + ts * Cfg::STAGE_COLS;
@@ -248,8 +282,10 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
               const uint64_t db = umma_smem_desc(b_base + b_off, lbo_b, 128);
               if (!(p.debug_flags & 2)) umma_f16(d_base + j * COUT, da, db, IDESC, (t > 0 || kk > 0) ? 1u : 0u);
               if (SPLIT && !(p.debug_flags & 3)) {
-                umma_f16(d_base + j * COUT, umma_smem_desc(a_base + Cfg::A_ONE + a_off, lbo_a, 128), db, IDESC, 1u);
-                umma_f16(d_base + j * COUT, da, umma_smem_desc(b_base + Cfg::B_ONE + b_off, lbo_b, 128), IDESC, 1u);
+                if (!(p.debug_flags & 128))
+                  umma_f16(d_base + j * COUT, umma_smem_desc(a_base + Cfg::A_ONE + a_off, lbo_a, 128), db, IDESC, 1u);
+                if (!(p.debug_flags & 256))
+                  umma_f16(d_base + j * COUT, da, umma_smem_desc(b_base + Cfg::B_ONE + b_off, lbo_b, 128), IDESC, 1u);
               }
             }
           }
@@ -263,8 +299,10 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
               const uint64_t db = umma_smem_desc(b_base + b_off, lbo_b, 128);
               umma_f16(d_base + (MT + j) * COUT, da, db, IDESC, kk > 0 ? 1u : 0u);
               if (SPLIT) {
-                umma_f16(d_base + (MT + j) * COUT, umma_smem_desc(a_base + Cfg::A_ONE + a_off, lbo_a, 128), db, IDESC, 1u);
-                umma_f16(d_base + (MT + j) * COUT, da, umma_smem_desc(b_base + Cfg::B_ONE + b_off, lbo_b, 128), IDESC, 1u);
+                if (!(p.debug_flags & 128))
+                  umma_f16(d_base + (MT + j) * COUT, umma_smem_desc(a_base + Cfg::A_ONE + a_off, lbo_a, 128), db, IDESC, 1u);
+                if (!(p.debug_flags & 256))
+                  umma_f16(d_base + (MT + j) * COUT, da, umma_smem_desc(b_base + Cfg::B_ONE + b_off, lbo_b, 128), IDESC, 1u);
               }
             }
           }
@@ -282,14 +320,17 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
           tph ^= 1;
         }
       }
+      if (lane == 0) wc.publish(p, 12);
     }
   } else if (warp < kStreamFirstTransformWarp) {
     // ---------------- epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) ----------------
     const int quad = warp & 3;
+    const int epi_half = (warp - 2) >> 2;  // which share of the (column group, sub-tile) items this warp takes
     const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
     int ts = 0;
     uint32_t tph = 0;
     int cur_b = -1;
+    WaitClock wc;
     constexpr int NACC = REG_STATS ? NCG * 16 : NCG;
     float acc[NACC], acc2[NACC];
 #pragma unroll
@@ -327,7 +368,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
         cur_b = b;
       }
       const int o0 = (tile - b * tiles_per_sample) * POS;
-      mbar_wait(&t_full[ts], tph);
+      wc.wait(p, &t_full[ts], tph);
       tc_fence_after_sync();
       if (warp == 2 && lane == 0 && tile == tile_begin) dbg_ts(p, 6);
       const uint32_t d_base = tmem_base + ts * Cfg::STAGE_COLS + t_lane;
@@ -342,6 +383,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
 #pragma unroll 1
         for (int j = 0; j < MT; ++j) {
           float v[16];
+          if (EPI_SPLIT > 1 && ((cg * MT + j) % EPI_SPLIT) != epi_half) continue;
           if (p.debug_flags & 16) continue;
           tmem_ld16(d_base + j * COUT + cg * 16, v);
           const int o = o0 + j * 128 + quad * 32 + lane;
@@ -376,6 +418,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
 #pragma unroll
           for (int cg = 0; cg < NCG; ++cg) {
             float v[16];
+            if (EPI_SPLIT > 1 && ((cg * MT + j) % EPI_SPLIT) != epi_half) continue;
             tmem_ld16(d_base + (MT + j) * COUT + cg * 16, v);
             if (o < p.L_out && (o & 1) == 0) {
               store16<WOUT>(dsb, (size_t)(o >> 1) * COUT + cg * 16, v);
@@ -391,7 +434,10 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
         tph ^= 1;
       }
     }
-    if (warp == 2 && lane == 0) dbg_ts(p, 7);
+    if (warp == 2 && lane == 0) {
+      dbg_ts(p, 7);
+      wc.publish(p, 13);
+    }
     flush(cur_b);
     if (warp == 2 && lane == 0) dbg_ts(p, 8);
   } else {
@@ -402,6 +448,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
     int rs = 0, as = 0;
     uint32_t rph = 0, aph = 0;
     int cur_b = -1;
+    WaitClock wc_raw, wc_a;
     float2 sc[4], sh[4];  // per-channel scale / shift of this thread's 8 channels, as fp32x2 pairs
     float2 fws[4][3];     // PRO_FIR: conv1 taps pre-multiplied by the per-sample InstanceNorm scale
     float2 fw[4][3];      // block-0 fusion modes: conv1 taps (PRO_FIR) / downsample weight in [.][0] (PRO_NORM_RES_X)
@@ -448,8 +495,8 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
       const int o0 = (tile - b * tiles_per_sample) * POS;
       const int i0 = o0 * STRIDE - 1;
       if (tt == 0 && tile == tile_begin) dbg_ts(p, 3);
-      mbar_wait(&raw_full[rs], rph);
-      mbar_wait(&a_empty[as], aph ^ 1);
+      wc_raw.wait(p, &raw_full[rs], rph);
+      wc_a.wait(p, &a_empty[as], aph ^ 1);
       if (tt == 0 && tile == tile_begin) dbg_ts(p, 4);
       const uint32_t raw = smem_u32(sRaw + rs * Cfg::RAW_BYTES);
       const uint32_t adst = smem_u32(sA + as * Cfg::A_BYTES) + (uint32_t)cch * RP * 16;
@@ -478,12 +525,20 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
             if (WIN) r2 = lds128(raw + Cfg::RAW_ONE + (uint32_t)id * 32 + 16);
           }
           float xm = 0.0f, x0 = 0.0f, xp = 0.0f;
+          auto fin = [](float v) { return isinf(v) ? 0.0f : v; };  // the reference's -inf -> 0 rule, element-wise
           if (PRO == PRO_FIR) {
-            xm = xat(i0 + u - 1);
-            x0 = xat(i0 + u);
-            xp = xat(i0 + u + 1);
+            if (x_interior) {  // whole window staged: no per-element bounds checks
+              const float* xp3 = xraw + (i0 + u - 1 - xs0);
+              xm = fin(xp3[0]);
+              x0 = fin(xp3[1]);
+              xp = fin(xp3[2]);
+            } else {
+              xm = xat(i0 + u - 1);
+              x0 = xat(i0 + u);
+              xp = xat(i0 + u + 1);
+            }
           } else if (PRO == PRO_NORM_RES_X) {
-            x0 = xat(2 * (i0 + u));
+            x0 = x_interior ? fin(xraw[2 * (i0 + u) - xs0]) : xat(2 * (i0 + u));
           }
           const uint32_t yy[8] = {y.x, y.y, y.z, y.w, y2.x, y2.y, y2.z, y2.w};
           const uint32_t rr[8] = {r.x, r.y, r.z, r.w, r2.x, r2.y, r2.z, r2.w};
@@ -545,6 +600,10 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
         aph ^= 1;
       }
     }
+    if (tt == 0) {
+      wc_a.publish(p, 14);
+      if ((p.debug_flags & 64) && blockIdx.x == 0) g_stream_ts[10] = (unsigned long long)wc_raw.acc;
+    }
   }
 
   // ---------------- teardown ----------------
@@ -552,7 +611,6 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   __syncthreads();
   if (tid == 0) dbg_ts(p, 9);
   if (warp == 0) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-  if (tid == 0) dbg_ts(p, 10);
   if ((p.debug_flags & 64) && tid == 0 && blockIdx.x < 512) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
