@@ -59,6 +59,14 @@ W2S_DEVINL bool elect_one() {
   return pred != 0;
 }
 
+// 256-bit global store (STG.256, sm_100+): one instruction per 32-byte row chunk halves the LSU wavefronts of the
+// row-per-lane epilogue stores.  Address must be 32-byte aligned.
+W2S_DEVINL void stg256(void* ptr, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // fences
 // ----------------------------------------------------------------------------------------------

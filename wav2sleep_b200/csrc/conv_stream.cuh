@@ -72,13 +72,17 @@ W2S_DEVINL void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, u
 template <bool WIDE>
 W2S_DEVINL void store16(uint8_t* base, size_t elem, const float (&v)[16]) {
   if (WIDE) {
-    float4* dst = reinterpret_cast<float4*>(base + elem * 4);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    for (int h = 0; h < 2; ++h) {
+      uint32_t w[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) w[k] = __float_as_uint(v[8 * h + k]);
+      stg256(base + elem * 4 + 32 * h, w);
+    }
   } else {
-    uint4* dst = reinterpret_cast<uint4*>(base + elem * 2);
-    dst[0] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-    dst[1] = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+    const uint32_t w[8] = {pack_h2(v[0], v[1]),   pack_h2(v[2], v[3]),   pack_h2(v[4], v[5]),   pack_h2(v[6], v[7]),
+                           pack_h2(v[8], v[9]),   pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15])};
+    stg256(base + elem * 2, w);
   }
 }
 
