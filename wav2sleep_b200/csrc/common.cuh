@@ -67,6 +67,9 @@ W2S_DEVINL void stg256(void* ptr, const uint32_t (&v)[8]) {
                : "memory");
 }
 
+// 16 consecutive fp16 channels of one row (32-byte aligned) in one store
+W2S_DEVINL void store_h16(__half* dst, const float (&v)[16]);
+
 // ----------------------------------------------------------------------------------------------
 // fences
 // ----------------------------------------------------------------------------------------------
@@ -217,6 +220,12 @@ W2S_DEVINL uint32_t pack_h2(float lo, float hi) {
 W2S_DEVINL float2 unpack_h2(uint32_t u) {
   __half2 h = *reinterpret_cast<__half2*>(&u);
   return __half22float2(h);
+}
+
+W2S_DEVINL void store_h16(__half* dst, const float (&v)[16]) {
+  const uint32_t w[8] = {pack_h2(v[0], v[1]),   pack_h2(v[2], v[3]),   pack_h2(v[4], v[5]),   pack_h2(v[6], v[7]),
+                         pack_h2(v[8], v[9]),   pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15])};
+  stg256(dst, w);
 }
 
 // Transposing butterfly reduction over the 32 lanes of a warp for 16 per-lane values.

@@ -325,12 +325,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs
       const int o = o0 + j * 128 + quad * 32 + lane;
       const bool valid = o < p.L_out;
       if (valid) {
-        uint4 s0 = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-        uint4 s1 =
-            make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
-        uint4* dst = reinterpret_cast<uint4*>(outb + (size_t)o * COUT + cg * 16);
-        dst[0] = s0;
-        dst[1] = s1;
+        store_h16(outb + (size_t)o * COUT + cg * 16, v);
       }
       float sq[16];
 #pragma unroll
@@ -356,12 +351,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs
         tmem_ld16(tmem_base + t_lane + 128 + j * COUT + cg * 16, v);
         const int o = o0 + j * 128 + quad * 32 + lane;
         if (o < p.L_out && (o & 1) == 0) {
-          uint4 s0 = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-          uint4 s1 =
-              make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
-          uint4* dst = reinterpret_cast<uint4*>(dsb + (size_t)(o >> 1) * COUT + cg * 16);
-          dst[0] = s0;
-          dst[1] = s1;
+          store_h16(dsb + (size_t)(o >> 1) * COUT + cg * 16, v);
         }
       }
     }
@@ -409,9 +399,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs
             v[2 * k + 1] += r2.y;
           }
         }
-        uint4* dst = reinterpret_cast<uint4*>(p.out + off);
-        dst[0] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-        dst[1] = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+        store_h16(p.out + off, v);
       }
     }
   } else if (EPI == EPI_BIAS_GELU) {
@@ -424,12 +412,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs
       if (o < p.L_out) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) v[k] = gelu_erf(v[k] + __ldg(p.bias + cg * 16 + k));
-        uint4 s0 = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-        uint4 s1 =
-            make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
-        uint4* dst = reinterpret_cast<uint4*>(outb + (size_t)o * COUT + cg * 16);
-        dst[0] = s0;
-        dst[1] = s1;
+        store_h16(outb + (size_t)o * COUT + cg * 16, v);
       }
     }
   } else {  // EPI_LN_GELU / EPI_LN_GELU_RES : thread owns one row of all 128 channels
@@ -496,12 +479,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs
           }
         }
         if (valid) {
-          uint4 s0 = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-          uint4 s1 =
-              make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
-          uint4* dst = reinterpret_cast<uint4*>(p.out + rowoff + cg * 16);
-          dst[0] = s0;
-          dst[1] = s1;
+          store_h16(p.out + rowoff + cg * 16, v);
         }
       }
       if (EPI == EPI_LN_GELU_RES && p.head_w != nullptr && valid) {

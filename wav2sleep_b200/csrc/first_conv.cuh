@@ -64,15 +64,11 @@ __global__ void __launch_bounds__(kFirstConvThreads) first_conv_kernel(const Fir
         acc[c] += v[c];
         acc2[c] = fmaf(v[c], v[c], acc2[c]);
       }
-      uint4* dst = reinterpret_cast<uint4*>(p.y1 + ((size_t)b * p.T + pos) * 16);
-      dst[0] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-      dst[1] = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+      store_h16(p.y1 + ((size_t)b * p.T + pos) * 16, v);
       if ((pos & 1) == 0) {
 #pragma unroll
         for (int c = 0; c < 16; ++c) v[c] = sw[48 + c] * x0;
-        uint4* dr = reinterpret_cast<uint4*>(p.r0 + ((size_t)b * (p.T >> 1) + (pos >> 1)) * 16);
-        dr[0] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
-        dr[1] = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+        store_h16(p.r0 + ((size_t)b * (p.T >> 1) + (pos >> 1)) * 16, v);
       }
     }
   }
