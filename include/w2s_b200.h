@@ -220,9 +220,10 @@ int w2s_gemm_tn(const void* X, const void* Y, float* C, int M, int N, int taps, 
 int w2s_enc_act_fwd(const void* y, const void* r, const double* stats, void* a, const uint8_t* row_mask, int B, int L, int C,
                     float eps, void* stream);
 /* backward through GELU (and the block's residual add + GELU when r != NULL); writes d(x_hat), dr and accumulates the
- * two whole-night reductions of the InstanceNorm backward into sums[B, C, 2] (fp64, caller-zeroed). */
+ * two whole-night reductions of the InstanceNorm backward into sums[B, C, 2] (fp64, caller-zeroed).  a_out != NULL: also
+ * writes the activated tensor itself (= w2s_enc_act_fwd's output) for the weight gradient of the consuming conv. */
 int w2s_enc_act_bwd(const void* dout, const void* y, const void* r, const double* stats, void* dxh, void* dr, double* sums,
-                    const uint8_t* row_mask, int B, int L, int C, float eps, void* stream);
+                    void* a_out, const uint8_t* row_mask, int B, int L, int C, float eps, void* stream);
 /* dy = rstd * (dxh - mean(dxh) - x_hat * mean(dxh * x_hat)); upsample = 1 writes row 2l of a zeroed [B, 2L, C] tensor. */
 int w2s_enc_norm_bwd(const void* dxh, const void* y, const double* stats, const double* sums, void* dy,
                      const uint8_t* row_mask, int B, int L, int C, int upsample, float eps, void* stream);

@@ -132,7 +132,7 @@ SYMBOLS = {
                               C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_longlong, C.c_float, C.c_void_p,
                               C.c_void_p]),
     "w2s_enc_act_fwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
-    "w2s_enc_act_bwd": (C.c_int, [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "w2s_enc_act_bwd": (C.c_int, [C.c_void_p] * 9 + [C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "w2s_enc_norm_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "w2s_first_conv_wgrad": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p]),
     "w2s_row_ln_fwd": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_int, C.c_float, C.c_void_p]),

@@ -770,12 +770,12 @@ int w2s_enc_act_fwd(const void* y, const void* r, const double* stats, void* a, 
 }
 
 int w2s_enc_act_bwd(const void* dout, const void* y, const void* r, const double* stats, void* dxh, void* dr, double* sums,
-                    const uint8_t* row_mask, int B, int L, int Cc, float eps, void* stream) {
+                    void* a_out, const uint8_t* row_mask, int B, int L, int Cc, float eps, void* stream) {
   if (!dout || !y || !stats || !dxh || !sums || Cc % 8 || 256 % (Cc / 8)) return fail("enc_act_bwd: bad arguments");
   if (r && !dr) return fail("enc_act_bwd: dr missing");
   EncActBwdArgs p{(const act_t*)dout, (const act_t*)y, (const act_t*)r, stats, (act_t*)dxh, (act_t*)dr, sums, row_mask,
-                  B, L, Cc, eps};
-  LaunchScope scope((cudaStream_t)stream, "enc_act_bwd", (double)B * L * Cc * (r ? 10.0 : 6.0), 0);
+                  B, L, Cc, eps, (act_t*)a_out};
+  LaunchScope scope((cudaStream_t)stream, "enc_act_bwd", (double)B * L * Cc * ((r ? 10.0 : 6.0) + (a_out ? 2.0 : 0.0)), 0);
   const int rows_per_block = 256 / (Cc / 8);
   int gx = (L + rows_per_block * 8 - 1) / (rows_per_block * 8);
   if (gx > 4 * sm_count()) gx = 4 * sm_count();

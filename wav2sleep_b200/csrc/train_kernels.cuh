@@ -121,6 +121,7 @@ struct EncActBwdArgs {
   const act_t* dout; const act_t* y; const act_t* r; const double* stats;
   act_t* dxh; act_t* dr; double* sums; const uint8_t* row_mask;
   int B, L, C; float eps;
+  act_t* a_out;  // optional: the activated tensor itself (what enc_act_fwd would write), for the weight gradient
 };
 __global__ void __launch_bounds__(256) enc_act_bwd_kernel(const EncActBwdArgs p) {
   const int b = blockIdx.y;
@@ -148,16 +149,23 @@ __global__ void __launch_bounds__(256) enc_act_bwd_kernel(const EncActBwdArgs p)
     for (int k = 0; k < 8; ++k) {
       const float xh = (v[k] - mean[k]) * rstd[k];
       float g = d[k];
+      float a = 0.0f;
       if (p.r) {
-        g *= gelu_grad_tanh(gelu_tanh(xh) + rr[k]);
+        const float s = gelu_tanh(xh) + rr[k];
+        if (p.a_out) a = gelu_tanh(s);
+        g *= gelu_grad_tanh(s);
         rr[k] = g;  // dr
+      } else if (p.a_out) {
+        a = gelu_tanh(xh);
       }
       g *= gelu_grad_tanh(xh);
       d[k] = g;
+      v[k] = a;
       s0[k] += g;
       s1[k] = fmaf(g, xh, s1[k]);
     }
     *reinterpret_cast<uint4*>(p.dxh + off) = pack8(d);
+    if (p.a_out) *reinterpret_cast<uint4*>(p.a_out + off) = pack8(v);
     if (p.r) *reinterpret_cast<uint4*>(p.dr + off) = pack8(rr);
   }
   // block reduction over the threads that share a channel chunk

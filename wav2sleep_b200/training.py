@@ -452,65 +452,75 @@ class TrainEngine(ForwardEngine):
                       row_mask=mask)
         self.colsum(d_zpre, G(enc.linear.bias), B * S, 128, row_mask=mask, rows_per_sample=S)
         dout = d_a  # gradient wrt the activated output of the last block, [B, L/2, C]
+        # The activated input of a conv (needed by its weight gradient) is written by enc_act_bwd of the producing layer
+        # as a by-product, so weight gradients run one stage late: `pending` holds the conv1 / downsample weight
+        # gradients of the block above until this block's output activation exists.
+        pending = None
         for i in reversed(range(len(blocks))):
             bk, blk = blocks[i], enc.cnn[i]
             Cc, L = bk["C"], bk["L"]
             Lh = L // 2
-            # ---- conv3 (stride 2) + block output ----
+            # ---- block output: GELU(GELU(IN(y3)) + r) ----
             dxh, dr, sums = new(B, Lh, Cc), new(B, Lh, Cc), zeros64(Cc)
+            a_blk = new(B, Lh, Cc) if pending is not None else None
             _lib.check(lib.w2s_enc_act_bwd(dout.data_ptr(), bk["y3"].data_ptr(), bk["r"].data_ptr(), bk["s3"].data_ptr(),
-                                           dxh.data_ptr(), dr.data_ptr(), sums.data_ptr(), mask.data_ptr(), B, Lh, Cc, eps, st))
+                                           dxh.data_ptr(), dr.data_ptr(), sums.data_ptr(), _p(a_blk), mask.data_ptr(), B, Lh,
+                                           Cc, eps, st))
+            if pending is not None:
+                pending(a_blk)
+                pending = None
+            del a_blk
             dy_up = torch.zeros(B, L, Cc, dtype=F16, device=device)
             _lib.check(lib.w2s_enc_norm_bwd(dxh.data_ptr(), bk["y3"].data_ptr(), bk["s3"].data_ptr(), sums.data_ptr(),
                                             dy_up.data_ptr(), mask.data_ptr(), B, Lh, Cc, 1, eps, st))
-            a2 = new(B, L, Cc)
-            _lib.check(lib.w2s_enc_act_fwd(bk["y2"].data_ptr(), None, bk["s2"].data_ptr(), a2.data_ptr(), mask.data_ptr(),
-                                           B, L, Cc, eps, st))
-            dW = G(blk.conv3.conv.weight)
-            self.gemm_tn(dy_up, a2, dW, Cc, Cc, B, L, L, Cc * 3, 3, y_offset=-1, row_mask=mask, taps=3, ldc_t=1)
+            # ---- conv3 (stride 2): data gradient, then (once a2 exists) weight gradient ----
             d_a2 = new(B, L, Cc)
             self.conv(dy_up, tw["conv"][i][2], Cc, Cc, 3, B, L, L, d_a2, pad=1, row_mask=mask)
-            del dy_up, a2, dxh
-            # ---- conv2 ----
-            dxh, sums = new(B, L, Cc), zeros64(Cc)
+            a2, sums = new(B, L, Cc), zeros64(Cc)
+            dxh = new(B, L, Cc)
             _lib.check(lib.w2s_enc_act_bwd(d_a2.data_ptr(), bk["y2"].data_ptr(), None, bk["s2"].data_ptr(), dxh.data_ptr(),
-                                           None, sums.data_ptr(), mask.data_ptr(), B, L, Cc, eps, st))
+                                           None, sums.data_ptr(), a2.data_ptr(), mask.data_ptr(), B, L, Cc, eps, st))
+            self.gemm_tn(dy_up, a2, G(blk.conv3.conv.weight), Cc, Cc, B, L, L, Cc * 3, 3, y_offset=-1, row_mask=mask,
+                         taps=3, ldc_t=1)
+            del dy_up, a2
+            # ---- conv2 ----
             dy2 = d_a2  # reuse
             _lib.check(lib.w2s_enc_norm_bwd(dxh.data_ptr(), bk["y2"].data_ptr(), bk["s2"].data_ptr(), sums.data_ptr(),
                                             dy2.data_ptr(), mask.data_ptr(), B, L, Cc, 0, eps, st))
-            a1 = dxh  # reuse as a1 buffer after dy2 is written? no: dxh is read above only; safe to overwrite now
-            _lib.check(lib.w2s_enc_act_fwd(bk["y1"].data_ptr(), None, bk["s1"].data_ptr(), a1.data_ptr(), mask.data_ptr(),
-                                           B, L, Cc, eps, st))
-            dW = G(blk.conv2.conv.weight)
-            self.gemm_tn(dy2, a1, dW, Cc, Cc, B, L, L, Cc * 3, 3, y_offset=-1, row_mask=mask, taps=3, ldc_t=1)
             d_a1 = new(B, L, Cc)
             self.conv(dy2, tw["conv"][i][1], Cc, Cc, 3, B, L, L, d_a1, pad=1, row_mask=mask)
-            # ---- conv1 (+ 1x1 stride-2 residual branch) ----
-            dxh, sums = a1, zeros64(Cc)
+            a1, sums = new(B, L, Cc), zeros64(Cc)  # dxh (consumed by the norm backward above) is overwritten
             _lib.check(lib.w2s_enc_act_bwd(d_a1.data_ptr(), bk["y1"].data_ptr(), None, bk["s1"].data_ptr(), dxh.data_ptr(),
-                                           None, sums.data_ptr(), mask.data_ptr(), B, L, Cc, eps, st))
+                                           None, sums.data_ptr(), a1.data_ptr(), mask.data_ptr(), B, L, Cc, eps, st))
+            self.gemm_tn(dy2, a1, G(blk.conv2.conv.weight), Cc, Cc, B, L, L, Cc * 3, 3, y_offset=-1, row_mask=mask, taps=3,
+                         ldc_t=1)
+            del a1, dy2, d_a2
+            # ---- conv1 (+ 1x1 stride-2 residual branch) ----
             dy1 = d_a1
             _lib.check(lib.w2s_enc_norm_bwd(dxh.data_ptr(), bk["y1"].data_ptr(), bk["s1"].data_ptr(), sums.data_ptr(),
                                             dy1.data_ptr(), mask.data_ptr(), B, L, Cc, 0, eps, st))
+            del dxh
             if i == 0:
                 _lib.check(lib.w2s_first_conv_wgrad(e["x"].data_ptr(), dy1.data_ptr(), dr.data_ptr(),
                                                     G(blk.conv1.conv.weight).data_ptr(), G(blk.downsample.weight).data_ptr(),
                                                     mask.data_ptr(), B, L, st))
                 break
-            pb = blocks[i - 1]
-            Ci = pb["C"]
-            a_in = new(B, L, Ci)
-            _lib.check(lib.w2s_enc_act_fwd(pb["y3"].data_ptr(), pb["r"].data_ptr(), pb["s3"].data_ptr(), a_in.data_ptr(),
-                                           mask.data_ptr(), B, L, Ci, eps, st))
-            dW = G(blk.conv1.conv.weight)
-            self.gemm_tn(dy1, a_in, dW, Cc, Ci, B, L, L, Ci * 3, 3, y_offset=-1, row_mask=mask, taps=3, ldc_t=1)
-            self.gemm_tn(dr, a_in, G(blk.downsample.weight), Cc, Ci, B, Lh, L, Ci, 1, y_stride=2, y_offset=0, row_mask=mask)
+            Ci = blocks[i - 1]["C"]
             tmp = torch.zeros(B, L, Ci, dtype=F16, device=device)
             self.conv(dr, tw["ds"][i], Cc, Ci, 1, B, Lh, Lh, tmp, out_stride=2, out_offset=0, out_rows=L, row_mask=mask)
             d_in = new(B, L, Ci)
             self.conv(dy1, tw["conv"][i][0], Cc, Ci, 3, B, L, L, d_in, pad=1, res=tmp, row_mask=mask)
+            del tmp
+
+            def pending(a_in, dy1=dy1, dr=dr, blk=blk, Cc=Cc, Ci=Ci, L=L, Lh=Lh):
+                # a_in = the block input GELU(GELU(IN(y3)) + r) of the previous block, [B, L, Ci]
+                self.gemm_tn(dy1, a_in, G(blk.conv1.conv.weight), Cc, Ci, B, L, L, Ci * 3, 3, y_offset=-1, row_mask=mask,
+                             taps=3, ldc_t=1)
+                self.gemm_tn(dr, a_in, G(blk.downsample.weight), Cc, Ci, B, Lh, L, Ci, 1, y_stride=2, y_offset=0,
+                             row_mask=mask)
+
             dout = d_in
-            del tmp, a_in, dy1, dy2, dxh, d_a1, d_a2
+            del dy1, dr, d_a1
 
 
 class _TrainFn(torch.autograd.Function):
