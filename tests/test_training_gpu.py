@@ -42,7 +42,7 @@ def test_gemm_tn(cuda_device, M, N, L, ys, yo):
     assert (Cm - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
 
 
-@pytest.mark.parametrize("M,N,L", [(16, 16, 1000), (32, 16, 333), (32, 32, 700), (64, 64, 260)])
+@pytest.mark.parametrize("M,N,L", [(16, 16, 1000), (32, 16, 333), (32, 32, 700), (64, 64, 260), (64, 32, 515), (128, 64, 300)])
 def test_gemm_tn_conv_taps(cuda_device, M, N, L):
     """taps = 3: conv weight gradient dW[m, n, t] in one pass (fused kernel for small tiles, per-tap passes otherwise)."""
     lib = _lib.load()

@@ -739,7 +739,7 @@ int w2s_gemm_tn(const void* X, const void* Y, float* Cm, int M, int N, int taps,
                 const uint8_t* row_mask, void* stream) {
   if (!X || !Y || !Cm || B <= 0 || LX <= 0 || LY <= 0 || y_stride < 1 || taps < 1 || taps > 16) return fail("gemm_tn: bad arguments");
   // taps == 3 with unit tap stride on narrow operands: fused kernel (X and Y read once); else one grid slice per tap
-  const bool fused = (taps == 3 && tap_stride == 1 && y_stride == 1 && M <= 32 && N <= 32);
+  const bool fused = (taps == 3 && tap_stride == 1 && y_stride == 1 && M <= 64 && N <= 64);
   GemmTNArgs a;
   a.X = (const act_t*)X; a.Y = (const act_t*)Y; a.C = Cm; a.row_mask = row_mask;
   a.B = B; a.LX = LX; a.LY = LY; a.y_stride = y_stride; a.y_offset = y_offset;
@@ -753,7 +753,7 @@ int w2s_gemm_tn(const void* X, const void* Y, float* Cm, int M, int N, int taps,
   cudaError_t e = cudaErrorInvalidValue;
 #define W2S_TN(MM, NN, TT) if (M == MM && N == NN && ktaps == TT) e = launch_gemm_tn<MM, NN, TT>(a, sm_count(), st);
   W2S_TN(16, 16, 1) W2S_TN(32, 16, 1) W2S_TN(32, 32, 1) W2S_TN(64, 32, 1) W2S_TN(64, 64, 1) W2S_TN(128, 64, 1)
-  W2S_TN(128, 128, 1) W2S_TN(16, 16, 3) W2S_TN(32, 16, 3) W2S_TN(32, 32, 3)
+  W2S_TN(128, 128, 1) W2S_TN(16, 16, 3) W2S_TN(32, 16, 3) W2S_TN(32, 32, 3) W2S_TN(64, 32, 3) W2S_TN(64, 64, 3)
 #undef W2S_TN
   if (e == cudaErrorInvalidValue) return fail("gemm_tn: no kernel for M=%d N=%d taps=%d", M, N, taps);
   return e == cudaSuccess ? 0 : cuda_fail(e, "gemm_tn launch");

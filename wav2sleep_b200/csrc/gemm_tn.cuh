@@ -30,9 +30,10 @@ constexpr int kGemmTNThreads = 256;
 // round moves >= 16 KB per CTA and the per-tile synchronisation is amortised.
 constexpr int gemm_tn_rows(int m, int n) { return (m + n) <= 32 ? 512 : 128; }
 
-template <int M, int N>
+template <int M, int N, int TAPS = 1>
 struct GemmTNCfg {
-  static constexpr int MW = M < 64 ? M : 64;       // warp tile
+  // warp tile; fused-tap kernels keep TAPS accumulator sets, so their warp tile is halved to stay within registers
+  static constexpr int MW = (TAPS > 1 && M > 32) ? 32 : (M < 64 ? M : 64);
   static constexpr int NW = N < 32 ? N : 32;
   static constexpr int WARPS_MN = (M / MW) * (N / NW);
   static constexpr int KG = 8 / WARPS_MN;          // warps that split the rows of a tile
@@ -65,7 +66,7 @@ W2S_DEVINL void mma_16816_f16(float (&c)[4], const uint32_t (&a)[4], const uint3
 // haloed Y tile: X and Y are read once instead of TAPS times.
 template <int M, int N, int TAPS>
 __global__ void __launch_bounds__(kGemmTNThreads) gemm_tn_kernel(const GemmTNArgs p) {
-  using Cfg = GemmTNCfg<M, N>;
+  using Cfg = GemmTNCfg<M, N, TAPS>;
   constexpr int LDX = Cfg::LDX, LDY = Cfg::LDY, MT = Cfg::MT, NT = Cfg::NT, KG = Cfg::KG;
   constexpr int kGemmTNRows = Cfg::ROWS;
   extern __shared__ __align__(16) uint8_t gemm_tn_smem[];
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(kGemmTNThreads) gemm_tn_kernel(const GemmTNArg
 
 template <int M, int N, int TAPS>
 inline cudaError_t launch_gemm_tn(const GemmTNArgs& a, int sm_count, cudaStream_t stream) {
-  using Cfg = GemmTNCfg<M, N>;
+  using Cfg = GemmTNCfg<M, N, TAPS>;
   constexpr int kGemmTNRows = Cfg::ROWS;
   const long long tiles = (long long)((a.LX + kGemmTNRows - 1) / kGemmTNRows) * a.B;
   // every CTA ends with M*N*TAPS atomics into the same small C: give each CTA enough tiles to amortise them
