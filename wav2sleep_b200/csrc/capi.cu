@@ -531,8 +531,9 @@ int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T,
       xa.x = x; xa.xs = xs; xa.row_mask = row_mask; xa.T = L;
       {
         LaunchScope scope(st, "x_stats", (double)B * L * 4.0, (double)B * L * 8.0);
-        int gx = (L / 16 + 255) / 256;
-        if (gx > 4 * sm_count()) gx = 4 * sm_count();
+        int gx = (L / 4 + 255) / 256;
+        const int cap = (4 * sm_count() + B - 1) / B;  // ~4 long-lived blocks per SM over the whole batch
+        if (gx > cap) gx = cap;
         x_stats_kernel<<<dim3(gx < 1 ? 1 : gx, B), 256, 0, st>>>(xa);
         x_stats_finalize_kernel<<<(B * 16 + 127) / 128, 128, 0, st>>>(x, xs, d->w_first, row_mask, s1, B, L);
       }

@@ -113,28 +113,22 @@ __global__ void __launch_bounds__(256) x_stats_kernel(const XStatsArgs p) {
   if (blockIdx.x == 0 && threadIdx.x == 0) p.row_mask[b] = masked ? 1 : 0;
   if (masked) return;
   double s0 = 0.0, r0 = 0.0, r1 = 0.0, r2 = 0.0;
-  // 16 samples per thread and iteration: four 16-byte loads in flight + the two samples after them (T % 16 == 0)
-  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q * 16 < p.T; q += gridDim.x * blockDim.x) {
-    const int pos = q * 16;
-    float v[18];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float4 f = __ldg(reinterpret_cast<const float4*>(xb + pos) + k);
-      v[4 * k] = f.x; v[4 * k + 1] = f.y; v[4 * k + 2] = f.z; v[4 * k + 3] = f.w;
-    }
-    v[16] = pos + 16 < p.T ? __ldg(xb + pos + 16) : 0.0f;
-    v[17] = pos + 17 < p.T ? __ldg(xb + pos + 17) : 0.0f;
-#pragma unroll
-    for (int k = 0; k < 18; ++k) v[k] = isinf(v[k]) ? 0.0f : v[k];
-    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      a0 += v[k];
-      a1 = fmaf(v[k], v[k], a1);
-      a2 = fmaf(v[k], v[k + 1], a2);
-      a3 = fmaf(v[k], v[k + 2], a3);
-    }
-    s0 += a0; r0 += a1; r1 += a2; r2 += a3;
+  // 4 samples per thread and iteration: one coalesced 16-byte load + the two samples after it (an 8-byte load that
+  // hits the line the neighbouring lane just fetched); T % 4 == 0.  Few, long-lived blocks: the fp64 atomics at the
+  // end go to only 4 addresses per night.
+  const int n4 = p.T >> 2;
+  auto fin = [](float v) { return isinf(v) ? 0.0f : v; };
+#pragma unroll 4
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += gridDim.x * blockDim.x) {
+    float4 f = __ldg(reinterpret_cast<const float4*>(xb) + q);
+    float2 g = make_float2(0.0f, 0.0f);
+    if (q + 1 < n4) g = __ldg(reinterpret_cast<const float2*>(xb + 4 * (size_t)(q + 1)));
+    f.x = fin(f.x); f.y = fin(f.y); f.z = fin(f.z); f.w = fin(f.w);
+    g.x = fin(g.x); g.y = fin(g.y);
+    s0 += (double)((f.x + f.y) + (f.z + f.w));
+    r0 += (double)fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(f.z, f.z, f.w * f.w)));
+    r1 += (double)fmaf(f.x, f.y, fmaf(f.y, f.z, fmaf(f.z, f.w, f.w * g.x)));
+    r2 += (double)fmaf(f.x, f.z, fmaf(f.y, f.w, fmaf(f.z, g.x, f.w * g.y)));
   }
   for (int o = 16; o > 0; o >>= 1) {
     s0 += __shfl_xor_sync(0xffffffffu, s0, o);
@@ -142,11 +136,17 @@ __global__ void __launch_bounds__(256) x_stats_kernel(const XStatsArgs p) {
     r1 += __shfl_xor_sync(0xffffffffu, r1, o);
     r2 += __shfl_xor_sync(0xffffffffu, r2, o);
   }
+  __shared__ double red[8][4];
+  const int w = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&p.xs[b * 4 + 0], s0);
-    atomicAdd(&p.xs[b * 4 + 1], r0);
-    atomicAdd(&p.xs[b * 4 + 2], r1);
-    atomicAdd(&p.xs[b * 4 + 3], r2);
+    red[w][0] = s0; red[w][1] = r0; red[w][2] = r1; red[w][3] = r2;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    atomicAdd(&p.xs[b * 4 + threadIdx.x], t);
   }
 }
 // stats1[b, c] = (sum y_c, sum y_c^2) from the four sums; one thread per (b, c)
