@@ -80,7 +80,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([f.strip() for f in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.02)
 
     def summary(self):
         sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
