@@ -266,10 +266,13 @@ int w2s_ce_fwd_bwd(const float* logits, const long long* labels, long long N, in
                    float* loss, float* dlogits, void* stream);
 int w2s_head_bwd(const void* feat, const float* w, const float* dlogits, void* dfeat, float* dw, float* db, long long N, int C,
                  void* stream);
-/* out += sum g^2 (fp64); fused global-norm clip (torch clip_grad_norm_) + AdamW step on flat fp32 buffers. */
+/* out += sum g^2 (fp64); fused global-norm clip (torch clip_grad_norm_) + AdamW step on flat fp32 buffers.
+ * ema != NULL: the same pass also updates ema = ema_decay * ema + (1 - ema_decay) * p_new, the per-batch update of the
+ * reference's EMACallback (trainer/callbacks.py:54-66). */
 int w2s_sumsq(const float* g, long long n, double* out, void* stream);
 int w2s_adamw_step(float* p, const float* g, float* m, float* v, long long n, const double* gnorm_sq, float lr, float beta1,
-                   float beta2, float eps, float weight_decay, float max_norm, float grad_scale, long long step, void* stream);
+                   float beta2, float eps, float weight_decay, float max_norm, float grad_scale, long long step, float* ema,
+                   float ema_decay, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * fp32 check mode: straightforward fp32 CUDA-core restatement of every op (fp32 channels-last tensors, PyTorch weight

@@ -85,17 +85,45 @@ def test_ce_and_adamw_match_torch(cuda_device):
     opt = torch.optim.AdamW([p_ref], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4)
     p, mom, var = p0.clone(), torch.zeros(n, device=cuda_device), torch.zeros(n, device=cuda_device)
     nsq = torch.zeros(1, dtype=torch.float64, device=cuda_device)
+    ema, ema_ref, decay = p0.clone(), p0.clone(), 0.99  # EMACallback: ema = decay * ema + (1 - decay) * p after each step
     for step in range(1, 4):
         g = torch.randn(n, device=cuda_device) * 0.05
         p_ref.grad = g.clone()
         torch.nn.utils.clip_grad_norm_([p_ref], 1.0)
         opt.step()
+        ema_ref.mul_(decay).add_(p_ref.detach(), alpha=1 - decay)
         nsq.zero_()
         _lib.check(lib.w2s_sumsq(g.data_ptr(), n, nsq.data_ptr(), G.stream()))
         _lib.check(lib.w2s_adamw_step(p.data_ptr(), g.data_ptr(), mom.data_ptr(), var.data_ptr(), n, nsq.data_ptr(), 1e-3,
-                                      0.9, 0.999, 1e-8, 1e-4, 1.0, 1.0, step, G.stream()))
+                                      0.9, 0.999, 1e-8, 1e-4, 1.0, 1.0, step, ema.data_ptr(), decay, G.stream()))
     torch.cuda.synchronize()
     assert (p - p_ref.detach()).abs().max().item() < 2e-6
+    assert (ema - ema_ref).abs().max().item() < 2e-6
+
+
+def test_fused_adamw_ema_swap(cuda_device):
+    """FusedAdamW(ema_decay=...) mirrors EMACallback: update after every step from start_step on, swap for evaluation."""
+    from wav2sleep_b200.optim import FusedAdamW
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(8, 8).to(cuda_device)
+    opt = FusedAdamW(lin.parameters(), lr=1e-2, weight_decay=0.0, ema_decay=0.5, ema_start_step=2)
+    w0 = lin.weight.detach().clone()
+    hist = []
+    for _ in range(3):
+        opt.zero_grad()
+        lin(torch.randn(4, 8, device=cuda_device)).pow(2).sum().backward()
+        opt.step()
+        hist.append(lin.weight.detach().clone())
+    # steps 2 and 3 update the average (start_step = 2): ema = 0.5 * (0.5 * w0 + 0.5 * w2) + 0.5 * w3
+    expect = 0.5 * (0.5 * w0 + 0.5 * hist[1]) + 0.5 * hist[2]
+    opt.swap_to_ema()
+    assert (lin.weight.detach() - expect).abs().max().item() < 1e-6
+    with pytest.raises(RuntimeError):
+        opt.step()
+    opt.swap_to_original()
+    assert torch.equal(lin.weight.detach(), hist[2])
+    with pytest.raises(ValueError):
+        FusedAdamW(lin.parameters(), ema_decay=1.5)
 
 
 def _grad_report(model, grads_ref):

@@ -156,7 +156,8 @@ SYMBOLS = {
                                  C.c_void_p, C.c_void_p]),
     "w2s_head_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_longlong, C.c_int, C.c_void_p]),
     "w2s_sumsq": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
-    "w2s_adamw_step": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_void_p] + [C.c_float] * 7 + [C.c_longlong, C.c_void_p]),
+    "w2s_adamw_step": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_void_p] + [C.c_float] * 7
+                       + [C.c_longlong, C.c_void_p, C.c_float, C.c_void_p]),
     "w2s_chk_conv": (C.c_int, [C.c_void_p] * 8 + [C.c_int] * 12 + [C.c_float, C.c_void_p]),
     "w2s_chk_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "w2s_chk_rowln": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_int, C.c_float, C.c_void_p]),

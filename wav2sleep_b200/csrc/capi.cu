@@ -973,14 +973,17 @@ int w2s_sumsq(const float* g, long long n, double* out, void* stream) {
   W2S_LAUNCH_CHECK("sumsq");
 }
 int w2s_adamw_step(float* p_, const float* g, float* m, float* v, long long n, const double* gnorm_sq, float lr, float beta1,
-                   float beta2, float eps, float weight_decay, float max_norm, float grad_scale, long long step, void* stream) {
+                   float beta2, float eps, float weight_decay, float max_norm, float grad_scale, long long step, float* ema,
+                   float ema_decay, void* stream) {
   if (!p_ || !g || !m || !v || n <= 0 || step < 1) return fail("adamw_step: bad arguments");
+  if (ema != nullptr && !(ema_decay >= 0.0f && ema_decay <= 1.0f)) return fail("decay must be in [0, 1], got %g", ema_decay);
   AdamWArgs a;
   a.p = p_; a.g = g; a.m = m; a.v = v; a.n = n; a.gnorm_sq = gnorm_sq; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
   a.weight_decay = weight_decay; a.max_norm = max_norm; a.grad_scale = grad_scale;
   a.bias_c1 = (float)(1.0 - pow((double)beta1, (double)step));
   a.bias_c2 = (float)(1.0 - pow((double)beta2, (double)step));
-  LaunchScope scope((cudaStream_t)stream, "adamw_step", (double)n * 28.0, (double)n * 12.0);
+  a.ema = ema; a.ema_decay = ema_decay;
+  LaunchScope scope((cudaStream_t)stream, "adamw_step", (double)n * (ema ? 36.0 : 28.0), (double)n * 12.0);
   adamw_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(a);
   W2S_LAUNCH_CHECK("adamw_step");
 }

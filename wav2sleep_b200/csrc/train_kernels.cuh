@@ -810,6 +810,7 @@ struct AdamWArgs {
   const double* gnorm_sq;  // device scalar: sum of squares of the (already reduced) gradient, or null = no clipping
   float lr, beta1, beta2, eps, weight_decay, max_norm, grad_scale;
   float bias_c1, bias_c2;  // 1 - beta1^t, 1 - beta2^t
+  float* ema; float ema_decay;  // optional EMA of the parameters (reference trainer/callbacks.py:54-66), same pass
 };
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamWArgs a) {
   float coef = a.grad_scale;
@@ -828,7 +829,9 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamWArgs a) {
     a.m[i] = m;
     a.v[i] = v;
     const float denom = sqrtf(v) * inv_sqrt_c2 + a.eps;
-    a.p[i] = p - step_size * m / denom;
+    p -= step_size * m / denom;
+    a.p[i] = p;
+    if (a.ema != nullptr) a.ema[i] = a.ema_decay * a.ema[i] + (1.0f - a.ema_decay) * p;
   }
 }
 

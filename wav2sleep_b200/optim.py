@@ -20,7 +20,12 @@ WEIGHTS_EPOCH = 0  # bumped after every in-place parameter update so that engine
 
 
 class FusedAdamW(Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=None):
+    """``ema_decay``: also keep an exponential moving average of the parameters, updated inside the same kernel from step
+    ``ema_start_step`` on (reference ``EMACallback(decay, start_step)``, trainer/callbacks.py:12-66); ``swap_to_ema`` /
+    ``swap_to_original`` exchange it with the live weights around validation like the callback does."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=None,
+                 ema_decay: float | None = None, ema_start_step: int = 0):
         params = [p for p in params if p.requires_grad]
         if not params:
             raise ValueError("optimizer got an empty parameter list")
@@ -45,6 +50,11 @@ class FusedAdamW(Optimizer):
             self.offsets[id(p)] = (off, k)
             off += k
         self._step = 0
+        if ema_decay is not None and not 0.0 <= ema_decay <= 1.0:
+            raise ValueError(f"decay must be in [0, 1], got {ema_decay}")  # callbacks.py:33-34
+        self.ema_decay, self.ema_start_step = ema_decay, ema_start_step
+        self.ema = self.flat_param.clone() if ema_decay is not None else None  # callbacks.py:44-49
+        self._swapped = None
         self.grad_scale = 1.0  # e.g. 1 / world_size after a SUM all-reduce
         self._bump()
 
@@ -78,11 +88,32 @@ class FusedAdamW(Optimizer):
             _lib.check(lib.w2s_sumsq(self.flat_grad.data_ptr(), n, self.gnorm_sq.data_ptr(), st))
             gn_ptr = self.gnorm_sq.data_ptr()
         b1, b2 = g["betas"]
+        if self._swapped is not None:
+            raise RuntimeError("step() while the EMA weights are swapped in")
+        ema_on = self.ema is not None and self._step >= self.ema_start_step  # callbacks.py:51-53, 76-78
         _lib.check(lib.w2s_adamw_step(self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.exp_avg.data_ptr(),
                                       self.exp_avg_sq.data_ptr(), n, gn_ptr, float(g["lr"]), b1, b2, g["eps"],
-                                      g["weight_decay"], float(clip or 0.0), float(self.grad_scale), self._step, st))
+                                      g["weight_decay"], float(clip or 0.0), float(self.grad_scale), self._step,
+                                      self.ema.data_ptr() if ema_on else None, float(self.ema_decay or 0.0), st))
         self._bump()
         return loss
+
+    @torch.no_grad()
+    def swap_to_ema(self):
+        """Evaluate with the averaged weights (callbacks.py:80-86); parameters stay views of the flat buffer."""
+        if self.ema is None or self._swapped is not None:
+            return
+        self._swapped = self.flat_param.clone()
+        self.flat_param.copy_(self.ema)
+        self._bump()
+
+    @torch.no_grad()
+    def swap_to_original(self):
+        if self._swapped is None:
+            return
+        self.flat_param.copy_(self._swapped)
+        self._swapped = None
+        self._bump()
 
     def grad_norm(self) -> float:
         """Global L2 norm of the (scaled) gradient seen by the last step (host sync; for logging)."""

@@ -173,6 +173,17 @@ class SleepLightningModule(nn.Module):
         with torch.no_grad():
             return self._step(batch, VAL, dataloader_idx)
 
+    # EMACallback hooks (reference trainer/callbacks.py:88-110): evaluate with the averaged weights kept by the optimizer
+    def on_validation_epoch_start(self) -> None:
+        if isinstance(self._opt, FusedAdamW):
+            self._opt.swap_to_ema()
+
+    def on_validation_epoch_end(self) -> None:
+        if isinstance(self._opt, FusedAdamW):
+            self._opt.swap_to_original()
+
+    on_test_epoch_start, on_test_epoch_end = on_validation_epoch_start, on_validation_epoch_end
+
     def configure_optimizers(self) -> dict:
         optimizer = self.optimizer(self.model.parameters())
         out = {"optimizer": optimizer}
