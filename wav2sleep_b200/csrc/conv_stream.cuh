@@ -286,9 +286,9 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
               const uint64_t db = umma_smem_desc(b_base + b_off, lbo_b, 128);
               if (!(p.debug_flags & 2)) umma_f16(d_base + j * COUT, da, db, IDESC, (t > 0 || kk > 0) ? 1u : 0u);
               if (SPLIT && !(p.debug_flags & 3)) {
-                if (!(p.debug_flags & 128))
+                if (!(p.debug_flags & 128) && !(CIN == 32 && (p.debug_flags & 512)))
                   umma_f16(d_base + j * COUT, umma_smem_desc(a_base + Cfg::A_ONE + a_off, lbo_a, 128), db, IDESC, 1u);
-                if (!(p.debug_flags & 256))
+                if (!(p.debug_flags & 256) && !(CIN == 32 && (p.debug_flags & 1024)))
                   umma_f16(d_base + j * COUT, da, umma_smem_desc(b_base + Cfg::B_ONE + b_off, lbo_b, 128), IDESC, 1u);
               }
             }

@@ -35,6 +35,18 @@ W2S_DEVINL float gelu_grad_tanh(float x) {
   const float dq = x2 < 25.0f ? 2.0f * x2 * fmaf(t, -7.0318528e-4f, 0.037005995f) : 0.0f;  // x * dq/dx
   return 0.5f * (1.0f + th) + 0.5f * x * (1.0f - th * th) * (q + dq);
 }
+// value and derivative together (one MUFU.TANH instead of two)
+W2S_DEVINL void gelu_tanh_both(float x, float& val, float& grad) {
+  const float x2 = x * x;
+  const float t = fminf(x2, 25.0f);
+  const float q = fmaf(fmaf(t, -3.5159264e-4f, 0.037005995f), t, 0.79750759f);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(x * q));
+  const float h = 0.5f * x;
+  val = fmaf(h, th, h);
+  const float dq = x2 < 25.0f ? 2.0f * x2 * fmaf(t, -7.0318528e-4f, 0.037005995f) : 0.0f;  // x * dq/dx
+  grad = 0.5f * (1.0f + th) + h * (1.0f - th * th) * (q + dq);
+}
 W2S_DEVINL void unpack8(const uint4& u, float* v) {
   const uint32_t* w = reinterpret_cast<const uint32_t*>(&u);
 #pragma unroll
@@ -149,16 +161,15 @@ __global__ void __launch_bounds__(256) enc_act_bwd_kernel(const EncActBwdArgs p)
     for (int k = 0; k < 8; ++k) {
       const float xh = (v[k] - mean[k]) * rstd[k];
       float g = d[k];
-      float a = 0.0f;
+      float a, da;
+      gelu_tanh_both(xh, a, da);
       if (p.r) {
-        const float s = gelu_tanh(xh) + rr[k];
-        if (p.a_out) a = gelu_tanh(s);
-        g *= gelu_grad_tanh(s);
+        float ds;
+        gelu_tanh_both(a + rr[k], a, ds);
+        g *= ds;
         rr[k] = g;  // dr
-      } else if (p.a_out) {
-        a = gelu_tanh(xh);
       }
-      g *= gelu_grad_tanh(xh);
+      g *= da;
       d[k] = g;
       v[k] = a;
       s0[k] += g;
