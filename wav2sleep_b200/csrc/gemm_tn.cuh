@@ -28,7 +28,7 @@ struct GemmTNArgs {
 constexpr int kGemmTNThreads = 256;
 // X rows per smem tile (tiles never straddle two samples): long tiles for narrow operands, so that every staging
 // round moves >= 16 KB per CTA and the per-tile synchronisation is amortised.
-constexpr int gemm_tn_rows(int m, int n) { return (m + n) <= 32 ? 512 : 128; }
+constexpr int gemm_tn_rows(int m, int n) { return (m + n) <= 64 ? 512 : 128; }
 
 template <int M, int N, int TAPS = 1>
 struct GemmTNCfg {
@@ -69,15 +69,21 @@ __global__ void __launch_bounds__(kGemmTNThreads) gemm_tn_kernel(const GemmTNArg
   using Cfg = GemmTNCfg<M, N, TAPS>;
   constexpr int LDX = Cfg::LDX, LDY = Cfg::LDY, MT = Cfg::MT, NT = Cfg::NT, KG = Cfg::KG;
   constexpr int kGemmTNRows = Cfg::ROWS;
+  // Staged Y rows per tile: with taps the haloed run of consecutive rows (y_stride == 1); without, exactly the rows
+  // the X rows map to (row k of the tile <-> Y row ybase + k * y_stride), stored compactly.
+  constexpr int YR = TAPS == 1 ? kGemmTNRows : kGemmTNRows + TAPS - 1;
+  constexpr int XN = kGemmTNRows * (M / 8) / kGemmTNThreads;
+  constexpr int YN = (YR * (N / 8) + kGemmTNThreads - 1) / kGemmTNThreads;
+  static_assert(kGemmTNRows * (M / 8) % kGemmTNThreads == 0, "X staging");
   extern __shared__ __align__(16) uint8_t gemm_tn_smem[];
   __half* sX = reinterpret_cast<__half*>(gemm_tn_smem);
   __half* sY = sX + kGemmTNRows * LDX;
-  const int y_rows = (kGemmTNRows - 1) * p.y_stride + TAPS;  // staged Y rows per tile
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wmn = warp % Cfg::WARPS_MN, kg = warp / Cfg::WARPS_MN;
   const int m0 = (wmn / (N / Cfg::NW)) * Cfg::MW;
   const int n0 = (wmn % (N / Cfg::NW)) * Cfg::NW;
+  const int ystep = TAPS == 1 ? p.y_stride : 1;
 
   float acc[TAPS][MT][NT][4];
 #pragma unroll
@@ -93,63 +99,58 @@ __global__ void __launch_bounds__(kGemmTNThreads) gemm_tn_kernel(const GemmTNArg
   const long long tiles = (long long)tiles_per_sample * p.B;
   const long long t_begin = tiles * blockIdx.x / gridDim.x, t_end = tiles * (blockIdx.x + 1) / gridDim.x;
 
-  for (long long tile = t_begin; tile < t_end; ++tile) {
+  // next tile of this CTA whose sample is not masked (uniform over the CTA)
+  auto next_tile = [&](long long t) {
+    while (t < t_end && p.row_mask != nullptr && p.row_mask[(int)(t / tiles_per_sample)]) ++t;
+    return t;
+  };
+  // Register double buffering: the global loads of tile i+1 are issued before the MMAs of tile i and land while they
+  // run; they are written to shared memory after the MMAs are done.
+  uint4 xv[XN], yv[YN];
+  auto load_tile = [&](long long tile) {
     const int b = (int)(tile / tiles_per_sample);
-    if (p.row_mask != nullptr && p.row_mask[b]) continue;  // uniform over the CTA
     const int l0 = (int)(tile - (long long)b * tiles_per_sample) * kGemmTNRows;
     const act_t* Xb = p.X + ((size_t)b * p.LX) * M;
     const act_t* Yb = p.Y + ((size_t)b * p.LY) * N;
     const int ybase = l0 * p.y_stride + p.y_offset + (int)blockIdx.y * p.tap_stride;
-    __syncthreads();
-    {  // all loads of the tile are issued before the first shared-memory store (memory-level parallelism)
-      constexpr int XN = kGemmTNRows * (M / 8) / kGemmTNThreads;
-      static_assert(kGemmTNRows * (M / 8) % kGemmTNThreads == 0, "X staging");
-      uint4 xv[XN];
 #pragma unroll
-      for (int i = 0; i < XN; ++i) {
-        const int id = tid + i * kGemmTNThreads;
-        const int k = id / (M / 8), c = id % (M / 8);
-        xv[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (l0 + k < p.LX) xv[i] = __ldg(reinterpret_cast<const uint4*>(Xb + (size_t)(l0 + k) * M) + c);
-      }
-      constexpr int YN = (kGemmTNRows * (N / 8) + kGemmTNThreads - 1) / kGemmTNThreads;  // y_stride == 1 part
-      const int y_total = y_rows * (N / 8);
-      if (p.y_stride == 1) {
-        uint4 yv[YN + 1];
-#pragma unroll
-        for (int i = 0; i < YN + 1; ++i) {
-          const int id = tid + i * kGemmTNThreads;
-          const int k = id / (N / 8), c = id % (N / 8);
-          const int ly = ybase + k;
-          yv[i] = make_uint4(0u, 0u, 0u, 0u);
-          if (id < y_total && ly >= 0 && ly < p.LY) yv[i] = __ldg(reinterpret_cast<const uint4*>(Yb + (size_t)ly * N) + c);
-        }
-#pragma unroll
-        for (int i = 0; i < XN; ++i) {
-          const int id = tid + i * kGemmTNThreads;
-          *reinterpret_cast<uint4*>(sX + (id / (M / 8)) * LDX + (id % (M / 8)) * 8) = xv[i];
-        }
-#pragma unroll
-        for (int i = 0; i < YN + 1; ++i) {
-          const int id = tid + i * kGemmTNThreads;
-          if (id < y_total) *reinterpret_cast<uint4*>(sY + (id / (N / 8)) * LDY + (id % (N / 8)) * 8) = yv[i];
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < XN; ++i) {
-          const int id = tid + i * kGemmTNThreads;
-          *reinterpret_cast<uint4*>(sX + (id / (M / 8)) * LDX + (id % (M / 8)) * 8) = xv[i];
-        }
-        for (int id = tid; id < y_total; id += kGemmTNThreads) {
-          const int k = id / (N / 8), c = id % (N / 8);
-          const int ly = ybase + k;
-          uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          if (ly >= 0 && ly < p.LY) v = __ldg(reinterpret_cast<const uint4*>(Yb + (size_t)ly * N) + c);
-          *reinterpret_cast<uint4*>(sY + k * LDY + c * 8) = v;
-        }
-      }
+    for (int i = 0; i < XN; ++i) {
+      const int id = tid + i * kGemmTNThreads;
+      const int k = id / (M / 8), c = id % (M / 8);
+      xv[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (l0 + k < p.LX) xv[i] = __ldg(reinterpret_cast<const uint4*>(Xb + (size_t)(l0 + k) * M) + c);
     }
+#pragma unroll
+    for (int i = 0; i < YN; ++i) {
+      const int id = tid + i * kGemmTNThreads;
+      const int k = id / (N / 8), c = id % (N / 8);
+      const long long ly = (long long)ybase + (long long)k * ystep;
+      yv[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (id < YR * (N / 8) && ly >= 0 && ly < p.LY && (TAPS > 1 || l0 + k < p.LX))
+        yv[i] = __ldg(reinterpret_cast<const uint4*>(Yb + (size_t)ly * N) + c);
+    }
+  };
+  auto store_tile = [&]() {
+#pragma unroll
+    for (int i = 0; i < XN; ++i) {
+      const int id = tid + i * kGemmTNThreads;
+      *reinterpret_cast<uint4*>(sX + (id / (M / 8)) * LDX + (id % (M / 8)) * 8) = xv[i];
+    }
+#pragma unroll
+    for (int i = 0; i < YN; ++i) {
+      const int id = tid + i * kGemmTNThreads;
+      if (id < YR * (N / 8)) *reinterpret_cast<uint4*>(sY + (id / (N / 8)) * LDY + (id % (N / 8)) * 8) = yv[i];
+    }
+  };
+
+  long long tile = next_tile(t_begin);
+  if (tile < t_end) load_tile(tile);
+  while (tile < t_end) {
+    __syncthreads();  // the MMAs of the previous tile are done with the staging buffers
+    store_tile();
     __syncthreads();
+    tile = next_tile(tile + 1);
+    if (tile < t_end) load_tile(tile);
     constexpr int KSTEPS = kGemmTNRows / 16 / KG;
 #pragma unroll
     for (int ks = 0; ks < KSTEPS; ++ks) {
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(kGemmTNThreads) gemm_tn_kernel(const GemmTNArg
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
           uint32_t bf[2];
-          const int yrow = (k0 + ((lane >> 3) & 1) * 8 + (lane & 7)) * p.y_stride + t;
+          const int yrow = k0 + ((lane >> 3) & 1) * 8 + (lane & 7) + t;
           ldmatrix_x2_trans(bf, sY + yrow * LDY + n0 + j * 8);
 #pragma unroll
           for (int i = 0; i < MT; ++i) mma_16816_f16(acc[t][i][j], a[i], bf);
@@ -226,7 +227,7 @@ inline cudaError_t launch_gemm_tn(const GemmTNArgs& a, int sm_count, cudaStream_
   long long grid = 4LL * sm_count;
   if (grid > tiles / kMinTiles) grid = tiles / kMinTiles;
   if (grid < 1) grid = 1;
-  const int y_rows = (kGemmTNRows - 1) * a.y_stride + TAPS;
+  constexpr int y_rows = TAPS == 1 ? kGemmTNRows : kGemmTNRows + TAPS - 1;
   int smem = (kGemmTNRows * Cfg::LDX + y_rows * Cfg::LDY) * 2;
   if (Cfg::KG > 1 && smem < M * N * TAPS * 4) smem = M * N * TAPS * 4;
   static int configured = 0;
