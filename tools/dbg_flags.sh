@@ -1,1 +1,2 @@
-for f in 0 512 1024 1536; do echo "== flags $f"; W2S_DEBUG_FLAGS=$f timeout 600 python -m pytest tests/test_forward_gpu.py -q -m gpu -s -p no:cacheprovider -k "full_night" 2>&1 | grep -E "max-abs|passed|failed" | grep -v "wide_blocks=2\|wide_blocks=0" | cut -c1-150; done
+python tools/time_wide.py 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_forward_gpu.py -q -m gpu -s -p no:cacheprovider -k "eog" 2>&1 | grep -E "max-abs|passed|failed" | cut -c1-150

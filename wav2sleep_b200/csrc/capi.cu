@@ -239,13 +239,13 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
     W2S_STREAM(128, 128, 2, PRO_NORM, false, 1, 1, 1, 14)
     W2S_STREAM(128, 128, 1, PRO_NORM_RES, true, 1, 1, 1, 14)
     // wide (fp32) storage of the leading <= 32-channel blocks            MT NR NA NTW  in     out
-    W2S_STREAMW(16, 16, 1, PRO_FIR, false, 4, 3, 2, 18, false, true)
+    W2S_STREAMW(16, 16, 1, PRO_FIR, false, 8, 3, 2, 18, false, true)
     W2S_STREAMW(16, 16, 1, PRO_NORM_RES_X, true, 4, 3, 2, 14, true, true)
-    W2S_STREAMW(16, 16, 1, PRO_NORM, false, 4, 3, 2, 18, true, true)
-    W2S_STREAMW(16, 16, 2, PRO_NORM, false, 2, 3, 2, 18, true, true)
+    W2S_STREAMW(16, 16, 1, PRO_NORM, false, 6, 2, 2, 18, true, true)
+    W2S_STREAMW(16, 16, 2, PRO_NORM, false, 3, 2, 2, 18, true, true)
     W2S_STREAMW(16, 32, 1, PRO_NORM_RES, true, 4, 2, 2, 10, true, false)
     W2S_STREAMW(16, 32, 1, PRO_NORM_RES, true, 4, 2, 2, 10, true, true)
-    W2S_STREAMW(32, 32, 1, PRO_NORM, false, 2, 3, 2, 10, true, true)
+    W2S_STREAMW(32, 32, 1, PRO_NORM, false, 3, 2, 2, 10, true, true)
     W2S_STREAMW(32, 32, 2, PRO_NORM, false, 1, 3, 2, 10, true, true)
     W2S_STREAMW(32, 32, 1, PRO_NORM_RES, true, 2, 2, 2, 10, true, true)
     W2S_STREAMW(32, 64, 1, PRO_NORM_RES, true, 2, 2, 2, 14, true, false)
