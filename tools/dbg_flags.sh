@@ -1,2 +1,3 @@
-python tools/time_wide.py 2>&1 | tail -3
-timeout 600 python -m pytest tests/test_forward_gpu.py -q -m gpu -s -p no:cacheprovider -k "eog" 2>&1 | grep -E "max-abs|passed|failed" | cut -c1-150
+W2S_DEBUG_FLAGS=64 python tools/profile_conv.py --cin 64 --cout 64 --L 76800 --iters 3 2>&1 | grep -E "blocked|CTA entry" | cut -c1-230
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-train 2>/dev/null | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'])"
