@@ -140,7 +140,9 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   constexpr int KSTEPS = CIN / 16;
   constexpr int NCG = COUT / 16;
   constexpr uint32_t IDESC = umma_idesc_f16(128, COUT, false);
-  constexpr bool REG_STATS = (COUT <= 32);  // per-thread accumulators across tiles; else per-tile butterfly
+  // per-thread accumulators across tiles for COUT = 16; wider outputs reduce per tile (butterfly), which keeps the
+  // register count low enough for more transform warps
+  constexpr bool REG_STATS = (COUT <= 16);
 
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sRaw = smem;
