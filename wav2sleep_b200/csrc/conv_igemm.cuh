@@ -62,7 +62,11 @@ struct ConvArgs {
   const float* w_first;   // [16, 3]
   const float* w_first_ds;  // [16]
   int T_raw;
-  int debug_flags;        // profiling experiments only (0 in production): 1 skip lo MMAs, 2 skip all MMAs, 4 skip GELU
+  // Profiling experiments only (W2S_DEBUG_FLAGS in the environment; 0 in production, results are wrong otherwise):
+  //   1 skip the lo-operand MMAs, 2 skip all MMAs, 4 skip GELU, 8 skip epilogue stores, 16 skip epilogue TMEM loads,
+  //   32 skip the transform, 64 record timestamps / per-role wait cycles (results stay correct), 128 / 256 skip only the
+  //   A_lo / W_lo MMA, 512 / 1024 the same for CIN = 32 layers only.
+  int debug_flags;
 };
 
 constexpr int kConvThreads = 256;
