@@ -56,7 +56,8 @@ int w2s_pack_linear_frag(const float* w, int n, int k, void* out_fp16, void* str
  * Replaces ConvLayer1D.forward (models/blocks.py:173-186) + the consumer-side InstanceNorm/GELU of its input.
  * ------------------------------------------------------------------------------------------------------- */
 enum { W2S_PRO_NONE = 0, W2S_PRO_NORM = 1, W2S_PRO_NORM_RES = 2, W2S_PRO_FIR = 3, W2S_PRO_NORM_RES_X = 4 };
-enum { W2S_EPI_STATS = 0, W2S_EPI_BIAS_GELU = 1, W2S_EPI_LN_GELU = 2, W2S_EPI_LN_GELU_RES = 3, W2S_EPI_PLAIN = 4 };
+enum { W2S_EPI_STATS = 0, W2S_EPI_BIAS_GELU = 1, W2S_EPI_LN_GELU = 2, W2S_EPI_LN_GELU_RES = 3, W2S_EPI_PLAIN = 4,
+       W2S_EPI_ACT_BWD = 5 };
 
 typedef struct w2s_conv_call {
   int32_t cin, cout, taps, stride, dilation, pad;
@@ -92,6 +93,16 @@ typedef struct w2s_conv_call {
   /* wide storage (encoder EPI_STATS convs with cin, cout <= 64 only): in / in_res, resp. out / out_ds, are fp32
    * instead of fp16 tensors of the same shape. */
   int32_t in_wide, out_wide;
+  /* W2S_EPI_ACT_BWD (training): data-gradient conv fused with the backward through the activation of the layer that
+   * produced this conv's input: da = acc (+ res); with x_hat = InstanceNorm(act_y) [block outputs: s = GELU(x_hat) +
+   * act_r, ds = da GELU'(s), act_dr = ds] out = d(x_hat) = ds GELU'(x_hat); act_a = the activated tensor (may be
+   * NULL); out_stats[B, cout, 2] += (sum d(x_hat), sum d(x_hat) x_hat) (fp64, caller-zeroed).  All [B, L_out, cout]. */
+  const void* act_y;
+  const void* act_r;
+  const double* act_stats;
+  void* act_a;
+  void* act_dr;
+  float act_eps;
 } w2s_conv_call;
 
 int w2s_conv1d_fwd(const w2s_conv_call* call, void* stream);

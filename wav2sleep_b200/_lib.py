@@ -25,7 +25,7 @@ MAX_DILATIONS = 8
 ABI_VERSION = 1
 
 PRO_NONE, PRO_NORM, PRO_NORM_RES, PRO_FIR, PRO_NORM_RES_X = 0, 1, 2, 3, 4
-EPI_STATS, EPI_BIAS_GELU, EPI_LN_GELU, EPI_LN_GELU_RES, EPI_PLAIN = 0, 1, 2, 3, 4
+EPI_STATS, EPI_BIAS_GELU, EPI_LN_GELU, EPI_LN_GELU_RES, EPI_PLAIN, EPI_ACT_BWD = 0, 1, 2, 3, 4, 5
 
 
 def nvcc_path() -> str:
@@ -70,6 +70,8 @@ class ConvCall(C.Structure):
         ("out_stride", C.c_int32), ("out_offset", C.c_int32), ("out_rows", C.c_int32),
         ("x_raw", C.c_void_p), ("w_first", C.c_void_p), ("w_first_ds", C.c_void_p), ("T_raw", C.c_int32),
         ("in_wide", C.c_int32), ("out_wide", C.c_int32),
+        ("act_y", C.c_void_p), ("act_r", C.c_void_p), ("act_stats", C.c_void_p), ("act_a", C.c_void_p),
+        ("act_dr", C.c_void_p), ("act_eps", C.c_float),
     ]
 
 

@@ -182,6 +182,8 @@ ConvArgs to_args(const w2s_conv_call& c) {
   a.out_stride = c.out_stride > 0 ? c.out_stride : 1;
   a.out_offset = c.out_offset;
   a.out_rows = c.out_rows > 0 ? c.out_rows : c.L_out;
+  a.ab_y = (const act_t*)c.act_y; a.ab_r = (const act_t*)c.act_r; a.ab_stats = c.act_stats;
+  a.ab_a = (act_t*)c.act_a; a.ab_dr = (act_t*)c.act_dr; a.ab_eps = c.act_eps;
   { const char* dbg = getenv("W2S_DEBUG_FLAGS"); a.debug_flags = dbg ? atoi(dbg) : 0; }
   return a;
 }
@@ -193,6 +195,12 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
   if (c.n_classes > 8) return fail("conv1d: n_classes=%d > 8", c.n_classes);
   if ((c.in_wide || c.out_wide) && (c.epilogue != W2S_EPI_STATS || g_conv_impl.load() != 0))
     return fail("conv1d: wide storage is only built for the streaming encoder kernels");
+  if (c.epilogue == W2S_EPI_ACT_BWD) {
+    if (!c.act_y || !c.act_stats || !c.out_stats || (c.act_r && !c.act_dr))
+      return fail("conv1d: W2S_EPI_ACT_BWD needs act_y, act_stats, out_stats (and act_dr with act_r)");
+    if (c.out_stride > 1 || c.out_offset != 0 || (c.out_rows > 0 && c.out_rows != c.L_out))
+      return fail("conv1d: W2S_EPI_ACT_BWD writes dense rows only");
+  }
   const ConvArgs a = to_args(c);
   cudaError_t e = cudaErrorInvalidValue;
   bool found = false;
@@ -207,8 +215,11 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
                             (c.prologue == W2S_PRO_NORM_RES_X ? (double)c.B * c.L_in * 8.0 : 0.0);
   const double out_b = (double)c.B * c.L_out * c.cout * eout * (c.has_ds ? 1.5 : 1.0) +
                        (c.epilogue == W2S_EPI_LN_GELU_RES ? (double)c.B * c.L_out * c.cout * 2.0 : 0.0);
+  const double ab_b = c.epilogue == W2S_EPI_ACT_BWD
+                          ? (double)c.B * c.L_out * c.cout * 2.0 * (1.0 + (c.res ? 1.0 : 0.0) + (c.act_r ? 2.0 : 0.0) + (c.act_a ? 1.0 : 0.0))
+                          : 0.0;
   const double fl = 2.0 * c.B * (double)c.L_out * c.cout * c.cin * (c.taps + (c.has_ds ? 0.5 : 0.0));
-  LaunchScope scope(st, label, in_b + out_b, fl);
+  LaunchScope scope(st, label, in_b + out_b + ab_b, fl);
   if (c.epilogue == W2S_EPI_STATS && c.taps == 3 && c.dilation == 1 && c.pad == 1 && g_conv_impl.load() == 0 &&
       ((c.stride == 1 && c.L_out == c.L_in) || (c.stride == 2 && c.L_out == (c.L_in + 1) / 2))) {
     const int sms = sm_count();
@@ -297,6 +308,14 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
   W2S_CASE(64, 64, 3, 3, PRO_NONE, EPI_PLAIN, false)
   W2S_CASE(128, 64, 3, 3, PRO_NONE, EPI_PLAIN, false)
   W2S_CASE(128, 128, 3, 3, PRO_NONE, EPI_PLAIN, false)
+  // training: data-gradient convs fused with the activation backward of the producing layer
+  W2S_CASE(16, 16, 3, 3, PRO_NONE, EPI_ACT_BWD, false)
+  W2S_CASE(32, 16, 3, 3, PRO_NONE, EPI_ACT_BWD, false)
+  W2S_CASE(32, 32, 3, 3, PRO_NONE, EPI_ACT_BWD, false)
+  W2S_CASE(64, 32, 3, 3, PRO_NONE, EPI_ACT_BWD, false)
+  W2S_CASE(64, 64, 3, 3, PRO_NONE, EPI_ACT_BWD, false)
+  W2S_CASE(128, 64, 3, 3, PRO_NONE, EPI_ACT_BWD, false)
+  W2S_CASE(128, 128, 3, 3, PRO_NONE, EPI_ACT_BWD, false)
   W2S_CASE(16, 16, 1, 1, PRO_NONE, EPI_PLAIN, false)
   W2S_CASE(32, 16, 1, 1, PRO_NONE, EPI_PLAIN, false)
   W2S_CASE(32, 32, 1, 1, PRO_NONE, EPI_PLAIN, false)

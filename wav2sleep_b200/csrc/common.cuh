@@ -262,4 +262,48 @@ W2S_DEVINL void butterfly16(float* v, int lane) {
   v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+// ----------------------------------------------------------------------------------------------
+// training-path element math shared by train_kernels.cuh and the fused dgrad epilogue of conv_igemm.cuh
+// ----------------------------------------------------------------------------------------------
+// tanh-form GELU and derivative (same fitted exponent as the forward prologue, one MUFU.TANH): used on the whole-night
+// encoder tensors where erff/expf would make the element-wise kernels compute bound.
+W2S_DEVINL float gelu_tanh(float x) {
+  const float t = fminf(x * x, 25.0f);
+  const float q = fmaf(fmaf(t, -3.5159264e-4f, 0.037005995f), t, 0.79750759f);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(x * q));
+  const float h = 0.5f * x;
+  return fmaf(h, th, h);
+}
+W2S_DEVINL float gelu_grad_tanh(float x) {
+  const float x2 = x * x;
+  const float t = fminf(x2, 25.0f);
+  const float q = fmaf(fmaf(t, -3.5159264e-4f, 0.037005995f), t, 0.79750759f);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(x * q));
+  const float dq = x2 < 25.0f ? 2.0f * x2 * fmaf(t, -7.0318528e-4f, 0.037005995f) : 0.0f;  // x * dq/dx
+  return 0.5f * (1.0f + th) + 0.5f * x * (1.0f - th * th) * (q + dq);
+}
+// value and derivative together (one MUFU.TANH instead of two)
+W2S_DEVINL void gelu_tanh_both(float x, float& val, float& grad) {
+  const float x2 = x * x;
+  const float t = fminf(x2, 25.0f);
+  const float q = fmaf(fmaf(t, -3.5159264e-4f, 0.037005995f), t, 0.79750759f);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(x * q));
+  const float h = 0.5f * x;
+  val = fmaf(h, th, h);
+  const float dq = x2 < 25.0f ? 2.0f * x2 * fmaf(t, -7.0318528e-4f, 0.037005995f) : 0.0f;  // x * dq/dx
+  grad = 0.5f * (1.0f + th) + h * (1.0f - th * th) * (q + dq);
+}
+// per-(sample, channel) InstanceNorm constants from fp64 sums
+W2S_DEVINL void in_consts(const double* stats, int b, int C, int c, int L, float eps, float& mean, float& rstd) {
+  const double s0 = stats[((size_t)b * C + c) * 2], s1 = stats[((size_t)b * C + c) * 2 + 1];
+  const double m = s0 / (double)L;
+  const double var = fmax(s1 / (double)L - m * m, 0.0);
+  mean = (float)m;
+  rstd = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+
 }  // namespace w2s

@@ -19,6 +19,10 @@
 //   EPI_BIAS_GELU : + bias, exact GELU, stores fp16
 //   EPI_LN_GELU   : LayerNorm over the 128 channels of the thread's row, affine, GELU
 //   EPI_LN_GELU_RES: ... + block input, GELU, optional fused classifier head
+//   EPI_ACT_BWD   : training data-gradient conv fused with the backward through the producing layer's activation:
+//                   da = acc (+ res); x_hat = IN(ab_y); [block outputs: s = GELU(x_hat) + ab_r, ds = da GELU'(s), dr = ds]
+//                   d(x_hat) = ds GELU'(x_hat) -> out; the activated tensor itself -> ab_a (operand of the weight
+//                   gradient); sum d(x_hat), sum d(x_hat) x_hat per (sample, channel) -> out_stats (fp64)
 //   EPI_PLAIN     : (+ bias) (+ residual tensor) -> fp16, output rows at o*out_stride + out_offset (plain GEMMs and
 //                   data-gradient convolutions of the training path)
 #pragma once
@@ -27,7 +31,7 @@
 namespace w2s {
 
 enum : int { PRO_NONE = 0, PRO_NORM = 1, PRO_NORM_RES = 2, PRO_FIR = 3, PRO_NORM_RES_X = 4 };
-enum : int { EPI_STATS = 0, EPI_BIAS_GELU = 1, EPI_LN_GELU = 2, EPI_LN_GELU_RES = 3, EPI_PLAIN = 4 };
+enum : int { EPI_STATS = 0, EPI_BIAS_GELU = 1, EPI_LN_GELU = 2, EPI_LN_GELU_RES = 3, EPI_PLAIN = 4, EPI_ACT_BWD = 5 };
 
 struct ConvArgs {
   // input side
@@ -57,6 +61,13 @@ struct ConvArgs {
   int out_stride;         // EPI_PLAIN: output row = o * out_stride + out_offset inside a sample of out_rows rows
   int out_offset;
   int out_rows;
+  // EPI_ACT_BWD: the producing layer's pre-norm output / residual branch / statistics, and the extra outputs
+  const act_t* ab_y;      // [B, L_out, COUT]
+  const act_t* ab_r;      // [B, L_out, COUT] or null (plain layer)
+  const double* ab_stats; // [B, COUT, 2] sum, sumsq of ab_y over L_out
+  act_t* ab_a;            // [B, L_out, COUT] activated tensor (may be null)
+  act_t* ab_dr;           // [B, L_out, COUT] gradient of the residual branch (ab_r != null)
+  float ab_eps;
   // streaming kernel, block-0 fusion (PRO_FIR / PRO_NORM_RES_X): the raw signal and the Cin = 1 weights of block 0
   const float* x_raw;     // [B, T_raw] fp32
   const float* w_first;   // [16, 3]
@@ -100,10 +111,11 @@ __host__ __device__ inline size_t conv_smem_bytes(int stride, int taps, int dil)
 
 template <int CIN, int COUT, int TAPS, int GT /*taps resident per weight group*/, int PRO, int EPI, bool HAS_DS,
           bool SPLIT>
-__global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs p) {
+__global__ void __launch_bounds__(kConvThreads, (EPI == EPI_ACT_BWD && COUT <= 64) ? 3 : 1) conv_igemm_kernel(const ConvArgs p) {
   static_assert(!SPLIT || (GT == TAPS && PRO != PRO_NONE), "split operands: single weight group, computed prologue");
   static_assert(CIN % 16 == 0 && COUT % 16 == 0 && COUT <= 128, "UMMA shape");
-  static_assert(EPI == EPI_STATS || EPI == EPI_PLAIN || COUT == 128, "row-wise epilogues need the full channel dim in one tile");
+  static_assert(EPI == EPI_STATS || EPI == EPI_PLAIN || EPI == EPI_ACT_BWD || COUT == 128,
+                "row-wise epilogues need the full channel dim in one tile");
   constexpr int CH = CIN / 8;                 // 16-byte chunks per input row
   constexpr int MT = ConvTile<COUT>::MT;
   constexpr int POS = ConvTile<COUT>::POS;
@@ -153,6 +165,12 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs
     const float rstd = (float)(1.0 / sqrt(var + (double)p.in_eps));
     sScale[c] = rstd;
     sShift[c] = (float)(-mean) * rstd;
+  }
+  if (EPI == EPI_ACT_BWD && tid >= 64 && tid < 64 + COUT) {  // InstanceNorm constants of the layer that produced ab_y
+    float mean, rstd;
+    in_consts(p.ab_stats, b, COUT, tid - 64, p.L_out, p.ab_eps, mean, rstd);
+    sScale[tid - 64] = rstd;
+    sShift[tid - 64] = mean;
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -374,6 +392,84 @@ __global__ void __launch_bounds__(kConvThreads) conv_igemm_kernel(const ConvArgs
         }
       }
       // fp64 atomics: the cross-CTA summation order no longer changes the fp32 result (run-to-run determinism)
+      atomicAdd(&p.out_stats[((size_t)b * COUT + tid) * 2 + 0], (double)s0);
+      atomicAdd(&p.out_stats[((size_t)b * COUT + tid) * 2 + 1], (double)s1);
+    }
+  } else if (EPI == EPI_ACT_BWD) {
+    constexpr int UNITS = MT * (COUT / 16);  // == 8
+#pragma unroll 1
+    for (int unit = wg; unit < UNITS; unit += 2) {
+      const int j = unit / (COUT / 16);
+      const int cg = unit % (COUT / 16);
+      float v[16], gx[16];
+      tmem_ld16(tmem_base + t_lane + j * COUT + cg * 16, v);
+      const int o = o0 + j * 128 + quad * 32 + lane;
+      const bool valid = o < p.L_out;
+      if (valid) {
+        const size_t off = ((size_t)b * p.L_out + o) * COUT + cg * 16;
+        auto load16 = [&](const act_t* src, float* dst) {
+          const uint4* q = reinterpret_cast<const uint4*>(src + off);
+          const uint4 z[2] = {__ldg(q), __ldg(q + 1)};
+          const uint32_t* w = reinterpret_cast<const uint32_t*>(z);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float2 f = unpack_h2(w[k]);
+            dst[2 * k] = f.x;
+            dst[2 * k + 1] = f.y;
+          }
+        };
+        float y[16], r[16], act[16];
+        load16(p.ab_y, y);
+        if (p.res != nullptr) {  // second gradient contribution (1x1 stride-2 residual branch of the consumer block)
+          load16(p.res, r);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] += r[k];
+        }
+        if (p.ab_r != nullptr) load16(p.ab_r, r);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float xh = (y[k] - sShift[cg * 16 + k]) * sScale[cg * 16 + k];
+          float g = v[k], a, da;
+          gelu_tanh_both(xh, a, da);
+          if (p.ab_r != nullptr) {
+            float ds;
+            gelu_tanh_both(a + r[k], a, ds);
+            g *= ds;
+            r[k] = g;  // dr
+          }
+          g *= da;
+          v[k] = g;
+          gx[k] = g * xh;
+          act[k] = a;
+        }
+        store_h16(p.out + off, v);
+        if (p.ab_a != nullptr) store_h16(p.ab_a + off, act);
+        if (p.ab_r != nullptr) store_h16(p.ab_dr + off, r);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = gx[k] = 0.0f;
+      }
+      butterfly16(v, lane);
+      butterfly16(gx, lane);
+      if ((lane & 1) == 0) {
+        const int slot = (warp * 4 + (unit >> 1)) * 16 + butterfly16_channel(lane);
+        sPartSum[slot] = v[0];
+        sPartSq[slot] = gx[0];
+      }
+    }
+    __syncthreads();
+    if (tid < COUT) {
+      float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+      for (int j = 0; j < MT; ++j) {
+        const int unit = j * (COUT / 16) + (tid >> 4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int slot = (((unit & 1) * 4 + q) * 4 + (unit >> 1)) * 16 + (tid & 15);
+          s0 += sPartSum[slot];
+          s1 += sPartSq[slot];
+        }
+      }
       atomicAdd(&p.out_stats[((size_t)b * COUT + tid) * 2 + 0], (double)s0);
       atomicAdd(&p.out_stats[((size_t)b * COUT + tid) * 2 + 1], (double)s1);
     }

@@ -16,37 +16,6 @@ W2S_DEVINL float gelu_grad(float x) {  // d/dx [x Phi(x)] = Phi(x) + x phi(x)
   const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
-// tanh-form GELU and derivative (same fitted exponent as the forward prologue, one MUFU.TANH): used on the whole-night
-// encoder tensors where erff/expf would make the element-wise kernels compute bound.
-W2S_DEVINL float gelu_tanh(float x) {
-  const float t = fminf(x * x, 25.0f);
-  const float q = fmaf(fmaf(t, -3.5159264e-4f, 0.037005995f), t, 0.79750759f);
-  float th;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(x * q));
-  const float h = 0.5f * x;
-  return fmaf(h, th, h);
-}
-W2S_DEVINL float gelu_grad_tanh(float x) {
-  const float x2 = x * x;
-  const float t = fminf(x2, 25.0f);
-  const float q = fmaf(fmaf(t, -3.5159264e-4f, 0.037005995f), t, 0.79750759f);
-  float th;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(x * q));
-  const float dq = x2 < 25.0f ? 2.0f * x2 * fmaf(t, -7.0318528e-4f, 0.037005995f) : 0.0f;  // x * dq/dx
-  return 0.5f * (1.0f + th) + 0.5f * x * (1.0f - th * th) * (q + dq);
-}
-// value and derivative together (one MUFU.TANH instead of two)
-W2S_DEVINL void gelu_tanh_both(float x, float& val, float& grad) {
-  const float x2 = x * x;
-  const float t = fminf(x2, 25.0f);
-  const float q = fmaf(fmaf(t, -3.5159264e-4f, 0.037005995f), t, 0.79750759f);
-  float th;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(x * q));
-  const float h = 0.5f * x;
-  val = fmaf(h, th, h);
-  const float dq = x2 < 25.0f ? 2.0f * x2 * fmaf(t, -7.0318528e-4f, 0.037005995f) : 0.0f;  // x * dq/dx
-  grad = 0.5f * (1.0f + th) + h * (1.0f - th * th) * (q + dq);
-}
 W2S_DEVINL void unpack8(const uint4& u, float* v) {
   const uint32_t* w = reinterpret_cast<const uint32_t*>(&u);
 #pragma unroll
@@ -59,15 +28,6 @@ W2S_DEVINL void unpack8(const uint4& u, float* v) {
 W2S_DEVINL uint4 pack8(const float* v) {
   return make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
 }
-// per-(sample, channel) InstanceNorm constants from fp64 sums
-W2S_DEVINL void in_consts(const double* stats, int b, int C, int c, int L, float eps, float& mean, float& rstd) {
-  const double s0 = stats[((size_t)b * C + c) * 2], s1 = stats[((size_t)b * C + c) * 2 + 1];
-  const double m = s0 / (double)L;
-  const double var = fmax(s1 / (double)L - m * m, 0.0);
-  mean = (float)m;
-  rstd = (float)(1.0 / sqrt(var + (double)eps));
-}
-
 // Block-wide InstanceNorm constants: the fp64 division / square root is done once per (block, channel) by the first C
 // threads and shared through smem (doing it per thread made the element-wise kernels fp64-bound).
 // sm: [4][128] floats = mean, rstd, m1, m2

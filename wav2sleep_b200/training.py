@@ -22,7 +22,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import ConvCall, EPI_PLAIN, PRO_NONE
+from ._lib import ConvCall, EPI_ACT_BWD, EPI_PLAIN, PRO_NONE
 from .engine import ForwardEngine, _stream
 
 F16 = torch.float16
@@ -125,6 +125,25 @@ class TrainEngine(ForwardEngine):
         c.res = res.data_ptr() if res is not None else None
         c.row_mask = row_mask.data_ptr() if row_mask is not None else None
         c.out_stride, c.out_offset, c.out_rows = out_stride, out_offset, out_rows
+        _lib.check(self.lib.w2s_conv1d_fwd(C.byref(c), _stream()))
+
+    def conv_act_bwd(self, dy, w, cin, cout, B, L, y, stats, sums, dxh, a_out, eps, row_mask, res=None, r=None, dr=None):
+        """Data gradient of a k=3 / pad=1 / stride-1 conv (flipped, transposed weights w) fused with the backward through
+        the activation of the layer that produced the conv's input: writes d(x_hat) of that layer (dxh), its activated
+        output (a_out, operand of this conv's weight gradient), d(residual branch) (dr, block outputs) and accumulates
+        the two InstanceNorm-backward reductions into sums."""
+        c = ConvCall()
+        c.cin, c.cout, c.taps, c.stride, c.dilation, c.pad = cin, cout, 3, 1, 1, 1
+        c.prologue, c.epilogue, c.has_ds = PRO_NONE, EPI_ACT_BWD, 0
+        c.B, c.L_in, c.L_out = B, L, L
+        c.in_, c.w, c.out = dy.data_ptr(), w.data_ptr(), dxh.data_ptr()
+        c.res = res.data_ptr() if res is not None else None
+        c.row_mask = row_mask.data_ptr() if row_mask is not None else None
+        c.out_stats = sums.data_ptr()
+        c.act_y, c.act_stats, c.act_eps = y.data_ptr(), stats.data_ptr(), eps
+        c.act_a = a_out.data_ptr() if a_out is not None else None
+        c.act_r = r.data_ptr() if r is not None else None
+        c.act_dr = dr.data_ptr() if dr is not None else None
         _lib.check(self.lib.w2s_conv1d_fwd(C.byref(c), _stream()))
 
     def gemm_tn(self, X, Y, Cbuf, M, N, B, LX, LY, ldc_m, ldc_n, y_stride=1, y_offset=0, row_mask=None, c_off=0, taps=1,
@@ -451,52 +470,42 @@ class TrainEngine(ForwardEngine):
             self.conv(d_zpre, tw["lin_dgrad"][t], 128, Cl, 1, B, S, S, d_a, out_stride=4, out_offset=t, out_rows=L4,
                       row_mask=mask)
         self.colsum(d_zpre, G(enc.linear.bias), B * S, 128, row_mask=mask, rows_per_sample=S)
-        dout = d_a  # gradient wrt the activated output of the last block, [B, L/2, C]
-        # The activated input of a conv (needed by its weight gradient) is written by enc_act_bwd of the producing layer
-        # as a by-product, so weight gradients run one stage late: `pending` holds the conv1 / downsample weight
-        # gradients of the block above until this block's output activation exists.
-        pending = None
-        for i in reversed(range(len(blocks))):
+        # The backward through a layer's activation (GELU', residual add, the two InstanceNorm reductions) runs in the
+        # epilogue of the data-gradient conv that produces its input gradient (EPI_ACT_BWD), which also writes the
+        # activated tensor that conv's own weight gradient needs - so each weight gradient runs right after its data
+        # gradient.  Only the last block's output (fed by the Linear) goes through the stand-alone enc_act_bwd kernel.
+        nb = len(blocks)
+        last_bk = blocks[-1]
+        Cc, Lh = last_bk["C"], last_bk["L"] // 2
+        dxh, dr, sums = new(B, Lh, Cc), new(B, Lh, Cc), zeros64(Cc)
+        _lib.check(lib.w2s_enc_act_bwd(d_a.data_ptr(), last_bk["y3"].data_ptr(), last_bk["r"].data_ptr(),
+                                       last_bk["s3"].data_ptr(), dxh.data_ptr(), dr.data_ptr(), sums.data_ptr(), None,
+                                       mask.data_ptr(), B, Lh, Cc, eps, st))
+        for i in reversed(range(nb)):
             bk, blk = blocks[i], enc.cnn[i]
             Cc, L = bk["C"], bk["L"]
             Lh = L // 2
-            # ---- block output: GELU(GELU(IN(y3)) + r) ----
-            dxh, dr, sums = new(B, Lh, Cc), new(B, Lh, Cc), zeros64(Cc)
-            a_blk = new(B, Lh, Cc) if pending is not None else None
-            _lib.check(lib.w2s_enc_act_bwd(dout.data_ptr(), bk["y3"].data_ptr(), bk["r"].data_ptr(), bk["s3"].data_ptr(),
-                                           dxh.data_ptr(), dr.data_ptr(), sums.data_ptr(), _p(a_blk), mask.data_ptr(), B, Lh,
-                                           Cc, eps, st))
-            if pending is not None:
-                pending(a_blk)
-                pending = None
-            del a_blk
+            # here: dxh / dr / sums = backward through this block's output activation GELU(GELU(IN(y3)) + r)
             dy_up = torch.zeros(B, L, Cc, dtype=F16, device=device)
             _lib.check(lib.w2s_enc_norm_bwd(dxh.data_ptr(), bk["y3"].data_ptr(), bk["s3"].data_ptr(), sums.data_ptr(),
                                             dy_up.data_ptr(), mask.data_ptr(), B, Lh, Cc, 1, eps, st))
-            # ---- conv3 (stride 2): data gradient, then (once a2 exists) weight gradient ----
-            d_a2 = new(B, L, Cc)
-            self.conv(dy_up, tw["conv"][i][2], Cc, Cc, 3, B, L, L, d_a2, pad=1, row_mask=mask)
-            a2, sums = new(B, L, Cc), zeros64(Cc)
-            dxh = new(B, L, Cc)
-            _lib.check(lib.w2s_enc_act_bwd(d_a2.data_ptr(), bk["y2"].data_ptr(), None, bk["s2"].data_ptr(), dxh.data_ptr(),
-                                           None, sums.data_ptr(), a2.data_ptr(), mask.data_ptr(), B, L, Cc, eps, st))
+            # ---- conv3 (stride 2): data gradient + backward through GELU(IN(y2)) in one kernel ----
+            dxh, a2, sums = new(B, L, Cc), new(B, L, Cc), zeros64(Cc)
+            self.conv_act_bwd(dy_up, tw["conv"][i][2], Cc, Cc, B, L, bk["y2"], bk["s2"], sums, dxh, a2, eps, mask)
             self.gemm_tn(dy_up, a2, G(blk.conv3.conv.weight), Cc, Cc, B, L, L, Cc * 3, 3, y_offset=-1, row_mask=mask,
                          taps=3, ldc_t=1)
-            del dy_up, a2
+            del dy_up
             # ---- conv2 ----
-            dy2 = d_a2  # reuse
+            dy2 = a2  # a2 is consumed: reuse its storage
             _lib.check(lib.w2s_enc_norm_bwd(dxh.data_ptr(), bk["y2"].data_ptr(), bk["s2"].data_ptr(), sums.data_ptr(),
                                             dy2.data_ptr(), mask.data_ptr(), B, L, Cc, 0, eps, st))
-            d_a1 = new(B, L, Cc)
-            self.conv(dy2, tw["conv"][i][1], Cc, Cc, 3, B, L, L, d_a1, pad=1, row_mask=mask)
-            a1, sums = new(B, L, Cc), zeros64(Cc)  # dxh (consumed by the norm backward above) is overwritten
-            _lib.check(lib.w2s_enc_act_bwd(d_a1.data_ptr(), bk["y1"].data_ptr(), None, bk["s1"].data_ptr(), dxh.data_ptr(),
-                                           None, sums.data_ptr(), a1.data_ptr(), mask.data_ptr(), B, L, Cc, eps, st))
+            a1, sums = new(B, L, Cc), zeros64(Cc)
+            self.conv_act_bwd(dy2, tw["conv"][i][1], Cc, Cc, B, L, bk["y1"], bk["s1"], sums, dxh, a1, eps, mask)
             self.gemm_tn(dy2, a1, G(blk.conv2.conv.weight), Cc, Cc, B, L, L, Cc * 3, 3, y_offset=-1, row_mask=mask, taps=3,
                          ldc_t=1)
-            del a1, dy2, d_a2
+            del dy2, a2
             # ---- conv1 (+ 1x1 stride-2 residual branch) ----
-            dy1 = d_a1
+            dy1 = a1
             _lib.check(lib.w2s_enc_norm_bwd(dxh.data_ptr(), bk["y1"].data_ptr(), bk["s1"].data_ptr(), sums.data_ptr(),
                                             dy1.data_ptr(), mask.data_ptr(), B, L, Cc, 0, eps, st))
             del dxh
@@ -505,22 +514,22 @@ class TrainEngine(ForwardEngine):
                                                     G(blk.conv1.conv.weight).data_ptr(), G(blk.downsample.weight).data_ptr(),
                                                     mask.data_ptr(), B, L, st))
                 break
-            Ci = blocks[i - 1]["C"]
+            pb = blocks[i - 1]
+            Ci = pb["C"]
             tmp = torch.zeros(B, L, Ci, dtype=F16, device=device)
             self.conv(dr, tw["ds"][i], Cc, Ci, 1, B, Lh, Lh, tmp, out_stride=2, out_offset=0, out_rows=L, row_mask=mask)
-            d_in = new(B, L, Ci)
-            self.conv(dy1, tw["conv"][i][0], Cc, Ci, 3, B, L, L, d_in, pad=1, res=tmp, row_mask=mask)
+            # data gradient of conv1 (+ the residual-branch gradient) fused with the backward through the previous
+            # block's output activation; a_in is this block's input, needed by the two weight gradients below
+            dxh_p, dr_p, a_in, sums = new(B, L, Ci), new(B, L, Ci), new(B, L, Ci), zeros64(Ci)
+            self.conv_act_bwd(dy1, tw["conv"][i][0], Cc, Ci, B, L, pb["y3"], pb["s3"], sums, dxh_p, a_in, eps, mask,
+                              res=tmp, r=pb["r"], dr=dr_p)
             del tmp
-
-            def pending(a_in, dy1=dy1, dr=dr, blk=blk, Cc=Cc, Ci=Ci, L=L, Lh=Lh):
-                # a_in = the block input GELU(GELU(IN(y3)) + r) of the previous block, [B, L, Ci]
-                self.gemm_tn(dy1, a_in, G(blk.conv1.conv.weight), Cc, Ci, B, L, L, Ci * 3, 3, y_offset=-1, row_mask=mask,
-                             taps=3, ldc_t=1)
-                self.gemm_tn(dr, a_in, G(blk.downsample.weight), Cc, Ci, B, Lh, L, Ci, 1, y_stride=2, y_offset=0,
-                             row_mask=mask)
-
-            dout = d_in
-            del dy1, dr, d_a1
+            self.gemm_tn(dy1, a_in, G(blk.conv1.conv.weight), Cc, Ci, B, L, L, Ci * 3, 3, y_offset=-1, row_mask=mask,
+                         taps=3, ldc_t=1)
+            self.gemm_tn(dr, a_in, G(blk.downsample.weight), Cc, Ci, B, Lh, L, Ci, 1, y_stride=2, y_offset=0,
+                         row_mask=mask)
+            del dy1, dr, a_in, a1
+            dxh, dr = dxh_p, dr_p
 
 
 class _TrainFn(torch.autograd.Function):
