@@ -235,7 +235,8 @@ int w2s_enc_act_fwd(const void* y, const void* r, const double* stats, void* a, 
  * writes the activated tensor itself (= w2s_enc_act_fwd's output) for the weight gradient of the consuming conv. */
 int w2s_enc_act_bwd(const void* dout, const void* y, const void* r, const double* stats, void* dxh, void* dr, double* sums,
                     void* a_out, const uint8_t* row_mask, int B, int L, int C, float eps, void* stream);
-/* dy = rstd * (dxh - mean(dxh) - x_hat * mean(dxh * x_hat)); upsample = 1 writes row 2l of a zeroed [B, 2L, C] tensor. */
+/* dy = rstd * (dxh - mean(dxh) - x_hat * mean(dxh * x_hat)); upsample = 1 writes row 2l of a [B, 2L, C] tensor and zeros to
+ * row 2l+1 (rows of masked samples are not touched). */
 int w2s_enc_norm_bwd(const void* dxh, const void* y, const double* stats, const double* sums, void* dy,
                      const uint8_t* row_mask, int B, int L, int C, int upsample, float eps, void* stream);
 /* weight gradients of the Cin = 1 layers of block 0 (conv1 [16,1,3] and downsample [16,1,1]). */

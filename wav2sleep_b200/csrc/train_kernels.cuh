@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) enc_act_bwd_kernel(const EncActBwdArgs p)
 
 // ------------------------------------------------------------------------------------------------------------
 // C. InstanceNorm backward: dy = rstd * (dxh - mean_L(dxh) - xh * mean_L(dxh * xh)); optional 2x zero-upsampling
-//    of the output rows (row 2l of a pre-zeroed [B, 2L, C] tensor) for the transposed stride-2 convolution.
+//    of the output rows (row 2l of a [B, 2L, C] tensor, zeros written to row 2l+1) for the transposed stride-2 conv.
 // ------------------------------------------------------------------------------------------------------------
 struct EncNormBwdArgs {
   const act_t* dxh; const act_t* y; const double* stats; const double* sums; act_t* dy; const uint8_t* row_mask;
@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(256) enc_norm_bwd_kernel(const EncNormBwdArgs 
     }
     const size_t oo = p.upsample ? ((size_t)b * 2 * p.L + 2 * l) * p.C + c8 * 8 : off;
     *reinterpret_cast<uint4*>(p.dy + oo) = pack8(d);
+    if (p.upsample) *reinterpret_cast<uint4*>(p.dy + oo + p.C) = make_uint4(0u, 0u, 0u, 0u);  // odd rows: zeros
   }
 }
 

@@ -486,7 +486,7 @@ class TrainEngine(ForwardEngine):
             Cc, L = bk["C"], bk["L"]
             Lh = L // 2
             # here: dxh / dr / sums = backward through this block's output activation GELU(GELU(IN(y3)) + r)
-            dy_up = torch.zeros(B, L, Cc, dtype=F16, device=device)
+            dy_up = new(B, L, Cc)  # even rows = dy, odd rows = zeros (written by the kernel): transposed stride-2 conv
             _lib.check(lib.w2s_enc_norm_bwd(dxh.data_ptr(), bk["y3"].data_ptr(), bk["s3"].data_ptr(), sums.data_ptr(),
                                             dy_up.data_ptr(), mask.data_ptr(), B, Lh, Cc, 1, eps, st))
             # ---- conv3 (stride 2): data gradient + backward through GELU(IN(y2)) in one kernel ----
