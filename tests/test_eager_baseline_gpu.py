@@ -48,3 +48,39 @@ def test_eager_torch_baseline_on_the_same_gpu(cuda_device):
           f"this repo {t_ours:.2f} ms = {B * 10 / t_ours * 1e3:.0f} recording-h/s; ratio {t_eager / t_ours:.1f}x; "
           f"argmax agreement between the two GPU paths {agree:.4f}")
     assert agree > 0.99 and t_ours < t_eager
+
+
+def test_eager_torch_training_step_baseline(cuda_device):
+    """fwd + CE + bwd of the same graph through torch autograd (eager cuDNN / cuBLAS, fp32, no dropout) vs this repo's
+    training path, 4 nights (the eager graph keeps every fp32 intermediate: 16 nights would not be a safe allocation)."""
+    B, S = 4, 1200
+    model = build_default(CARDIO, 4, seed=0).to(cuda_device)
+    model.epoch_mixer.dropout = 0.0
+    for blk in model.sequence_mixer.dilated_convs:
+        blk.dropout.p = 0.0
+    x = {k: v.to(cuda_device) for k, v in make_inputs(CARDIO, B, S, seed=42).items()}
+    y = torch.randint(0, 4, (B, S), device=cuda_device)
+    cfg = oracle.cardio_config()
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+
+    def eager():
+        for p in params.values():
+            p.grad = None
+        z = oracle.signal_encoders(x, params, cfg)
+        s = oracle.sequence_mixer(oracle.epoch_mixer(z, params, cfg), params, cfg)
+        logits = s @ params["classifier.weight"].t() + params["classifier.bias"]
+        torch.nn.functional.cross_entropy(logits.view(-1, 4), y.view(-1)).backward()
+
+    model.train()
+
+    def ours():
+        model.zero_grad(set_to_none=True)
+        torch.nn.functional.cross_entropy(model(x).view(-1, 4), y.view(-1)).backward()
+
+    t_eager, t_ours = _time(eager, n=2), _time(ours, n=3)
+    g_ref = params["signal_encoders.encoders.ECG.cnn.3.conv2.conv.weight"].grad
+    g = model.signal_encoders.get_encoder("ECG").cnn[3].conv2.conv.weight.grad
+    cos = torch.nn.functional.cosine_similarity(g.flatten().float(), g_ref.flatten(), dim=0).item()
+    print(f"eager torch fwd+bwd {t_eager:.1f} ms vs this repo {t_ours:.1f} ms for {B} nights: {t_eager / t_ours:.1f}x; "
+          f"peak eager memory {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB; cos(grad) {cos:.5f}")
+    assert cos > 0.99 and t_ours < t_eager  # both sides are reduced precision here (TF32 convolutions vs fp16 storage)
