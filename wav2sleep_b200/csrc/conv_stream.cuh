@@ -120,7 +120,7 @@ struct StreamCfg {
   static constexpr int B_BYTES = B_ONE * (SPLIT ? 2 : 1);
   static constexpr int STAGE_COLS = MT * COUT * (HAS_DS ? 2 : 1);
   static constexpr int TMEM_COLS = (2 * STAGE_COLS <= 32) ? 32 : (2 * STAGE_COLS <= 64) ? 64 : (2 * STAGE_COLS <= 128) ? 128 : (2 * STAGE_COLS <= 256) ? 256 : 512;
-  static constexpr int CTL_BYTES = 256;
+  static constexpr int CTL_BYTES = 512;  // mbarriers + TMEM slot (first 256 B), live-sample list (second 256 B)
   static constexpr int SMEM_BYTES = NR * RAW_BYTES + NA * A_BYTES + B_BYTES + CTL_BYTES;
   static_assert(2 * STAGE_COLS <= 512, "TMEM budget");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -158,8 +158,14 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile_begin = (int)((long long)blockIdx.x * total_tiles / gridDim.x);
-  const int tile_end = (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x);
+  // Samples without this signal (row_mask) are compacted away before the tiles are split over the CTAs, so that masked
+  // nights cost nothing and the remaining work stays balanced (training with the modality masker, inference with
+  // missing signals).  sLive[i] = i-th live sample; batches larger than the list fall back to skipping tile by tile.
+  constexpr int kMaxLive = 120;
+  uint16_t* sLive = reinterpret_cast<uint16_t*>(sCtl + 256);
+  int& sNLive = *reinterpret_cast<int*>(sCtl + 256 + 2 * kMaxLive);
+  const int n_samples = total_tiles / tiles_per_sample;
+  const bool compact = p.row_mask != nullptr && n_samples <= kMaxLive;
 
   // ---------------- one-time setup ----------------
   if (tid == 0) dbg_ts(p, 0);
@@ -203,11 +209,26 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
       }
     }
   }
+  if (compact && tid == 64) {
+    int n = 0;
+    for (int b = 0; b < n_samples; ++b)
+      if (!p.row_mask[b]) sLive[n++] = (uint16_t)b;
+    sNLive = n;
+  }
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const int live_tiles = compact ? sNLive * tiles_per_sample : total_tiles;
+  const int tile_begin = (int)((long long)blockIdx.x * live_tiles / gridDim.x);
+  const int tile_end = (int)((long long)(blockIdx.x + 1) * live_tiles / gridDim.x);
+  // sample of a tile; false = masked sample (only possible without compaction)
+  auto sample_of = [&](int tile, int& b) {
+    const int s = tile / tiles_per_sample;
+    b = compact ? (int)sLive[s] : s;
+    return compact || p.row_mask == nullptr || !p.row_mask[b];
+  };
   if (tid == 0) dbg_ts(p, 2);
 
   // ======================================================================================================
@@ -219,9 +240,9 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
       WaitClock wc;
       const long long cta_t0 = clock64();
       for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const int b = tile / tiles_per_sample;
-        if (p.row_mask != nullptr && p.row_mask[b]) continue;
-        const int o0 = (tile - b * tiles_per_sample) * POS;
+        int b;
+        if (!sample_of(tile, b)) continue;
+        const int o0 = (tile % tiles_per_sample) * POS;
         const int i0 = o0 * STRIDE - 1;
         const int lo = i0 < 0 ? 0 : i0;
         const int hi = (i0 + R < p.L_in) ? i0 + R : p.L_in;
@@ -266,8 +287,8 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
       const uint32_t b_base = smem_u32(sB);
       constexpr uint32_t lbo_a = RP * 16, lbo_b = COUT * 16;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const int b = tile / tiles_per_sample;
-        if (p.row_mask != nullptr && p.row_mask[b]) continue;
+        int b;
+        if (!sample_of(tile, b)) continue;
         wc.wait(p, &a_full[as], aph);
         wc.wait(p, &t_empty[ts], tph ^ 1);
         tc_fence_after_sync();
@@ -367,13 +388,13 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
     };
 
     for (int tile = tile_begin; tile < tile_end; ++tile) {
-      const int b = tile / tiles_per_sample;
-      if (p.row_mask != nullptr && p.row_mask[b]) continue;
+      int b;
+      if (!sample_of(tile, b)) continue;
       if (b != cur_b) {
         flush(cur_b);
         cur_b = b;
       }
-      const int o0 = (tile - b * tiles_per_sample) * POS;
+      const int o0 = (tile % tiles_per_sample) * POS;
       wc.wait(p, &t_full[ts], tph);
       tc_fence_after_sync();
       if (warp == 2 && lane == 0 && tile == tile_begin) dbg_ts(p, 6);
@@ -466,8 +487,8 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
       }
     }
     for (int tile = tile_begin; tile < tile_end; ++tile) {
-      const int b = tile / tiles_per_sample;
-      if (p.row_mask != nullptr && p.row_mask[b]) continue;
+      int b;
+      if (!sample_of(tile, b)) continue;
       if (b != cur_b) {
         cur_b = b;
         const double inv_len = 1.0 / (double)p.L_in;
@@ -498,7 +519,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
           }
         }
       }
-      const int o0 = (tile - b * tiles_per_sample) * POS;
+      const int o0 = (tile % tiles_per_sample) * POS;
       const int i0 = o0 * STRIDE - 1;
       if (tt == 0 && tile == tile_begin) dbg_ts(p, 3);
       wc_raw.wait(p, &raw_full[rs], rph);

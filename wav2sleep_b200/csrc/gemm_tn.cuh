@@ -96,20 +96,37 @@ __global__ void __launch_bounds__(kGemmTNThreads) gemm_tn_kernel(const GemmTNArg
         for (int q = 0; q < 4; ++q) acc[t][i][j][q] = 0.0f;
 
   const int tiles_per_sample = (p.LX + kGemmTNRows - 1) / kGemmTNRows;
-  const long long tiles = (long long)tiles_per_sample * p.B;
+  // masked samples are compacted away before the tiles are split over the CTAs (balanced work under the modality
+  // masker); batches larger than the list fall back to skipping tile by tile
+  constexpr int kMaxLive = 512;
+  __shared__ uint16_t sLive[kMaxLive];
+  __shared__ int sNLive;
+  const bool compact = p.row_mask != nullptr && p.B <= kMaxLive;
+  if (compact) {
+    if (tid == 0) {
+      int n = 0;
+      for (int b = 0; b < p.B; ++b)
+        if (!p.row_mask[b]) sLive[n++] = (uint16_t)b;
+      sNLive = n;
+    }
+    __syncthreads();
+  }
+  const long long tiles = (long long)tiles_per_sample * (compact ? sNLive : p.B);
   const long long t_begin = tiles * blockIdx.x / gridDim.x, t_end = tiles * (blockIdx.x + 1) / gridDim.x;
+  auto sample_of = [&](long long t) { return compact ? (int)sLive[t / tiles_per_sample] : (int)(t / tiles_per_sample); };
+  if (t_begin >= t_end) return;  // no work (e.g. every sample masked): also no atomics into C
 
   // next tile of this CTA whose sample is not masked (uniform over the CTA)
   auto next_tile = [&](long long t) {
-    while (t < t_end && p.row_mask != nullptr && p.row_mask[(int)(t / tiles_per_sample)]) ++t;
+    while (!compact && t < t_end && p.row_mask != nullptr && p.row_mask[(int)(t / tiles_per_sample)]) ++t;
     return t;
   };
   // Register double buffering: the global loads of tile i+1 are issued before the MMAs of tile i and land while they
   // run; they are written to shared memory after the MMAs are done.
   uint4 xv[XN], yv[YN];
   auto load_tile = [&](long long tile) {
-    const int b = (int)(tile / tiles_per_sample);
-    const int l0 = (int)(tile - (long long)b * tiles_per_sample) * kGemmTNRows;
+    const int b = sample_of(tile);
+    const int l0 = (int)(tile % tiles_per_sample) * kGemmTNRows;
     const act_t* Xb = p.X + ((size_t)b * p.LX) * M;
     const act_t* Yb = p.Y + ((size_t)b * p.LY) * N;
     const int ybase = l0 * p.y_stride + p.y_offset + (int)blockIdx.y * p.tap_stride;
