@@ -48,6 +48,20 @@ size_t w2s_packed_conv_weight_bytes(int cout, int cin, int taps, int split);
  * packed with split = 1 (hi block followed by lo block, twice the bytes).  True for cin <= 32 and cout <= 32. */
 int w2s_conv_uses_split(int cin, int cout);
 
+/* Batched re-packing (one launch for every weight of a model, used after each optimizer step).  jobs: DEVICE array.
+ * kind 0: packed[n][c][t] = w[n*sn + c*sc + t*st] (element strides, may be negative: flipped / transposed / sliced views
+ * of the fp32 parameters) -> UMMA conv layout of w2s_pack_conv_weight (split: hi block then lo block).
+ * kind 1: linear weight element (row, col) = w[row*sn + col*sc], cout = rows n, cin = columns k -> w2s_pack_linear_frag
+ * order.  max_elems = largest cout*cin*taps among the jobs. */
+typedef struct w2s_pack_job {
+  const float* w;
+  void* out;
+  int32_t kind, cout, cin, taps;
+  int64_t sn, sc, st;
+  int32_t split, reserved;
+} w2s_pack_job;
+int w2s_pack_batch(const w2s_pack_job* jobs_device, int n_jobs, int max_elems, void* stream);
+
 /* nn.Linear weight [n, k] fp32 -> fp16 mma.sync B-fragment order [n/8][k/16][32 lanes][4] (epoch mixer). */
 int w2s_pack_linear_frag(const float* w, int n, int k, void* out_fp16, void* stream);
 

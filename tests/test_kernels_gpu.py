@@ -45,9 +45,11 @@ def test_first_conv(cuda_device, B, T):
     if B > 1:
         x[1] = float("-inf")
     # run the whole encoder in keep mode and look at block 0's first tensors in the workspace
-    from wav2sleep_b200.engine import _PackedEncoder
+    from wav2sleep_b200.engine import PackPlan, _PackedEncoder
     lib = _lib.load()
-    pe = _PackedEncoder(lib, enc, cuda_device)
+    plan = PackPlan(lib, cuda_device)
+    pe = _PackedEncoder(lib, enc, cuda_device, plan)
+    plan.run()
     ws_bytes = lib.w2s_encoder_workspace_bytes(C.byref(pe.desc), B, T, 1)
     ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=cuda_device)
     z = torch.zeros(B, T // 256, 128, dtype=torch.float16, device=cuda_device)
@@ -224,3 +226,41 @@ def test_seq_conv_layer(cuda_device, dil, S, res):
     assert (out.float() - ref).abs().max().item() < 5e-3
     if res:
         assert (logits - (ref @ hw.t() + hb)).abs().max().item() < 5e-3
+
+
+def test_pack_batch_matches_single_packs(cuda_device):
+    """w2s_pack_batch (strided sources, one launch) against w2s_pack_conv_weight / w2s_pack_linear_frag, incl. the
+    flipped + transposed view used for data-gradient weights and the taps-major view of a Linear."""
+    from wav2sleep_b200.engine import PackPlan
+    lib = _lib.load()
+    torch.manual_seed(3)
+    w = torch.randn(32, 16, 3, device=cuda_device)
+    lin = torch.randn(128, 256, device=cuda_device)  # Linear(4 * 64 -> 128)
+    fr = torch.randn(384, 128, device=cuda_device)
+    plan = PackPlan(lib, cuda_device)
+    jobs = [(plan.conv(w, split=1), w, 0, 1), (plan.conv(w.permute(1, 0, 2), flip=True), w.flip(2).permute(1, 0, 2).contiguous(), 0, 0),
+            (plan.conv(lin.view(128, 4, 64).permute(0, 2, 1)), lin, 1, 0)]
+    p_frag = plan.frag(fr)
+    plan.run()
+    torch.cuda.synchronize()
+    bufs = {t.data_ptr(): t for t in plan.keep}
+    for ptr, src, taps_major, split in jobs:
+        if taps_major:
+            cout, cin, taps = src.shape[0], src.shape[1] // 4, 4
+        else:
+            cout, cin, taps = src.shape
+        ref = torch.empty(cout * cin * taps * (2 if split else 1), dtype=torch.float16, device=cuda_device)
+        _lib.check(lib.w2s_pack_conv_weight(src.data_ptr(), cout, cin, taps, taps_major, split, ref.data_ptr(), G.stream()))
+        torch.cuda.synchronize()
+        assert torch.equal(bufs[ptr], ref)
+    ref = torch.empty(fr.numel(), dtype=torch.float16, device=cuda_device)
+    _lib.check(lib.w2s_pack_linear_frag(fr.data_ptr(), 384, 128, ref.data_ptr(), G.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(bufs[p_frag], ref)
+    # values change in place -> run() again picks them up without rebuilding
+    w.mul_(2.0)
+    plan.run()
+    ref = torch.empty(32 * 16 * 3 * 2, dtype=torch.float16, device=cuda_device)
+    _lib.check(lib.w2s_pack_conv_weight(w.data_ptr(), 32, 16, 3, 0, 1, ref.data_ptr(), G.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(bufs[jobs[0][0]], ref)

@@ -31,6 +31,13 @@ def test_masker_keeps_at_least_one_signal_and_respects_backups():
     assert 0.6 < drops["ABD"] / n < 0.8 and 0.4 < drops["ECG"] / n < 0.6 and drops["PPG"] / n < 0.25
     with pytest.raises(ValueError):
         SignalMasker({"ECG": 0.5})({"ECG": torch.full((2, 4), float("-inf"))})
+    with pytest.raises(ValueError):
+        SignalMasker({"ECG": 1.5})
+    with pytest.raises(ValueError):
+        SignalMasker({"ECG": 1.0, "PPG": 1.0})({"ECG": torch.randn(2, 4), "PPG": torch.randn(2, 4)})
+    with pytest.raises(ValueError):  # no backup channel available for a sample whose draws all failed
+        SignalMasker({"ECG": 0.5, "ABD": 0.5}, backups=["ECG"])({"ECG": torch.full((2, 4), float("-inf")),
+                                                                  "ABD": torch.randn(2, 4)})
 
 
 def test_invert_signals_and_confusion_matrix():

@@ -245,3 +245,30 @@ def test_lightning_shaped_module_fit_with_masker(cuda_device):
     with torch.no_grad():
         out = model({k: v.to(cuda_device) for k, v in make_inputs(CARDIO, 4, 8, seed=3).items()})
     assert torch.isfinite(out).all()
+
+
+def test_masker_on_device_defers_data_errors(cuda_device):
+    """On CUDA the masker never synchronises: a night with every signal unavailable is reported by the next call /
+    check(); the dropout statistics are those of the reference masker."""
+    from wav2sleep_b200.trainer import SignalMasker
+    torch.manual_seed(0)
+    masker = SignalMasker({"ABD": 0.7, "THX": 0.7, "ECG": 0.5, "PPG": 0.1}, backups=["ECG", "PPG"])
+    n, drops = 0, torch.zeros(4, device=cuda_device)
+    for _ in range(40):
+        x = {k: torch.randn(32, 8, device=cuda_device) for k in ("ABD", "THX", "ECG", "PPG")}
+        masker(x)
+        miss = torch.stack([torch.isinf(v[:, 0]) for v in x.values()], -1)
+        assert not miss.all(-1).any()
+        drops += miss.sum(0)
+        n += 32
+    masker.check()
+    frac = (drops / n).tolist()
+    assert 0.6 < frac[0] < 0.8 and 0.6 < frac[1] < 0.8 and 0.4 < frac[2] < 0.6 and frac[3] < 0.25
+    bad = {k: torch.full((2, 8), float("-inf"), device=cuda_device) for k in ("ECG", "PPG")}
+    masker(bad)  # recorded, not raised
+    with pytest.raises(ValueError):
+        masker.check()
+    masker({k: torch.randn(2, 8, device=cuda_device) for k in ("ECG", "PPG")})  # flag was consumed
+    strict = SignalMasker({"ECG": 0.5}, deferred_errors=False)
+    with pytest.raises(ValueError):
+        strict({"ECG": torch.full((2, 8), float("-inf"), device=cuda_device)})

@@ -55,6 +55,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
+class PackJob(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("out", C.c_void_p), ("kind", C.c_int32), ("cout", C.c_int32), ("cin", C.c_int32),
+                ("taps", C.c_int32), ("sn", C.c_int64), ("sc", C.c_int64), ("st", C.c_int64), ("split", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 class ConvCall(C.Structure):
     _fields_ = [
         ("cin", C.c_int32), ("cout", C.c_int32), ("taps", C.c_int32), ("stride", C.c_int32),
@@ -117,6 +123,7 @@ SYMBOLS = {
                                        C.c_void_p]),
     "w2s_packed_conv_weight_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "w2s_conv_uses_split": (C.c_int, [C.c_int, C.c_int]),
+    "w2s_pack_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "w2s_pack_linear_frag": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "w2s_conv1d_fwd": (C.c_int, [C.POINTER(ConvCall), C.c_void_p]),
     "w2s_set_conv_impl": (C.c_int, [C.c_int]),

@@ -112,6 +112,44 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, int cout, int cin,
   }
 }
 
+// All weight re-packing of a model in ONE launch (after every optimizer step): blockIdx.y = job.  A job reads its source
+// through explicit element strides (so flipped / transposed / sliced views of the fp32 master parameters need no torch
+// copies) and writes either the UMMA conv layout (kind 0, optionally hi + lo) or the mma.sync fragment order (kind 1).
+__global__ void pack_batch_kernel(const w2s_pack_job* __restrict__ jobs) {
+  const w2s_pack_job j = jobs[blockIdx.y];
+  __half* out = reinterpret_cast<__half*>(j.out);
+  if (j.kind == 0) {
+    const int cout = j.cout, cin = j.cin, taps = j.taps;
+    const int total = taps * cin * cout;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+      const int k = idx & 7;
+      int r = idx >> 3;
+      const int n = r % cout;
+      r /= cout;
+      const int c8 = r % (cin / 8);
+      const int t = r / (cin / 8);
+      const int c = c8 * 8 + k;
+      const float v = j.w[(long long)n * j.sn + (long long)c * j.sc + (long long)t * j.st];
+      const __half hi = __float2half_rn(v);
+      out[idx] = hi;
+      if (j.split) out[total + idx] = __float2half_rn(v - __half2float(hi));
+    }
+  } else {  // nn.Linear weight [n, k] (row stride sn, column stride sc) -> mma.sync B-fragment order
+    const int n_ = j.cout, k_ = j.cin;
+    const int total = n_ * k_;
+    const int KT = k_ / 16;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+      const int q = idx & 3;
+      const int lane = (idx >> 2) & 31;
+      const int tile = idx >> 7;
+      const int kt = tile % KT, nt = tile / KT;
+      const int row = nt * 8 + (lane >> 2);
+      const int col = kt * 16 + (lane & 3) * 2 + (q & 1) + (q >> 1) * 8;
+      out[idx] = __float2half_rn(j.w[(long long)row * j.sn + (long long)col * j.sc]);
+    }
+  }
+}
+
 __global__ void pack_frag_kernel(const float* __restrict__ w, int n, int k, __half* __restrict__ out) {
   const int total = n * k;
   const int KT = k / 16;
@@ -392,6 +430,16 @@ int w2s_pack_conv_weight(const float* w, int cout, int cin, int taps, int taps_m
   pack_conv_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, cout, cin, taps, taps_major, split, (__half*)out);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : cuda_fail(e, "pack_conv");
+}
+
+int w2s_pack_batch(const w2s_pack_job* jobs_device, int n_jobs, int max_elems, void* stream) {
+  if (jobs_device == nullptr || n_jobs <= 0 || n_jobs > 65535 || max_elems <= 0) return fail("pack_batch: bad arguments");
+  int gx = (max_elems + 255) / 256;
+  if (gx > 64) gx = 64;  // grid-stride inside a job: keeps the launch at n_jobs x 64 blocks
+  LaunchScope scope((cudaStream_t)stream, "pack_batch", 0, 0);
+  pack_batch_kernel<<<dim3(gx, n_jobs), 256, 0, (cudaStream_t)stream>>>(jobs_device);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "pack_batch");
 }
 
 int w2s_pack_linear_frag(const float* w, int n, int k, void* out, void* stream) {

@@ -19,14 +19,92 @@ def _ptr(t: Tensor | None) -> int | None:
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """Raw handle of the current CUDA stream of the current device (the fast C accessor: this is called per launch)."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+    except AttributeError:  # older / newer torch without the private accessors
+        return torch.cuda.current_stream().cuda_stream
+
+
+class PackPlan:
+    """Weight re-packing as data: every job reads a (possibly flipped / transposed / sliced) *view* of an fp32 master
+    parameter through explicit strides and writes a persistent fp16 buffer, and all jobs of a model run in ONE launch
+    (``w2s_pack_batch``).  After an optimizer step only ``run()`` is needed: no torch copies, no re-allocation, the
+    descriptors keep pointing at the same buffers."""
+
+    def __init__(self, lib, device):
+        self.lib, self.device = lib, device
+        self.jobs: list[_lib.PackJob] = []
+        self.keep: list[Tensor] = []          # destinations (+ fp32 copies of non-fp32 sources)
+        self.refresh: list[tuple[Tensor, Tensor]] = []  # (source parameter, fp32 copy) pairs to re-copy before a run
+        self.max_elems = 0
+        self._dev_jobs = None
+
+    def _source(self, view: Tensor) -> Tensor:
+        v = view.detach()
+        if v.dtype == torch.float32 and v.device == self.device:
+            return v  # alias of the live parameter: in-place updates are seen by the next run
+        c = v.to(device=self.device, dtype=torch.float32)
+        self.keep.append(c)
+        self.refresh.append((v, c))
+        return c
+
+    def f32(self, t: Tensor) -> Tensor:
+        """A small tensor the kernels read as fp32 (bias, LayerNorm weight ...): the live parameter itself when it is
+        contiguous fp32 on the device, else a copy that is refreshed before every run."""
+        v = t.detach()
+        if v.dtype == torch.float32 and v.device == self.device and v.is_contiguous():
+            return v
+        c = v.to(device=self.device, dtype=torch.float32).contiguous()
+        self.keep.append(c)
+        self.refresh.append((v, c))
+        return c
+
+    def conv(self, view: Tensor, split: int = 0, flip: bool = False) -> int:
+        """view: [cout, cin, taps] (any strides).  flip: reverse the taps (data-gradient weights).  -> device pointer."""
+        v = self._source(view)
+        cout, cin, taps = v.shape
+        sn, sc, st = v.stride()
+        ptr = v.data_ptr()
+        if flip:
+            ptr += (taps - 1) * st * 4
+            st = -st
+        n = cout * cin * taps
+        out = torch.empty(n * (2 if split else 1), dtype=torch.float16, device=self.device)
+        self.keep.append(out)
+        self.jobs.append(_lib.PackJob(ptr, out.data_ptr(), 0, cout, cin, taps, sn, sc, st, int(split), 0))
+        self.max_elems = max(self.max_elems, n)
+        self._dev_jobs = None
+        return out.data_ptr()
+
+    def frag(self, view: Tensor) -> int:
+        """view: nn.Linear weight [n, k] -> mma.sync fragment order."""
+        v = self._source(view)
+        n, k = v.shape
+        sn, sc = v.stride()
+        out = torch.empty(n * k, dtype=torch.float16, device=self.device)
+        self.keep.append(out)
+        self.jobs.append(_lib.PackJob(v.data_ptr(), out.data_ptr(), 1, n, k, 1, sn, sc, 0, 0, 0))
+        self.max_elems = max(self.max_elems, n * k)
+        self._dev_jobs = None
+        return out.data_ptr()
+
+    def run(self) -> None:
+        if not self.jobs:
+            return
+        for src, dst in self.refresh:
+            dst.copy_(src)
+        if self._dev_jobs is None:
+            arr = (_lib.PackJob * len(self.jobs))(*self.jobs)
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            self._dev_jobs = host.to(self.device)
+        _lib.check(self.lib.w2s_pack_batch(self._dev_jobs.data_ptr(), len(self.jobs), self.max_elems, _stream()))
 
 
 class _PackedEncoder:
-    """fp16 UMMA-layout copies of one SignalEncoder's weights + the C descriptor pointing at them."""
+    """The C descriptor of one SignalEncoder, pointing at the plan's packed fp16 weights and at the live fp32 tensors."""
 
-    def __init__(self, lib, enc, device):
-        self.keep: list[Tensor] = []
+    def __init__(self, lib, enc, device, plan: PackPlan):
         d = EncoderDesc()
         d.n_blocks = len(enc.channels)
         for i, c in enumerate(enc.channels):
@@ -34,26 +112,11 @@ class _PackedEncoder:
         d.feature_dim = enc.feature_dim
         d.norm_eps = enc.norm_eps
         d.wide_blocks = int(getattr(enc, "wide_blocks", 0))
-        st = _stream()
+        f32 = plan.f32
 
-        def f32(t):
-            t = t.detach().to(device=device, dtype=torch.float32).contiguous()
-            self.keep.append(t)
-            return t
-
-        def pack(w, taps_major=0, taps=None):
-            w = f32(w)
-            if taps_major:
-                cout, cin = w.shape[0], w.shape[1] // taps
-                split = 0
-            else:
-                cout, cin, taps = w.shape
-                split = lib.w2s_conv_uses_split(cin, cout)
-            nbytes = lib.w2s_packed_conv_weight_bytes(cout, cin, taps, split)
-            out = torch.empty(nbytes // 2, dtype=torch.float16, device=device)
-            _lib.check(lib.w2s_pack_conv_weight(w.data_ptr(), cout, cin, taps, taps_major, split, out.data_ptr(), st))
-            self.keep.append(out)
-            return out.data_ptr()
+        def pack(w):
+            cout, cin, _ = w.shape
+            return plan.conv(w, split=lib.w2s_conv_uses_split(cin, cout))
 
         blk0 = enc.cnn[0]
         d.w_first = f32(blk0.conv1.conv.weight[:, 0, :]).data_ptr()
@@ -64,7 +127,8 @@ class _PackedEncoder:
                 d.w_ds[i] = pack(blk.downsample.weight)
             d.w_conv[i][1] = pack(blk.conv2.conv.weight)
             d.w_conv[i][2] = pack(blk.conv3.conv.weight)
-        d.w_lin = pack(enc.linear.weight, taps_major=1, taps=4)
+        F, K = enc.linear.weight.shape  # Linear(4C -> F) as a 4-tap conv: input index = tap * C + c
+        d.w_lin = plan.conv(enc.linear.weight.view(F, 4, K // 4).permute(0, 2, 1))
         d.b_lin = f32(enc.linear.bias).data_ptr()
         self.desc = d
         self.samples_per_epoch = enc.samples_per_epoch
@@ -83,30 +147,26 @@ class ForwardEngine:
 
     # ------------------------------------------------------------------ weights
     def _params_key(self, device):
-        from . import optim  # WEIGHTS_EPOCH: in-place updates by the fused optimizer do not bump tensor versions
+        """(structure, values): the structure (device, storage policy, parameter addresses) decides whether the pack plan
+        and the descriptors are still valid; the values (tensor versions + the fused optimizer's epoch, whose in-place
+        updates do not bump versions) decide whether the plan has to run again."""
+        from . import optim
+        params = list(self.model.parameters())
         wide = tuple(int(getattr(e, "wide_blocks", 0)) for e in self.model.signal_encoders.encoders.values())
-        return (str(device), optim.WEIGHTS_EPOCH, wide) + tuple((p.data_ptr(), p._version)
-                                                                for p in self.model.parameters())
+        return ((str(device), wide) + tuple(p.data_ptr() for p in params),
+                (optim.WEIGHTS_EPOCH,) + tuple(p._version for p in params))
 
     def _ensure_packed(self, device):
-        key = self._params_key(device)
-        if key == self._weights_key:
+        skey, vkey = self._params_key(device)
+        if self._weights_key is not None and self._weights_key[0] == skey:
+            if self._weights_key[1] != vkey:
+                self.plan.run()  # same tensors, new values: one launch
+                self._weights_key = (skey, vkey)
             return
-        m, lib, st = self.model, self.lib, _stream()
-        self.keep: list[Tensor] = []
-        self.enc = {name: _PackedEncoder(lib, enc, device) for name, enc in m.signal_encoders.encoders.items()}
-
-        def f32(t):
-            t = t.detach().to(device=device, dtype=torch.float32).contiguous()
-            self.keep.append(t)
-            return t
-
-        def frag(w):
-            w = f32(w)
-            out = torch.empty(w.numel(), dtype=torch.float16, device=device)
-            _lib.check(lib.w2s_pack_linear_frag(w.data_ptr(), w.shape[0], w.shape[1], out.data_ptr(), st))
-            self.keep.append(out)
-            return out.data_ptr()
+        m, lib = self.model, self.lib
+        plan = self.plan = PackPlan(lib, device)
+        f32 = plan.f32
+        self.enc = {name: _PackedEncoder(lib, enc, device, plan) for name, enc in m.signal_encoders.encoders.items()}
 
         mix = m.epoch_mixer
         md = MixerDesc()
@@ -116,10 +176,10 @@ class ForwardEngine:
         md.cls = f32(mix.register_tokens[0, 0, :, 0]).data_ptr()
         for l, layer in enumerate(mix.transformer_encoder.layers):
             L = md.layer[l]
-            L.in_w = frag(layer.self_attn.in_proj_weight)
-            L.out_w = frag(layer.self_attn.out_proj.weight)
-            L.ff1_w = frag(layer.linear1.weight)
-            L.ff2_w = frag(layer.linear2.weight)
+            L.in_w = plan.frag(layer.self_attn.in_proj_weight)
+            L.out_w = plan.frag(layer.self_attn.out_proj.weight)
+            L.ff1_w = plan.frag(layer.linear1.weight)
+            L.ff2_w = plan.frag(layer.linear2.weight)
             L.in_b = f32(layer.self_attn.in_proj_bias).data_ptr()
             L.out_b = f32(layer.self_attn.out_proj.bias).data_ptr()
             L.ff1_b = f32(layer.linear1.bias).data_ptr()
@@ -138,18 +198,14 @@ class ForwardEngine:
         sd.ln_eps = seq.dilated_convs[0].conv_layers[0].norm.eps
         for b, blk in enumerate(seq.dilated_convs):
             for k, layer in enumerate(blk.conv_layers):
-                w = f32(layer.conv.weight)
-                cout, cin, taps = w.shape
-                out = torch.empty(w.numel(), dtype=torch.float16, device=device)
-                _lib.check(lib.w2s_pack_conv_weight(w.data_ptr(), cout, cin, taps, 0, 0, out.data_ptr(), st))
-                self.keep.append(out)
-                sd.w[b][k] = out.data_ptr()
+                sd.w[b][k] = plan.conv(layer.conv.weight)
                 sd.ln_w[b][k] = f32(layer.norm.weight.reshape(-1)).data_ptr()
                 sd.ln_b[b][k] = f32(layer.norm.bias.reshape(-1)).data_ptr()
         sd.head_w = f32(m.classifier.weight).data_ptr()
         sd.head_b = f32(m.classifier.bias).data_ptr()
         self.seq_desc = sd
-        self._weights_key = key
+        plan.run()
+        self._weights_key = (skey, vkey)
         self._ws.clear()  # workspace sizes depend on the encoders' storage policy
 
     # ------------------------------------------------------------------ buffers
@@ -233,14 +289,14 @@ class ForwardEngine:
             in_bytes = sum(t.numel() * 4 for t in xs.values())
             if (self.use_graph and in_bytes <= self.GRAPH_MAX_INPUT_BYTES and buf.get("calls", 0) >= 1
                     and not torch.cuda.is_current_stream_capturing()):
-                if buf.get("graph") is None or buf.get("graph_wkey") != self._weights_key:
+                if buf.get("graph") is None or buf.get("graph_wkey") != self._weights_key[0]:
                     buf["xin"] = {n: torch.empty_like(xs[n]) for n in names}
                     buf["logits"] = torch.empty(B, S, self.model.num_classes, dtype=torch.float32, device=device)
                     l0 = self.lib.w2s_launch_count()
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
                         self._launch(buf, buf["xin"], names, B, S, buf["logits"])
-                    buf.update(graph=g, graph_wkey=self._weights_key, graph_launches=self.lib.w2s_launch_count() - l0)
+                    buf.update(graph=g, graph_wkey=self._weights_key[0], graph_launches=self.lib.w2s_launch_count() - l0)
                 for n in names:
                     buf["xin"][n].copy_(xs[n], non_blocking=True)
                 buf["graph"].replay()

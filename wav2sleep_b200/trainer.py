@@ -26,23 +26,52 @@ TRAIN, VAL, TEST = "train", "val", "test"
 
 class SignalMasker:
     """Stochastic modality dropout (reference trainer/masker.py:5-51): per sample keep signal i with prob 1 - p_i; if
-    nothing is left, draw one of the available backup signals; dropped signals become rows of -inf, in place."""
+    nothing is left, draw one of the available backup signals; dropped signals become rows of -inf, in place.
 
-    def __init__(self, dropouts: dict[str, float], backups: list[str] | None = None):
+    On CUDA tensors nothing here synchronises the host with the device (no boolean-mask indexing, no ``if tensor``): the
+    two data errors of the reference (a night with every signal unavailable, no backup channel available) are written to
+    a device flag, copied to pinned memory asynchronously and raised by the *next* call or by ``check()`` - one step
+    late, so that the host can keep enqueueing the training step ahead of the GPU.  ``deferred_errors=False`` restores
+    the immediate (synchronising) raise; CPU tensors always raise immediately."""
+
+    def __init__(self, dropouts: dict[str, float], backups: list[str] | None = None, deferred_errors: bool = True):
         self.channel_dropouts = dropouts
         self.backup_channels = backups
+        self.deferred_errors = deferred_errors
+        self._pending = None  # (pinned flags [2], event)
+        self._p_cache = {}    # (device, names) -> probabilities on the device (torch.tensor from a list synchronises)
+        for v in dropouts.values():  # host-side checks: the probabilities are Python floats
+            if v < 0 or v > 1:
+                raise ValueError("dropout probabilities must be in [0, 1]")
+
+    def check(self) -> None:
+        """Raise the data error recorded by the previous call, if any."""
+        if self._pending is None:
+            return
+        flags, ev = self._pending
+        self._pending = None
+        ev.synchronize()
+        self._raise(bool(flags[0]), bool(flags[1]))
+
+    @staticmethod
+    def _raise(all_missing: bool, no_backup: bool) -> None:
+        if all_missing:
+            raise ValueError("Found batch element with all signals unavailable.")
+        if no_backup:
+            raise ValueError("No backup channels for stochastic sampling were available")
 
     def __call__(self, signals: dict[str, Tensor]) -> dict[str, Tensor]:
+        self.check()
         names = list(signals.keys())
         dev = signals[names[0]].device
-        missing = torch.stack([torch.isinf(signals[n][:, 0]) for n in names], dim=-1)  # [B, C] True = unavailable
-        if missing.all(dim=-1).any():
-            raise ValueError("Found batch element with all signals unavailable.")
-        p = torch.tensor([self.channel_dropouts.get(n, 0.0) for n in names], device=dev)
-        if ((p < 0) | (p > 1)).any():
-            raise ValueError("dropout probabilities must be in [0, 1]")
-        if (p == 1).all():
+        ps = [float(self.channel_dropouts.get(n, 0.0)) for n in names]
+        if all(v == 1 for v in ps):
             raise ValueError("Dropout probability equal to 1 for all channels.")
+        missing = torch.stack([torch.isinf(signals[n][:, 0]) for n in names], dim=-1)  # [B, C] True = unavailable
+        key = (str(dev), tuple(names))
+        p = self._p_cache.get(key)
+        if p is None:
+            p = self._p_cache[key] = torch.tensor(ps, device=dev)
         B = missing.size(0)
         keep = torch.rand(B, len(names), device=dev) >= p  # Bernoulli(1 - p)
         if self.backup_channels is not None:
@@ -50,13 +79,22 @@ class SignalMasker:
                              for i, n in enumerate(names)], dim=-1)
         else:
             w = (~missing).float() * (1 - p)
-        if (w == 0).all(dim=-1).any():
-            raise ValueError("No backup channels for stochastic sampling were available")
+        flags = torch.stack([missing.all(dim=-1).any(), (w == 0).all(dim=-1).any()])
+        if dev.type == "cuda" and self.deferred_errors:
+            host = torch.empty(2, dtype=torch.bool).pin_memory()
+            host.copy_(flags, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            self._pending = (host, ev)
+            w = w + (w == 0).all(dim=-1, keepdim=True).float()  # keep multinomial well defined on a bad row
+        else:
+            f = flags.tolist()
+            self._raise(f[0], f[1])
         backup = torch.nn.functional.one_hot(torch.multinomial(w, 1).squeeze(-1), len(names)).bool()
-        none_left = (missing | ~keep).all(dim=-1)
-        keep[none_left] = backup[none_left]
+        none_left = (missing | ~keep).all(dim=-1, keepdim=True)
+        keep = torch.where(none_left, backup, keep)
         for i, n in enumerate(names):
-            signals[n][~keep[:, i]] = float("-inf")
+            signals[n].masked_fill_(~keep[:, i:i + 1], float("-inf"))
         return signals
 
 
@@ -69,10 +107,12 @@ def invert_signals(signals: dict[str, Tensor]) -> dict[str, Tensor]:
 
 
 def confusion_matrix(logits_NC: Tensor, y_N: Tensor, num_classes: int, ignore_index: int = -1) -> Tensor:
+    """[true, predicted] counts; scatter-add instead of boolean indexing + bincount, so nothing synchronises the host."""
     pred = logits_NC.argmax(-1)
-    ok = y_N != ignore_index
-    idx = y_N[ok].long() * num_classes + pred[ok]
-    return torch.bincount(idx, minlength=num_classes * num_classes).view(num_classes, num_classes)
+    nn_ = num_classes * num_classes
+    idx = torch.where(y_N != ignore_index, y_N.long() * num_classes + pred, torch.full_like(pred, nn_))
+    cm = torch.zeros(nn_ + 1, dtype=torch.int64, device=pred.device).scatter_add_(0, idx, torch.ones_like(idx))
+    return cm[:nn_].view(num_classes, num_classes)
 
 
 def sum_if_distributed(t: Tensor) -> Tensor:

@@ -62,56 +62,58 @@ class TrainEngine(ForwardEngine):
         return m
 
     # ------------------------------------------------------------------ weight packing for the backward
-    def _pack(self, w: Tensor, taps_major=0, taps=None) -> Tensor:
-        """fp32 [cout, cin, taps] (or [cout, taps*cin] with taps_major) -> fp16 UMMA layout (no hi/lo split)."""
-        lib, st = self.lib, _stream()
-        w = w.detach().to(torch.float32).contiguous()
-        if taps_major:
-            cout, cin = w.shape[0], w.shape[1] // taps
-        else:
-            cout, cin, taps = w.shape
-        out = torch.empty(taps * cin * cout, dtype=F16, device=w.device)
-        _lib.check(lib.w2s_pack_conv_weight(w.data_ptr(), cout, cin, taps, taps_major, 0, out.data_ptr(), st))
-        self._tk.append(w)
-        return out
-
     def _ensure_train_packed(self, device):
+        """fp16 UMMA-layout weights of the training path (no hi/lo split): forward GEMM weights of the un-fused mixers and
+        the flipped / transposed weights of every data-gradient conv, as jobs of a second PackPlan over views of the live
+        parameters - re-packed with one launch after each optimizer step."""
         self._ensure_packed(device)
-        if self._train_key == self._weights_key:
+        skey, vkey = self._weights_key
+        if self._train_key is not None and self._train_key[0] == skey:
+            if self._train_key[1] != vkey:
+                self.tplan.run()
+                self._train_key = (skey, vkey)
             return
+        from .engine import PackPlan
         m = self.model
-        self._tk: list[Tensor] = []
-        flipT = lambda w: w.flip(2).permute(1, 0, 2)  # conv weight for the data gradient (transposed conv)
+        plan = self.tplan = PackPlan(self.lib, device)
+
+        class _W:  # packed weight handle: the kernels only need the device pointer
+            def __init__(self, ptr):
+                self.ptr = ptr
+
+            def data_ptr(self):
+                return self.ptr
+
+        P = lambda view, flip=False: _W(plan.conv(view, split=0, flip=flip))
+        dgrad = lambda w: P(w.permute(1, 0, 2), flip=True)  # conv weight of the data gradient (transposed conv)
         self.tw = {"enc": {}, "mix": [], "seq": []}
         for name, enc in m.signal_encoders.encoders.items():
             e = {"conv": [], "ds": [], "lin_fwd": None, "lin_dgrad": []}
             for i, blk in enumerate(enc.cnn):
-                e["conv"].append([
-                    self._pack(flipT(blk.conv1.conv.weight)) if i > 0 else None,
-                    self._pack(flipT(blk.conv2.conv.weight)),
-                    self._pack(flipT(blk.conv3.conv.weight)),
-                ])
-                e["ds"].append(self._pack(blk.downsample.weight.permute(1, 0, 2)) if i > 0 else None)
+                e["conv"].append([dgrad(blk.conv1.conv.weight) if i > 0 else None, dgrad(blk.conv2.conv.weight),
+                                  dgrad(blk.conv3.conv.weight)])
+                e["ds"].append(P(blk.downsample.weight.permute(1, 0, 2)) if i > 0 else None)
             Cl = enc.channels[-1]
-            e["lin_fwd"] = self._pack(enc.linear.weight, taps_major=1, taps=4)
-            e["lin_dgrad"] = [self._pack(enc.linear.weight[:, t * Cl:(t + 1) * Cl].t().unsqueeze(-1)) for t in range(4)]
+            Wl = enc.linear.weight
+            e["lin_fwd"] = P(Wl.view(Wl.shape[0], 4, Cl).permute(0, 2, 1))
+            e["lin_dgrad"] = [P(Wl[:, t * Cl:(t + 1) * Cl].t().unsqueeze(-1)) for t in range(4)]
             self.tw["enc"][name] = e
         for layer in m.epoch_mixer.transformer_encoder.layers:
             Win, W1, W2 = layer.self_attn.in_proj_weight, layer.linear1.weight, layer.linear2.weight
             Wo = layer.self_attn.out_proj.weight
             self.tw["mix"].append({
-                "qkv": [self._pack(Win[j * 128:(j + 1) * 128].unsqueeze(-1)) for j in range(3)],
-                "qkv_T": [self._pack(Win[j * 128:(j + 1) * 128].t().unsqueeze(-1)) for j in range(3)],
-                "o": self._pack(Wo.unsqueeze(-1)), "o_T": self._pack(Wo.t().unsqueeze(-1)),
-                "ff1": [self._pack(W1[j * 128:(j + 1) * 128].unsqueeze(-1)) for j in range(4)],
-                "ff1_T": self._pack(W1.view(4, 128, 128).permute(2, 1, 0)),          # taps=4 conv for d(h2)
-                "ff2": self._pack(W2, taps_major=1, taps=4),
-                "ff2_T": [self._pack(W2[:, j * 128:(j + 1) * 128].t().unsqueeze(-1)) for j in range(4)],
+                "qkv": [P(Win[j * 128:(j + 1) * 128].unsqueeze(-1)) for j in range(3)],
+                "qkv_T": [P(Win[j * 128:(j + 1) * 128].t().unsqueeze(-1)) for j in range(3)],
+                "o": P(Wo.unsqueeze(-1)), "o_T": P(Wo.t().unsqueeze(-1)),
+                "ff1": [P(W1[j * 128:(j + 1) * 128].unsqueeze(-1)) for j in range(4)],
+                "ff1_T": P(W1.view(4, 128, 128).permute(2, 1, 0)),          # taps=4 conv for d(h2)
+                "ff2": P(W2.view(W2.shape[0], 4, 128).permute(0, 2, 1)),
+                "ff2_T": [P(W2[:, j * 128:(j + 1) * 128].t().unsqueeze(-1)) for j in range(4)],
             })
         for blk in m.sequence_mixer.dilated_convs:
-            self.tw["seq"].append([{"fwd": self._pack(l.conv.weight), "T": self._pack(flipT(l.conv.weight))}
-                                   for l in blk.conv_layers])
-        self._train_key = self._weights_key
+            self.tw["seq"].append([{"fwd": P(l.conv.weight), "T": dgrad(l.conv.weight)} for l in blk.conv_layers])
+        plan.run()
+        self._train_key = (skey, vkey)
 
     # ------------------------------------------------------------------ kernel helpers
     def conv(self, inp, w, cin, cout, taps, B, L_in, L_out, out, stride=1, dil=1, pad=0, bias=None, res=None,
