@@ -275,10 +275,10 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
     W2S_STREAM(16, 16, 1, PRO_NORM, false, 8, 2, 2, 18)
     W2S_STREAM(16, 16, 2, PRO_NORM, false, 4, 2, 2, 18)
     W2S_STREAM(16, 16, 1, PRO_NORM_RES, true, 4, 3, 2, 14)
-    W2S_STREAM(16, 32, 1, PRO_NORM_RES, true, 4, 3, 2, 14)
+    W2S_STREAM(16, 32, 1, PRO_NORM_RES, true, 4, 3, 2, 10)
     W2S_STREAM(32, 32, 1, PRO_NORM, false, 4, 2, 2, 14)
     W2S_STREAM(32, 32, 2, PRO_NORM, false, 2, 2, 2, 14)
-    W2S_STREAM(32, 32, 1, PRO_NORM_RES, true, 2, 3, 2, 14)
+    W2S_STREAM(32, 32, 1, PRO_NORM_RES, true, 2, 3, 2, 10)
     W2S_STREAM(32, 64, 1, PRO_NORM_RES, true, 2, 3, 2, 14)
     W2S_STREAM(64, 64, 1, PRO_NORM, false, 3, 2, 2, 14)
     W2S_STREAM(64, 64, 2, PRO_NORM, false, 1, 3, 2, 14)
@@ -292,11 +292,11 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
     W2S_STREAMW(16, 16, 1, PRO_NORM_RES_X, true, 4, 3, 2, 14, true, true)
     W2S_STREAMW(16, 16, 1, PRO_NORM, false, 6, 2, 2, 18, true, true)
     W2S_STREAMW(16, 16, 2, PRO_NORM, false, 3, 2, 2, 18, true, true)
-    W2S_STREAMW(16, 32, 1, PRO_NORM_RES, true, 4, 2, 2, 14, true, false)
-    W2S_STREAMW(16, 32, 1, PRO_NORM_RES, true, 4, 2, 2, 14, true, true)
+    W2S_STREAMW(16, 32, 1, PRO_NORM_RES, true, 4, 2, 2, 10, true, false)
+    W2S_STREAMW(16, 32, 1, PRO_NORM_RES, true, 4, 2, 2, 10, true, true)
     W2S_STREAMW(32, 32, 1, PRO_NORM, false, 3, 2, 2, 14, true, true)
     W2S_STREAMW(32, 32, 2, PRO_NORM, false, 1, 3, 2, 14, true, true)
-    W2S_STREAMW(32, 32, 1, PRO_NORM_RES, true, 2, 2, 2, 14, true, true)
+    W2S_STREAMW(32, 32, 1, PRO_NORM_RES, true, 2, 2, 2, 10, true, true)
     W2S_STREAMW(32, 64, 1, PRO_NORM_RES, true, 2, 2, 2, 14, true, false)
 #undef W2S_STREAM
 #undef W2S_STREAMW

@@ -140,9 +140,10 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   constexpr int KSTEPS = CIN / 16;
   constexpr int NCG = COUT / 16;
   constexpr uint32_t IDESC = umma_idesc_f16(128, COUT, false);
-  // per-thread accumulators across tiles for COUT = 16; wider outputs reduce per tile (butterfly), which keeps the
+  // per-thread accumulators across tiles for COUT = 16 (and for the 32-channel conv1 kernels, whose epilogue also drains
+  // the residual-branch accumulator: measured faster); other outputs reduce per tile (butterfly), which keeps the
   // register count low enough for more transform warps
-  constexpr bool REG_STATS = (COUT <= 16);
+  constexpr bool REG_STATS = (COUT <= 16) || (COUT <= 32 && HAS_DS);
 
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sRaw = smem;
@@ -223,13 +224,23 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   const int live_tiles = compact ? sNLive * tiles_per_sample : total_tiles;
   const int tile_begin = (int)((long long)blockIdx.x * live_tiles / gridDim.x);
   const int tile_end = (int)((long long)(blockIdx.x + 1) * live_tiles / gridDim.x);
-  // sample of a tile; false = masked sample (only possible without compaction)
-  auto sample_of = [&](int tile, int& b) {
-    const int s = tile / tiles_per_sample;
-    b = compact ? (int)sLive[s] : s;
+  // Position of a tile as (entry of the sample list, tile inside the sample), advanced incrementally: no division in
+  // the per-tile loops of the four roles.
+  struct TilePos {
+    int s, r;
+  };
+  const TilePos pos0 = {tile_begin / tiles_per_sample, tile_begin % tiles_per_sample};
+  auto advance = [&](TilePos& t) {
+    if (++t.r == tiles_per_sample) {
+      t.r = 0;
+      ++t.s;
+    }
+  };
+  // sample of a tile position; false = masked sample (only possible without compaction)
+  auto sample_of = [&](const TilePos& t, int& b) {
+    b = compact ? (int)sLive[t.s] : t.s;
     return compact || p.row_mask == nullptr || !p.row_mask[b];
   };
-  if (tid == 0) dbg_ts(p, 2);
 
   // ======================================================================================================
   if (warp == 0) {
@@ -239,10 +250,11 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
       uint32_t ph = 0;
       WaitClock wc;
       const long long cta_t0 = clock64();
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
+      TilePos tp = pos0;
+      for (int tile = tile_begin; tile < tile_end; ++tile, advance(tp)) {
         int b;
-        if (!sample_of(tile, b)) continue;
-        const int o0 = (tile % tiles_per_sample) * POS;
+        if (!sample_of(tp, b)) continue;
+        const int o0 = tp.r * POS;
         const int i0 = o0 * STRIDE - 1;
         const int lo = i0 < 0 ? 0 : i0;
         const int hi = (i0 + R < p.L_in) ? i0 + R : p.L_in;
@@ -286,9 +298,10 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
       WaitClock wc;
       const uint32_t b_base = smem_u32(sB);
       constexpr uint32_t lbo_a = RP * 16, lbo_b = COUT * 16;
-      for (int tile = tile_begin; tile < tile_end; ++tile) {
+      TilePos tp = pos0;
+      for (int tile = tile_begin; tile < tile_end; ++tile, advance(tp)) {
         int b;
-        if (!sample_of(tile, b)) continue;
+        if (!sample_of(tp, b)) continue;
         wc.wait(p, &a_full[as], aph);
         wc.wait(p, &t_empty[ts], tph ^ 1);
         tc_fence_after_sync();
@@ -387,14 +400,15 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
       for (int k = 0; k < NACC; ++k) acc[k] = acc2[k] = 0.0f;
     };
 
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
+    TilePos tp = pos0;
+    for (int tile = tile_begin; tile < tile_end; ++tile, advance(tp)) {
       int b;
-      if (!sample_of(tile, b)) continue;
+      if (!sample_of(tp, b)) continue;
       if (b != cur_b) {
         flush(cur_b);
         cur_b = b;
       }
-      const int o0 = (tile % tiles_per_sample) * POS;
+      const int o0 = tp.r * POS;
       wc.wait(p, &t_full[ts], tph);
       tc_fence_after_sync();
       if (warp == 2 && lane == 0 && tile == tile_begin) dbg_ts(p, 6);
@@ -486,9 +500,10 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
         fw[q][0] = make_float2(__ldg(p.w_first_ds + c), __ldg(p.w_first_ds + c + 1));
       }
     }
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
+    TilePos tp = pos0;
+    for (int tile = tile_begin; tile < tile_end; ++tile, advance(tp)) {
       int b;
-      if (!sample_of(tile, b)) continue;
+      if (!sample_of(tp, b)) continue;
       if (b != cur_b) {
         cur_b = b;
         const double inv_len = 1.0 / (double)p.L_in;
@@ -519,7 +534,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
           }
         }
       }
-      const int o0 = (tile % tiles_per_sample) * POS;
+      const int o0 = tp.r * POS;
       const int i0 = o0 * STRIDE - 1;
       if (tt == 0 && tile == tile_begin) dbg_ts(p, 3);
       wc_raw.wait(p, &raw_full[rs], rph);
