@@ -162,6 +162,17 @@ def test_cuda_graph_replay_matches_eager(cuda_device):
             model.classifier.bias.add_(1.0)
         gc = model(xa)
         assert torch.allclose(gc, ea + 1.0, atol=1e-6)
+        # a packed (fp16 operand) weight changes in place: one batched re-pack into the same buffers, the captured graph
+        # keeps replaying and must see the new values
+        replays = eng.replayed_launches
+        with torch.no_grad():
+            model.signal_encoders.get_encoder("ECG").cnn[2].conv2.conv.weight.mul_(1.25)
+            model.sequence_mixer.dilated_convs[0].conv_layers[1].conv.weight.mul_(0.8)
+        gd = model(xa).clone()
+        assert eng.replayed_launches > replays
+        eng.use_graph = False
+        ed = model(xa)
+        assert torch.equal(gd, ed) and (gd - gc).abs().max().item() > 1e-3
 
 
 def test_predict_is_argmax(cuda_device):
