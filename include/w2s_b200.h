@@ -253,19 +253,21 @@ int w2s_enc_act_bwd(const void* dout, const void* y, const void* r, const double
  * row 2l+1 (rows of masked samples are not touched). */
 int w2s_enc_norm_bwd(const void* dxh, const void* y, const double* stats, const double* sums, void* dy,
                      const uint8_t* row_mask, int B, int L, int C, int upsample, float eps, void* stream);
-/* weight gradients of the Cin = 1 layers of block 0 (conv1 [16,1,3] and downsample [16,1,1]). */
+/* weight gradients of the Cin = 1 layers of block 0 (conv1 [16,1,3] and downsample [16,1,1]), accumulated times scale. */
 int w2s_first_conv_wgrad(const float* x, const void* dy1, const void* dr, float* dw1, float* dwds, const uint8_t* row_mask,
-                         int B, int T, void* stream);
+                         int B, int T, float scale, void* stream);
 /* LayerNorm over 128 features per row (+GELU, + residual add + GELU): nn.LayerNorm / ConvLayerNorm (models/utils.py:9-23). */
 int w2s_row_ln_fwd(const void* x, const void* res, const float* g, const float* b, void* out, long long rows, int gelu,
                    float eps, void* stream);
+/* dg / db are accumulated times gscale (the inverse loss scale, see below). */
 int w2s_row_ln_bwd(const void* x, const void* res, const float* g, const float* b, const void* dout, const void* dadd,
-                   void* dx, void* ds, float* dg, float* db, long long rows, int gelu, float eps, void* stream);
+                   void* dx, void* ds, float* dg, float* db, long long rows, int gelu, float eps, float gscale,
+                   void* stream);
 int w2s_gelu_fwd(const void* pre, void* out, long long n, void* stream);
 int w2s_gelu_bwd(const void* pre, const void* dout, void* din, long long n, void* stream);
-/* out[c] += sum over rows r of x[(r*row_stride + row_offset), c]  (bias gradients), C <= 128. */
+/* out[c] += scale * sum over rows r of x[(r*row_stride + row_offset), c]  (bias gradients), C <= 128. */
 int w2s_colsum(const void* x, float* out, long long rows, int C, int row_stride, int row_offset, const uint8_t* row_mask,
-               long long rows_per_sample, void* stream);
+               long long rows_per_sample, float scale, void* stream);
 /* nn.Dropout of the training path (nn.TransformerEncoderLayer dropout / dropout1 / dropout2, DilatedConvBlock.dropout,
  * models/blocks.py:111,123): out[i] = (keep(seed, site, i) ? x[i] / (1 - p) : 0) + (res ? res[i] : 0) over n fp16
  * elements (n % 8 == 0).  keep() is a counter-based hash of (seed, site, i), so calling it again on a gradient with the
@@ -283,15 +285,22 @@ int w2s_attn_bwd(const void* q, const void* k, const void* v, const void* dout, 
 int w2s_tokens_fwd(const void* const* z, const uint8_t* const* row_mask, const float* cls, void* tokens, uint8_t* key_mask,
                    int N, int S, int n_sig, void* stream);
 int w2s_tokens_bwd(const void* dtokens, void* const* dz, const uint8_t* const* row_mask, float* dcls, int N, int S, int n_sig,
-                   void* stream);
+                   float cls_scale, void* stream);
 /* out[n] = in[n*stride + offset] (scatter = 0) or out[n*stride + offset] = in[n] (scatter = 1); rows of 128 fp16. */
 int w2s_rows_gather(const void* in, void* out, long long n_rows, int stride, int offset, int scatter, void* stream);
 /* classifier forward, CrossEntropyLoss(mean, ignore_index) forward+backward, classifier backward. */
 int w2s_head_fwd(const void* feat, const float* w, const float* b, float* logits, long long N, int C, void* stream);
 int w2s_ce_fwd_bwd(const float* logits, const long long* labels, long long N, int C, long long ignore_index, double* scratch2,
                    float* loss, float* dlogits, void* stream);
+/* LOSS SCALING of the backward pass.  Activation gradients are stored in fp16; with the mean cross entropy over B*S
+ * epochs they are ~1e-7 at B*S = 19 200 (below fp16's normal range), so the backward runs on gradients multiplied by a
+ * power of two: w2s_head_bwd writes dfeat = dfeat_scale * dlogits W (dw, db stay unscaled), every later kernel is
+ * linear in the incoming gradient, and every kernel that accumulates a PARAMETER gradient multiplies by the inverse
+ * (w2s_gemm_tn scale, w2s_colsum scale, w2s_row_ln_bwd gscale, w2s_first_conv_wgrad scale, w2s_tokens_bwd cls_scale),
+ * so fp32 parameter gradients come out unscaled.  Reference numerics being matched: fp32 autograd
+ * (scripts/config/training/main.yaml:16 `precision: 32-true`). */
 int w2s_head_bwd(const void* feat, const float* w, const float* dlogits, void* dfeat, float* dw, float* db, long long N, int C,
-                 void* stream);
+                 float dfeat_scale, void* stream);
 /* out += sum g^2 (fp64); fused global-norm clip (torch clip_grad_norm_) + AdamW step on flat fp32 buffers.
  * ema != NULL: the same pass also updates ema = ema_decay * ema + (1 - ema_decay) * p_new, the per-batch update of the
  * reference's EMACallback (trainer/callbacks.py:54-66). */

@@ -1,10 +1,14 @@
 """-m gpu: training path.  Gradients of every parameter against torch autograd over the CPU oracle (fp32), plus the
 building blocks (gemm_tn, cross entropy, clip + AdamW) against torch.
 
-Tolerances: activations and activation gradients are stored in fp16 and the whole-night InstanceNorm backward couples
-millions of positions, so parameter gradients are compared by relative L2 error (<= 1e-1; measured: median 1e-2,
-worst 6e-2 on the block-0 weights, 24 fp16 layers deep) and cosine similarity (>= 0.995) per tensor.  Dropout is
-tested both off (p = 0 on both sides) and on: the CUDA path's counter-based keep masks are dumped through the
+Tolerances: activations and activation gradients are stored in fp16 (the gradients loss-scaled by a power of two, see
+training.py) and the whole-night InstanceNorm backward couples millions of positions, so parameter gradients are
+compared per tensor by relative L2 error and cosine similarity against fp32 autograd:
+  * small batches (B = 2, S = 24; few positions per weight, so fp16 rounding does not average out): rel <= REL_SMALL,
+    cos >= COS_SMALL;
+  * one full 10-h night with d(loss)/d(logits) scaled exactly as in the benchmarked batches (B = 16 cardio, B = 32
+    ECG-only): rel <= REL_FULL, cos >= COS_FULL on all 183 tensors.
+Dropout is tested both off (p = 0 on both sides) and on: the CUDA path's counter-based keep masks are dumped through the
 ``w2s_dropout`` test hook and handed to the oracle, which applies exactly those masks in the reference's training graph."""
 import ctypes as C
 
@@ -18,6 +22,9 @@ from wav2sleep_b200 import _lib, build_default
 
 pytestmark = pytest.mark.gpu
 CARDIO = {"ABD": "ABD", "THX": "THX", "ECG": "ECG", "PPG": "PPG"}
+EOG = {"EOG-L": "EOG-L", "EOG-R": "EOG-R"}
+REL_SMALL, COS_SMALL = 6e-2, 0.998
+REL_FULL, COS_FULL = 3e-2, 0.999
 
 
 @pytest.mark.parametrize("M,N,L,ys,yo", [(16, 16, 1000, 1, -1), (32, 16, 777, 1, 1), (128, 128, 300, 1, 0),
@@ -31,9 +38,11 @@ def test_gemm_tn(cuda_device, M, N, L, ys, yo):
     Y = torch.randn(B, LY, N, device=cuda_device).half()
     mask = torch.tensor([0, 1, 0], dtype=torch.uint8, device=cuda_device)
     Cm = torch.zeros(M, N, device=cuda_device)
-    _lib.check(lib.w2s_gemm_tn(X.data_ptr(), Y.data_ptr(), Cm.data_ptr(), M, N, 1, 1, B, L, LY, ys, yo, N, 1, 0, 1.0,
+    # scale = 0.25: the inverse loss scale folded into the accumulation
+    _lib.check(lib.w2s_gemm_tn(X.data_ptr(), Y.data_ptr(), Cm.data_ptr(), M, N, 1, 1, B, L, LY, ys, yo, N, 1, 0, 0.25,
                                mask.data_ptr(), G.stream()))
     torch.cuda.synchronize()
+    Cm = Cm * 4.0
     ref = torch.zeros(M, N, device=cuda_device)
     for b in (0, 2):
         idx = torch.arange(L, device=cuda_device) * ys + yo
@@ -192,11 +201,181 @@ def test_parameter_gradients_match_oracle_autograd(cuda_device, masked, dropout)
         print(f"{name:70s} |g_ref| {rn:.3e} rel {rel:.3e} cos {cos:.5f}")
     import statistics
     print("median rel", statistics.median(r[2] for r in rows if r[1] > 0))
+    _assert_grads(model, rows, REL_SMALL, COS_SMALL)
+
+
+def _assert_grads(model, rows, rel_max, cos_min):
+    import statistics
+    worst = sorted(rows, key=lambda r: -r[2])
+    for name, rn, rel, cos in worst[:12] + worst[-4:]:
+        print(f"{name:70s} |g_ref| {rn:.3e} rel {rel:.3e} cos {cos:.5f}")
+    print("median rel", statistics.median(r[2] for r in rows if r[1] > 0), "worst rel", worst[0][2],
+          "min cos", min(r[3] for r in rows))
     for name, rn, rel, cos in rows:
         if rn == 0.0:  # parameters of fully masked encoders get exact zero gradients
             assert model.get_parameter(name).grad.abs().max().item() == 0.0, name
             continue
-        assert rel < 1e-1 and cos > 0.995, (name, rn, rel, cos)
+        assert rel < rel_max and cos > cos_min, (name, rn, rel, cos)
+
+
+def _no_dropout(model):
+    model.epoch_mixer.dropout = 0.0
+    for blk in model.sequence_mixer.dilated_convs:
+        blk.dropout.p = 0.0
+
+
+def _oracle_grads(model, x, labels, cfg, n_classes, loss_div=1.0):
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    lo = oracle.forward_with_grad(x, params, cfg)
+    loss = torch.nn.functional.cross_entropy(lo.view(-1, n_classes), labels.view(-1), ignore_index=-1) / loss_div
+    loss.backward()
+    return loss.item(), {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in params.items()}
+
+
+@pytest.mark.parametrize("case,batch,masked", [("cardio_b16", 16, ()), ("ecg_only_b32", 32, ("ABD", "THX", "PPG"))])
+def test_full_night_gradients_at_benchmark_scale(cuda_device, case, batch, masked):
+    """BASELINE configs[3] / [4] numerics: one 10-h night whose d(loss)/d(logits) is 1/batch of its own mean-CE gradient,
+    i.e. exactly what this night sees inside a batch of `batch` nights (mean over batch * 1200 epochs), with the loss scale
+    the engine picks for that batch.  Unscaled, every encoder activation gradient would be an fp16 subnormal
+    (median 1e-7); all 183 parameter gradients must match fp32 autograd of the reference graph."""
+    torch.manual_seed(0)
+    S = 1200
+    model = build_default(CARDIO, 4, seed=0)
+    _no_dropout(model)
+    x = make_inputs(CARDIO, 1, S, masked=[(n, 0) for n in masked], seed=11)
+    labels = torch.randint(0, 4, (1, S))
+    labels[torch.rand(1, S) < 0.05] = -1
+    loss_ref, grads_ref = _oracle_grads(model, x, labels, oracle.cardio_config(), 4, loss_div=float(batch))
+    model = model.to(cuda_device).train()
+    eng = model._get_engine()
+    eng.loss_scale = eng.auto_loss_scale(batch * S)
+    logits = model({k: v.to(cuda_device) for k, v in x.items()})
+    loss = torch.nn.functional.cross_entropy(logits.view(-1, 4), labels.to(cuda_device).view(-1), ignore_index=-1) / batch
+    loss.backward()
+    torch.cuda.synchronize()
+    assert eng.last_loss_scale == eng.auto_loss_scale(batch * S) and eng.last_loss_scale >= 2 ** 16
+    assert abs(loss.item() - loss_ref) < 5e-3 / batch
+    _assert_grads(model, _grad_report(model, grads_ref), REL_FULL, COS_FULL)
+
+
+def test_unscaled_backward_underflows_at_benchmark_scale(cuda_device):
+    """Why the loss scale exists: with loss_scale = 1 the same full-night backward loses the encoder gradients
+    (fp16 subnormals), so the scaled run above is not passing by accident."""
+    torch.manual_seed(0)
+    S, batch = 1200, 16
+    sig = {"ABD": "ABD"}
+    model = build_default(sig, 4, seed=0)
+    _no_dropout(model)
+    x = make_inputs(sig, 1, S, seed=11)
+    labels = torch.randint(0, 4, (1, S))
+    _, grads_ref = _oracle_grads(model, x, labels, oracle.OracleConfig(signal_map=sig, num_classes=4), 4, float(batch))
+    model = model.to(cuda_device).train()
+    eng = model._get_engine()
+    worst = {}
+    for scale in (1.0, None):
+        eng.loss_scale = scale if scale is not None else eng.auto_loss_scale(batch * S)
+        model.zero_grad()
+        logits = model({k: v.to(cuda_device) for k, v in x.items()})
+        (torch.nn.functional.cross_entropy(logits.view(-1, 4), labels.to(cuda_device).view(-1)) / batch).backward()
+        rows = [r for r in _grad_report(model, grads_ref) if "encoders" in r[0]]
+        worst[scale] = max(r[2] for r in rows)
+    print("worst encoder rel error: unscaled", worst[1.0], "scaled", worst[None])
+    assert worst[None] < REL_FULL and worst[1.0] > 3 * worst[None]
+
+
+def test_eog_model_gradients(cuda_device):
+    """The 10-block EOG encoders (30 convs deep, 128-channel tail blocks) through the same backward."""
+    torch.manual_seed(0)
+    B, S = 2, 4
+    model = build_default(EOG, 5, seed=0)
+    _no_dropout(model)
+    x = make_inputs(EOG, B, S, seed=3)
+    labels = torch.randint(0, 5, (B, S))
+    loss_ref, grads_ref = _oracle_grads(model, x, labels, oracle.eog_config(), 5)
+    model = model.to(cuda_device).train()
+    logits = model({k: v.to(cuda_device) for k, v in x.items()})
+    loss = torch.nn.functional.cross_entropy(logits.view(-1, 5), labels.to(cuda_device).view(-1), ignore_index=-1)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - loss_ref) < 5e-3
+    _assert_grads(model, _grad_report(model, grads_ref), REL_SMALL, COS_SMALL)
+
+
+def test_two_forwards_before_backward(cuda_device):
+    """Saved activations live with the autograd graph (ctx), not in one engine slot: forward(a), forward(b),
+    backward(a), backward(b) gives the gradients of a and of b, as with torch autograd."""
+    sig = {"ABD": "ABD"}
+    model = build_default(sig, 4, seed=0)
+    _no_dropout(model)
+    model = model.to(cuda_device).train()
+    xa = {k: v.to(cuda_device) for k, v in make_inputs(sig, 2, 8, seed=1).items()}
+    xb = {k: v.to(cuda_device) for k, v in make_inputs(sig, 2, 8, seed=2).items()}
+    w = model.classifier.weight
+
+    def grad_of(x):
+        model.zero_grad()
+        model(x).square().sum().backward()
+        return {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+
+    ga, gb = grad_of(xa), grad_of(xb)
+    model.zero_grad()
+    la, lb = model(xa).square().sum(), model(xb).square().sum()
+    la.backward()
+    got_a = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+    lb.backward()  # accumulates
+    for n, p in model.named_parameters():
+        assert torch.allclose(got_a[n], ga[n], rtol=1e-4, atol=1e-6), n
+        assert torch.allclose(p.grad, ga[n] + gb[n], rtol=1e-3, atol=1e-5), n
+    with pytest.raises(RuntimeError):
+        la.backward()  # a graph can be back-propagated once
+    assert w.grad is not None
+
+
+def test_fused_adamw_checkpoint_resume_and_realias(cuda_device):
+    """state_dict()/load_state_dict() carry the Adam moments, the step count and the EMA; a foreign model.zero_grad()
+    (p.grad = None -> fresh autograd tensors) does not make step() read a stale flat buffer."""
+    from wav2sleep_b200.optim import FusedAdamW
+    torch.manual_seed(0)
+
+    def make():
+        torch.manual_seed(1)
+        return torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 4)).to(cuda_device)
+
+    xs = [torch.randn(5, 8, device=cuda_device) for _ in range(6)]
+    ref = make()
+    opt_ref = FusedAdamW(ref.parameters(), lr=1e-2, weight_decay=1e-2, max_grad_norm=1.0, ema_decay=0.9)
+    ckpt = None
+    for i, x in enumerate(xs):
+        if i == 3:
+            ckpt = (ref.state_dict(), opt_ref.state_dict())
+            ckpt = ({k: v.clone() for k, v in ckpt[0].items()}, ckpt[1])
+        ref.zero_grad()  # set_to_none=True: breaks the alias on purpose; step() must gather the fresh gradients
+        ref(x).square().sum().backward()
+        opt_ref.step()
+    assert "fused" in ckpt[1] and ckpt[1]["fused"]["step"] == 3
+    resumed = make()
+    resumed.load_state_dict(ckpt[0])
+    opt = FusedAdamW(resumed.parameters(), lr=1e-2, weight_decay=1e-2, max_grad_norm=1.0, ema_decay=0.9)
+    opt.load_state_dict(ckpt[1])
+    for x in xs[3:]:
+        opt.zero_grad()
+        resumed(x).square().sum().backward()
+        opt.step()
+    for (n, a), (_, b) in zip(ref.named_parameters(), resumed.named_parameters()):
+        assert torch.allclose(a, b, rtol=0, atol=1e-7), n
+    assert torch.allclose(opt.ema, opt_ref.ema, rtol=0, atol=1e-7)
+    # plain torch AdamW on the same gradients agrees as well (checks that zero_grad()'d gradients were really used)
+    tref = make()
+    topt = torch.optim.AdamW(tref.parameters(), lr=1e-2, weight_decay=1e-2)
+    for x in xs:
+        tref.zero_grad()
+        tref(x).square().sum().backward()
+        torch.nn.utils.clip_grad_norm_(tref.parameters(), 1.0)
+        topt.step()
+    for (n, a), (_, b) in zip(ref.named_parameters(), tref.named_parameters()):
+        assert torch.allclose(a, b, rtol=0, atol=2e-6), n
+    with pytest.raises(ValueError):
+        FusedAdamW([{"params": list(ref[0].parameters())}, {"params": list(ref[1].parameters()), "lr": 1.0}])
 
 
 def test_training_reduces_loss(cuda_device):

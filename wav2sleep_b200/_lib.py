@@ -22,7 +22,7 @@ MAX_MIXER_LAYERS = 8
 MAX_SIGNALS = 4
 MAX_SEQ_BLOCKS = 4
 MAX_DILATIONS = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 PRO_NONE, PRO_NORM, PRO_NORM_RES, PRO_FIR, PRO_NORM_RES_X = 0, 1, 2, 3, 4
 EPI_STATS, EPI_BIAS_GELU, EPI_LN_GELU, EPI_LN_GELU_RES, EPI_PLAIN, EPI_ACT_BWD = 0, 1, 2, 3, 4, 5
@@ -143,13 +143,13 @@ SYMBOLS = {
     "w2s_enc_act_fwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "w2s_enc_act_bwd": (C.c_int, [C.c_void_p] * 9 + [C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "w2s_enc_norm_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
-    "w2s_first_conv_wgrad": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p]),
+    "w2s_first_conv_wgrad": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "w2s_row_ln_fwd": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_int, C.c_float, C.c_void_p]),
-    "w2s_row_ln_bwd": (C.c_int, [C.c_void_p] * 10 + [C.c_longlong, C.c_int, C.c_float, C.c_void_p]),
+    "w2s_row_ln_bwd": (C.c_int, [C.c_void_p] * 10 + [C.c_longlong, C.c_int, C.c_float, C.c_float, C.c_void_p]),
     "w2s_gelu_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "w2s_gelu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "w2s_colsum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong,
-                             C.c_void_p]),
+                             C.c_float, C.c_void_p]),
     "w2s_stage_zscore": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
     "w2s_debug_timestamps": (C.c_int, [C.c_void_p, C.c_void_p]),
     "w2s_dropout": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_float, C.c_uint64, C.c_uint32, C.c_void_p]),
@@ -158,12 +158,12 @@ SYMBOLS = {
     "w2s_tokens_fwd": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                  C.c_int, C.c_int, C.c_void_p]),
     "w2s_tokens_bwd": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int,
-                                 C.c_int, C.c_void_p]),
+                                 C.c_int, C.c_float, C.c_void_p]),
     "w2s_rows_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "w2s_head_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "w2s_ce_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p]),
-    "w2s_head_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_longlong, C.c_int, C.c_void_p]),
+    "w2s_head_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_longlong, C.c_int, C.c_float, C.c_void_p]),
     "w2s_sumsq": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "w2s_adamw_step": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_void_p] + [C.c_float] * 7
                        + [C.c_longlong, C.c_void_p, C.c_float, C.c_void_p]),

@@ -118,7 +118,8 @@ def predict_sharded(predict_fn, n_items: int, epochs: int) -> torch.Tensor:
     idx = list(shard_range(n_items, rank, world))
     local = predict_fn(idx) if idx else torch.empty(0, epochs, dtype=torch.int64)
     max_n = (n_items + world - 1) // world
-    dev = local.device if dist.get_backend() == "nccl" else torch.device("cpu")
+    # NCCL moves device memory only: under an NCCL-only group the (CPU) predictions travel through this rank's GPU
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
     pad = torch.full((max_n, epochs), -1, dtype=torch.int64, device=dev)
     pad[: local.size(0)] = local.to(dev)
     gathered = [torch.empty_like(pad) for _ in range(world)]

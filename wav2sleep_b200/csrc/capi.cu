@@ -414,7 +414,7 @@ int check_encoder_desc(const w2s_encoder_desc* d) {
 
 extern "C" {
 
-int w2s_abi_version(void) { return 1; }
+int w2s_abi_version(void) { return 2; }
 const char* w2s_last_error(void) { return g_err.c_str(); }
 
 int w2s_conv_uses_split(int cin, int cout) { return (cin <= 32 && cout <= 32) ? 1 : 0; }
@@ -863,9 +863,9 @@ int w2s_enc_norm_bwd(const void* dxh, const void* y, const double* stats, const 
 }
 
 int w2s_first_conv_wgrad(const float* x, const void* dy1, const void* dr, float* dw1, float* dwds, const uint8_t* row_mask,
-                         int B, int T, void* stream) {
+                         int B, int T, float scale, void* stream) {
   if (!x || !dy1 || !dr || !dw1 || !dwds) return fail("first_conv_wgrad: bad arguments");
-  FirstWgradArgs p{x, (const act_t*)dy1, (const act_t*)dr, dw1, dwds, row_mask, B, T};
+  FirstWgradArgs p{x, (const act_t*)dy1, (const act_t*)dr, dw1, dwds, row_mask, B, T, scale};
   LaunchScope scope((cudaStream_t)stream, "first_conv_wgrad", (double)B * T * (4.0 + 32.0 + 16.0), 0);
   int gx = (T + 256 * 16 - 1) / (256 * 16);
   dim3 grid(gx < 1 ? 1 : gx, B);
@@ -886,12 +886,14 @@ int w2s_row_ln_fwd(const void* x, const void* res, const float* g, const float* 
 }
 
 int w2s_row_ln_bwd(const void* x, const void* res, const float* g, const float* b, const void* dout, const void* dadd,
-                   void* dx, void* ds, float* dg, float* db, long long rows, int gelu, float eps, void* stream) {
+                   void* dx, void* ds, float* dg, float* db, long long rows, int gelu, float eps, float gscale,
+                   void* stream) {
   if (!x || !g || !b || !dout || !dx || !dg || !db || rows <= 0) return fail("row_ln_bwd: bad arguments");
   RowLnArgs p;
   memset(&p, 0, sizeof(p));
   p.x = (const act_t*)x; p.res = (const act_t*)res; p.g = g; p.b = b; p.out = (act_t*)dx; p.dout = (const act_t*)dout;
   p.dadd = (const act_t*)dadd; p.ds = (act_t*)ds; p.dg = dg; p.db = db; p.rows = rows; p.gelu = gelu; p.eps = eps;
+  p.gscale = gscale;
   LaunchScope scope((cudaStream_t)stream, "row_ln_bwd", (double)rows * 128 * 8.0, 0);
   int gx = ew_grid(rows * 32);
   if (gx > 2 * sm_count()) gx = 2 * sm_count();
@@ -913,13 +915,14 @@ int w2s_gelu_bwd(const void* pre, const void* dout, void* din, long long n, void
 }
 
 int w2s_colsum(const void* x, float* out, long long rows, int Cc, int row_stride, int row_offset, const uint8_t* row_mask,
-               long long rows_per_sample, void* stream) {
+               long long rows_per_sample, float scale, void* stream) {
   if (!x || !out || rows <= 0 || Cc % 8 || Cc > 128 || 256 % (Cc / 8)) return fail("colsum: bad arguments");
   LaunchScope scope((cudaStream_t)stream, "colsum", (double)rows * Cc * 2.0, 0);
   int gx = ew_grid(rows * (Cc / 8));
   if (gx > 2 * sm_count()) gx = 2 * sm_count();
   colsum_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>((const act_t*)x, out, rows, Cc, row_stride > 0 ? row_stride : 1,
-                                                      row_offset, row_mask, rows_per_sample > 0 ? rows_per_sample : rows);
+                                                      row_offset, row_mask, rows_per_sample > 0 ? rows_per_sample : rows,
+                                                      scale);
   W2S_LAUNCH_CHECK("colsum");
 }
 
@@ -974,12 +977,12 @@ int w2s_tokens_fwd(const void* const* z, const uint8_t* const* row_mask, const f
   W2S_LAUNCH_CHECK("tokens_fwd");
 }
 int w2s_tokens_bwd(const void* dtokens, void* const* dz, const uint8_t* const* row_mask, float* dcls, int N, int S, int n_sig,
-                   void* stream) {
+                   float cls_scale, void* stream) {
   if (!dtokens || !dz || !dcls || n_sig < 1 || n_sig > 4) return fail("tokens_bwd: bad arguments");
   TokenArgs p;
   memset(&p, 0, sizeof(p));
   for (int i = 0; i < n_sig; ++i) { p.dz[i] = (act_t*)dz[i]; p.row_mask[i] = row_mask ? row_mask[i] : nullptr; }
-  p.dtokens = (const act_t*)dtokens; p.dcls = dcls; p.N = N; p.S = S; p.n_sig = n_sig;
+  p.dtokens = (const act_t*)dtokens; p.dcls = dcls; p.N = N; p.S = S; p.n_sig = n_sig; p.cls_scale = cls_scale;
   LaunchScope scope((cudaStream_t)stream, "tokens_bwd", (double)N * (n_sig + 1) * 128 * 4.0, 0);
   int gx = ew_grid((long long)N * (n_sig + 1) * 16);
   if (gx > 2 * sm_count()) gx = 2 * sm_count();
@@ -1019,11 +1022,12 @@ int w2s_ce_fwd_bwd(const float* logits, const long long* labels, long long N, in
   W2S_LAUNCH_CHECK("ce_fwd_bwd");
 }
 int w2s_head_bwd(const void* feat, const float* w, const float* dlogits, void* dfeat, float* dw, float* db, long long N, int Cc,
-                 void* stream) {
+                 float dfeat_scale, void* stream) {
   if (!feat || !w || !dlogits || !dfeat || !dw || !db || N <= 0 || Cc < 1 || Cc > 8) return fail("head_bwd: bad arguments");
   HeadArgs p;
   memset(&p, 0, sizeof(p));
   p.feat = (const act_t*)feat; p.w = w; p.dlogits = dlogits; p.dfeat = (act_t*)dfeat; p.dw = dw; p.db = db; p.N = N; p.C = Cc;
+  p.dfeat_scale = dfeat_scale;
   LaunchScope scope((cudaStream_t)stream, "head_bwd", (double)N * 128 * 4.0, 0);
   int gx = ew_grid(N * 32);
   if (gx > sm_count()) gx = sm_count();

@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(256) enc_norm_bwd_kernel(const EncNormBwdArgs 
 struct FirstWgradArgs {
   const float* x; const act_t* dy1; const act_t* dr; float* dw1; float* dwds; const uint8_t* row_mask;
   int B, T;
+  float scale;  // 1 / loss scale of the incoming activation gradients
 };
 __global__ void __launch_bounds__(256) first_conv_wgrad_kernel(const FirstWgradArgs p) {
   const int b = blockIdx.y;
@@ -248,8 +249,8 @@ __global__ void __launch_bounds__(256) first_conv_wgrad_kernel(const FirstWgradA
     if ((threadIdx.x & 31) == 0) atomicAdd(&red[k], v);
   }
   __syncthreads();
-  if (threadIdx.x < 48) atomicAdd(&p.dw1[threadIdx.x], red[threadIdx.x]);
-  else if (threadIdx.x < 64) atomicAdd(&p.dwds[threadIdx.x - 48], red[threadIdx.x]);
+  if (threadIdx.x < 48) atomicAdd(&p.dw1[threadIdx.x], red[threadIdx.x] * p.scale);
+  else if (threadIdx.x < 64) atomicAdd(&p.dwds[threadIdx.x - 48], red[threadIdx.x] * p.scale);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -268,6 +269,7 @@ struct RowLnArgs {
   act_t* ds;           // bwd (res != null): gradient flowing to the residual branch (= dout * GELU'(s))
   float* dg; float* db;
   long long rows; int gelu; float eps;
+  float gscale;        // bwd: dg / db are accumulated times gscale (1 / loss scale of dout)
 };
 W2S_DEVINL float warp_sum(float v) {
 #pragma unroll
@@ -376,8 +378,8 @@ __global__ void __launch_bounds__(256) row_ln_bwd_kernel(const RowLnArgs p) {
     float t = 0.0f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x];
-    if (threadIdx.x < 128) atomicAdd(&p.dg[threadIdx.x], t);
-    else atomicAdd(&p.db[threadIdx.x - 128], t);
+    if (threadIdx.x < 128) atomicAdd(&p.dg[threadIdx.x], t * p.gscale);
+    else atomicAdd(&p.db[threadIdx.x - 128], t * p.gscale);
   }
 }
 
@@ -409,7 +411,7 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const act_t* pre, const a
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_kernel(const act_t* x, float* out, long long rows, int C, int row_stride,
                                                      int row_offset, const uint8_t* row_mask,
-                                                     long long rows_per_sample) {
+                                                     long long rows_per_sample, float scale) {
   const int CH = C / 8;
   const int c8 = threadIdx.x % CH;
   const int rpi = blockDim.x / CH;
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const act_t* x, float* out,
     const int cc = threadIdx.x / 8, k = threadIdx.x % 8;
     float t = 0.0f;
     for (int j = cc; j < rpi * CH; j += CH) t += red[j * 8 + k];
-    atomicAdd(&out[threadIdx.x], t);
+    atomicAdd(&out[threadIdx.x], t * scale);
   }
 }
 
@@ -586,6 +588,7 @@ struct TokenArgs {
   act_t* tokens; uint8_t* key_mask;   // [N, D, 128], [N, D]
   const act_t* dtokens; act_t* dz[4]; float* dcls;
   int N, S, n_sig;
+  float cls_scale;  // bwd: dcls is accumulated times cls_scale (1 / loss scale of dtokens)
 };
 __global__ void __launch_bounds__(256) tokens_fwd_kernel(const TokenArgs p) {
   const int D = p.n_sig + 1;
@@ -635,7 +638,7 @@ __global__ void __launch_bounds__(256) tokens_bwd_kernel(const TokenArgs p) {
   }
   if (my_ck >= 0) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(&p.dcls[my_ck * 8 + k], cls_acc[k]);
+    for (int k = 0; k < 8; ++k) atomicAdd(&p.dcls[my_ck * 8 + k], cls_acc[k] * p.cls_scale);
   }
 }
 // strided row gather / scatter: out[n] = in[n * stride + offset]  (CLS rows <-> dense [N, 128])
@@ -664,6 +667,7 @@ struct HeadArgs {
   act_t* dfeat;           // [N, 128]
   float* dw; float* db;
   long long N; int C; long long ignore_index;
+  float dfeat_scale;      // bwd: dfeat = dfeat_scale * dlogits W (loss scaling of the fp16 activation gradients)
 };
 __global__ void __launch_bounds__(256) head_fwd_kernel(const HeadArgs p) {  // logits = feat W^T + b (training fwd)
   const int lane = threadIdx.x & 31;
@@ -744,8 +748,8 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const HeadArgs p) {
       }
     }
     uint2 w2;
-    w2.x = pack_h2(o[0], o[1]);
-    w2.y = pack_h2(o[2], o[3]);
+    w2.x = pack_h2(o[0] * p.dfeat_scale, o[1] * p.dfeat_scale);
+    w2.y = pack_h2(o[2] * p.dfeat_scale, o[3] * p.dfeat_scale);
     *(reinterpret_cast<uint2*>(p.dfeat + r * 128) + lane) = w2;
   }
 #pragma unroll

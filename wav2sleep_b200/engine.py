@@ -144,6 +144,12 @@ class ForwardEngine:
         self._ws: dict = {}
         self.use_graph = True          # CUDA-graph replay of small-batch forwards (see forward)
         self.replayed_launches = 0     # kernels launched through graph replays (not seen by w2s_launch_count)
+        # One CUDA stream per signal encoder: the encoders are independent chains of ~25 persistent kernels, each of
+        # which ends with a tail (CTAs finish 3-20 % apart) and starts with a ~5 us pipeline fill.  On separate
+        # streams the next chain's CTAs take over the SMs the moment a kernel's early finishers release them, so
+        # fill and tail of one encoder are covered by the other encoders' work.  W2S_ENC_STREAMS=0 serialises them.
+        import os
+        self.enc_streams = os.environ.get("W2S_ENC_STREAMS", "1") != "0"
 
     # ------------------------------------------------------------------ weights
     def _params_key(self, device):
@@ -210,19 +216,26 @@ class ForwardEngine:
 
     # ------------------------------------------------------------------ buffers
     def _buffers(self, device, names, B, S):
-        key = (str(device), tuple(names), B, S)
+        key = (str(device), tuple(names), B, S, self.enc_streams)
         buf = self._ws.get(key)
         if buf is not None:
             return buf
         self._ws.clear()  # one live shape at a time keeps the footprint bounded
         lib = self.lib
-        enc_ws = 0
+        sizes = {}
         for n in names:
             pe = self.enc[self.model.signal_encoders.signal_map[n]]
-            enc_ws = max(enc_ws, lib.w2s_encoder_workspace_bytes(C.byref(pe.desc), B, S * pe.samples_per_epoch, 0))
+            sizes[n] = lib.w2s_encoder_workspace_bytes(C.byref(pe.desc), B, S * pe.samples_per_epoch, 0)
         seq_ws = lib.w2s_seqmixer_workspace_bytes(C.byref(self.seq_desc), B, S, 0)
+        concurrent = self.enc_streams and len(names) > 1
+        if concurrent:  # encoders run side by side: one workspace each
+            enc_ws = {n: torch.empty(sizes[n], dtype=torch.uint8, device=device) for n in names}
+        else:           # encoders run back to back: one workspace of the largest size
+            shared = torch.empty(max(sizes.values()), dtype=torch.uint8, device=device)
+            enc_ws = {n: shared for n in names}
         buf = {
-            "enc_ws": torch.empty(enc_ws, dtype=torch.uint8, device=device),
+            "enc_ws": enc_ws,
+            "streams": [torch.cuda.Stream(device=device) for _ in names] if concurrent else None,
             "seq_ws": torch.empty(seq_ws, dtype=torch.uint8, device=device),
             "z": {n: torch.empty(B, S, 128, dtype=torch.float16, device=device) for n in names},
             "mask": {n: torch.zeros(B, dtype=torch.uint8, device=device) for n in names},
@@ -260,11 +273,27 @@ class ForwardEngine:
     def _launch(self, buf, xs: dict[str, Tensor], names, B: int, S: int, logits: Tensor) -> None:
         """Enqueue the three stage calls on the current stream (also what gets captured into a CUDA graph)."""
         lib, st = self.lib, _stream()
-        for n in names:
+        streams = buf["streams"]
+        if streams is not None:
+            cur = torch.cuda.current_stream()
+            fork = torch.cuda.Event()
+            fork.record(cur)
+        # longest chains first (they set the critical path when the encoders overlap)
+        for i, n in enumerate(sorted(names, key=lambda k: -xs[k].size(1))):
             pe = self.enc[self.model.signal_encoders.signal_map[n]]
-            _lib.check(lib.w2s_encoder_fwd(C.byref(pe.desc), xs[n].data_ptr(), B, xs[n].size(1), buf["enc_ws"].data_ptr(),
-                                           buf["enc_ws"].numel(), 0, buf["z"][n].data_ptr(), buf["mask"][n].data_ptr(), st),
+            ws = buf["enc_ws"][n]
+            if streams is not None:
+                streams[i].wait_event(fork)
+                est = streams[i].cuda_stream
+            else:
+                est = st
+            _lib.check(lib.w2s_encoder_fwd(C.byref(pe.desc), xs[n].data_ptr(), B, xs[n].size(1), ws.data_ptr(),
+                                           ws.numel(), 0, buf["z"][n].data_ptr(), buf["mask"][n].data_ptr(), est),
                        ValueError)
+            if streams is not None:
+                join = torch.cuda.Event()
+                join.record(streams[i])
+                cur.wait_event(join)
         zs = (C.c_void_p * len(names))(*[buf["z"][n].data_ptr() for n in names])
         ms = (C.c_void_p * len(names))(*[buf["mask"][n].data_ptr() for n in names])
         _lib.check(lib.w2s_epoch_mixer_fwd(C.byref(self.mixer_desc), zs, ms, len(names), B, S, buf["mix"].data_ptr(), st))
@@ -290,8 +319,11 @@ class ForwardEngine:
             if (self.use_graph and in_bytes <= self.GRAPH_MAX_INPUT_BYTES and buf.get("calls", 0) >= 1
                     and not torch.cuda.is_current_stream_capturing()):
                 if buf.get("graph") is None or buf.get("graph_wkey") != self._weights_key[0]:
-                    buf["xin"] = {n: torch.empty_like(xs[n]) for n in names}
-                    buf["logits"] = torch.empty(B, S, self.model.num_classes, dtype=torch.float32, device=device)
+                    # static graph buffers must be ordinary tensors: created under inference_mode they could not be
+                    # written by a later call that runs under plain no_grad
+                    with torch.inference_mode(False):
+                        buf["xin"] = {n: torch.empty(xs[n].shape, dtype=torch.float32, device=device) for n in names}
+                        buf["logits"] = torch.empty(B, S, self.model.num_classes, dtype=torch.float32, device=device)
                     l0 = self.lib.w2s_launch_count()
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):

@@ -239,6 +239,13 @@ class Wav2Sleep(nn.Module):
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from .training import forward_with_grad
             return forward_with_grad(self, x)
+        if self.training and (self.epoch_mixer.dropout > 0 or any(b.dropout.p > 0 for b in
+                                                                   self.sequence_mixer.dilated_convs)):
+            # train() under no_grad: dropout stays active, as in the reference (nn.Dropout follows .training, not grad mode)
+            eng = self._get_engine()
+            logits = eng.forward_train(x)
+            eng.saved = None
+            return logits
         return self._get_engine().forward(x)
 
     def predict(self, x: dict[str, Tensor]) -> Tensor:

@@ -26,6 +26,12 @@ class FusedAdamW(Optimizer):
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=None,
                  ema_decay: float | None = None, ema_start_step: int = 0):
+        params = list(params)
+        if params and isinstance(params[0], dict):
+            if len(params) != 1:
+                raise ValueError("FusedAdamW updates one flat buffer with one set of hyper-parameters: pass a single "
+                                 "parameter group")
+            params = list(params[0]["params"])
         params = [p for p in params if p.requires_grad]
         if not params:
             raise ValueError("optimizer got an empty parameter list")
@@ -41,6 +47,7 @@ class FusedAdamW(Optimizer):
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.gnorm_sq = torch.zeros(1, dtype=torch.float64, device=dev)
         self.offsets = {}
+        self._params = params
         off = 0
         for p in params:
             k = p.numel()
@@ -73,10 +80,75 @@ class FusedAdamW(Optimizer):
         end = max(s + k for s, k in spans)
         return start, end
 
+    def add_param_group(self, param_group):
+        if getattr(self, "param_groups", None):
+            raise ValueError("FusedAdamW supports a single parameter group")
+        super().add_param_group(param_group)
+
+    @torch.no_grad()
+    def _realias(self) -> None:
+        """``step`` reads only the flat buffers, so ``p.data`` / ``p.grad`` must still be views of them.  A foreign
+        ``model.zero_grad()`` (``p.grad = None``, after which autograd installs fresh gradient tensors), ``p.grad = t``
+        or ``model.to(...)`` breaks the alias: gather what the user left in ``p.grad`` / ``p.data`` into the flat
+        buffers and re-point the parameter (a missing gradient counts as zero).  Cost: 2 pointer compares per tensor."""
+        gp, pp = self.flat_grad.data_ptr(), self.flat_param.data_ptr()
+        for p in self._params:
+            off, k = self.offsets[id(p)]
+            if p.data_ptr() != pp + 4 * off or p.dtype != torch.float32:
+                if p.device != self.flat_param.device:
+                    raise RuntimeError("FusedAdamW: a parameter left the optimizer's device; rebuild the optimizer "
+                                       "after model.to(...)")
+                self.flat_param[off:off + k].copy_(p.detach().reshape(-1).to(torch.float32))
+                p.data = self.flat_param[off:off + k].view(p.shape)
+                self._bump()
+            gr = p.grad
+            if gr is None:
+                self.flat_grad[off:off + k].zero_()
+                p.grad = self.flat_grad[off:off + k].view(p.shape)
+            elif gr.data_ptr() != gp + 4 * off or gr.dtype != torch.float32 or not gr.is_contiguous():
+                self.flat_grad[off:off + k].copy_(gr.detach().reshape(-1).to(torch.float32))
+                p.grad = self.flat_grad[off:off + k].view(p.shape)
+
+    def grads_aliased(self) -> bool:
+        """True when every ``p.grad`` is still its view of the flat gradient buffer (what the bucketed data-parallel
+        all-reduce, which runs before ``step``, relies on)."""
+        gp = self.flat_grad.data_ptr()
+        return all(p.grad is not None and p.grad.data_ptr() == gp + 4 * self.offsets[id(p)][0] for p in self._params)
+
+    # ---- checkpointing: what torch.optim.AdamW keeps in ``state`` (+ the EMACallback's state_dict) lives in flat buffers
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["fused"] = {"step": self._step, "exp_avg": self.exp_avg.detach().clone(),
+                       "exp_avg_sq": self.exp_avg_sq.detach().clone(),
+                       "ema": None if self.ema is None else self.ema.detach().clone(),
+                       "ema_decay": self.ema_decay, "ema_start_step": self.ema_start_step,
+                       "numel": self.flat_param.numel()}
+        return sd
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        fused = state_dict.get("fused")
+        super().load_state_dict({k: v for k, v in state_dict.items() if k != "fused"})
+        if fused is None:
+            raise ValueError("not a FusedAdamW state_dict (no 'fused' entry): the Adam moments would be reset silently")
+        if fused["numel"] != self.flat_param.numel():
+            raise ValueError(f"state_dict holds {fused['numel']} elements, the optimizer {self.flat_param.numel()}")
+        self._step = int(fused["step"])
+        self.exp_avg.copy_(fused["exp_avg"])
+        self.exp_avg_sq.copy_(fused["exp_avg_sq"])
+        self.ema_decay, self.ema_start_step = fused["ema_decay"], fused["ema_start_step"]
+        if fused["ema"] is not None:
+            if self.ema is None:
+                self.ema = torch.empty_like(self.flat_param)
+            self.ema.copy_(fused["ema"])
+        else:
+            self.ema = None
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         lib = _lib.load()
+        self._realias()
         g = self.param_groups[0]
         self._step += 1
         st = torch.cuda.current_stream().cuda_stream

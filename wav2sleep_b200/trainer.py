@@ -5,9 +5,10 @@ Lightning (not installed here): same constructor keywords and the same ``forward
 (model.py -> training.py); the optimizer is the fused clip + AdamW (optim.py).
 
 Data parallelism: one process per GPU, replicated parameters, ONE exchange per step - the SUM
-all-reduce of the flat gradient buffer over NCCL/NVLink.  It is issued in two buckets from hooks inside the backward
-(``tail`` = classifier + sequence mixer + epoch mixer as soon as they are final, then ``encoders``) on a side stream, so
-the first bucket overlaps the encoder backward, which is >90 % of the step.
+all-reduce of the flat gradient buffer over NCCL/NVLink.  It is issued in buckets from hooks inside the backward
+(``tail`` = classifier + sequence mixer + epoch mixer as soon as they are final, then one bucket per signal encoder as
+its backward finishes, largest encoders first) on a side stream, so every bucket but the last, smallest one overlaps
+the encoder backward, which is >90 % of the step.
 """
 from __future__ import annotations
 
@@ -251,10 +252,21 @@ class SleepLightningModule(nn.Module):
             enc = list(self.model.signal_encoders.parameters())
             enc_ids = {id(p) for p in enc}
             tail = [p for p in self.model.parameters() if id(p) not in enc_ids]
-            segs = {"encoders": self._opt.segment(enc), "tail": self._opt.segment(tail)}
+            segs = {"tail": self._opt.segment(tail)}
+            for name, e in self.model.signal_encoders.encoders.items():
+                segs["encoder:" + name] = self._opt.segment(list(e.parameters()))
+            covered = sum(b - a for a, b in segs.values())
+            if covered != self._opt.flat_grad.numel():  # e.g. a parameter outside encoders / tail: one late bucket
+                segs = {"tail": segs["tail"], "encoders": self._opt.segment(enc)}
             self._reducer = GradReducer(self._opt.flat_grad, segs, process_group,
                                         overlap=os.environ.get("W2S_DDP_OVERLAP", "1") != "0")
             self._opt.grad_scale = 1.0 / self._reducer.world_size
+            if self._reducer.world_size > 1:
+                # what Lightning's DDP strategy does at start-up: every replica begins from rank 0's parameters
+                dist.broadcast(self._opt.flat_param, src=0, group=process_group)
+                if self._opt.ema is not None:
+                    dist.broadcast(self._opt.ema, src=0, group=process_group)
+                self._opt._bump()
             eng = self.model._get_train_engine()
             eng.bucket_hooks = [self._reducer]
 

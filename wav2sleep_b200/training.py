@@ -13,6 +13,13 @@ counter-based generator: the keep decision of an element is a hash of (step seed
 backward regenerates the masks instead of storing them, and a test can dump them (``w2s_dropout`` mask_out) to feed the
 oracle the very same masks.  The masks are therefore not the ones torch's Philox stream would draw - same distribution,
 different realisation.  Storage: fp16 activations and activation gradients, fp32 parameter gradients.
+
+Loss scaling: the reference trains in fp32 (scripts/config/training/main.yaml:16), where the ~1e-7 activation gradients
+of a mean cross entropy over B*S = 19 200 epochs are harmless; in fp16 they would be subnormal.  The backward therefore
+runs on gradients multiplied by a power of two (``TrainEngine.loss_scale``; default: 4 * 2^ceil(log2(B*S)), i.e. as if
+the loss were 4x the *sum* over epochs, which centres the activation gradients in fp16's range for any batch size), and
+every kernel that accumulates a parameter gradient multiplies by the inverse - fp32 parameter gradients are unscaled,
+exactly (powers of two), and nothing outside this file sees the scale.
 """
 from __future__ import annotations
 
@@ -48,6 +55,17 @@ class TrainEngine(ForwardEngine):
         self.direct = set()
         self.dropout_seed = None  # int: fixed seed for every step (tests); None: drawn from torch's CPU generator
         self.last_dropout_seed = 0
+        self.loss_scale = None    # power of two applied to the fp16 activation gradients; None = from B*S (see below)
+        self._inv_scale = 1.0
+        self.last_loss_scale = 1.0
+
+    @staticmethod
+    def auto_loss_scale(n_epochs: int) -> float:
+        """4 * 2^ceil(log2(B*S)): d(loss)/d(logits) of a mean cross entropy is (p - onehot) / n_valid, so this brings the
+        logit gradients to O(1..8) and the encoder activation gradients (measured ~1e-2 of that) to ~1e-2..1e-1, the
+        middle of fp16's normal range [6e-5, 65504], whatever the batch size."""
+        k = max(int(n_epochs) - 1, 0).bit_length() + 2
+        return float(2 ** min(k, 24))
 
     # dropout sites: 8 * layer + {0 attention weights, 1 after self-attention, 2 FF hidden, 3 after FF}; 64 + seq block
     def dropout(self, x: Tensor, site: int, p: float, seed: int, res: Tensor | None = None, out: Tensor | None = None):
@@ -151,7 +169,8 @@ class TrainEngine(ForwardEngine):
     def gemm_tn(self, X, Y, Cbuf, M, N, B, LX, LY, ldc_m, ldc_n, y_stride=1, y_offset=0, row_mask=None, c_off=0, taps=1,
                 ldc_t=0, tap_stride=1):
         _lib.check(self.lib.w2s_gemm_tn(X.data_ptr(), Y.data_ptr(), Cbuf.data_ptr() + 4 * c_off, M, N, taps, tap_stride, B,
-                                        LX, LY, y_stride, y_offset, ldc_m, ldc_n, ldc_t, 1.0, _p(row_mask), _stream()))
+                                        LX, LY, y_stride, y_offset, ldc_m, ldc_n, ldc_t, self._inv_scale, _p(row_mask),
+                                        _stream()))
 
     def ln_fwd(self, x, g, b, rows, gelu, eps, res=None):
         out = torch.empty_like(x)
@@ -164,12 +183,12 @@ class TrainEngine(ForwardEngine):
         ds = torch.empty_like(x) if want_ds else None
         _lib.check(self.lib.w2s_row_ln_bwd(x.data_ptr(), _p(res), g.data_ptr(), b.data_ptr(), dout.data_ptr(), _p(dadd),
                                            dx.data_ptr(), _p(ds), dg.data_ptr(), db.data_ptr(), rows, gelu, eps,
-                                           _stream()))
+                                           self._inv_scale, _stream()))
         return dx, ds
 
     def colsum(self, x, out, rows, Cc, row_stride=1, row_offset=0, row_mask=None, rows_per_sample=0, out_off=0):
         _lib.check(self.lib.w2s_colsum(x.data_ptr(), out.data_ptr() + 4 * out_off, rows, Cc, row_stride, row_offset,
-                                       _p(row_mask), rows_per_sample, _stream()))
+                                       _p(row_mask), rows_per_sample, self._inv_scale, _stream()))
 
     # ------------------------------------------------------------------ gradients storage
     def _grad(self, p: Tensor) -> Tensor:
@@ -186,7 +205,10 @@ class TrainEngine(ForwardEngine):
 
     # ================================================================== forward (training)
     @torch.no_grad()
-    def forward_train(self, x: dict[str, Tensor]) -> Tensor:
+    def forward_train(self, x: dict[str, Tensor], return_saved: bool = False):
+        """Training-mode forward.  The activations the backward needs are returned (``return_saved``: the autograd bridge
+        keeps them on its ``ctx``, so several forwards may precede their backwards, like with torch autograd) and also
+        remembered as ``self.saved`` for a direct ``backward(dlogits)`` call."""
         B, S, device = self._check_inputs(x)
         lib, m = self.lib, self.model
         with torch.cuda.device(device):
@@ -328,7 +350,7 @@ class TrainEngine(ForwardEngine):
             _lib.check(lib.w2s_head_fwd(feat.data_ptr(), wc.data_ptr(), bc.data_ptr(), logits.data_ptr(), N, m.num_classes, st))
             sv.update(feat=feat, wc=wc)
             self.saved = sv
-        return logits
+        return (logits, sv) if return_saved else logits
 
     def _f32(self, t: Tensor) -> Tensor:
         t = t.detach()
@@ -336,15 +358,22 @@ class TrainEngine(ForwardEngine):
 
     # ================================================================== backward
     @torch.no_grad()
-    def backward(self, dlogits: Tensor) -> dict[int, Tensor]:
-        """Back-propagates d(loss)/d(logits) through the saved forward; returns {id(param): fp32 grad}."""
-        sv, lib, m = self.saved, self.lib, self.model
+    def backward(self, dlogits: Tensor, saved: dict | None = None) -> dict[int, Tensor]:
+        """Back-propagates d(loss)/d(logits) through a saved forward (``saved``: what forward_train returned; default:
+        the most recent forward); returns {id(param): fp32 grad}.  A saved forward can be back-propagated once."""
+        sv, lib, m = (self.saved if saved is None else saved), self.lib, self.model
         if sv is None:
             raise RuntimeError("backward called without a preceding forward_train")
+        if sv.get("consumed"):
+            raise RuntimeError("this forward has already been back-propagated (its activations were released)")
         B, S, device = sv["B"], sv["S"], sv["device"]
         N = B * S
         self.grads = {}
         self.direct = set()
+        scale = float(self.loss_scale) if self.loss_scale is not None else self.auto_loss_scale(N)
+        if scale <= 0 or (scale != 2.0 ** round(__import__("math").log2(scale))):
+            raise ValueError(f"loss_scale must be a positive power of two, got {scale}")
+        self.last_loss_scale, self._inv_scale = scale, 1.0 / scale
         with torch.cuda.device(device):
             st = _stream()
             G = self._grad
@@ -353,7 +382,7 @@ class TrainEngine(ForwardEngine):
             dfeat = torch.empty(N, 128, dtype=F16, device=device)
             _lib.check(lib.w2s_head_bwd(sv["feat"].data_ptr(), sv["wc"].data_ptr(), dlogits.data_ptr(), dfeat.data_ptr(),
                                         G(m.classifier.weight).data_ptr(), G(m.classifier.bias).data_ptr(), N,
-                                        m.num_classes, st))
+                                        m.num_classes, scale, st))
             # ---- sequence mixer ----
             dout = dfeat
             for bi in reversed(range(len(sv["seq"]))):
@@ -439,17 +468,36 @@ class TrainEngine(ForwardEngine):
             dz = {n: torch.zeros(B, S, 128, dtype=F16, device=device) for n in names}
             dzs = (C.c_void_p * len(names))(*[dz[n].data_ptr() for n in names])
             ms = (C.c_void_p * len(names))(*[sv["enc"][n]["mask"].data_ptr() for n in names])
-            dcls = torch.zeros(128, dtype=torch.float32, device=device)
-            _lib.check(lib.w2s_tokens_bwd(dx.data_ptr(), dzs, ms, dcls.data_ptr(), N, S, len(names), st))
-            G(mix.register_tokens).view(-1).add_(dcls)  # register_tokens is [1, 1, 128, 1]
+            # register_tokens is [1, 1, 128, 1]: with no extra register tokens its gradient is the 128 CLS sums
+            _lib.check(lib.w2s_tokens_bwd(dx.data_ptr(), dzs, ms, G(mix.register_tokens).data_ptr(), N, S, len(names),
+                                          self._inv_scale, st))
             # ---- encoders ----
             for hook in self.bucket_hooks:
                 hook("tail")  # classifier + sequence mixer + epoch mixer gradients are final
-            for n in names:
+            if self.bucket_hooks and len(self.direct) != len(self.grads):
+                raise RuntimeError("gradient bucket hooks (data-parallel all-reduce) need every p.grad to be its view of "
+                                   "the optimizer's flat buffer during the backward: clear gradients with "
+                                   "FusedAdamW.zero_grad(), not model.zero_grad() / p.grad = None")
+            # largest encoders first, so that the exposed tail of the data-parallel exchange is the smallest bucket
+            order = sorted(names, key=lambda n: -sv["enc"][n]["T"])
+            smap = m.signal_encoders.signal_map
+            pending = {}  # encoder name -> signals still to back-propagate (encoders may be shared between signals)
+            for n in order:
+                pending[smap[n]] = pending.get(smap[n], 0) + 1
+            for n in order:
                 self._encoder_backward(sv["enc"][n], dz[n], B, S)
+                sv["enc"][n] = None  # release this encoder's activations
+                pending[smap[n]] -= 1
+                if pending[smap[n]] == 0:
+                    for hook in self.bucket_hooks:
+                        hook("encoder:" + smap[n])  # this encoder's parameter gradients are final
             for hook in self.bucket_hooks:
                 hook("encoders")
-            self.saved = None
+            sv["consumed"] = True
+            for k in ("layers", "seq", "feat", "key_mask"):
+                sv.pop(k, None)
+            if self.saved is sv:
+                self.saved = None
         return self.grads
 
     def _encoder_backward(self, e, dz, B, S):
@@ -514,7 +562,7 @@ class TrainEngine(ForwardEngine):
             if i == 0:
                 _lib.check(lib.w2s_first_conv_wgrad(e["x"].data_ptr(), dy1.data_ptr(), dr.data_ptr(),
                                                     G(blk.conv1.conv.weight).data_ptr(), G(blk.downsample.weight).data_ptr(),
-                                                    mask.data_ptr(), B, L, st))
+                                                    mask.data_ptr(), B, L, self._inv_scale, st))
                 break
             pb = blocks[i - 1]
             Ci = pb["C"]
@@ -541,11 +589,13 @@ class _TrainFn(torch.autograd.Function):
     def forward(ctx, engine, x, *params):
         ctx.engine = engine
         ctx.params = params
-        return engine.forward_train(x)
+        logits, ctx.saved = engine.forward_train(x, return_saved=True)  # per-graph state, like autograd's saved tensors
+        return logits
 
     @staticmethod
     def backward(ctx, dlogits):
-        grads = ctx.engine.backward(dlogits)
+        grads = ctx.engine.backward(dlogits, ctx.saved)
+        ctx.saved = None
         out = []
         for p in ctx.params:
             g = grads.get(id(p))
