@@ -292,16 +292,32 @@ def run_cuda(args):
         # ---------------- per-kernel profile (CUDA events around every launch, 2 extra steps) ----------------
         prof = []
         if rank == 0:
+            eng = model._get_engine()
+            streams_on, eng.enc_streams = eng.enc_streams, False  # isolated per-kernel durations: encoders back to back
+            model.predict(devb[0])
             lib.w2s_profile_enable(1)
             for i in range(2):
                 model.predict(devb[i % 2])
             torch.cuda.synchronize()
             prof = collect_profile(lib)
             lib.w2s_profile_enable(0)
+            eng.enc_streams = streams_on
+            eng._ws.clear()
 
-    train = None
+    del stage, stage16, host16, devb
+    model._get_engine()._ws.clear()
+    torch.cuda.empty_cache()
+    train = train_ecg = eog = None
     if not args.no_train:
         train = time_train_step(model, dev, world, rank, barrier, max_over_ranks, lib)
+        # the same step with every rank drawing the SAME modality masks: separates mask stragglers from communication
+        train["same_mask_on_all_ranks"] = time_train_step(model, dev, world, rank, barrier, max_over_ranks, lib,
+                                                          same_seed=True)["ms_per_step"] if world > 1 else None
+        torch.cuda.empty_cache()
+        train_ecg = time_train_step(model, dev, world, rank, barrier, max_over_ranks, lib, batch=32, only=("ECG",))
+        torch.cuda.empty_cache()
+    if not args.no_eog and world == 1:
+        eog = time_eog(dev, lib, hbm_peak, tf_peak)
 
     if rank != 0:
         if world > 1:
@@ -363,26 +379,47 @@ def run_cuda(args):
         "kernels": kernels[:8],
         "cpu_baseline": cpu,
         "train": train,
+        "train_ecg_only": train_ecg,
+        "eog": eog,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def time_train_step(model, dev, world, rank, barrier, max_over_ranks, lib, steps=5, warmup=3):
-    """Secondary metric (BASELINE.json "train step ms", configs[3]): cardio training step at 16 nights per GPU =
-    polarity flip + config masker + forward (activations kept) + CE + backward + bucketed gradient all-reduce + fused
-    clip + AdamW.  Dropout is p = 0 (DESIGN.md)."""
+def clocks_during(fn, index):
+    """Run fn() while sampling nvidia-smi clocks; returns (result, clocks summary)."""
+    sampler = ClockSampler(index)
+    sampler.start()
+    try:
+        out = fn()
+    finally:
+        sampler.stop_flag.set()
+        sampler.join(timeout=3)
+    return out, sampler.summary()
+
+
+def time_train_step(model, dev, world, rank, barrier, max_over_ranks, lib, steps=5, warmup=3, batch=BATCH, only=None,
+                    same_seed=False):
+    """Secondary metric (BASELINE.json "train step ms").  configs[3]: cardio training step at 16 nights per GPU = polarity
+    flip + config masker + forward (activations kept, dropout 0.1 in both mixers) + CE + loss-scaled fp16 backward +
+    bucketed gradient all-reduce + fused clip + AdamW.  configs[4] (``only=("ECG",)``, batch 32): the same 4-signal model
+    with PPG / ABD / THX missing for every night (rows of -inf, what the masker emits), no random masking."""
+    import torch.distributed as dist
     from wav2sleep_b200.optim import FusedAdamW
     from wav2sleep_b200.trainer import SignalMasker, SleepLightningModule
-    torch.manual_seed(1234 + rank)
-    masker = SignalMasker({"ABD": 0.7, "THX": 0.7, "ECG": 0.5, "PPG": 0.1}, backups=["ECG", "PPG"])
+    torch.manual_seed(1234 + (0 if same_seed else rank))
+    masker = None if only else SignalMasker({"ABD": 0.7, "THX": 0.7, "ECG": 0.5, "PPG": 0.1}, backups=["ECG", "PPG"])
     pl = SleepLightningModule(model, optimizer=lambda ps: FusedAdamW(ps, lr=1e-3, weight_decay=1e-4, max_grad_norm=1.0),
                               num_classes=4, masker=masker)
     pl.setup_training()
-    src = {k: v.to(dev) for k, v in make_night_batch(BATCH, seed=7 + rank).items()}
-    y = torch.randint(0, 4, (BATCH, S_EPOCHS), device=dev)
-    y[torch.rand(BATCH, S_EPOCHS, device=dev) < 0.05] = -1
+    src = {k: v.to(dev) for k, v in make_night_batch(batch, seed=7 + rank).items()}
+    if only:
+        for k in src:
+            if k not in only:
+                src[k].fill_(float("-inf"))
+    y = torch.randint(0, 4, (batch, S_EPOCHS), device=dev)
+    y[torch.rand(batch, S_EPOCHS, device=dev) < 0.05] = -1
 
     def one():
         x = {k: v.clone() for k, v in src.items()}
@@ -393,17 +430,83 @@ def time_train_step(model, dev, world, rank, barrier, max_over_ranks, lib, steps
     barrier()
     l0 = lib.w2s_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        loss = one()
-    e1.record()
-    barrier()
+
+    def timed():
+        e0.record()
+        for _ in range(steps):
+            loss = one()
+        e1.record()
+        barrier()
+        return loss
+
+    loss, clocks = clocks_during(timed, dev.index or 0)
+    own = e0.elapsed_time(e1) / steps
     ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    per_rank = [own]
+    if world > 1:
+        t = torch.tensor([own], device=dev, dtype=torch.float64)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [float(v.item()) for v in allt]
+    eng = model._get_engine()
+    eng.bucket_hooks = []
     model.eval()
-    return {"ms_per_step": ms, "nights_per_gpu": BATCH, "n_gpus": world, "steps": steps, "warmup": warmup,
-            "last_loss": float(loss), "gpu_launches_per_step": int((lib.w2s_launch_count() - l0) / steps),
-            "masker": "config cardiorespiratory/all.yaml (ABD .7, THX .7, ECG .5, PPG .1; backups ECG, PPG)",
-            "dropout": float(model.epoch_mixer.dropout), "optimizer": "fused clip(1.0) + AdamW(lr 1e-3, wd 1e-4)"}
+    return {"ms_per_step": ms, "nights_per_gpu": batch, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "recording_hours_per_s": batch * HOURS_PER_NIGHT * world / (ms * 1e-3),
+            "per_rank_ms": per_rank, "last_loss": float(loss),
+            "gpu_launches_per_step": int((lib.w2s_launch_count() - l0) / steps),
+            "signals": list(only) if only else "all four, config masker cardiorespiratory/all.yaml (ABD .7, THX .7, ECG .5, "
+                                               "PPG .1; backups ECG, PPG)",
+            "loss_scale": eng.last_loss_scale, "grad_dtype": "f16 activations (loss-scaled), f32 parameters",
+            "dropout": float(model.epoch_mixer.dropout), "optimizer": "fused clip(1.0) + AdamW(lr 1e-3, wd 1e-4)",
+            "clocks": clocks}
+
+
+def time_eog(dev, lib, hbm_peak, tf_peak, steps=5, warmup=3):
+    """BASELINE configs[1]: wav2sleep-eog (EOG-L + EOG-R, 4096 samples per epoch, 10-block encoders, 5 classes), batch of
+    16 synthetic 14-h nights (S = 1680) on one GPU, inputs resident in HBM.  Same metric as the headline."""
+    from wav2sleep_b200 import build_default
+    S, B, hours = 1680, 16, 14.0
+    model = build_default({"EOG-L": "EOG-L", "EOG-R": "EOG-R"}, 5, seed=0).to(dev).eval()
+    g = torch.Generator().manual_seed(42)
+    xs = [{k: torch.randn(B, S * 4096, generator=g).to(dev) for k in ("EOG-L", "EOG-R")} for _ in range(2)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.inference_mode():
+        for i in range(warmup):
+            model.predict(xs[i % 2])
+        torch.cuda.synchronize()
+        l0 = lib.w2s_launch_count()
+
+        def timed():
+            e0.record()
+            for i in range(steps):
+                model.predict(xs[i % 2])
+            e1.record()
+            torch.cuda.synchronize()
+
+        _, clocks = clocks_during(timed, dev.index or 0)
+        launches = lib.w2s_launch_count() - l0
+        ms = e0.elapsed_time(e1) / steps
+        eng = model._get_engine()
+        eng.enc_streams = False
+        model.predict(xs[0])
+        lib.w2s_profile_enable(1)
+        model.predict(xs[1])
+        torch.cuda.synchronize()
+        prof = collect_profile(lib)
+        lib.w2s_profile_enable(0)
+    kms = sum(r[1] for r in prof) or 1.0
+    by, fl = sum(r[2] for r in prof), sum(r[3] for r in prof)
+    wide = [int(e.wide_blocks) for e in model.signal_encoders.encoders.values()]
+    del xs, model
+    torch.cuda.empty_cache()
+    return {"metric": METRIC, "value": B * hours / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "warmup": warmup, "gpu_launches": int(launches), "clocks": clocks,
+            "config": {"workload": "wav2sleep-eog (EOG-L, EOG-R) 5-class inference, 16 synthetic 14-h nights on 1 GPU "
+                                   "(BASELINE configs[1])", "epochs_per_night": S, "wide_blocks": wide},
+            "roofline": {"bound": "hbm", "achieved": by / kms * 1e-6, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": by / kms * 1e-6 / hbm_peak, "scope": "whole step, algorithmic bytes of every launch / "
+                         "summed kernel time", "algo_TFLOPs": fl / kms * 1e-9, "kernel_ms_per_step": kms}}
 
 
 def main():
@@ -413,7 +516,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-train", action="store_true", help="skip the secondary train-step timing")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary train-step timings")
+    ap.add_argument("--no-eog", action="store_true", help="skip the secondary EOG-model timing (BASELINE configs[1])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else max(args.warmup, 1)
     if args.impl == "reference":
