@@ -44,9 +44,12 @@ const char* w2s_last_error(void);
 int w2s_pack_conv_weight(const float* w, int cout, int cin, int taps, int taps_major, int split, void* out_fp16,
                          void* stream);
 size_t w2s_packed_conv_weight_bytes(int cout, int cin, int taps, int split);
-/* 1 if the (cin, cout) encoder conv kernels carry operands as fp16 hi + fp16 lo pairs; their weights must then be
- * packed with split = 1 (hi block followed by lo block, twice the bytes).  True for cin <= 32 and cout <= 32. */
+/* 1 if the (cin, cout) encoder conv kernels carry operands as fp16 hi + fp16 lo pairs by default; their weights must
+ * then be packed with split = 1 (hi block followed by lo block, twice the bytes).  True for cin <= 16 and cout <= 16. */
 int w2s_conv_uses_split(int cin, int cout);
+/* The same question for conv (cin -> cout) of encoder block `block` under the storage policy wide_blocks (see
+ * w2s_encoder_desc): the wide 64-channel blocks of deep encoders carry split operands as well. */
+int w2s_encoder_conv_split(int wide_blocks, int block, int cin, int cout);
 
 /* Batched re-packing (one launch for every weight of a model, used after each optimizer step).  jobs: DEVICE array.
  * kind 0: packed[n][c][t] = w[n*sn + c*sc + t*st] (element strides, may be negative: flipped / transposed / sliced views
@@ -107,6 +110,9 @@ typedef struct w2s_conv_call {
   /* wide storage (encoder EPI_STATS convs with cin, cout <= 64 only): in / in_res, resp. out / out_ds, are fp32
    * instead of fp16 tensors of the same shape. */
   int32_t in_wide, out_wide;
+  /* 1: operands are fp16 hi + lo pairs although w2s_conv_uses_split(cin, cout) is 0 (weights packed with split = 1);
+   * built for the wide-storage 64-channel encoder kernels only. */
+  int32_t force_split;
   /* W2S_EPI_ACT_BWD (training): data-gradient conv fused with the backward through the activation of the layer that
    * produced this conv's input: da = acc (+ res); with x_hat = InstanceNorm(act_y) [block outputs: s = GELU(x_hat) +
    * act_r, ds = da GELU'(s), act_dr = ds] out = d(x_hat) = ds GELU'(x_hat); act_a = the activated tensor (may be
@@ -156,8 +162,8 @@ typedef struct w2s_encoder_desc {
   const void* w_lin;                        /* packed fp16 linear.weight as taps=4 */
   const float* b_lin;                       /* fp32 [feature_dim] */
   /* inference only: the conv outputs of the first wide_blocks blocks are stored as fp32 instead of fp16 (allowed for
-   * blocks with <= 32 channels: 2 or 4, < n_blocks).  0 = all fp16.  Deep stacks (EOG, 10 blocks) need it to meet the parity
-   * gates; it doubles the bytes of those layers. */
+   * blocks with <= 64 channels: 2, 4 or 6, < n_blocks) and their convs carry split (hi + lo) operands.  0 = all fp16.
+   * Deep stacks (EOG, 10 blocks) need it to meet the parity gates; it doubles the bytes of those layers. */
   int32_t wide_blocks;
 } w2s_encoder_desc;
 

@@ -79,14 +79,16 @@ def test_full_night_argmax(cuda_device):
 
 
 def test_full_night_argmax_eog(cuda_device):
-    """Config-2 shape (EOG model, one 14-h night, S=1680, 6.9 M samples per signal): the deepest encoder stack, with
-    its default storage policy (fp32 storage of the four 16/32-channel blocks) and with all-fp16 storage."""
+    """Config-2 shape (EOG model, 14-h nights, S=1680, 6.9 M samples per signal): the deepest encoder stack, with its
+    default storage policy (fp32 storage + split operands for the six blocks up to 64 channels) and with less.
+    Three nights = 5040 epochs, so that the 99.9 % argmax gate is a statistic (<= 5 flips) rather than one coin flip:
+    with the random-init weights the median top-2 logit margin is 0.34 and every disagreeing epoch is a near-tie."""
     model = build_default(EOG, 5, seed=0)
-    x = make_inputs(EOG, 1, 1680, seed=42)
+    x = make_inputs(EOG, 3, 1680, seed=42)
     ref = oracle.forward(x, model.state_dict(), oracle.eog_config())
     srt = ref.sort(-1).values
     res = {}
-    for wide in (4, 2, 0):
+    for wide in (6, 4, 0):
         for enc in model.signal_encoders.encoders.values():
             enc.wide_blocks = wide
         out = run_cuda(model, x, cuda_device)
@@ -100,12 +102,9 @@ def test_full_night_argmax_eog(cuda_device):
             worst = (srt[..., -1] - srt[..., -2])[flipped].max().item()
             print(f"    {int(flipped.sum())} flipped epochs, largest reference top-2 margin among them {worst:.2e}")
             assert worst < 2 * err.max().item()
-    assert model.signal_encoders.get_encoder("EOG-L").__class__.__name__ == "SignalEncoder"
-    assert build_default(EOG, 5).signal_encoders.get_encoder("EOG-L").wide_blocks == 4  # the default policy
-    assert res[4][0] < TOL
-    # argmax gate: 99.9 % asks for <= 1 flip in 1680 epochs at a median top-2 margin of 0.34 (random-init logits);
-    # measured value is printed above and recorded in DESIGN.md "Numerics".
-    assert res[4][1] >= 0.997
+    assert build_default(EOG, 5).signal_encoders.get_encoder("EOG-L").wide_blocks == 6  # the default policy
+    assert res[6][0] < TOL and res[6][1] >= 0.999   # both north-star gates with the default policy
+    assert res[4][0] < TOL and res[4][1] >= 0.997   # round-1 policy: max-abs gate only
     # all-fp16 storage of this 30-conv stack sits on the gate (2.0-2.2e-2 / 99.5 %): kept as a documented option only
     assert res[0][0] < 2.5e-2 and res[0][1] >= 0.99
 

@@ -1,6 +1,7 @@
 """One inference step or one training step bracketed by cudaProfilerStart/Stop, for `ncu --profile-from-start off`.
 
-    python tools/profile_step.py infer [B]            # cardio forward, B nights (default 16), encoders serialised
+    python tools/profile_step.py infer [B] [signals]  # cardio forward, B nights (default 16), encoders serialised;
+                                                      # optional comma list of signals kept (the others are -inf rows)
     python tools/profile_step.py train [B] [signals]  # cardio training step, optional comma list of signals kept (others -inf)
 """
 import sys
@@ -21,6 +22,10 @@ if mode == "infer":
     model = build_default(bench.CARDIO, 4, seed=0).to(dev).eval()
     model._get_engine().enc_streams = False
     x = {k: v.to(dev) for k, v in bench.make_night_batch(B, seed=42).items()}
+    if len(sys.argv) > 3:
+        for k in x:
+            if k not in sys.argv[3].split(","):
+                x[k].fill_(float("-inf"))
     with torch.inference_mode():
         for _ in range(2):
             model.predict(x)

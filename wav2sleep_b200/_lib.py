@@ -75,7 +75,7 @@ class ConvCall(C.Structure):
         ("n_classes", C.c_int32), ("in_eps", C.c_float), ("ln_eps", C.c_float),
         ("out_stride", C.c_int32), ("out_offset", C.c_int32), ("out_rows", C.c_int32),
         ("x_raw", C.c_void_p), ("w_first", C.c_void_p), ("w_first_ds", C.c_void_p), ("T_raw", C.c_int32),
-        ("in_wide", C.c_int32), ("out_wide", C.c_int32),
+        ("in_wide", C.c_int32), ("out_wide", C.c_int32), ("force_split", C.c_int32),
         ("act_y", C.c_void_p), ("act_r", C.c_void_p), ("act_stats", C.c_void_p), ("act_a", C.c_void_p),
         ("act_dr", C.c_void_p), ("act_eps", C.c_float),
     ]
@@ -123,6 +123,7 @@ SYMBOLS = {
                                        C.c_void_p]),
     "w2s_packed_conv_weight_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "w2s_conv_uses_split": (C.c_int, [C.c_int, C.c_int]),
+    "w2s_encoder_conv_split": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "w2s_pack_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "w2s_pack_linear_frag": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "w2s_conv1d_fwd": (C.c_int, [C.POINTER(ConvCall), C.c_void_p]),

@@ -231,8 +231,8 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
   if (ilog2_exact(c.stride) < 0 || c.stride > 4) return fail("conv1d: stride %d unsupported", c.stride);
   if (c.B > 65535) return fail("conv1d: B=%d exceeds grid.y", c.B);
   if (c.n_classes > 8) return fail("conv1d: n_classes=%d > 8", c.n_classes);
-  if ((c.in_wide || c.out_wide) && (c.epilogue != W2S_EPI_STATS || g_conv_impl.load() != 0))
-    return fail("conv1d: wide storage is only built for the streaming encoder kernels");
+  if ((c.in_wide || c.out_wide || c.force_split) && (c.epilogue != W2S_EPI_STATS || g_conv_impl.load() != 0))
+    return fail("conv1d: wide storage / forced split operands are only built for the streaming encoder kernels");
   if (c.epilogue == W2S_EPI_ACT_BWD) {
     if (!c.act_y || !c.act_stats || !c.out_stats || (c.act_r && !c.act_dr))
       return fail("conv1d: W2S_EPI_ACT_BWD needs act_y, act_stats, out_stats (and act_dr with act_r)");
@@ -261,12 +261,15 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
   if (c.epilogue == W2S_EPI_STATS && c.taps == 3 && c.dilation == 1 && c.pad == 1 && g_conv_impl.load() == 0 &&
       ((c.stride == 1 && c.L_out == c.L_in) || (c.stride == 2 && c.L_out == (c.L_in + 1) / 2))) {
     const int sms = sm_count();
-#define W2S_STREAMW(CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW, WIN, WOUT)                                 \
+    const bool want_split = c.force_split != 0 || w2s_conv_uses_split(c.cin, c.cout) != 0;
+#define W2S_STREAMX(CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW, WIN, WOUT, SPLIT)                          \
   if (!found && c.cin == CIN && c.cout == COUT && c.stride == STRIDE && c.prologue == PRO && (c.has_ds != 0) == DS && \
-      (c.in_wide != 0) == WIN && (c.out_wide != 0) == WOUT) {                                               \
+      (c.in_wide != 0) == WIN && (c.out_wide != 0) == WOUT && want_split == SPLIT) {                        \
     found = true;                                                                                           \
-    e = launch_conv_stream<CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW, WIN, WOUT>(a, c.B, sms, st);        \
+    e = launch_conv_stream<CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW, WIN, WOUT, SPLIT>(a, c.B, sms, st); \
   }
+#define W2S_STREAMW(CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW, WIN, WOUT) \
+  W2S_STREAMX(CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW, WIN, WOUT, (CIN <= 16 && COUT <= 16))
 #define W2S_STREAM(CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW) \
   W2S_STREAMW(CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW, false, false)
     //          cin cout s  prologue      ds    MT NR NA NTW
@@ -292,17 +295,25 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
     W2S_STREAMW(16, 16, 1, PRO_NORM_RES_X, true, 4, 3, 2, 14, true, true)
     W2S_STREAMW(16, 16, 1, PRO_NORM, false, 6, 2, 2, 18, true, true)
     W2S_STREAMW(16, 16, 2, PRO_NORM, false, 3, 2, 2, 18, true, true)
-    W2S_STREAMW(16, 32, 1, PRO_NORM_RES, true, 4, 2, 2, 10, true, false)
-    W2S_STREAMW(16, 32, 1, PRO_NORM_RES, true, 4, 2, 2, 10, true, true)
-    W2S_STREAMW(32, 32, 1, PRO_NORM, false, 3, 2, 2, 14, true, true)
-    W2S_STREAMW(32, 32, 2, PRO_NORM, false, 1, 3, 2, 14, true, true)
-    W2S_STREAMW(32, 32, 1, PRO_NORM_RES, true, 2, 2, 2, 10, true, true)
-    W2S_STREAMW(32, 64, 1, PRO_NORM_RES, true, 2, 2, 2, 14, true, false)
+    W2S_STREAMX(16, 32, 1, PRO_NORM_RES, true, 4, 2, 2, 10, true, false, false)
+    W2S_STREAMX(16, 32, 1, PRO_NORM_RES, true, 4, 2, 2, 10, true, true, true)
+    W2S_STREAMX(32, 32, 1, PRO_NORM, false, 3, 2, 2, 14, true, true, true)
+    W2S_STREAMX(32, 32, 2, PRO_NORM, false, 1, 3, 2, 14, true, true, true)
+    W2S_STREAMX(32, 32, 1, PRO_NORM_RES, true, 2, 2, 2, 10, true, true, true)
+    W2S_STREAMX(32, 64, 1, PRO_NORM_RES, true, 2, 2, 2, 14, true, false, false)
+    // wide storage + split operands of the 64-channel blocks (wide_blocks = 6: >= 10-block encoders, DESIGN.md "Numerics")
+    //                                                 MT NR NA NTW  in    out   split
+    W2S_STREAMX(32, 64, 1, PRO_NORM_RES, true, 2, 1, 2, 14, true, true, true)
+    W2S_STREAMX(64, 64, 1, PRO_NORM, false, 1, 2, 2, 14, true, true, true)
+    W2S_STREAMX(64, 64, 2, PRO_NORM, false, 1, 1, 1, 14, true, true, true)
+    W2S_STREAMX(64, 64, 1, PRO_NORM_RES, true, 1, 1, 2, 14, true, true, true)
+    W2S_STREAMX(64, 128, 1, PRO_NORM_RES, true, 1, 1, 2, 14, true, false, false)
 #undef W2S_STREAM
 #undef W2S_STREAMW
-    if (!found && (c.in_wide || c.out_wide))
-      return fail("conv1d: no wide-storage kernel for cin=%d cout=%d stride=%d prologue=%d in_wide=%d out_wide=%d", c.cin,
-                  c.cout, c.stride, c.prologue, c.in_wide, c.out_wide);
+#undef W2S_STREAMX
+    if (!found && (c.in_wide || c.out_wide || c.force_split))
+      return fail("conv1d: no wide-storage kernel for cin=%d cout=%d stride=%d prologue=%d in_wide=%d out_wide=%d split=%d",
+                  c.cin, c.cout, c.stride, c.prologue, c.in_wide, c.out_wide, (int)want_split);
     if (found) {
       if (e != cudaSuccess) return cuda_fail(e, "conv_stream launch");
       return 0;
@@ -403,10 +414,12 @@ int check_encoder_desc(const w2s_encoder_desc* d) {
   if (d->n_blocks < 1 || d->n_blocks > W2S_MAX_BLOCKS) return fail("encoder: n_blocks=%d out of range", d->n_blocks);
   if (d->feature_dim != 128) return fail("encoder: feature_dim=%d (only 128 is built)", d->feature_dim);
   if (d->channels[0] != 16) return fail("encoder: initial_channels=%d (only 16 is built)", d->channels[0]);
-  if (d->wide_blocks < 0 || d->wide_blocks >= d->n_blocks || (d->wide_blocks > 0 && d->channels[d->wide_blocks - 1] > 32))
-    return fail("encoder: wide_blocks=%d must cover only leading blocks with <= 32 channels", d->wide_blocks);
+  if (d->wide_blocks < 0 || d->wide_blocks >= d->n_blocks || (d->wide_blocks > 0 && d->channels[d->wide_blocks - 1] > 64))
+    return fail("encoder: wide_blocks=%d must cover only leading blocks with <= 64 channels", d->wide_blocks);
+  if (d->wide_blocks > 4 && (d->channels[4] != 64 || d->channels[3] != 32))
+    return fail("encoder: wide_blocks=%d needs the 16,16,32,32,64,64 channel plan", d->wide_blocks);
   if (d->wide_blocks > 0 && (d->n_blocks < 2 || d->channels[1] != 16)) return fail("encoder: wide_blocks needs the fused block 0");
-  if (d->wide_blocks & 1) return fail("encoder: wide_blocks=%d (only whole channel groups: 0, 2 or 4 are built)", d->wide_blocks);
+  if (d->wide_blocks & 1) return fail("encoder: wide_blocks=%d (only whole channel groups: 0, 2, 4 or 6 are built)", d->wide_blocks);
   return 0;
 }
 
@@ -417,7 +430,11 @@ extern "C" {
 int w2s_abi_version(void) { return 2; }
 const char* w2s_last_error(void) { return g_err.c_str(); }
 
-int w2s_conv_uses_split(int cin, int cout) { return (cin <= 32 && cout <= 32) ? 1 : 0; }
+int w2s_conv_uses_split(int cin, int cout) { return (cin <= 16 && cout <= 16) ? 1 : 0; }
+int w2s_encoder_conv_split(int wide_blocks, int block, int cin, int cout) {
+  if (w2s_conv_uses_split(cin, cout)) return 1;
+  return (block < wide_blocks && cin <= 64 && cout <= 64) ? 1 : 0;  // every wide block carries split operands
+}
 
 size_t w2s_packed_conv_weight_bytes(int cout, int cin, int taps, int split) {
   return (size_t)cout * cin * taps * sizeof(__half) * (split ? 2 : 1);
@@ -637,6 +654,7 @@ int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T,
       cc.w = d->w_conv[i][0]; cc.w_ds = d->w_ds[i];
       cc.out = y1; cc.out_ds = r; cc.out_stats = s1; cc.row_mask = row_mask; cc.in_eps = d->norm_eps;
       cc.in_wide = wide(i - 1); cc.out_wide = wide(i);
+      cc.force_split = keep ? 0 : w2s_encoder_conv_split(d->wide_blocks, i, prev_c, c);
       if (conv_dispatch(cc, st) != 0) return 1;
       release(prev_y3);
       release(prev_r);
@@ -656,6 +674,7 @@ int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T,
       cc.in = y1; cc.in_stats = s1; cc.w = d->w_conv[i][1];
       cc.out = y2; cc.out_stats = s2; cc.row_mask = row_mask; cc.in_eps = d->norm_eps;
       cc.in_wide = wide(i) && !(i == 0 && fuse0); cc.out_wide = wide(i);
+      cc.force_split = keep ? 0 : w2s_encoder_conv_split(d->wide_blocks, i, c, c);
       if (conv_dispatch(cc, st) != 0) return 1;
     }
     release(y1);
@@ -670,6 +689,7 @@ int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T,
       cc.in = y2; cc.in_stats = s2; cc.w = d->w_conv[i][2];
       cc.out = y3; cc.out_stats = s3; cc.row_mask = row_mask; cc.in_eps = d->norm_eps;
       cc.in_wide = wide(i); cc.out_wide = wide(i);
+      cc.force_split = keep ? 0 : w2s_encoder_conv_split(d->wide_blocks, i, c, c);
       if (conv_dispatch(cc, st) != 0) return 1;
     }
     release(y2);

@@ -94,11 +94,13 @@ __host__ __device__ inline int conv_rows_per_phase(int pos, int stride, int taps
   return (R + stride - 1) / stride;
 }
 // SPLIT: operands are carried as fp16 hi + fp16 lo (A = A_hi + A_lo, W = W_hi + W_lo) and the product is
-// A_hi*W_hi + A_lo*W_hi + A_hi*W_lo: ~22-bit operands on the fp16 tensor pipe.  Used for the C<=32 layers, where
-// operand rounding dominates the logit error (DESIGN.md "Numerics") and the tensor pipe is idle anyway.
+// A_hi*W_hi + A_lo*W_hi + A_hi*W_lo: ~22-bit operands on the fp16 tensor pipe.  Default rule: the 16-channel layers,
+// whose operand rounding dominates the logit error (tools/emulate_16bit.py: cardio mean error 1.9e-3 without any split,
+// 1.5e-3 with the 16-channel layers split, 1.3e-3 with the 32-channel layers split as well - not worth 3x the MMAs
+// on 27 % of the step).  Deep encoders (wide storage) override it per layer up to 64 channels.
 template <int CIN, int COUT>
 struct ConvSplit {
-  static constexpr bool value = (CIN <= 32 && COUT <= 32);
+  static constexpr bool value = (CIN <= 16 && COUT <= 16);
 };
 constexpr int kConvCtlBytes = 16 + 2 * 128 * 4 + 2 * 512 * 4;  // barrier+tmem slot, scale/shift, stats partials
 template <int CIN, int COUT, int GT, bool HAS_DS, bool SPLIT>

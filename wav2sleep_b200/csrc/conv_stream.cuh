@@ -660,9 +660,10 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   }
 }
 
-template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, int MT, int NR, int NA, int NTW, bool WIN = false, bool WOUT = false>
+// SPLIT defaults to the (CIN, COUT) rule of ConvSplit; the wide-storage 64-channel kernels of deep encoders override it.
+template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, int MT, int NR, int NA, int NTW, bool WIN = false, bool WOUT = false,
+          bool SPLIT = ConvSplit<CIN, COUT>::value>
 inline cudaError_t launch_conv_stream(const ConvArgs& a, int B, int sm_count, cudaStream_t stream) {
-  constexpr bool SPLIT = ConvSplit<CIN, COUT>::value;
   using Cfg = StreamCfg<CIN, COUT, STRIDE, PRO, HAS_DS, SPLIT, MT, NR, NA, NTW, WIN, WOUT>;
   auto kern = conv_stream_kernel<CIN, COUT, STRIDE, PRO, HAS_DS, SPLIT, MT, NR, NA, NTW, WIN, WOUT>;
   static bool configured = false;

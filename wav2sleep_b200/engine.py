@@ -114,19 +114,19 @@ class _PackedEncoder:
         d.wide_blocks = int(getattr(enc, "wide_blocks", 0))
         f32 = plan.f32
 
-        def pack(w):
+        def pack(w, block):
             cout, cin, _ = w.shape
-            return plan.conv(w, split=lib.w2s_conv_uses_split(cin, cout))
+            return plan.conv(w, split=lib.w2s_encoder_conv_split(d.wide_blocks, block, cin, cout))
 
         blk0 = enc.cnn[0]
         d.w_first = f32(blk0.conv1.conv.weight[:, 0, :]).data_ptr()
         d.w_first_ds = f32(blk0.downsample.weight[:, 0, 0]).data_ptr()
         for i, blk in enumerate(enc.cnn):
             if i > 0:
-                d.w_conv[i][0] = pack(blk.conv1.conv.weight)
-                d.w_ds[i] = pack(blk.downsample.weight)
-            d.w_conv[i][1] = pack(blk.conv2.conv.weight)
-            d.w_conv[i][2] = pack(blk.conv3.conv.weight)
+                d.w_conv[i][0] = pack(blk.conv1.conv.weight, i)
+                d.w_ds[i] = pack(blk.downsample.weight, i)
+            d.w_conv[i][1] = pack(blk.conv2.conv.weight, i)
+            d.w_conv[i][2] = pack(blk.conv3.conv.weight, i)
         F, K = enc.linear.weight.shape  # Linear(4C -> F) as a 4-tap conv: input index = tap * C + c
         d.w_lin = plan.conv(enc.linear.weight.view(F, 4, K // 4).permute(0, 2, 1))
         d.b_lin = f32(enc.linear.bias).data_ptr()

@@ -96,9 +96,11 @@ class SignalEncoder(nn.Module):
         self.channels = [min(initial_channels * 2 ** (i // 2), max_channels) for i in range(num_blocks)]
         self.norm_eps = 1e-2  # models/wav2sleep.py:213-215
         # Inference storage policy (not a reference argument): number of leading blocks whose conv outputs are kept as
-        # fp32 instead of fp16 (0, 2 or 4).  Stacks of >= 10 blocks (EOG) default to 4: their 16/32-channel layers
-        # otherwise push the logits to the edge of the 2e-2 parity gate (DESIGN.md "Numerics").
-        self.wide_blocks = 4 if num_blocks >= 10 else 0
+        # fp32 instead of fp16 and whose convs carry split (hi + lo) operands (0, 2, 4 or 6).  Stacks of >= 10 blocks
+        # (EOG: 30 convs, 6.9 M samples) default to 6 = every block up to 64 channels: with all-fp16 storage the logits
+        # sit on the 2e-2 gate, and the 99.9 % argmax gate needs the 64-channel blocks as well (DESIGN.md "Numerics",
+        # tools/emulate_16bit.py).
+        self.wide_blocks = 6 if num_blocks >= 10 else 0
         blocks, cin = [], input_dim
         for cout in self.channels:
             blocks.append(ConvBlock1D(cin, cout, norm_eps=self.norm_eps))
