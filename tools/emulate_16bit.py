@@ -37,10 +37,16 @@ def rnd(x, kind):
     raise ValueError(kind)
 
 
-def gelu_tanh_fit(x):
+def gelu_tanh_fit(x, approx_amp=0.0):
+    """The conv prologues' GELU: 0.5 x (1 + tanh(x q(min(x^2, 25)))).  approx_amp > 0 models MUFU.TANH (tanh.approx.f32,
+    max relative error 2^-11): a deterministic, oscillating relative error of that amplitude on the tanh value."""
     t = (x * x).clamp(max=25.0)
     q = (t * -3.5159264e-4 + 0.037005995) * t + 0.79750759
-    return 0.5 * x * (1.0 + torch.tanh(x * q))
+    u = x * q
+    th = torch.tanh(u)
+    if approx_amp > 0:
+        th = th * (1.0 + approx_amp * torch.sin(u * 4096.0))
+    return 0.5 * x * (1.0 + th)
 
 
 class Policy:
@@ -58,6 +64,8 @@ class Policy:
         return self.split_kind if (hi <= self.split_max and lo >= self.split_min) else self.op
 
     def act(self, x):
+        if self.gelu == "tanh_approx":
+            return gelu_tanh_fit(x, approx_amp=2.0 ** -11.5)
         return gelu_tanh_fit(x) if self.gelu == "tanh" else oracle.gelu(x)
 
     def __repr__(self):

@@ -283,11 +283,11 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
     W2S_STREAM(32, 32, 2, PRO_NORM, false, 2, 2, 2, 14)
     W2S_STREAM(32, 32, 1, PRO_NORM_RES, true, 2, 3, 2, 10)
     W2S_STREAM(32, 64, 1, PRO_NORM_RES, true, 2, 3, 2, 14)
-    W2S_STREAM(64, 64, 1, PRO_NORM, false, 3, 2, 2, 14)
+    W2S_STREAM(64, 64, 1, PRO_NORM, false, 2, 2, 2, 14)
     W2S_STREAM(64, 64, 2, PRO_NORM, false, 1, 3, 2, 14)
     W2S_STREAM(64, 64, 1, PRO_NORM_RES, true, 1, 3, 2, 14)
     W2S_STREAM(64, 128, 1, PRO_NORM_RES, true, 1, 3, 2, 14)
-    W2S_STREAM(128, 128, 1, PRO_NORM, false, 1, 3, 1, 14)
+    W2S_STREAM(128, 128, 1, PRO_NORM, false, 1, 2, 1, 14)
     W2S_STREAM(128, 128, 2, PRO_NORM, false, 1, 1, 1, 14)
     W2S_STREAM(128, 128, 1, PRO_NORM_RES, true, 1, 1, 1, 14)
     // wide (fp32) storage of the leading <= 32-channel blocks            MT NR NA NTW  in     out

@@ -121,7 +121,19 @@ struct StreamCfg {
   static constexpr int STAGE_COLS = MT * COUT * (HAS_DS ? 2 : 1);
   static constexpr int TMEM_COLS = (2 * STAGE_COLS <= 32) ? 32 : (2 * STAGE_COLS <= 64) ? 64 : (2 * STAGE_COLS <= 128) ? 128 : (2 * STAGE_COLS <= 256) ? 256 : 512;
   static constexpr int CTL_BYTES = 512;  // mbarriers + TMEM slot (first 256 B), live-sample list (second 256 B)
-  static constexpr int SMEM_BYTES = NR * RAW_BYTES + NA * A_BYTES + B_BYTES + CTL_BYTES;
+  static constexpr int SMEM_BASE = NR * RAW_BYTES + NA * A_BYTES + B_BYTES + CTL_BYTES;
+  // per-thread statistics accumulators across tiles for COUT = 16 (and for the 32-channel conv1 kernels, whose epilogue
+  // also drains the residual-branch accumulator: measured faster)
+  static constexpr bool REG_STATS = (COUT <= 16) || (COUT <= 32 && HAS_DS);
+  // Staged epilogue (all other fp16-output kernels, where shared memory allows): each epilogue warp transposes its
+  // 32 rows through a private, XOR-swizzled staging buffer, so that (i) global stores are full 128-byte lines written
+  // by 8 adjacent lanes instead of 32 scattered 32-byte sectors per instruction, and (ii) every lane keeps a fixed set
+  // of 8 channels, whose sum / sum of squares live in registers across tiles - no per-tile warp butterflies (they were
+  // ~60 shuffles per 16 channels per tile, the busiest stage of the 64/128-channel kernels).
+  static constexpr int SEG = COUT < 64 ? COUT : 64;  // channels per staged row segment (64 or 128 bytes)
+  static constexpr int STAGE_WARP_BYTES = 32 * SEG * 2;
+  static constexpr bool STAGED = !REG_STATS && !WOUT && (SMEM_BASE + 4 * STAGE_WARP_BYTES <= 232448);
+  static constexpr int SMEM_BYTES = SMEM_BASE + (STAGED ? 4 * STAGE_WARP_BYTES : 0);
   static_assert(2 * STAGE_COLS <= 512, "TMEM budget");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert((NTW * 32) % CH == 0, "fixed channel chunk per transform thread");
@@ -140,10 +152,8 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   constexpr int KSTEPS = CIN / 16;
   constexpr int NCG = COUT / 16;
   constexpr uint32_t IDESC = umma_idesc_f16(128, COUT, false);
-  // per-thread accumulators across tiles for COUT = 16 (and for the 32-channel conv1 kernels, whose epilogue also drains
-  // the residual-branch accumulator: measured faster); other outputs reduce per tile (butterfly), which keeps the
-  // register count low enough for more transform warps
-  constexpr bool REG_STATS = (COUT <= 16) || (COUT <= 32 && HAS_DS);
+  constexpr bool REG_STATS = Cfg::REG_STATS;
+  constexpr bool STAGED = Cfg::STAGED;
 
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sRaw = smem;
@@ -157,6 +167,8 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   uint64_t* t_full = a_empty + NA;
   uint64_t* t_empty = t_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  uint8_t* sStage = sCtl + Cfg::CTL_BYTES;  // STAGED: 4 warp-private staging buffers
+  (void)sStage;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // Samples without this signal (row_mask) are compacted away before the tiles are split over the CTAs, so that masked
@@ -364,6 +376,139 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
     }
   } else if (warp < kStreamFirstTransformWarp) {
     // ---------------- epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) ----------------
+    if constexpr (STAGED) {
+      static_assert(Cfg::EPI_WARPS == 4, "one epilogue warp per TMEM lane quadrant");
+      constexpr int SEG = Cfg::SEG, SEGB = SEG * 2;
+      constexpr int LPR = SEGB / 16;   // lanes per row segment in the copy-out (4 or 8)
+      constexpr int RPI = 32 / LPR;    // rows per copy-out instruction (8 or 4)
+      constexpr int NSEG = COUT / SEG;
+      const int quad = warp & 3;
+      const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
+      const uint32_t stg = smem_u32(sStage + (warp - 2) * Cfg::STAGE_WARP_BYTES);
+      const int crow = lane / LPR, cchunk = lane % LPR;  // this lane's role in the copy-out: row in group, 16-B chunk
+      // 16-B chunk c of staged row r sits at r * SEGB + ((c ^ swz(r)) * 16): conflict-free for the row-per-lane writes
+      // (8 rows x same chunk per quarter-warp) and for the row-segment reads (LPR lanes x consecutive chunks)
+      auto swz = [](int r) { return SEGB == 128 ? (r & 7) : ((r >> 1) & 3); };
+      int ts = 0;
+      uint32_t tph = 0;
+      int cur_b = -1;
+      WaitClock wc;
+      float2 ssum[NSEG][4], ssq[NSEG][4];  // this lane's 8 channels of each segment, over every row it copies out
+#pragma unroll
+      for (int sg = 0; sg < NSEG; ++sg)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ssum[sg][k] = ssq[sg][k] = make_float2(0.0f, 0.0f);
+      auto flush = [&](int b) {
+        if (b < 0) return;
+#pragma unroll
+        for (int sg = 0; sg < NSEG; ++sg) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float v[4] = {ssum[sg][k].x, ssum[sg][k].y, ssq[sg][k].x, ssq[sg][k].y};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+#pragma unroll
+              for (int off = LPR; off < 32; off <<= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], off);
+            }
+            if (lane < LPR) {
+              const int c = sg * SEG + cchunk * 8 + 2 * k;
+              atomicAdd(&p.out_stats[((size_t)b * COUT + c) * 2 + 0], (double)v[0]);
+              atomicAdd(&p.out_stats[((size_t)b * COUT + c + 1) * 2 + 0], (double)v[1]);
+              atomicAdd(&p.out_stats[((size_t)b * COUT + c) * 2 + 1], (double)v[2]);
+              atomicAdd(&p.out_stats[((size_t)b * COUT + c + 1) * 2 + 1], (double)v[3]);
+            }
+            ssum[sg][k] = ssq[sg][k] = make_float2(0.0f, 0.0f);
+          }
+        }
+      };
+      // TMEM columns [col, col + SEG) of this warp's 32 lanes -> staging (lane = row)
+      auto stage_in = [&](uint32_t taddr) {
+#pragma unroll
+        for (int q = 0; q < SEG / 16; ++q) {
+          float v[16];
+          tmem_ld16(taddr + q * 16, v);
+          const uint4 lo = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+          const uint4 hi = make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15]));
+          sts128(stg + lane * SEGB + (((2 * q) ^ swz(lane)) * 16), lo);
+          sts128(stg + lane * SEGB + (((2 * q + 1) ^ swz(lane)) * 16), hi);
+        }
+      };
+      TilePos tp = pos0;
+      for (int tile = tile_begin; tile < tile_end; ++tile, advance(tp)) {
+        int b;
+        if (!sample_of(tp, b)) continue;
+        if (b != cur_b) {
+          flush(cur_b);
+          cur_b = b;
+        }
+        const int o0 = tp.r * POS;
+        wc.wait(p, &t_full[ts], tph);
+        tc_fence_after_sync();
+        const uint32_t d_base = tmem_base + ts * Cfg::STAGE_COLS + t_lane;
+        uint8_t* outb = reinterpret_cast<uint8_t*>(p.out) + (size_t)b * p.L_out * COUT * 2;
+#pragma unroll 1
+        for (int j = 0; j < MT; ++j) {
+          const int obase = o0 + j * 128 + quad * 32;
+#pragma unroll
+          for (int sg = 0; sg < NSEG; ++sg) {
+            if (!(p.debug_flags & 16)) stage_in(d_base + j * COUT + sg * SEG);
+            __syncwarp();
+            if (!HAS_DS && j == MT - 1 && sg == NSEG - 1) {  // accumulators drained: hand the TMEM stage back early
+              tc_fence_before_sync();
+              if (lane == 0) mbar_arrive(&t_empty[ts]);
+            }
+#pragma unroll
+            for (int it = 0; it < 32 / RPI; ++it) {
+              const int r = it * RPI + crow;
+              const int o = obase + r;
+              const uint4 val = lds128(stg + r * SEGB + ((cchunk ^ swz(r)) * 16));
+              if (o < p.L_out && !(p.debug_flags & 8)) {
+                *reinterpret_cast<uint4*>(outb + ((size_t)o * COUT + sg * SEG + cchunk * 8) * 2) = val;
+                const uint32_t w4[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 f = unpack_h2(w4[k]);
+                  ssum[sg][k] = __fadd2_rn(ssum[sg][k], f);
+                  ssq[sg][k] = __ffma2_rn(f, f, ssq[sg][k]);
+                }
+              }
+            }
+            __syncwarp();
+          }
+        }
+        if (HAS_DS) {
+          uint8_t* dsb = reinterpret_cast<uint8_t*>(p.out_ds) + (size_t)b * (p.L_out >> 1) * COUT * 2;
+#pragma unroll 1
+          for (int j = 0; j < MT; ++j) {
+            const int obase = o0 + j * 128 + quad * 32;  // even
+#pragma unroll
+            for (int sg = 0; sg < NSEG; ++sg) {
+              stage_in(d_base + (MT + j) * COUT + sg * SEG);
+              __syncwarp();
+              if (j == MT - 1 && sg == NSEG - 1) {
+                tc_fence_before_sync();
+                if (lane == 0) mbar_arrive(&t_empty[ts]);
+              }
+#pragma unroll
+              for (int it = 0; it < 16 / RPI; ++it) {  // even rows only: the 1x1 branch has stride 2
+                const int r = 2 * (it * RPI + crow);
+                const int o = obase + r;
+                const uint4 val = lds128(stg + r * SEGB + ((cchunk ^ swz(r)) * 16));
+                if (o < p.L_out)
+                  *reinterpret_cast<uint4*>(dsb + ((size_t)(o >> 1) * COUT + sg * SEG + cchunk * 8) * 2) = val;
+              }
+              __syncwarp();
+            }
+          }
+        }
+        if (++ts == 2) {
+          ts = 0;
+          tph ^= 1;
+        }
+      }
+      if (warp == 2 && lane == 0) wc.publish(p, 13);
+      flush(cur_b);
+    } else {
     const int quad = warp & 3;
     const int epi_half = (warp - 2) >> 2;  // which share of the (column group, sub-tile) items this warp takes
     const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
@@ -481,6 +626,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
     }
     flush(cur_b);
     if (warp == 2 && lane == 0) dbg_ts(p, 8);
+    }
   } else {
     // ---------------- transform warps ----------------
     const int tt = tid - kStreamFirstTransformWarp * 32;  // 0..255
