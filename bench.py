@@ -339,6 +339,8 @@ def run_cuda(args):
         kernels.append({"kernel": label, "launches_per_step": n // 2, "share": ms / total_ms,
                         "avg_ms": ms / n, "algo_bytes": by / n, "algo_GBps": by / ms * 1e-6 if ms > 0 else None,
                         "algo_TFLOPs": fl / ms * 1e-9 if ms > 0 else None})
+    if args.kernels_out:
+        Path(args.kernels_out).write_text(json.dumps(kernels, indent=1))
     roofline = None
     if kernels:
         k = kernels[0]
@@ -518,6 +520,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary train-step timings")
     ap.add_argument("--no-eog", action="store_true", help="skip the secondary EOG-model timing (BASELINE configs[1])")
+    ap.add_argument("--kernels-out", default=None, help="also write the full per-kernel profile (JSON list) to this file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else max(args.warmup, 1)
     if args.impl == "reference":

@@ -10,6 +10,7 @@ values.  Usage (prints max-abs / mean logit error and argmax agreement against t
 
     python tools/emulate_16bit.py cardio            # fp16 vs bf16 decision, cardio model, 2 nights
     python tools/emulate_16bit.py eog [nights]      # EOG model (14-h nights): which layers need more than fp16
+    python tools/emulate_16bit.py grad              # gradient error caused by a 16-bit FORWARD alone (fp32 backward)
 """
 import math
 import sys
@@ -169,8 +170,49 @@ def report(tag, out, ref):
           flush=True)
 
 
-@torch.no_grad()
+def grad_floor():
+    """Parameter-gradient error of an fp32 backward through a forward whose activations / operands are rounded like the
+    CUDA path's (straight-through rounding): the floor of any 16-bit-forward training path.  One 10-h ECG night, the
+    loss divided by 16 as inside a batch of 16 nights."""
+    global rnd
+    exact = rnd
+
+    def rnd_st(x, kind):
+        r = exact(x, kind)
+        return x if r is x else x + (r - x).detach()
+
+    rnd = rnd_st
+    sig, S = {"ECG": "ECG"}, 1200
+    torch.manual_seed(0)
+    model = build_default(sig, 4, seed=0)
+    x = make_inputs(sig, 1, S, seed=11)
+    labels = torch.randint(0, 4, (1, S))
+    cfg = oracle.OracleConfig(signal_map=sig, num_classes=4)
+
+    def grads(fwd):
+        params = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+        loss = F.cross_entropy(fwd(params).view(-1, 4), labels.view(-1)) / 16
+        loss.backward()
+        return {k: v.grad for k, v in params.items()}
+
+    g_ref = grads(lambda p: oracle.forward_with_grad(x, p, cfg))
+    for pol in (Policy(split_max=16), Policy(split_max=32)):
+        g = grads(lambda p: forward(x, p, cfg, pol))
+        rows = sorted(((g[k] - g_ref[k]).norm().item() / max(g_ref[k].norm().item(), 1e-20), k) for k in g_ref)
+        print(pol)
+        for rel, k in rows[-5:][::-1]:
+            print(f"    {k:62s} rel {rel:.3e}")
+        print(f"    median over {len(rows)} tensors {rows[len(rows) // 2][0]:.3e}", flush=True)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "grad":
+        return grad_floor()
+    with torch.no_grad():
+        return _main()
+
+
+def _main():
     which = sys.argv[1] if len(sys.argv) > 1 else "cardio"
     if which == "cardio":
         smap, ncls, S, nights, cfg = {"ABD": "ABD", "THX": "THX", "ECG": "ECG", "PPG": "PPG"}, 4, 1200, 2, oracle.cardio_config()

@@ -45,6 +45,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
         "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "1886", "-o", str(LIB_PATH),
     ] + [str(s) for s in SOURCES]
+    cmd[1:1] = os.environ.get("W2S_NVCC_FLAGS", "").split()  # e.g. -DW2S_DEBUG_KNOCKOUTS for tools/dbg_flags.sh
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

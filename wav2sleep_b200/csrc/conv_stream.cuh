@@ -17,11 +17,19 @@
 
 namespace w2s {
 
+// Profiling experiments (stage knock-outs, timestamps, per-role wait accounting) are compiled in only with
+// -DW2S_DEBUG_KNOCKOUTS (tools/dbg_flags.sh builds such a library): in the production build ConvArgs::debug_flags is
+// ignored and none of the checks below cost an instruction.
+#ifdef W2S_DEBUG_KNOCKOUTS
+#define W2S_DBG(p, mask) ((p).debug_flags & (mask))
+#else
+#define W2S_DBG(p, mask) 0
+#endif
 // debug_flags & 64: CTA 0 records %globaltimer at its pipeline milestones (read back with w2s_debug_timestamps)
 __device__ unsigned long long g_stream_ts[16];
 __device__ unsigned long long g_stream_cta_ts[2 * 512];  // debug_flags & 64: entry / exit time of every CTA
 W2S_DEVINL void dbg_ts(const ConvArgs& p, int slot) {
-  if ((p.debug_flags & 64) && blockIdx.x == 0) {
+  if (W2S_DBG(p, 64) && blockIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     g_stream_ts[slot] = t;
@@ -33,7 +41,7 @@ W2S_DEVINL void dbg_ts(const ConvArgs& p, int slot) {
 struct WaitClock {
   long long acc = 0;
   W2S_DEVINL void wait(const ConvArgs& p, uint64_t* bar, uint32_t parity) {
-    if (p.debug_flags & 64) {
+    if (W2S_DBG(p, 64)) {
       const long long t0 = clock64();
       mbar_wait(bar, parity);
       acc += clock64() - t0;
@@ -42,7 +50,7 @@ struct WaitClock {
     }
   }
   W2S_DEVINL void publish(const ConvArgs& p, int slot) const {
-    if ((p.debug_flags & 64) && blockIdx.x == 0) g_stream_ts[slot] = (unsigned long long)acc;
+    if (W2S_DBG(p, 64) && blockIdx.x == 0) g_stream_ts[slot] = (unsigned long long)acc;
   }
 };
 
@@ -166,7 +174,8 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   uint64_t* a_empty = a_full + NA;
   uint64_t* t_full = a_empty + NA;
   uint64_t* t_empty = t_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  uint64_t* w_full = t_empty + 2;  // weights landed in sB (one bulk-copy transaction group per CTA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
   uint8_t* sStage = sCtl + Cfg::CTL_BYTES;  // STAGED: 4 warp-private staging buffers
   (void)sStage;
 
@@ -182,7 +191,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
 
   // ---------------- one-time setup ----------------
   if (tid == 0) dbg_ts(p, 0);
-  if ((p.debug_flags & 64) && tid == 0 && blockIdx.x < 512) {
+  if (W2S_DBG(p, 64) && tid == 0 && blockIdx.x < 512) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     g_stream_cta_ts[2 * blockIdx.x] = t;
@@ -202,25 +211,8 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
       mbar_init(&t_full[s], 1);
       mbar_init(&t_empty[s], Cfg::EPI_WARPS);
     }
+    mbar_init(w_full, 1);
     fence_mbar_init();
-  }
-  {  // weights -> smem (hi [, lo] blocks; ds after the taps), once per CTA
-    constexpr int n16 = 3 * CH * COUT;
-    const uint4* src = reinterpret_cast<const uint4*>(p.w);
-    uint4* dst = reinterpret_cast<uint4*>(sB);
-    for (int k = tid; k < n16; k += kStreamThreads) dst[k] = __ldg(src + k);
-    if (SPLIT) {
-      uint4* dlo = reinterpret_cast<uint4*>(sB + Cfg::B_ONE);
-      for (int k = tid; k < n16; k += kStreamThreads) dlo[k] = __ldg(src + n16 + k);
-    }
-    if (HAS_DS) {
-      const uint4* srcd = reinterpret_cast<const uint4*>(p.w_ds);
-      for (int k = tid; k < CH * COUT; k += kStreamThreads) dst[n16 + k] = __ldg(srcd + k);
-      if (SPLIT) {
-        uint4* dlo = reinterpret_cast<uint4*>(sB + Cfg::B_ONE);
-        for (int k = tid; k < CH * COUT; k += kStreamThreads) dlo[n16 + k] = __ldg(srcd + CH * COUT + k);
-      }
-    }
   }
   if (compact && tid == 64) {
     int n = 0;
@@ -258,6 +250,21 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   if (warp == 0) {
     // ---------------- producer (whole warp runs the loop; one elected lane issues) ----------------
     {
+      // weights -> smem once per CTA (hi [, lo] blocks; the 1x1 branch after the taps): plain bulk copies of the packed
+      // layout, off every other role's critical path (only the MMA issuer waits for them)
+      if (tile_begin < tile_end && elect_one()) {  // (a CTA without tiles must not leave a copy in flight when it exits)
+        constexpr uint32_t wbytes = 3u * CH * COUT * 16u, dbytes = (uint32_t)CH * COUT * 16u;
+        mbar_arrive_expect_tx(w_full, (wbytes + (HAS_DS ? dbytes : 0u)) * (SPLIT ? 2u : 1u));
+        const uint8_t* gw = reinterpret_cast<const uint8_t*>(p.w);
+        bulk_g2s(sB, gw, wbytes, w_full);
+        if (SPLIT) bulk_g2s(sB + Cfg::B_ONE, gw + wbytes, wbytes, w_full);
+        if (HAS_DS) {
+          const uint8_t* gd = reinterpret_cast<const uint8_t*>(p.w_ds);
+          bulk_g2s(sB + wbytes, gd, dbytes, w_full);
+          if (SPLIT) bulk_g2s(sB + Cfg::B_ONE + wbytes, gd + dbytes, dbytes, w_full);
+        }
+      }
+      __syncwarp();
       int s = 0;
       uint32_t ph = 0;
       WaitClock wc;
@@ -299,7 +306,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
       }
       if (lane == 0) {
         wc.publish(p, 11);
-        if ((p.debug_flags & 64) && blockIdx.x == 0) g_stream_ts[15] = (unsigned long long)(clock64() - cta_t0);
+        if (W2S_DBG(p, 64) && blockIdx.x == 0) g_stream_ts[15] = (unsigned long long)(clock64() - cta_t0);
       }
     }
   } else if (warp == 1) {
@@ -311,6 +318,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
       const uint32_t b_base = smem_u32(sB);
       constexpr uint32_t lbo_a = RP * 16, lbo_b = COUT * 16;
       TilePos tp = pos0;
+      if (tile_begin < tile_end) mbar_wait(w_full, 0);
       for (int tile = tile_begin; tile < tile_end; ++tile, advance(tp)) {
         int b;
         if (!sample_of(tp, b)) continue;
@@ -332,11 +340,11 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
               const uint32_t b_off = (uint32_t)(t * CH + 2 * kk) * COUT * 16;
               const uint64_t da = umma_smem_desc(a_base + a_off, lbo_a, 128);
               const uint64_t db = umma_smem_desc(b_base + b_off, lbo_b, 128);
-              if (!(p.debug_flags & 2)) umma_f16(d_base + j * COUT, da, db, IDESC, (t > 0 || kk > 0) ? 1u : 0u);
-              if (SPLIT && !(p.debug_flags & 3)) {
-                if (!(p.debug_flags & 128) && !(CIN == 32 && (p.debug_flags & 512)))
+              if (!W2S_DBG(p, 2)) umma_f16(d_base + j * COUT, da, db, IDESC, (t > 0 || kk > 0) ? 1u : 0u);
+              if (SPLIT && !W2S_DBG(p, 3)) {
+                if (!W2S_DBG(p, 128) && !(CIN == 32 && W2S_DBG(p, 512)))
                   umma_f16(d_base + j * COUT, umma_smem_desc(a_base + Cfg::A_ONE + a_off, lbo_a, 128), db, IDESC, 1u);
-                if (!(p.debug_flags & 256) && !(CIN == 32 && (p.debug_flags & 1024)))
+                if (!W2S_DBG(p, 256) && !(CIN == 32 && W2S_DBG(p, 1024)))
                   umma_f16(d_base + j * COUT, da, umma_smem_desc(b_base + Cfg::B_ONE + b_off, lbo_b, 128), IDESC, 1u);
               }
             }
@@ -351,9 +359,9 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
               const uint64_t db = umma_smem_desc(b_base + b_off, lbo_b, 128);
               umma_f16(d_base + (MT + j) * COUT, da, db, IDESC, kk > 0 ? 1u : 0u);
               if (SPLIT) {
-                if (!(p.debug_flags & 128))
+                if (!W2S_DBG(p, 128))
                   umma_f16(d_base + (MT + j) * COUT, umma_smem_desc(a_base + Cfg::A_ONE + a_off, lbo_a, 128), db, IDESC, 1u);
-                if (!(p.debug_flags & 256))
+                if (!W2S_DBG(p, 256))
                   umma_f16(d_base + (MT + j) * COUT, da, umma_smem_desc(b_base + Cfg::B_ONE + b_off, lbo_b, 128), IDESC, 1u);
               }
             }
@@ -451,7 +459,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
           const int obase = o0 + j * 128 + quad * 32;
 #pragma unroll
           for (int sg = 0; sg < NSEG; ++sg) {
-            if (!(p.debug_flags & 16)) stage_in(d_base + j * COUT + sg * SEG);
+            if (!W2S_DBG(p, 16)) stage_in(d_base + j * COUT + sg * SEG);
             __syncwarp();
             if (!HAS_DS && j == MT - 1 && sg == NSEG - 1) {  // accumulators drained: hand the TMEM stage back early
               tc_fence_before_sync();
@@ -462,7 +470,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
               const int r = it * RPI + crow;
               const int o = obase + r;
               const uint4 val = lds128(stg + r * SEGB + ((cchunk ^ swz(r)) * 16));
-              if (o < p.L_out && !(p.debug_flags & 8)) {
+              if (o < p.L_out && !W2S_DBG(p, 8)) {
                 *reinterpret_cast<uint4*>(outb + ((size_t)o * COUT + sg * SEG + cchunk * 8) * 2) = val;
                 const uint32_t w4[4] = {val.x, val.y, val.z, val.w};
 #pragma unroll
@@ -570,10 +578,10 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
         for (int j = 0; j < MT; ++j) {
           float v[16];
           if (EPI_SPLIT > 1 && ((cg * MT + j) % EPI_SPLIT) != epi_half) continue;
-          if (p.debug_flags & 16) continue;
+          if (W2S_DBG(p, 16)) continue;
           tmem_ld16(d_base + j * COUT + cg * 16, v);
           const int o = o0 + j * 128 + quad * 32 + lane;
-          if (o < p.L_out && !((p.debug_flags & 8) && v[0] != 123.456f)) {
+          if (o < p.L_out && !(W2S_DBG(p, 8) && v[0] != 123.456f)) {
             store16<WOUT>(outb, (size_t)o * COUT + cg * 16, v);
 #pragma unroll
             for (int k = 0; k < 16; k += 2) {  // packed fp32x2: one FADD2 + one FFMA2 per channel pair
@@ -748,7 +756,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
               yv = pair(yy, q);
               a = __ffma2_rn(yv, sc[q], sh[q]);
             }
-            if (!(p.debug_flags & 4)) a = gelu_fast2(a);
+            if (!W2S_DBG(p, 4)) a = gelu_fast2(a);
             if (PRO == PRO_NORM_RES) a = gelu_fast2(__fadd2_rn(a, pair(rr, q)));
             if (PRO == PRO_NORM_RES_X) a = gelu_fast2(__ffma2_rn(fw[q][0], make_float2(x0, x0), a));
             oo[q] = pack_h2(a.x, a.y);
@@ -762,7 +770,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
         sts128(adst + soff, o);
         if (SPLIT) sts128(adst + Cfg::A_ONE + soff, olo);
       };
-      if (p.debug_flags & 32) {
+      if (W2S_DBG(p, 32)) {
       } else if (interior) {
 #pragma unroll 2
         for (int id = tt; id < R * CH; id += NTT) chunk(id, true);
@@ -790,7 +798,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
     }
     if (tt == 0) {
       wc_a.publish(p, 14);
-      if ((p.debug_flags & 64) && blockIdx.x == 0) g_stream_ts[10] = (unsigned long long)wc_raw.acc;
+      if (W2S_DBG(p, 64) && blockIdx.x == 0) g_stream_ts[10] = (unsigned long long)wc_raw.acc;
     }
   }
 
@@ -799,7 +807,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   __syncthreads();
   if (tid == 0) dbg_ts(p, 9);
   if (warp == 0) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-  if ((p.debug_flags & 64) && tid == 0 && blockIdx.x < 512) {
+  if (W2S_DBG(p, 64) && tid == 0 && blockIdx.x < 512) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     g_stream_cta_ts[2 * blockIdx.x + 1] = t;

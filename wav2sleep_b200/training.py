@@ -23,6 +23,7 @@ exactly (powers of two), and nothing outside this file sees the scale.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 
 import torch
@@ -55,6 +56,7 @@ class TrainEngine(ForwardEngine):
         self.direct = set()
         self.dropout_seed = None  # int: fixed seed for every step (tests); None: drawn from torch's CPU generator
         self.last_dropout_seed = 0
+        self._side_streams = {}   # device -> per-encoder CUDA streams (same overlap of kernel tails as in inference)
         self.loss_scale = None    # power of two applied to the fp16 activation gradients; None = from B*S (see below)
         self._inv_scale = 1.0
         self.last_loss_scale = 1.0
@@ -66,6 +68,26 @@ class TrainEngine(ForwardEngine):
         middle of fp16's normal range [6e-5, 65504], whatever the batch size."""
         k = max(int(n_epochs) - 1, 0).bit_length() + 2
         return float(2 ** min(k, 24))
+
+    def _encoder_streams(self, device, n):
+        """n side streams (one per signal encoder) that have been made to wait for the current stream, or None."""
+        if not self.enc_streams or n < 2:
+            return None
+        pool = self._side_streams.setdefault(str(device), [])
+        while len(pool) < n:
+            pool.append(torch.cuda.Stream(device=device))
+        fork = torch.cuda.Event()
+        fork.record(torch.cuda.current_stream(device))
+        for st in pool[:n]:
+            st.wait_event(fork)
+        return pool[:n]
+
+    @staticmethod
+    def _join(streams, device):
+        if streams is not None:
+            cur = torch.cuda.current_stream(device)
+            for st in streams:
+                cur.wait_stream(st)
 
     # dropout sites: 8 * layer + {0 attention weights, 1 after self-attention, 2 FF hidden, 3 after FF}; 64 + seq block
     def dropout(self, x: Tensor, site: int, p: float, seed: int, res: Tensor | None = None, out: Tensor | None = None):
@@ -203,6 +225,50 @@ class TrainEngine(ForwardEngine):
             self.grads[id(p)] = g
         return g
 
+    def _encoder_forward_train(self, n, x_n, B, S, device, side_stream):
+        """One signal encoder with every layer output kept (on the current stream); returns its saved-state dict."""
+        lib, m = self.lib, self.model
+        st = _stream()
+        enc = m.signal_encoders.get_encoder(n)
+        pe = self.enc[m.signal_encoders.signal_map[n]]
+        xs = x_n.detach().to(torch.float32).contiguous()
+        if side_stream is not None:
+            xs.record_stream(side_stream)
+        T = xs.size(1)
+        ws_bytes = lib.w2s_encoder_workspace_bytes(C.byref(pe.desc), B, T, 1)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+        mask = torch.zeros(B, dtype=torch.uint8, device=device)
+        z_unused = torch.empty(B, S, 128, dtype=F16, device=device)
+        _lib.check(lib.w2s_encoder_fwd(C.byref(pe.desc), xs.data_ptr(), B, T, ws.data_ptr(), ws_bytes, 1,
+                                       z_unused.data_ptr(), mask.data_ptr(), st), ValueError)
+        nb = len(enc.channels)
+        offs = (C.c_int64 * (7 * nb))()
+        _lib.check(lib.w2s_encoder_layout(C.byref(pe.desc), B, T, offs))
+        e = {"x": xs, "ws": ws, "mask": mask, "T": T, "blocks": [], "enc": enc,
+             "tw": self.tw["enc"][m.signal_encoders.signal_map[n]]}
+        L = T
+        for i, c in enumerate(enc.channels):
+            o = offs[7 * i:7 * i + 7]
+            view = lambda off, rows, ch: ws[off: off + B * rows * ch * 2].view(F16).view(B, rows, ch)
+            stat = lambda off, ch: ws[off: off + B * ch * 16].view(torch.float64).view(B, ch, 2)
+            e["blocks"].append({"C": c, "L": L, "s1": stat(o[0], c), "s2": stat(o[1], c), "s3": stat(o[2], c),
+                                "y1": view(o[3], L, c), "r": view(o[4], L // 2, c), "y2": view(o[5], L, c),
+                                "y3": view(o[6], L // 2, c)})
+            L //= 2
+        # time-distributed linear on the re-materialised activated block output
+        last = e["blocks"][-1]
+        Cl, L4 = last["C"], last["L"] // 2  # L4 = 4 * S
+        a_last = torch.empty(B, L4, Cl, dtype=F16, device=device)
+        _lib.check(lib.w2s_enc_act_fwd(last["y3"].data_ptr(), last["r"].data_ptr(), last["s3"].data_ptr(),
+                                       a_last.data_ptr(), mask.data_ptr(), B, L4, Cl, enc.norm_eps, st))
+        z_pre = torch.zeros(B, S, 128, dtype=F16, device=device)
+        bl = self._f32(enc.linear.bias)
+        self.conv(a_last, e["tw"]["lin_fwd"], Cl, 128, 4, B, L4, S, z_pre, stride=4, bias=bl, row_mask=mask)
+        z = torch.zeros(B, S, 128, dtype=F16, device=device)
+        _lib.check(lib.w2s_gelu_fwd(z_pre.data_ptr(), z.data_ptr(), z.numel(), st))
+        e.update(a_last=a_last, z_pre=z_pre, z=z)
+        return e
+
     # ================================================================== forward (training)
     @torch.no_grad()
     def forward_train(self, x: dict[str, Tensor], return_saved: bool = False):
@@ -224,45 +290,15 @@ class TrainEngine(ForwardEngine):
             self.last_dropout_seed = seed
             p_mix = float(m.epoch_mixer.dropout) if m.training else 0.0
             sv.update(seed=seed, p_mix=p_mix)
-            # ---- encoders (streaming kernels, every layer output kept) ----
-            for n in names:
-                enc = m.signal_encoders.get_encoder(n)
-                pe = self.enc[m.signal_encoders.signal_map[n]]
-                xs = x[n].detach().to(torch.float32).contiguous()
-                T = xs.size(1)
-                ws_bytes = lib.w2s_encoder_workspace_bytes(C.byref(pe.desc), B, T, 1)
-                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
-                mask = torch.zeros(B, dtype=torch.uint8, device=device)
-                z_unused = torch.empty(B, S, 128, dtype=F16, device=device)
-                _lib.check(lib.w2s_encoder_fwd(C.byref(pe.desc), xs.data_ptr(), B, T, ws.data_ptr(), ws_bytes, 1,
-                                               z_unused.data_ptr(), mask.data_ptr(), st), ValueError)
-                nb = len(enc.channels)
-                offs = (C.c_int64 * (7 * nb))()
-                _lib.check(lib.w2s_encoder_layout(C.byref(pe.desc), B, T, offs))
-                e = {"x": xs, "ws": ws, "mask": mask, "T": T, "blocks": [], "enc": enc,
-                     "tw": self.tw["enc"][m.signal_encoders.signal_map[n]]}
-                L = T
-                for i, c in enumerate(enc.channels):
-                    o = offs[7 * i:7 * i + 7]
-                    view = lambda off, rows, ch: ws[off: off + B * rows * ch * 2].view(F16).view(B, rows, ch)
-                    stat = lambda off, ch: ws[off: off + B * ch * 16].view(torch.float64).view(B, ch, 2)
-                    e["blocks"].append({"C": c, "L": L, "s1": stat(o[0], c), "s2": stat(o[1], c), "s3": stat(o[2], c),
-                                        "y1": view(o[3], L, c), "r": view(o[4], L // 2, c), "y2": view(o[5], L, c),
-                                        "y3": view(o[6], L // 2, c)})
-                    L //= 2
-                # time-distributed linear on the re-materialised activated block output
-                last = e["blocks"][-1]
-                Cl, L4 = last["C"], last["L"] // 2  # L4 = 4 * S
-                a_last = torch.empty(B, L4, Cl, dtype=F16, device=device)
-                _lib.check(lib.w2s_enc_act_fwd(last["y3"].data_ptr(), last["r"].data_ptr(), last["s3"].data_ptr(),
-                                               a_last.data_ptr(), mask.data_ptr(), B, L4, Cl, enc.norm_eps, st))
-                z_pre = torch.zeros(B, S, 128, dtype=F16, device=device)
-                bl = self._f32(enc.linear.bias)
-                self.conv(a_last, e["tw"]["lin_fwd"], Cl, 128, 4, B, L4, S, z_pre, stride=4, bias=bl, row_mask=mask)
-                z = torch.zeros(B, S, 128, dtype=F16, device=device)
-                _lib.check(lib.w2s_gelu_fwd(z_pre.data_ptr(), z.data_ptr(), z.numel(), st))
-                e.update(a_last=a_last, z_pre=z_pre, z=z)
-                sv["enc"][n] = e
+            # ---- encoders (streaming kernels, every layer output kept), one CUDA stream each, longest first ----
+            order = sorted(names, key=lambda k: -x[k].size(1))
+            streams = self._encoder_streams(device, len(order))
+            for si, n in enumerate(order):
+                with (torch.cuda.stream(streams[si]) if streams is not None else contextlib.nullcontext()):
+                    sv["enc"][n] = self._encoder_forward_train(n, x[n], B, S, device,
+                                                               streams[si] if streams is not None else None)
+            self._join(streams, device)
+            st = _stream()
             # ---- epoch mixer (un-fused) ----
             mix = m.epoch_mixer
             D = len(names) + 1
@@ -484,13 +520,19 @@ class TrainEngine(ForwardEngine):
             pending = {}  # encoder name -> signals still to back-propagate (encoders may be shared between signals)
             for n in order:
                 pending[smap[n]] = pending.get(smap[n], 0) + 1
-            for n in order:
-                self._encoder_backward(sv["enc"][n], dz[n], B, S)
-                sv["enc"][n] = None  # release this encoder's activations
-                pending[smap[n]] -= 1
-                if pending[smap[n]] == 0:
-                    for hook in self.bucket_hooks:
-                        hook("encoder:" + smap[n])  # this encoder's parameter gradients are final
+            shared = len(set(smap[n] for n in order)) < len(order)  # a shared encoder: its passes stay in stream order
+            streams = None if shared else self._encoder_streams(device, len(order))
+            for si, n in enumerate(order):
+                with (torch.cuda.stream(streams[si]) if streams is not None else contextlib.nullcontext()):
+                    if streams is not None:
+                        dz[n].record_stream(streams[si])
+                    self._encoder_backward(sv["enc"][n], dz[n], B, S)
+                    sv["enc"][n] = None  # release this encoder's activations
+                    pending[smap[n]] -= 1
+                    if pending[smap[n]] == 0:
+                        for hook in self.bucket_hooks:
+                            hook("encoder:" + smap[n])  # this encoder's parameter gradients are final
+            self._join(streams, device)
             for hook in self.bucket_hooks:
                 hook("encoders")
             sv["consumed"] = True
