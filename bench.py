@@ -197,18 +197,28 @@ def run_cuda(args):
             return float(t.item())
         return ms
 
+    def run_steps(n, batches):
+        """n forward steps through the public throughput API (Wav2Sleep.predict_async: two batches in flight on
+        alternating stream sets; every step does all of its work, the last results are awaited before returning)."""
+        pend, out = [], None
+        for i in range(n):
+            pend.append(model.predict_async(batches[i % 2]))
+            if len(pend) > 2:
+                out = pend.pop(0).wait()
+        for q in pend:
+            out = q.wait()
+        return out
+
     # ---------------- device-resident timing ----------------
     with torch.inference_mode():
-        for i in range(args.warmup):
-            model.predict(devb[i % 2])
+        run_steps(args.warmup, devb)
         barrier()
         sampler = ClockSampler(local_rank)
         sampler.start()
         l0 = lib.w2s_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(args.steps):
-            pred = model.predict(devb[i % 2])
+        pred = run_steps(args.steps, devb)
         e1.record()
         barrier()
         launches = lib.w2s_launch_count() - l0 + model._get_engine().replayed_launches
@@ -221,25 +231,32 @@ def run_cuda(args):
         out_host = [torch.empty(BATCH, S_EPOCHS, dtype=torch.int64).pin_memory() for _ in range(2)]
         ready = [torch.cuda.Event() for _ in range(2)]
         consumed = [torch.cuda.Event() for _ in range(2)]
+        read_done = [None, None]  # completion of the last forward that read stage[b]
 
         def upload(i):
             with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(consumed[i % 2])
+                if read_done[i % 2] is not None:
+                    copy_stream.wait_event(read_done[i % 2])
                 for k in stage[i % 2]:
                     stage[i % 2][k].copy_(host[i % 2][k], non_blocking=True)
                 ready[i % 2].record(copy_stream)
 
         def e2e_loop(n):
-            for b in range(2):
-                consumed[b].record(main)
+            read_done[0] = read_done[1] = None
             upload(0)
+            pend = []
             for i in range(n):
                 if i + 1 < n:
                     upload(i + 1)
                 main.wait_event(ready[i % 2])
-                p = model.predict(stage[i % 2])
-                consumed[i % 2].record(main)
-                out_host[i % 2].copy_(p, non_blocking=True)
+                p = model.predict_async(stage[i % 2])
+                read_done[i % 2] = p.done
+                pend.append((p, i))
+                if len(pend) > 1:  # the previous batch's predictions go back to the host while this batch runs
+                    q, j = pend.pop(0)
+                    out_host[j % 2].copy_(q.wait(), non_blocking=True)
+            for q, j in pend:
+                out_host[j % 2].copy_(q.wait(), non_blocking=True)
             torch.cuda.synchronize()
 
         e2e_loop(min(args.warmup, 3))
@@ -271,14 +288,19 @@ def run_cuda(args):
             for b in range(2):
                 consumed[b].record(main)
             upload16(0)
+            pend = []
             for i in range(n):
                 if i + 1 < n:
                     upload16(i + 1)
                 main.wait_event(ready[i % 2])
                 x = {k: zscore_on_device(v) for k, v in stage16[i % 2].items()}
                 consumed[i % 2].record(main)
-                p = model.predict(x)
-                out_host[i % 2].copy_(p, non_blocking=True)
+                pend.append((model.predict_async(x), i, x))
+                if len(pend) > 1:
+                    q, j, _ = pend.pop(0)
+                    out_host[j % 2].copy_(q.wait(), non_blocking=True)
+            for q, j, _ in pend:
+                out_host[j % 2].copy_(q.wait(), non_blocking=True)
             torch.cuda.synchronize()
 
         staged_loop(2)
@@ -302,10 +324,10 @@ def run_cuda(args):
             prof = collect_profile(lib)
             lib.w2s_profile_enable(0)
             eng.enc_streams = streams_on
-            eng._ws.clear()
+            eng._release_buffers()
 
     del stage, stage16, host16, devb
-    model._get_engine()._ws.clear()
+    model._get_engine()._release_buffers()
     torch.cuda.empty_cache()
     train = train_ecg = eog = None
     if not args.no_train:
@@ -368,6 +390,7 @@ def run_cuda(args):
         "dtype": "f16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "nights_per_gpu_per_step": BATCH, "epochs_per_night": S_EPOCHS,
                    "parallelism": f"replicas x{world} (no data-path collective)",
+                   "api": "Wav2Sleep.predict_async, 2 batches in flight per GPU (W2S_LANES=1 / Wav2Sleep.predict: one)",
                    "l2": "inputs+activations > L2, 2 alternating batches"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e / args.steps},
@@ -475,14 +498,19 @@ def time_eog(dev, lib, hbm_peak, tf_peak, steps=5, warmup=3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.inference_mode():
         for i in range(warmup):
-            model.predict(xs[i % 2])
+            model.predict_async(xs[i % 2]).wait()
         torch.cuda.synchronize()
         l0 = lib.w2s_launch_count()
 
         def timed():
             e0.record()
+            pend = []
             for i in range(steps):
-                model.predict(xs[i % 2])
+                pend.append(model.predict_async(xs[i % 2]))
+                if len(pend) > 2:
+                    pend.pop(0).wait()
+            for q in pend:
+                q.wait()
             e1.record()
             torch.cuda.synchronize()
 

@@ -90,10 +90,13 @@ def predict(model, batches: Iterable[dict], device: str = "auto") -> torch.Tenso
     """``model(x).argmax(-1)`` over an iterable of input dicts (reference api.py:163-190); returns int64 [N, S] on CPU.
     Device->host copies are queued per batch and synchronised once at the end."""
     device = _resolve_device(device)
-    outs = []
+    outs, pending = [], []
     for x in batches:
         x = {k: v.to(device, non_blocking=True) for k, v in x.items()}
-        outs.append(model.predict(x))
+        pending.append((model.predict_async(x), x))  # two batches in flight (x kept alive until its result is awaited)
+        if len(pending) > 2:
+            outs.append(pending.pop(0)[0].wait())
+    outs += [p.wait() for p, _ in pending]
     if not outs:
         return torch.empty(0, 0, dtype=torch.int64)
     return torch.cat(outs, dim=0).cpu()

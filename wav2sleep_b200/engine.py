@@ -134,6 +134,20 @@ class _PackedEncoder:
         self.samples_per_epoch = enc.samples_per_epoch
 
 
+class Pending:
+    """Result of an asynchronous forward: ``wait()`` makes the *current stream* wait for it (no host synchronisation) and
+    returns the tensor."""
+
+    def __init__(self, tensor: Tensor, done: "torch.cuda.Event"):
+        self.tensor, self.done = tensor, done
+
+    def wait(self) -> Tensor:
+        cur = torch.cuda.current_stream(self.tensor.device)
+        cur.wait_event(self.done)
+        self.tensor.record_stream(cur)
+        return self.tensor
+
+
 class ForwardEngine:
     """Inference forward of ``Wav2Sleep`` on one CUDA device."""
 
@@ -150,6 +164,11 @@ class ForwardEngine:
         # fill and tail of one encoder are covered by the other encoders' work.  W2S_ENC_STREAMS=0 serialises them.
         import os
         self.enc_streams = os.environ.get("W2S_ENC_STREAMS", "1") != "0"
+        # Asynchronous forwards (forward_async / predict_async) alternate between n_lanes independent sets of streams and
+        # workspaces, so that consecutive batches overlap: the latency-bound tail of one batch (epoch mixer, sequence
+        # mixer: few CTAs, ~0.8 ms) runs under the encoders of the next one.
+        self.n_lanes = int(os.environ.get("W2S_LANES", "2"))
+        self._lane = 0
 
     # ------------------------------------------------------------------ weights
     def _params_key(self, device):
@@ -212,22 +231,31 @@ class ForwardEngine:
         self.seq_desc = sd
         plan.run()
         self._weights_key = (skey, vkey)
-        self._ws.clear()  # workspace sizes depend on the encoders' storage policy
+        self._release_buffers()  # workspace sizes depend on the encoders' storage policy
 
     # ------------------------------------------------------------------ buffers
-    def _buffers(self, device, names, B, S):
-        key = (str(device), tuple(names), B, S, self.enc_streams)
+    def _release_buffers(self) -> None:
+        """Drop every workspace.  Batches still in flight on the lanes' own streams must finish before their memory goes
+        back to the allocator of the current stream."""
+        for old in self._ws.values():
+            if old.get("tail_done") is not None:
+                torch.cuda.current_stream(old["mix"].device).wait_event(old["tail_done"])
+        self._ws.clear()
+
+    def _buffers(self, device, names, B, S, lane: int = -1):
+        key = (str(device), tuple(names), B, S, self.enc_streams, lane)
         buf = self._ws.get(key)
         if buf is not None:
             return buf
-        self._ws.clear()  # one live shape at a time keeps the footprint bounded
+        if any(k[:5] != key[:5] for k in self._ws):
+            self._release_buffers()  # one live shape at a time keeps the footprint bounded
         lib = self.lib
         sizes = {}
         for n in names:
             pe = self.enc[self.model.signal_encoders.signal_map[n]]
             sizes[n] = lib.w2s_encoder_workspace_bytes(C.byref(pe.desc), B, S * pe.samples_per_epoch, 0)
         seq_ws = lib.w2s_seqmixer_workspace_bytes(C.byref(self.seq_desc), B, S, 0)
-        concurrent = self.enc_streams and len(names) > 1
+        concurrent = (self.enc_streams and len(names) > 1) or lane >= 0
         if concurrent:  # encoders run side by side: one workspace each
             enc_ws = {n: torch.empty(sizes[n], dtype=torch.uint8, device=device) for n in names}
         else:           # encoders run back to back: one workspace of the largest size
@@ -236,6 +264,8 @@ class ForwardEngine:
         buf = {
             "enc_ws": enc_ws,
             "streams": [torch.cuda.Stream(device=device) for _ in names] if concurrent else None,
+            "tail": torch.cuda.Stream(device=device) if lane >= 0 else None,   # mixer + sequence mixer + head of a lane
+            "tail_done": None,
             "seq_ws": torch.empty(seq_ws, dtype=torch.uint8, device=device),
             "z": {n: torch.empty(B, S, 128, dtype=torch.float16, device=device) for n in names},
             "mask": {n: torch.zeros(B, dtype=torch.uint8, device=device) for n in names},
@@ -299,6 +329,65 @@ class ForwardEngine:
         _lib.check(lib.w2s_epoch_mixer_fwd(C.byref(self.mixer_desc), zs, ms, len(names), B, S, buf["mix"].data_ptr(), st))
         _lib.check(lib.w2s_seqmixer_head_fwd(C.byref(self.seq_desc), buf["mix"].data_ptr(), B, S, buf["seq_ws"].data_ptr(),
                                              buf["seq_ws"].numel(), 0, None, logits.data_ptr(), st))
+
+    def _launch_async(self, buf, xs: dict[str, Tensor], names, B: int, S: int, argmax: bool) -> Pending:
+        """The whole forward on the lane's own streams: nothing is enqueued on the current stream except the fork event."""
+        lib = self.lib
+        cur = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        tail, streams = buf["tail"], buf["streams"]
+        tail.wait_event(fork)
+        for i, n in enumerate(sorted(names, key=lambda k: -xs[k].size(1))):
+            st = streams[i]
+            st.wait_event(fork)
+            if buf["tail_done"] is not None:
+                st.wait_event(buf["tail_done"])  # the lane's previous batch has finished reading z / masks
+            xs[n].record_stream(st)
+            pe = self.enc[self.model.signal_encoders.signal_map[n]]
+            ws = buf["enc_ws"][n]
+            _lib.check(lib.w2s_encoder_fwd(C.byref(pe.desc), xs[n].data_ptr(), B, xs[n].size(1), ws.data_ptr(), ws.numel(), 0,
+                                           buf["z"][n].data_ptr(), buf["mask"][n].data_ptr(), st.cuda_stream), ValueError)
+            ev = torch.cuda.Event()
+            ev.record(st)
+            tail.wait_event(ev)
+        with torch.cuda.stream(tail):
+            logits = torch.empty(B, S, self.model.num_classes, dtype=torch.float32, device=buf["mix"].device)
+            zs = (C.c_void_p * len(names))(*[buf["z"][n].data_ptr() for n in names])
+            ms = (C.c_void_p * len(names))(*[buf["mask"][n].data_ptr() for n in names])
+            ts = tail.cuda_stream
+            _lib.check(lib.w2s_epoch_mixer_fwd(C.byref(self.mixer_desc), zs, ms, len(names), B, S, buf["mix"].data_ptr(), ts))
+            _lib.check(lib.w2s_seqmixer_head_fwd(C.byref(self.seq_desc), buf["mix"].data_ptr(), B, S,
+                                                 buf["seq_ws"].data_ptr(), buf["seq_ws"].numel(), 0, None,
+                                                 logits.data_ptr(), ts))
+            out = logits
+            if argmax:
+                out = torch.empty(B, S, dtype=torch.int64, device=logits.device)
+                _lib.check(lib.w2s_argmax(logits.data_ptr(), B * S, self.model.num_classes, out.data_ptr(), ts))
+            done = torch.cuda.Event()
+            done.record(tail)
+        buf["tail_done"] = done
+        return Pending(out, done)
+
+    @torch.no_grad()
+    def forward_async(self, x: dict[str, Tensor], argmax: bool = False) -> Pending:
+        """Enqueue a forward on the next lane and return at once; ``.wait()`` on the result orders the current stream
+        after it.  Up to ``n_lanes`` batches are in flight on the GPU; inputs must stay untouched until then."""
+        B, S, device = self._check_inputs(x)
+        with torch.cuda.device(device):
+            self._ensure_packed(device)
+            names = sorted(x.keys())
+            lane = self._lane
+            self._lane = (lane + 1) % max(self.n_lanes, 1)
+            buf = self._buffers(device, names, B, S, lane)
+            xs = {}
+            for n in names:
+                t = x[n].detach()
+                xs[n] = t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
+            return self._launch_async(buf, xs, names, B, S, argmax)
+
+    def predict_async(self, x: dict[str, Tensor]) -> Pending:
+        return self.forward_async(x, argmax=True)
 
     # Small batches are launch-latency bound (~100 launches for ~2 ms of GPU work at B = 1): from the second call with
     # the same shape on, the whole forward is replayed from one CUDA graph over static input / output buffers.

@@ -254,6 +254,12 @@ class Wav2Sleep(nn.Module):
         """Most likely class per epoch, int64 [B, S]  (argmax kernel on the logits)."""
         return self._get_engine().predict(x)
 
+    def predict_async(self, x: dict[str, Tensor]):
+        """``predict`` without ordering the current stream after it: returns a handle whose ``wait()`` does (and hands
+        back the int64 [B, S] tensor).  Consecutive calls alternate between two sets of streams and workspaces, so the
+        latency-bound tail of one batch overlaps the encoders of the next (throughput mode for loops over batches)."""
+        return self._get_engine().predict_async(x)
+
     def forward_fp32_check(self, x: dict[str, Tensor]) -> Tensor:
         """The same forward through the un-fused fp32 CUDA-core check kernels (check.py): slow, <= 1e-4 from the
         reference's fp32 logits.  A validation aid, not an inference path."""
