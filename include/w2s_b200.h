@@ -331,6 +331,38 @@ int w2s_chk_rowln(const float* x, const float* res, const float* g, const float*
 int w2s_chk_attn(const float* q, const float* k, const float* v, float* o, const uint8_t* key_mask, int N, int D, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * General fp32 path: the NON-DEFAULT model options of the reference - causal / chunk-causal encoders
+ * (models/wav2sleep.py:248-255, models/blocks.py:150-152,178-182), norms batch / layer / rms / group / auto
+ * (models/utils.py:77-96), activations relu / leaky / silu / linear (utils.py:61-74), any feature_dim / nhead / dim_ff,
+ * register tokens, signal embeddings, output norm, causal sequence mixer.  Dimension-generic fp32 CUDA-core kernels on
+ * channels-last fp32 tensors with PyTorch weight layouts; wav2sleep_b200/general.py strings them together.  The default
+ * configuration never takes this path (it runs on the tcgen05 kernels above).
+ * ------------------------------------------------------------------------------------------------------- */
+enum { W2S_ACT_LINEAR = 0, W2S_ACT_RELU = 1, W2S_ACT_LEAKY = 2, W2S_ACT_GELU = 3, W2S_ACT_SILU = 4 };
+enum { W2S_NORM_INSTANCE = 0, W2S_NORM_GROUP = 1, W2S_NORM_BATCH_EVAL = 2 };
+/* out[b, lo, co] = bias[co] + sum_{t, ci} in[b, lo*stride - pad_left + t*dil, ci] * w[co, ci, t] (zero outside the input;
+ * a causal ConvLayer1D is pad_left = (k-1)*dil, L_out = (L_in - 1) / stride + 1).  taps_major: w is [cout, taps*cin].
+ * raw_inf_to_zero: `in` is the raw signal, non-finite samples read as 0. */
+int w2s_gen_conv(const float* in, const float* w, const float* bias, float* out, const uint8_t* row_mask, int B, int L_in,
+                 int L_out, int cin, int cout, int taps, int stride, int dil, int pad_left, int taps_major,
+                 int raw_inf_to_zero, void* stream);
+/* stats[b, c] = (sum, sum of squares) over L of x[b, :, c], fp64. */
+int w2s_gen_stats(const float* x, double* stats, const uint8_t* row_mask, int B, int L, int C, void* stream);
+/* scale / shift [B, C] of y = x * scale + shift for InstanceNorm1d, GroupNorm(groups) or eval-mode BatchNorm1d. */
+int w2s_gen_norm_consts(const double* stats, const float* weight, const float* bias, const float* running_mean,
+                        const float* running_var, float* scale, float* shift, int B, int C, int L, int mode, int groups,
+                        float eps, void* stream);
+/* out = act(in * scale[b, c] + shift[b, c] + res) (each of scale / shift / res may be NULL; per_channel: scale / shift are [C]). */
+int w2s_gen_affine_act(const float* in, const float* scale, const float* shift, const float* res, float* out,
+                       const uint8_t* row_mask, int B, int L, int C, int act, int per_channel, void* stream);
+/* per-row LayerNorm (rms = 0) / RMSNorm (rms = 1) over C features, affine weight (+ bias), activation. */
+int w2s_gen_rownorm(const float* x, const float* weight, const float* bias, float* out, long long rows, int C, int rms, int act,
+                    float eps, void* stream);
+/* H-head attention over the D tokens of each of N epochs; q, k, v, o: [N, D, H*hd]; key_mask [N, D] (1 = masked). */
+int w2s_gen_attn(const float* q, const float* k, const float* v, float* o, const uint8_t* key_mask, int N, int D, int H, int hd,
+                 void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Measurement hooks (bench.py).  Not part of the data path.
  * ------------------------------------------------------------------------------------------------------- */
 /* Number of kernels this library has launched in this process (monotonic). */

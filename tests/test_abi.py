@@ -67,10 +67,14 @@ def test_reference_error_conventions():
         M.SignalEncoders(signal_map={"EEG": "EEG"}, feature_dim=128, activation="gelu")
     with pytest.raises(ValueError):
         M.SignalEncoder(feature_dim=128, samples_per_epoch=1000)
-    with pytest.raises(NotImplementedError):
-        M.SignalEncoders(signal_map={"ECG": "ECG"}, feature_dim=128, activation="relu")
-    with pytest.raises(NotImplementedError):
-        M.SequenceCNN(norm="batch")
+    with pytest.raises(ValueError):  # models/utils.py:73-74
+        M.SignalEncoders(signal_map={"ECG": "ECG"}, feature_dim=128, activation="tanh")
+    with pytest.raises(NotImplementedError):  # the one reference option without a CUDA path
+        M.SequenceCNN(norm="weight")
+    # non-default options construct (general fp32 kernels) and are routed away from the fused path
+    enc = M.SignalEncoders(signal_map={"ECG": "ECG"}, feature_dim=16, activation="relu", norm="batch", causal=True)
+    model = M.Wav2Sleep(enc, M.MultiModalAttentionEmbedder(feature_dim=16), M.SequenceCNN(feature_dim=16, causal=True), 4)
+    assert not model.fast_path and build_default({"ECG": "ECG"}, 4).fast_path
 
 
 def test_cpu_input_fails_loudly():

@@ -1,0 +1,85 @@
+"""Non-default model options on the general CUDA path (wav2sleep_b200/general.py).
+
+Chain of evidence: tests/golden/general_*.npz hold logits of the REAL reference for four non-default configurations
+(oracle/make_golden_general.py, run in the build container).  Not-gpu: this package's constructors reproduce the
+reference's parameters bit-for-bit for those configurations (stored SHA-256 of the whole state_dict).  gpu: the CUDA
+forward matches the reference logits to fp32 accuracy, and the reference's own model test
+(/root/reference/tests/model/test_causality.py:11-39) passes on the CUDA path.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import make_golden_general as G
+from wav2sleep_b200 import model as M
+
+TOL = 2e-4  # fp32 kernels vs fp32 reference; logits are O(1)
+
+
+@pytest.mark.parametrize("name", list(G.CASES))
+def test_mirror_reproduces_reference_parameters(name):
+    case = G.CASES[name]
+    model = G.build(M, case)
+    assert not model.fast_path
+    G.perturb(model, case["seed"])
+    gold = np.load(GOLDEN / f"{name}.npz")
+    assert len(model.state_dict()) == int(gold["n_keys"][0])
+    assert G.digest(model.state_dict()) == str(gold["sha"][0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(G.CASES))
+def test_general_path_matches_reference_logits(cuda_device, name):
+    case = G.CASES[name]
+    model = G.build(M, case)
+    G.perturb(model, case["seed"])
+    gold = np.load(GOLDEN / f"{name}.npz")
+    x = {k: v.to(cuda_device) for k, v in G.make_inputs(case).items()}
+    model = model.to(cuda_device).eval()
+    with torch.no_grad():
+        out = model(x)
+        pred = model.predict(x)
+    ref = torch.from_numpy(gold["logits"])
+    err = (out.float().cpu() - ref).abs().max().item()
+    print(f"{name}: max-abs logit error vs the reference {err:.3e}")
+    assert out.shape == ref.shape and err < TOL
+    assert torch.equal(pred.cpu(), out.argmax(-1).cpu())
+
+
+@pytest.mark.gpu
+def test_reference_causality_test_on_cuda_path(cuda_device):
+    """/root/reference/tests/model/test_causality.py:11-39, verbatim configuration and assertion: the prediction for
+    the first half of a 10-h night does not change when the second half is appended (causal + batch norm + ReLU,
+    feature_dim 16)."""
+    torch.manual_seed(0)
+    encoders = M.SignalEncoders(signal_map={"ECG": "ECG", "PPG": "PPG"}, feature_dim=16, activation="relu", norm="batch",
+                                causal=True)
+    model = M.Wav2Sleep(signal_encoders=encoders, epoch_mixer=M.MultiModalAttentionEmbedder(feature_dim=16),
+                        sequence_mixer=M.SequenceCNN(feature_dim=16, causal=True, norm="batch"), num_classes=4)
+    model = model.to(cuda_device).eval()
+    L = 1_228_800
+    x = torch.randn(1, L, device=cuda_device)
+    x2 = x[:, : L // 2].contiguous()
+    with torch.no_grad():
+        y = model({"ECG": x, "PPG": x})
+        y2 = model({"ECG": x2, "PPG": x2})
+    L_out = y2.shape[1]
+    assert y.shape == (1, 1200, 4) and L_out == 600
+    assert torch.allclose(y[:, :L_out], y2[:, :L_out])
+
+
+@pytest.mark.gpu
+def test_general_path_options_raise_like_the_reference(cuda_device):
+    enc = M.SignalEncoders(signal_map={"ECG": "ECG"}, feature_dim=16, activation="relu", norm="batch", causal=True)
+    model = M.Wav2Sleep(enc, M.MultiModalAttentionEmbedder(feature_dim=16), M.SequenceCNN(feature_dim=16, causal=True), 4)
+    model = model.to(cuda_device).eval()
+    with pytest.raises(ValueError):
+        model({"ECG": torch.zeros(1, 1000, device=cuda_device)})  # not a multiple of samples_per_epoch
+    with pytest.raises(ValueError):
+        model({})
+    with pytest.raises(RuntimeError):
+        model({"ECG": torch.zeros(1, 1024)})  # CPU tensor: no fallback
+    model.train()
+    with pytest.raises(NotImplementedError):
+        model({"ECG": torch.zeros(1, 1024, device=cuda_device)})

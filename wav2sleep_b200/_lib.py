@@ -173,6 +173,12 @@ SYMBOLS = {
     "w2s_chk_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "w2s_chk_rowln": (C.c_int, [C.c_void_p] * 5 + [C.c_longlong, C.c_int, C.c_float, C.c_void_p]),
     "w2s_chk_attn": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_void_p]),
+    "w2s_gen_conv": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 11 + [C.c_void_p]),
+    "w2s_gen_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "w2s_gen_norm_consts": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_float, C.c_void_p]),
+    "w2s_gen_affine_act": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 5 + [C.c_void_p]),
+    "w2s_gen_rownorm": (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "w2s_gen_attn": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p]),
     "w2s_launch_count": (C.c_longlong, []),
     "w2s_profile_enable": (C.c_int, [C.c_int]),
     "w2s_profile_count": (C.c_int, []),

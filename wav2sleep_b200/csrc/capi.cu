@@ -19,6 +19,7 @@
 #include "gemm_tn.cuh"
 #include "train_kernels.cuh"
 #include "check_fp32.cuh"
+#include "general.cuh"
 #include "staging.cuh"
 
 using namespace w2s;
@@ -1115,6 +1116,67 @@ int w2s_chk_attn(const float* q, const float* k, const float* v, float* o, const
   LaunchScope scope((cudaStream_t)stream, "chk_attn", (double)N * D * 128 * 16.0, 0);
   chk::attn_kernel<<<(N * 8 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(q, k, v, o, key_mask, N, D);
   W2S_LAUNCH_CHECK("chk_attn");
+}
+
+// ================================================================================================
+// general fp32 path for non-default model options (general.cuh), orchestrated by wav2sleep_b200/general.py
+// ================================================================================================
+int w2s_gen_conv(const float* in, const float* w, const float* bias, float* out, const uint8_t* row_mask, int B, int L_in,
+                 int L_out, int cin, int cout, int taps, int stride, int dil, int pad_left, int taps_major,
+                 int raw_inf_to_zero, void* stream) {
+  if (!in || !w || !out || B <= 0 || B > 65535 || L_in <= 0 || L_out <= 0 || cin < 1 || cout < 1 || taps < 1 || stride < 1 || dil < 1)
+    return fail("gen_conv: bad arguments (B=%d L_in=%d L_out=%d cin=%d cout=%d taps=%d)", B, L_in, L_out, cin, cout, taps);
+  gen::ConvArgs a{in, w, bias, out, row_mask, B, L_in, L_out, cin, cout, taps, stride, dil, pad_left, taps_major, raw_inf_to_zero};
+  long long gx = ((long long)L_out * cout + 255) / 256;
+  const long long cap = 32LL * sm_count() / B + 1;
+  if (gx > cap) gx = cap;
+  LaunchScope scope((cudaStream_t)stream, "gen_conv", 0, 2.0 * B * (double)L_out * cout * cin * taps);
+  gen::conv_kernel<<<dim3((unsigned)gx, B), 256, 0, (cudaStream_t)stream>>>(a);
+  W2S_LAUNCH_CHECK("gen_conv");
+}
+int w2s_gen_stats(const float* x, double* stats, const uint8_t* row_mask, int B, int L, int Cc, void* stream) {
+  if (!x || !stats || B <= 0 || B > 65535 || L <= 0 || Cc < 1) return fail("gen_stats: bad arguments");
+  LaunchScope scope((cudaStream_t)stream, "gen_stats", (double)B * L * Cc * 4.0, 0);
+  gen::stats_kernel<<<dim3(Cc, B), 256, 0, (cudaStream_t)stream>>>(x, stats, row_mask, L, Cc);
+  W2S_LAUNCH_CHECK("gen_stats");
+}
+int w2s_gen_norm_consts(const double* stats, const float* weight, const float* bias, const float* running_mean,
+                        const float* running_var, float* scale, float* shift, int B, int Cc, int L, int mode, int groups,
+                        float eps, void* stream) {
+  if (!scale || !shift || B <= 0 || Cc < 1 || mode < 0 || mode > 2) return fail("gen_norm_consts: bad arguments");
+  if (mode == gen::NORM_BATCH_EVAL ? (!running_mean || !running_var) : !stats) return fail("gen_norm_consts: statistics missing");
+  if (mode == gen::NORM_GROUP && (groups < 1 || Cc % groups)) return fail("gen_norm_consts: %d channels, %d groups", Cc, groups);
+  gen::NormConstArgs a{stats, weight, bias, running_mean, running_var, scale, shift, B, Cc, L, mode, groups, eps};
+  LaunchScope scope((cudaStream_t)stream, "gen_norm_consts", 0, 0);
+  gen::norm_consts_kernel<<<ew_grid((long long)B * Cc), 256, 0, (cudaStream_t)stream>>>(a);
+  W2S_LAUNCH_CHECK("gen_norm_consts");
+}
+int w2s_gen_affine_act(const float* in, const float* scale, const float* shift, const float* res, float* out,
+                       const uint8_t* row_mask, int B, int L, int Cc, int act, int per_channel, void* stream) {
+  if (!in || !out || B <= 0 || B > 65535 || L <= 0 || Cc < 1 || act < 0 || act > 4) return fail("gen_affine_act: bad arguments");
+  gen::AffineActArgs a{in, scale, shift, res, out, row_mask, B, L, Cc, act, per_channel};
+  long long gx = ((long long)L * Cc + 255) / 256;
+  const long long cap = 32LL * sm_count() / B + 1;
+  if (gx > cap) gx = cap;
+  LaunchScope scope((cudaStream_t)stream, "gen_affine_act", (double)B * L * Cc * 8.0, 0);
+  gen::affine_act_kernel<<<dim3((unsigned)gx, B), 256, 0, (cudaStream_t)stream>>>(a);
+  W2S_LAUNCH_CHECK("gen_affine_act");
+}
+int w2s_gen_rownorm(const float* x, const float* weight, const float* bias, float* out, long long rows, int Cc, int rms, int act,
+                    float eps, void* stream) {
+  if (!x || !out || rows <= 0 || Cc < 1 || act < 0 || act > 4) return fail("gen_rownorm: bad arguments");
+  gen::RowNormArgs a{x, weight, bias, out, rows, Cc, rms, act, eps};
+  LaunchScope scope((cudaStream_t)stream, "gen_rownorm", (double)rows * Cc * 8.0, 0);
+  gen::rownorm_kernel<<<ew_grid(rows * 32), 256, 0, (cudaStream_t)stream>>>(a);
+  W2S_LAUNCH_CHECK("gen_rownorm");
+}
+int w2s_gen_attn(const float* q, const float* k, const float* v, float* o, const uint8_t* key_mask, int N, int D, int H, int hd,
+                 void* stream) {
+  if (!q || !k || !v || !o || N <= 0 || D < 1 || H < 1 || hd < 1) return fail("gen_attn: bad arguments");
+  gen::AttnArgs a{q, k, v, o, key_mask, N, D, H, hd};
+  LaunchScope scope((cudaStream_t)stream, "gen_attn", (double)N * D * H * hd * 16.0, 0);
+  gen::attn_kernel<<<ew_grid((long long)N * D * H, 128), 128, 0, (cudaStream_t)stream>>>(a);
+  W2S_LAUNCH_CHECK("gen_attn");
 }
 
 int w2s_set_conv_impl(int impl) {

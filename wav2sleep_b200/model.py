@@ -11,10 +11,14 @@ consumption order as the reference, so ``torch.manual_seed(s)`` reproduces the r
 bit-for-bit), but their ``forward`` is never called.  All compute goes through ``engine.ForwardEngine`` ->
 ``libw2s_b200.so``.  There is no CPU or eager fallback: a CPU tensor or a missing library raises.
 
-Options of the reference that the CUDA path does not build yet raise ``NotImplementedError`` at construction
-(SURVEY.md section 8f, row N3): causal / chunk-causal mode, norms other than ``instance`` (encoders) and
-``layer`` (sequence mixer), activations other than ``gelu``, ``embed_signals``, ``register_tokens > 0``,
-``output_norm``, ``use_residual=False``, widths other than 16..128 / feature_dim 128.
+Two CUDA paths sit behind the same classes.  The default model family of the reference's configs (non-causal,
+instance-norm encoders with 16..128 channels, GELU, feature_dim 128, nhead 8, dim_ff 512, layer-norm sequence mixer with
+kernel 7) runs on the fused tcgen05 kernels (engine.py / training.py).  Every other option the reference constructors
+accept (causal / chunk-causal mode, norms batch / layer / rms / group / auto / none,
+activations relu / leaky / silu / linear, ``embed_signals``, ``register_tokens > 0``, ``output_norm``,
+``use_residual=False``, other widths and feature dims) runs on the dimension-generic fp32 kernels of csrc/general.cuh
+(general.py): inference only, same results as the reference to fp32 accuracy, not tuned.  ``norm='weight'`` (a
+parametrisation with different state_dict keys) is the one option that raises ``NotImplementedError``.
 """
 from __future__ import annotations
 
@@ -42,31 +46,104 @@ class ConvLayerNorm(nn.Module):
         self.eps = eps
 
 
+class ConvRMSNorm(nn.Module):
+    """Parameters of the channel-first RMS norm (reference models/utils.py:26-36)."""
+
+    def __init__(self, num_features: int, eps: float = 1e-5):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(1, num_features, 1))
+        self.eps = eps
+
+
+class ConvGroupNorm(nn.Module):
+    """Parameters of the group norm wrapper (reference models/utils.py:38-58): keys ``norm.weight`` / ``norm.bias``."""
+
+    def __init__(self, num_features: int, num_groups: int = 8, channels_per_group: int | None = None, eps: float = 1e-5):
+        super().__init__()
+        if channels_per_group is not None:
+            num_groups = num_features // channels_per_group
+        if num_features < num_groups:
+            num_groups = num_features
+        if num_features % num_groups != 0:
+            raise ValueError(f"{num_features=} must be divisible by {num_groups=}.")
+        self.norm = nn.GroupNorm(num_groups=num_groups, num_channels=num_features, eps=eps)
+
+
+ACTIVATIONS = ("relu", "leaky", "gelu", "silu", "swish", "linear")
+
+
+def get_activation(name: str) -> nn.Module:
+    """reference models/utils.py:61-74 (parameter-free modules; kept for attribute / repr compatibility)."""
+    if name not in ACTIVATIONS:
+        raise ValueError(f"{name=} is unsupported.")
+    return {"relu": nn.ReLU, "leaky": nn.LeakyReLU, "gelu": nn.GELU, "silu": nn.SiLU, "swish": nn.SiLU,
+            "linear": nn.Identity}[name]()
+
+
+def get_norm(name: str | None, num_features: int, norm_eps: float | None = None) -> nn.Module:
+    """reference models/utils.py:77-96: the parameter / buffer containers of each normalisation."""
+    if name == "batch":
+        return nn.BatchNorm1d(num_features)
+    if name == "layer":
+        return ConvLayerNorm(num_features)
+    if name == "rms":
+        return ConvRMSNorm(num_features)
+    if name is None:
+        return nn.Identity()
+    if name == "instance":
+        return nn.InstanceNorm1d(num_features, **({"eps": norm_eps} if norm_eps is not None else {}))
+    if name == "group":
+        return ConvGroupNorm(num_features)
+    if name == "weight":
+        _require(False, "norm='weight' (weight-norm parametrisation)")
+    raise ValueError(f"Normalisation with {name=} unknown.")
+
+
 class ConvLayer1D(nn.Module):
     """conv -> norm -> activation; holds ``conv.weight`` (+ ``norm.*``).  reference models/blocks.py:129-186."""
 
     def __init__(self, input_dim: int, output_dim: int, kernel_size: int = 3, stride: int = 1, padding: int = 1,
-                 dilation: int = 1, norm: str = "instance", norm_eps: float | None = None):
+                 dilation: int = 1, dropout: float = 0.0, causal: bool = False, groups: int = 1, activation: str = "relu",
+                 bias: bool = False, norm: str | None = "batch", norm_eps: float | None = None):
         super().__init__()
-        self.conv = nn.Conv1d(input_dim, output_dim, kernel_size=kernel_size, stride=stride, padding=padding,
-                              dilation=dilation, bias=False)
-        if norm == "instance":
-            self.norm = nn.InstanceNorm1d(output_dim, **({"eps": norm_eps} if norm_eps is not None else {}))
-        elif norm == "layer":
-            self.norm = ConvLayerNorm(output_dim)
-        else:
-            _require(False, f"norm={norm!r}")
+        _require(groups == 1, f"groups={groups}")
+        self.causal = causal
+        self.padding = (kernel_size - 1) * dilation if causal else padding  # blocks.py:150-153
+        self.kernel_size, self.stride, self.dilation = kernel_size, stride, dilation
+        self.norm_name, self.activation_name = norm, activation
+        self.conv = nn.Conv1d(input_dim, output_dim, kernel_size=kernel_size, stride=stride, padding=self.padding,
+                              dilation=dilation, bias=bias or norm is None)
+        self.norm = get_norm(norm, output_dim, norm_eps)
+        self.activation = get_activation(activation)
+        self.dropout = nn.Dropout(p=dropout)
+
+    def output_length(self, L: int) -> int:
+        """Length after the conv and, in causal mode, the right-trim of blocks.py:178-182."""
+        full = (L + 2 * self.padding - self.dilation * (self.kernel_size - 1) - 1) // self.stride + 1
+        if self.causal and self.padding > 0:
+            full -= max(self.padding - (self.stride - 1), 0)
+        return full
 
 
 class ConvBlock1D(nn.Module):
-    """Three conv layers + 1x1 stride-2 residual; out = GELU(conv3(conv2(conv1(x))) + downsample(x)).  blocks.py:8-71."""
+    """Three conv layers + 1x1 stride-2 residual; out = act(conv3(conv2(conv1(x))) + downsample(x)).  blocks.py:8-71."""
 
-    def __init__(self, input_dim: int, output_dim: int, norm_eps: float | None):
+    def __init__(self, input_dim: int, output_dim: int, dropout: float = 0.0, activation: str = "leaky",
+                 norm: str | None = "batch", causal: bool = False, norm_eps: float | None = None,
+                 use_residual: bool = True):
         super().__init__()
-        self.conv1 = ConvLayer1D(input_dim, output_dim, norm_eps=norm_eps)
-        self.conv2 = ConvLayer1D(output_dim, output_dim, norm_eps=norm_eps)
-        self.conv3 = ConvLayer1D(output_dim, output_dim, stride=2, norm_eps=norm_eps)
-        self.downsample = nn.Conv1d(input_dim, output_dim, kernel_size=1, stride=2, padding=0, bias=False)
+        self.use_residual = use_residual
+        kw = dict(kernel_size=3, padding=1, activation=activation, norm=norm, dropout=dropout, causal=causal,
+                  norm_eps=norm_eps)
+        self.conv1 = ConvLayer1D(input_dim, output_dim, **kw)
+        self.conv2 = ConvLayer1D(output_dim, output_dim, **kw)
+        self.conv3 = ConvLayer1D(output_dim, output_dim, stride=2, **kw)
+        self.activation = get_activation(activation)
+        self.activation_name = activation
+        if use_residual:
+            self.downsample = nn.Conv1d(input_dim, output_dim, kernel_size=1, stride=2, padding=0, bias=False)
+        else:
+            self.register_parameter("downsample", None)
 
 
 class SignalEncoder(nn.Module):
@@ -80,36 +157,39 @@ class SignalEncoder(nn.Module):
         if samples_per_epoch & (samples_per_epoch - 1) != 0:
             raise ValueError(f"samples_per_epoch must be a power of 2, got {samples_per_epoch}")
         _require(input_dim == 1, f"input_dim={input_dim}")
-        _require(activation == "gelu", f"activation={activation!r}")
-        _require(norm == "instance", f"encoder norm={norm!r}")
-        _require(not causal, "causal=True")
-        _require(not output_norm, "output_norm=True")
-        _require(use_residual, "use_residual=False")
-        _require(initial_channels == 16 and max_channels == 128, f"channels {initial_channels}..{max_channels}")
-        _require(feature_dim == 128, f"feature_dim={feature_dim}")
         self.feature_dim = feature_dim
         self.samples_per_epoch = samples_per_epoch
         self.causal = causal
         self.chunk_causal = chunk_causal
+        self.norm_name, self.activation_name, self.use_residual = norm, activation, use_residual
         num_blocks = int(math.log2(samples_per_epoch)) - 2
         _require(1 <= num_blocks <= 12, f"samples_per_epoch={samples_per_epoch}")
         self.channels = [min(initial_channels * 2 ** (i // 2), max_channels) for i in range(num_blocks)]
-        self.norm_eps = 1e-2  # models/wav2sleep.py:213-215
-        # Inference storage policy (not a reference argument): number of leading blocks whose conv outputs are kept as
-        # fp32 instead of fp16 and whose convs carry split (hi + lo) operands (0, 2, 4 or 6).  Stacks of >= 10 blocks
-        # (EOG: 30 convs, 6.9 M samples) default to 6 = every block up to 64 channels: with all-fp16 storage the logits
-        # sit on the 2e-2 gate, and the 99.9 % argmax gate needs the 64-channel blocks as well (DESIGN.md "Numerics",
-        # tools/emulate_16bit.py).
-        self.wide_blocks = 6 if num_blocks >= 10 else 0
+        self.norm_eps = 1e-2  # models/wav2sleep.py:213-215 (instance norm only)
+        causal_conv = causal and not chunk_causal  # wav2sleep.py:201
+        self.block_norms = []
         blocks, cin = [], input_dim
-        for cout in self.channels:
-            blocks.append(ConvBlock1D(cin, cout, norm_eps=self.norm_eps))
+        for i, cout in enumerate(self.channels):
+            norm_i = ("instance" if i < 2 else "layer") if norm == "auto" else norm  # wav2sleep.py:204-212
+            self.block_norms.append(norm_i)
+            blocks.append(ConvBlock1D(cin, cout, activation=activation, norm=norm_i,
+                                      norm_eps=self.norm_eps if norm_i == "instance" else None, causal=causal_conv,
+                                      use_residual=use_residual))
             cin = cout
         self.cnn = nn.Sequential(*blocks)
         self.epoch_dim = self.channels[-1] * 4
         self.linear = nn.Linear(self.epoch_dim, feature_dim)
-        self.activation = nn.GELU()
-        self.output_norm = nn.Identity()
+        self.activation = get_activation(activation)
+        self.output_norm = nn.LayerNorm(feature_dim) if output_norm else nn.Identity()
+        # True when this encoder is in the model family the fused tcgen05 kernels are built for
+        self.fast_path = (activation == "gelu" and norm == "instance" and not causal and not output_norm and use_residual
+                          and initial_channels == 16 and max_channels == 128 and feature_dim == 128)
+        # Inference storage policy of the fast path (not a reference argument): number of leading blocks whose conv
+        # outputs are kept as fp32 instead of fp16 and whose convs carry split (hi + lo) operands (0, 2, 4 or 6).
+        # Stacks of >= 10 blocks (EOG: 30 convs, 6.9 M samples) default to 6 = every block up to 64 channels: with
+        # all-fp16 storage the logits sit on the 2e-2 gate, and the argmax gate needs the 64-channel blocks as well
+        # (DESIGN.md "Numerics", tools/emulate_16bit.py).
+        self.wide_blocks = 6 if num_blocks >= 10 else 0
 
 
 class SignalEncoders(nn.Module):
@@ -120,7 +200,6 @@ class SignalEncoders(nn.Module):
                  initial_channels: int = 16, max_channels: int = 128, output_norm: bool = False,
                  use_residual: bool = True) -> None:
         super().__init__()
-        _require(not embed_signals, "embed_signals=True")
         self.feature_dim = feature_dim
         self.signal_map = dict(signal_map)
         self.causal = causal
@@ -138,7 +217,11 @@ class SignalEncoders(nn.Module):
         self.encoders = nn.ModuleDict(encoders)
         self.embed_signals = embed_signals
         self.sig_to_embedding_idx = {sig: i for i, sig in enumerate(sorted(self.signal_map.keys()))}
-        self.register_parameter("embedder", None)
+        if embed_signals:
+            self.embedder = nn.Embedding(num_embeddings=len(self.signal_map), embedding_dim=feature_dim)
+        else:
+            self.register_parameter("embedder", None)
+        self.fast_path = not embed_signals and all(e.fast_path for e in self.encoders.values())
 
     def __len__(self) -> int:
         return len(self.encoders)
@@ -153,29 +236,30 @@ class MultiModalAttentionEmbedder(nn.Module):
     def __init__(self, feature_dim: int, layers: int = 4, dropout: float = 0.0, dim_ff: int = 512,
                  activation: str = "gelu", norm_first: bool = True, nhead: int = 4, register_tokens: int = 0):
         super().__init__()
-        _require(feature_dim == 128 and nhead == 8 and dim_ff == 512,
-                 f"epoch mixer shape feature_dim={feature_dim}, nhead={nhead}, dim_ff={dim_ff}")
-        _require(activation == "gelu", f"activation={activation!r}")
-        _require(norm_first, "norm_first=False")
-        _require(register_tokens == 0, f"register_tokens={register_tokens}")
-        _require(1 <= layers <= 8, f"layers={layers}")
+        if feature_dim % nhead:
+            raise ValueError(f"feature_dim={feature_dim} must be divisible by nhead={nhead}")
         self.feature_dim = feature_dim
         self.dropout = dropout
         self.nhead = nhead
         self.dim_ff = dim_ff
-        encoder_layer = nn.TransformerEncoderLayer(d_model=feature_dim, dim_feedforward=dim_ff, activation=nn.GELU(),
-                                                   nhead=nhead, batch_first=True, dropout=dropout,
-                                                   norm_first=norm_first)
+        self.norm_first = norm_first
+        self.activation_name = activation
+        encoder_layer = nn.TransformerEncoderLayer(d_model=feature_dim, dim_feedforward=dim_ff,
+                                                   activation=get_activation(activation), nhead=nhead, batch_first=True,
+                                                   dropout=dropout, norm_first=norm_first)
         self.num_layers = layers
         self.transformer_encoder = nn.TransformerEncoder(encoder_layer, num_layers=layers, enable_nested_tensor=False)
         self.num_register_tokens = register_tokens
         self.register_tokens = nn.Parameter(torch.randn(1, 1, feature_dim, register_tokens + 1))
+        self.fast_path = (feature_dim == 128 and nhead == 8 and dim_ff == 512 and activation == "gelu" and norm_first
+                          and register_tokens == 0 and 1 <= layers <= 8)
 
 
 class DilatedConvBlock(nn.Module):
-    """num_dilations x (dilated conv k -> ConvLayerNorm -> GELU), dropout, + input, GELU.  models/blocks.py:74-126."""
+    """num_dilations x (dilated conv k -> norm -> act), dropout, + input, act.  models/blocks.py:74-126."""
 
-    def __init__(self, feature_dim: int = 128, dropout: float = 0.2, kernel_size: int = 7, num_dilations: int = 6):
+    def __init__(self, feature_dim: int = 128, dropout: float = 0.2, activation: str = "leaky", norm: str = "batch",
+                 kernel_size: int = 7, causal: bool = False, num_dilations: int = 6):
         super().__init__()
         self.kernel_size = kernel_size
         self.dilations = [2 ** i for i in range(num_dilations)]
@@ -183,10 +267,11 @@ class DilatedConvBlock(nn.Module):
         for d in self.dilations:
             k_eff = kernel_size + (kernel_size - 1) * (d - 1)
             layers.append(ConvLayer1D(feature_dim, feature_dim, kernel_size=kernel_size, stride=1, dilation=d,
-                                      padding=k_eff // 2, norm="layer"))
+                                      padding=k_eff // 2, activation=activation, norm=norm, causal=causal))
         self.dropout = nn.Dropout(p=dropout)
         self.conv_layers = nn.Sequential(*layers)
-        self.activation = nn.GELU()
+        self.activation = get_activation(activation)
+        self.activation_name = activation
 
 
 class SequenceCNN(nn.Module):
@@ -195,15 +280,13 @@ class SequenceCNN(nn.Module):
     def __init__(self, feature_dim: int = 128, dropout: float = 0.2, num_layers: int = 2, activation: str = "gelu",
                  norm: str = "batch", causal: bool = False, num_dilations: int = 6, kernel_size: int = 7) -> None:
         super().__init__()
-        _require(feature_dim == 128 and kernel_size == 7, f"sequence mixer feature_dim={feature_dim}, k={kernel_size}")
-        _require(activation == "gelu", f"activation={activation!r}")
-        _require(norm == "layer", f"sequence mixer norm={norm!r}")
-        _require(not causal, "causal=True")
-        _require(1 <= num_layers <= 4 and 1 <= num_dilations <= 8, f"num_layers={num_layers}, num_dilations={num_dilations}")
         self.feature_dim = feature_dim
+        self.causal = causal
         self.dilated_convs = nn.Sequential(*[
-            DilatedConvBlock(feature_dim=feature_dim, dropout=dropout, kernel_size=kernel_size,
-                             num_dilations=num_dilations) for _ in range(num_layers)])
+            DilatedConvBlock(feature_dim=feature_dim, dropout=dropout, activation=activation, norm=norm, causal=causal,
+                             kernel_size=kernel_size, num_dilations=num_dilations) for _ in range(num_layers)])
+        self.fast_path = (feature_dim == 128 and kernel_size == 7 and activation == "gelu" and norm == "layer"
+                          and not causal and 1 <= num_layers <= 4 and 1 <= num_dilations <= 8)
 
 
 class Wav2Sleep(nn.Module):
@@ -212,7 +295,6 @@ class Wav2Sleep(nn.Module):
     def __init__(self, signal_encoders: SignalEncoders, epoch_mixer: MultiModalAttentionEmbedder,
                  sequence_mixer: SequenceCNN, num_classes: int):
         super().__init__()
-        _require(1 <= num_classes <= 8, f"num_classes={num_classes}")
         self.signal_encoders = signal_encoders
         self.epoch_mixer = epoch_mixer
         self.sequence_mixer = sequence_mixer
@@ -220,6 +302,11 @@ class Wav2Sleep(nn.Module):
         self.num_classes = num_classes
         self.classifier = nn.Linear(in_features=self.feature_dim, out_features=num_classes)
         self._engine = None
+        self._general = None
+        # the fused tcgen05 path serves the default model family; everything else goes to the general fp32 kernels
+        self.fast_path = (signal_encoders.fast_path and epoch_mixer.fast_path and sequence_mixer.fast_path
+                          and 1 <= num_classes <= 8 and signal_encoders.feature_dim == epoch_mixer.feature_dim
+                          == sequence_mixer.feature_dim)
 
     @property
     def valid_signals(self) -> list[str]:
@@ -233,11 +320,23 @@ class Wav2Sleep(nn.Module):
 
     _get_train_engine = _get_engine
 
+    def _get_general(self):
+        from .general import GeneralEngine  # deferred: loads the CUDA library
+        if self._general is None:
+            object.__setattr__(self, "_general", GeneralEngine(self))
+        return self._general
+
     def forward(self, x: dict[str, Tensor]) -> Tensor:
         """dict of [B, S * samples_per_epoch] fp32 (rows of -inf = missing signal) -> logits [B, S, num_classes].
 
         Under ``train()`` with grad enabled the logits carry a grad_fn whose backward runs the CUDA backward pass
         (dropout with counter-based masks, see training.py); otherwise the fused inference kernels run."""
+        if not self.fast_path:
+            if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+                raise NotImplementedError("wav2sleep_b200: training is built for the default model family only; "
+                                          "non-default options (causal, other norms / activations / widths) run the "
+                                          "general inference kernels")
+            return self._get_general().forward(x)
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from .training import forward_with_grad
             return forward_with_grad(self, x)
@@ -252,12 +351,20 @@ class Wav2Sleep(nn.Module):
 
     def predict(self, x: dict[str, Tensor]) -> Tensor:
         """Most likely class per epoch, int64 [B, S]  (argmax kernel on the logits)."""
+        if not self.fast_path:
+            return self._get_general().predict(x)
         return self._get_engine().predict(x)
 
     def predict_async(self, x: dict[str, Tensor]):
         """``predict`` without ordering the current stream after it: returns a handle whose ``wait()`` does (and hands
         back the int64 [B, S] tensor).  Consecutive calls alternate between two sets of streams and workspaces, so the
         latency-bound tail of one batch overlaps the encoders of the next (throughput mode for loops over batches)."""
+        if not self.fast_path:
+            from .engine import Pending
+            out = self._get_general().predict(x)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(out.device))
+            return Pending(out, ev)
         return self._get_engine().predict_async(x)
 
     def forward_fp32_check(self, x: dict[str, Tensor]) -> Tensor:
