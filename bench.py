@@ -227,37 +227,49 @@ def run_cuda(args):
         # ---------------- end-to-end timing: pinned host inputs -> predictions on host ----------------
         copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream()
-        stage = [{k: torch.empty_like(v) for k, v in devb[0].items()} for _ in range(2)]
-        out_host = [torch.empty(BATCH, S_EPOCHS, dtype=torch.int64).pin_memory() for _ in range(2)]
-        ready = [torch.cuda.Event() for _ in range(2)]
-        consumed = [torch.cuda.Event() for _ in range(2)]
-        read_done = [None, None]  # completion of the last forward that read stage[b]
+        NS = 3  # staging buffers: uploads run two batches ahead of the forward that is starting
+        stage = [{k: torch.empty_like(v) for k, v in devb[0].items()} for _ in range(NS)]
+        out_host = [torch.empty(BATCH, S_EPOCHS, dtype=torch.int64).pin_memory() for _ in range(NS)]
+        ready = [torch.cuda.Event() for _ in range(NS)]
+        free = [None] * NS  # event after which staging buffer b may be overwritten
 
-        def upload(i):
-            with torch.cuda.stream(copy_stream):
-                if read_done[i % 2] is not None:
-                    copy_stream.wait_event(read_done[i % 2])
-                for k in stage[i % 2]:
-                    stage[i % 2][k].copy_(host[i % 2][k], non_blocking=True)
-                ready[i % 2].record(copy_stream)
+        def pipelined(n, upload_one, make_inputs):
+            """Every step: H2D copy of its inputs (copy stream, pinned source) -> forward (predict_async, two in
+            flight) -> D2H copy of its predictions; all inside the caller's timed region."""
+            for b in range(NS):
+                free[b] = None
 
-        def e2e_loop(n):
-            read_done[0] = read_done[1] = None
-            upload(0)
+            def upload(i):
+                with torch.cuda.stream(copy_stream):
+                    if free[i % NS] is not None:
+                        copy_stream.wait_event(free[i % NS])
+                    upload_one(i)
+                    ready[i % NS].record(copy_stream)
+
+            for i in range(min(2, n)):
+                upload(i)
             pend = []
             for i in range(n):
-                if i + 1 < n:
-                    upload(i + 1)
-                main.wait_event(ready[i % 2])
-                p = model.predict_async(stage[i % 2])
-                read_done[i % 2] = p.done
-                pend.append((p, i))
+                main.wait_event(ready[i % NS])
+                x, released = make_inputs(i)
+                p = model.predict_async(x)
+                free[i % NS] = released if released is not None else p.done
+                pend.append((p, i, x))
+                if i + 2 < n:
+                    upload(i + 2)
                 if len(pend) > 1:  # the previous batch's predictions go back to the host while this batch runs
-                    q, j = pend.pop(0)
-                    out_host[j % 2].copy_(q.wait(), non_blocking=True)
-            for q, j in pend:
-                out_host[j % 2].copy_(q.wait(), non_blocking=True)
+                    q, j, _ = pend.pop(0)
+                    out_host[j % NS].copy_(q.wait(), non_blocking=True)
+            for q, j, _ in pend:
+                out_host[j % NS].copy_(q.wait(), non_blocking=True)
             torch.cuda.synchronize()
+
+        def upload_f32(i):
+            for k in stage[i % NS]:
+                stage[i % NS][k].copy_(host[i % 2][k], non_blocking=True)
+
+        def e2e_loop(n):
+            pipelined(n, upload_f32, lambda i: (stage[i % NS], None))
 
         e2e_loop(min(args.warmup, 3))
         barrier()
@@ -275,35 +287,23 @@ def run_cuda(args):
         from wav2sleep_b200.staging import zscore_on_device
         host16 = [{k: (v * 1000.0).round().clamp(-32000, 32000).to(torch.int16).pin_memory() for k, v in hb.items()}
                   for hb in host]
-        stage16 = [{k: torch.empty(v.shape, dtype=torch.int16, device=dev) for k, v in host16[0].items()} for _ in range(2)]
+        stage16 = [{k: torch.empty(v.shape, dtype=torch.int16, device=dev) for k, v in host16[0].items()} for _ in range(NS)]
 
-        def upload16(i):
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(consumed[i % 2])
-                for k in stage16[i % 2]:
-                    stage16[i % 2][k].copy_(host16[i % 2][k], non_blocking=True)
-                ready[i % 2].record(copy_stream)
+        def upload_i16(i):
+            for k in stage16[i % NS]:
+                stage16[i % NS][k].copy_(host16[i % 2][k], non_blocking=True)
+
+        def zscored(i):
+            # normalised inputs go into the (now unused) fp32 staging buffers: no allocation in the loop
+            x = {k: zscore_on_device(v, out=stage[i % NS][k]) for k, v in stage16[i % NS].items()}
+            ev = torch.cuda.Event()
+            ev.record(main)  # the int16 buffer is free again once the z-score has read it
+            return x, ev
 
         def staged_loop(n):
-            for b in range(2):
-                consumed[b].record(main)
-            upload16(0)
-            pend = []
-            for i in range(n):
-                if i + 1 < n:
-                    upload16(i + 1)
-                main.wait_event(ready[i % 2])
-                x = {k: zscore_on_device(v) for k, v in stage16[i % 2].items()}
-                consumed[i % 2].record(main)
-                pend.append((model.predict_async(x), i, x))
-                if len(pend) > 1:
-                    q, j, _ = pend.pop(0)
-                    out_host[j % 2].copy_(q.wait(), non_blocking=True)
-            for q, j, _ in pend:
-                out_host[j % 2].copy_(q.wait(), non_blocking=True)
-            torch.cuda.synchronize()
+            pipelined(n, upload_i16, zscored)
 
-        staged_loop(2)
+        staged_loop(3)
         barrier()
         t0.record()
         staged_loop(args.steps)

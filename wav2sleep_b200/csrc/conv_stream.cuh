@@ -201,10 +201,10 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   if (tid == 32) {
     for (int s = 0; s < NR; ++s) {
       mbar_init(&raw_full[s], 1);
-      mbar_init(&raw_empty[s], kStreamTransformWarps);
+      mbar_init(&raw_empty[s], 1);  // one arrive per tile: the transform warps meet at a named barrier first
     }
     for (int s = 0; s < NA; ++s) {
-      mbar_init(&a_full[s], kStreamTransformWarps);
+      mbar_init(&a_full[s], 1);
       mbar_init(&a_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -780,10 +780,13 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
           chunk(id, i >= 0 && i < p.L_in);
         }
       }
+      // Hand-over: every transform thread publishes its shared-memory writes to the async proxy, the transform warps
+      // meet at a named barrier, and ONE thread signals the two mbarriers.  (One arrive per warp made 36 mbarrier
+      // events per tile; every such event wakes all parked waiters of the CTA - NANOSLEEP.SYNCS - for nothing.)
       fence_proxy_async_smem();
-      __syncwarp();
+      asm volatile("bar.sync 1, %0;" ::"n"(NTT) : "memory");
       if (tt == 0 && tile == tile_begin) dbg_ts(p, 5);
-      if (lane == 0) {
+      if (tt == 0) {
         mbar_arrive(&a_full[as]);
         mbar_arrive(&raw_empty[rs]);
       }

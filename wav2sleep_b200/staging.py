@@ -16,8 +16,9 @@ from .model import COLS_TO_SAMPLES_PER_EPOCH
 _DTYPES = {torch.float32: 0, torch.float16: 1, torch.int16: 2}
 
 
-def zscore_on_device(raw: Tensor, present: Tensor | None = None) -> Tensor:
-    """[B, T] raw nights on a CUDA device (fp32 / fp16 / int16) -> z-scored fp32 [B, T]; present[b] == False -> -inf row."""
+def zscore_on_device(raw: Tensor, present: Tensor | None = None, out: Tensor | None = None) -> Tensor:
+    """[B, T] raw nights on a CUDA device (fp32 / fp16 / int16) -> z-scored fp32 [B, T]; present[b] == False -> -inf row.
+    ``out``: optional preallocated fp32 [B, T] destination (steady-state loops re-use it instead of allocating)."""
     if raw.dim() != 2:
         raise ValueError(f"expected [B, T], got {tuple(raw.shape)}")
     if not raw.is_cuda:
@@ -27,7 +28,10 @@ def zscore_on_device(raw: Tensor, present: Tensor | None = None) -> Tensor:
     lib = _lib.load()
     raw = raw.contiguous()
     B, T = raw.shape
-    out = torch.empty(B, T, dtype=torch.float32, device=raw.device)
+    if out is None:
+        out = torch.empty(B, T, dtype=torch.float32, device=raw.device)
+    elif out.shape != (B, T) or out.dtype != torch.float32 or out.device != raw.device or not out.is_contiguous():
+        raise ValueError("out must be a contiguous fp32 [B, T] tensor on the device of raw")
     ws = torch.empty(B, 3, dtype=torch.float64, device=raw.device)
     pm = None
     if present is not None:
