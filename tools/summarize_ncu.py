@@ -86,6 +86,9 @@ if (g / "launches.csv").exists():
             if line.startswith("{") and "gpu_launches" in line:
                 d = json.loads(line)
                 last = d["gpu_launches"] // max(d["steps"], 1)
+    n_rows = sum(1 for l in (g / "launches.csv").read_text().splitlines() if l.startswith('"')) - 1
+    if not log.exists():
+        last = n_rows  # captured with --profile-from-start off around exactly one step
     summarize_launches(g / "launches.csv", OUT / f"{tag}_launch_list_bench_step.txt", last=last)
-for rep in sorted(g.glob("prof_*.ncu-rep")):
+for rep in sorted(g.glob(f"{tag}_prof_*.ncu-rep")):
     summarize_report(rep, OUT / f"{tag}_{rep.stem}.txt")

@@ -13,7 +13,8 @@ from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
 REPO_DIR = PKG_DIR.parent
-LIB_PATH = PKG_DIR / "libw2s_b200.so"
+# W2S_LIB_VARIANT=name selects libw2s_b200_<name>.so (A/B builds with other W2S_NVCC_FLAGS, tools/ab_build.sh)
+LIB_PATH = PKG_DIR / ("libw2s_b200" + ("_" + os.environ["W2S_LIB_VARIANT"] if os.environ.get("W2S_LIB_VARIANT") else "") + ".so")
 SOURCES = [PKG_DIR / "csrc" / "capi.cu"]
 HEADERS = sorted((PKG_DIR / "csrc").glob("*.cuh")) + [REPO_DIR / "include" / "w2s_b200.h"]
 

@@ -162,6 +162,11 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   constexpr uint32_t IDESC = umma_idesc_f16(128, COUT, false);
   constexpr bool REG_STATS = Cfg::REG_STATS;
   constexpr bool STAGED = Cfg::STAGED;
+#ifdef W2S_WARP_ARRIVE  // A/B build: one mbarrier arrive per transform warp instead of one per tile
+  constexpr int kTransformArrives = NTW;
+#else
+  constexpr int kTransformArrives = 1;
+#endif
 
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sRaw = smem;
@@ -201,10 +206,10 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   if (tid == 32) {
     for (int s = 0; s < NR; ++s) {
       mbar_init(&raw_full[s], 1);
-      mbar_init(&raw_empty[s], 1);  // one arrive per tile: the transform warps meet at a named barrier first
+      mbar_init(&raw_empty[s], kTransformArrives);
     }
     for (int s = 0; s < NA; ++s) {
-      mbar_init(&a_full[s], 1);
+      mbar_init(&a_full[s], kTransformArrives);
       mbar_init(&a_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -784,12 +789,19 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
       // meet at a named barrier, and ONE thread signals the two mbarriers.  (One arrive per warp made 36 mbarrier
       // events per tile; every such event wakes all parked waiters of the CTA - NANOSLEEP.SYNCS - for nothing.)
       fence_proxy_async_smem();
+#ifdef W2S_WARP_ARRIVE
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&a_full[as]);
+        mbar_arrive(&raw_empty[rs]);
+      }
+#else
       asm volatile("bar.sync 1, %0;" ::"n"(NTT) : "memory");
-      if (tt == 0 && tile == tile_begin) dbg_ts(p, 5);
       if (tt == 0) {
         mbar_arrive(&a_full[as]);
         mbar_arrive(&raw_empty[rs]);
       }
+#endif
       if (++rs == NR) {
         rs = 0;
         rph ^= 1;

@@ -216,17 +216,19 @@ class GeneralEngine:
         names = sorted(x.keys())  # token order of the mixer, wav2sleep.py:311
         zs, masks = [], []
         B = S = None
+        for n in names:
+            if n not in m.signal_encoders.signal_map:
+                raise KeyError(f"Signal {n!r} has no encoder (valid: {list(m.signal_encoders.signal_map)})")
+            t = x[n]
+            if not isinstance(t, Tensor) or t.dim() != 2:
+                raise ValueError(f"{n}: expected a [B, T] tensor")
+            if not t.is_cuda:
+                raise RuntimeError("wav2sleep_b200 runs on CUDA (sm_100a) only: move inputs with .to('cuda'); "
+                                   "there is no CPU fallback")
         dev = x[names[0]].device
         with torch.cuda.device(dev):
             for n in names:
-                if n not in m.signal_encoders.signal_map:
-                    raise KeyError(f"Signal {n!r} has no encoder (valid: {list(m.signal_encoders.signal_map)})")
                 t = x[n]
-                if not isinstance(t, Tensor) or t.dim() != 2:
-                    raise ValueError(f"{n}: expected a [B, T] tensor")
-                if not t.is_cuda:
-                    raise RuntimeError("wav2sleep_b200 runs on CUDA (sm_100a) only: move inputs with .to('cuda'); "
-                                       "there is no CPU fallback")
                 z, mask = self.encode(m.signal_encoders.get_encoder(n), t)
                 if B is None:
                     B, S = z.shape[0], z.shape[1]
