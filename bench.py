@@ -198,8 +198,9 @@ def run_cuda(args):
         return ms
 
     def run_steps(n, batches):
-        """n forward steps through the public throughput API (Wav2Sleep.predict_async: two batches in flight on
-        alternating stream sets; every step does all of its work, the last results are awaited before returning)."""
+        """n forward steps through the public throughput API (Wav2Sleep.predict_async: the forward runs on the engine's
+        own streams and the caller awaits results in order, up to two outstanding; every step does all of its work and
+        the last results are awaited before returning)."""
         pend, out = [], None
         for i in range(n):
             pend.append(model.predict_async(batches[i % 2]))
@@ -390,7 +391,7 @@ def run_cuda(args):
         "dtype": "f16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "nights_per_gpu_per_step": BATCH, "epochs_per_night": S_EPOCHS,
                    "parallelism": f"replicas x{world} (no data-path collective)",
-                   "api": "Wav2Sleep.predict_async, 2 batches in flight per GPU (W2S_LANES=1 / Wav2Sleep.predict: one)",
+                   "api": "Wav2Sleep.predict_async (engine-owned streams, results awaited in order)",
                    "l2": "inputs+activations > L2, 2 alternating batches"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e / args.steps},

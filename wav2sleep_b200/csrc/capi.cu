@@ -280,9 +280,15 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
     W2S_STREAM(16, 16, 2, PRO_NORM, false, 4, 2, 2, 18)
     W2S_STREAM(16, 16, 1, PRO_NORM_RES, true, 4, 3, 2, 14)
     W2S_STREAM(16, 32, 1, PRO_NORM_RES, true, 4, 3, 2, 10)
+#ifdef W2S_TUNE_MT32  // A/B build: larger tiles for the (now un-split) 32-channel kernels
+    W2S_STREAM(32, 32, 1, PRO_NORM, false, 6, 2, 2, 14)
+    W2S_STREAM(32, 32, 2, PRO_NORM, false, 3, 2, 2, 14)
+    W2S_STREAM(32, 32, 1, PRO_NORM_RES, true, 4, 2, 2, 10)
+#else
     W2S_STREAM(32, 32, 1, PRO_NORM, false, 4, 2, 2, 14)
     W2S_STREAM(32, 32, 2, PRO_NORM, false, 2, 2, 2, 14)
     W2S_STREAM(32, 32, 1, PRO_NORM_RES, true, 2, 3, 2, 10)
+#endif
     W2S_STREAM(32, 64, 1, PRO_NORM_RES, true, 2, 3, 2, 14)
     W2S_STREAM(64, 64, 1, PRO_NORM, false, 2, 2, 2, 14)
     W2S_STREAM(64, 64, 2, PRO_NORM, false, 1, 3, 2, 14)

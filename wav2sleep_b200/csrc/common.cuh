@@ -58,9 +58,15 @@ W2S_DEVINL bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) 
 W2S_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   uint32_t it = 0;
+#ifdef W2S_WAIT_PLAIN  // A/B build: plain try_wait polling (hardware-default suspend window), no NANOSLEEP
+  while (!mbar_try_wait(bar, parity)) {
+    if (++it > (1u << 28)) __trap();
+  }
+#else
   while (!mbar_try_wait_hint(bar, parity, 20000u)) {
     if (++it > (1u << 22)) __trap();
   }
+#endif
 }
 
 // One lane of a fully converged warp (warp-uniform code keeps operands in uniform registers, so single-thread

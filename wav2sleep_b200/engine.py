@@ -164,10 +164,12 @@ class ForwardEngine:
         # fill and tail of one encoder are covered by the other encoders' work.  W2S_ENC_STREAMS=0 serialises them.
         import os
         self.enc_streams = os.environ.get("W2S_ENC_STREAMS", "1") != "0"
-        # Asynchronous forwards (forward_async / predict_async) alternate between n_lanes independent sets of streams and
-        # workspaces, so that consecutive batches overlap: the latency-bound tail of one batch (epoch mixer, sequence
-        # mixer: few CTAs, ~0.8 ms) runs under the encoders of the next one.
-        self.n_lanes = int(os.environ.get("W2S_LANES", "2"))
+        # Asynchronous forwards (forward_async / predict_async) run on the engine's own streams (the current stream only
+        # records the fork event), alternating between n_lanes independent sets of streams and workspaces.  One lane is
+        # the default: with two, consecutive batches could overlap, but measured on B200 it buys nothing (6.91 vs 6.89 ms
+        # per step) - every kernel of the forward claims 150-230 KB of shared memory, so the mixer tail of one batch and
+        # the encoder kernels of the next cannot be co-resident on an SM - and it doubles the workspaces (EOG: 70 GB).
+        self.n_lanes = int(os.environ.get("W2S_LANES", "1"))
         self._lane = 0
 
     # ------------------------------------------------------------------ weights
