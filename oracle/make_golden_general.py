@@ -103,9 +103,35 @@ def digest(sd):
     return h.hexdigest()
 
 
+PPG_SEED = 7
+
+
+def build_ppgnet(cls):
+    torch.manual_seed(PPG_SEED)
+    return cls(n_classes=4, feature_dim=128).eval()
+
+
+def ppg_input(seed=42):
+    return torch.randn(1, 1228800, generator=torch.Generator().manual_seed(seed))
+
+
 def main():
     ref = import_reference()
     from wav2sleep_b200 import model as mirror
+    # SleepPPGNet baseline (models/ppgnet.py): one 10-h night
+    import wav2sleep.models.ppgnet as ref_ppg
+    from wav2sleep_b200 import ppgnet as mirror_ppg
+    rm, mm = build_ppgnet(ref_ppg.SleepPPGNet), build_ppgnet(mirror_ppg.SleepPPGNet)
+    assert list(rm.state_dict().keys()) == list(mm.state_dict().keys())
+    assert all(torch.equal(a, b) for a, b in zip(rm.state_dict().values(), mm.state_dict().values()))
+    perturb(rm, PPG_SEED)
+    perturb(mm, PPG_SEED)
+    assert digest(rm.state_dict()) == digest(mm.state_dict())
+    with torch.no_grad():
+        logits = rm(ppg_input())
+    np.savez_compressed(OUT / "general_ppgnet.npz", logits=logits.numpy().astype(np.float32), sha=np.array([digest(rm.state_dict())]),
+                        n_keys=np.array([len(rm.state_dict())]))
+    print(f"general_ppgnet: {len(rm.state_dict())} tensors, logits {tuple(logits.shape)} abs-max {logits.abs().max():.3f}")
     for name, case in CASES.items():
         rm, mm = build(ref, case), build(mirror, case)
         sd_r, sd_m = rm.state_dict(), mm.state_dict()

@@ -28,6 +28,33 @@ def test_mirror_reproduces_reference_parameters(name):
     assert G.digest(model.state_dict()) == str(gold["sha"][0])
 
 
+def test_ppgnet_mirror_reproduces_reference_parameters():
+    from wav2sleep_b200.ppgnet import SleepPPGNet
+    model = G.build_ppgnet(SleepPPGNet)
+    G.perturb(model, G.PPG_SEED)
+    gold = np.load(GOLDEN / "general_ppgnet.npz")
+    assert len(model.state_dict()) == int(gold["n_keys"][0])
+    assert G.digest(model.state_dict()) == str(gold["sha"][0])
+    with pytest.raises(ValueError):  # models/ppgnet.py:50-51
+        model(torch.zeros(1, 1000))
+
+
+@pytest.mark.gpu
+def test_ppgnet_matches_reference_logits(cuda_device):
+    """SleepPPGNet baseline (models/ppgnet.py) on the general CUDA path: one 10-h night vs the reference."""
+    from wav2sleep_b200.ppgnet import SleepPPGNet
+    model = G.build_ppgnet(SleepPPGNet)
+    G.perturb(model, G.PPG_SEED)
+    model = model.to(cuda_device).eval()
+    gold = np.load(GOLDEN / "general_ppgnet.npz")
+    with torch.no_grad():
+        out = model(G.ppg_input().to(cuda_device))
+    ref = torch.from_numpy(gold["logits"])
+    err = (out.float().cpu() - ref).abs().max().item()
+    print(f"SleepPPGNet: max-abs logit error vs the reference {err:.3e}")
+    assert out.shape == ref.shape and err < TOL
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", list(G.CASES))
 def test_general_path_matches_reference_logits(cuda_device, name):

@@ -24,6 +24,7 @@ _TARGETS = {
     "wav2sleep.models.wav2sleep.SignalEncoders": _model.SignalEncoders,
     "wav2sleep.models.wav2sleep.MultiModalAttentionEmbedder": _model.MultiModalAttentionEmbedder,
     "wav2sleep.models.wav2sleep.SequenceCNN": _model.SequenceCNN,
+    "wav2sleep.models.ppgnet.SleepPPGNet": "wav2sleep_b200.ppgnet.SleepPPGNet",  # scripts/config/model/ppgnet.yaml
 }
 
 
@@ -35,6 +36,9 @@ def instantiate(cfg):
             return built
         target = cfg["_target_"]
         cls = _TARGETS.get(target)
+        if isinstance(cls, str):
+            mod, name = cls.rsplit(".", 1)
+            cls = getattr(importlib.import_module(mod), name)
         if cls is None:
             if not target.startswith("wav2sleep_b200."):
                 raise ValueError(f"_target_ {target!r} is not part of the wav2sleep model tree")

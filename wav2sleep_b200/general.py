@@ -119,6 +119,28 @@ class GeneralEngine:
                       pad_left=layer.padding, mask=mask, raw=raw)
         return self.norm_act(y, layer, layer.activation_name, mask=mask)
 
+    def conv_block(self, a: Tensor, blk, mask=None, raw=0) -> Tensor:
+        """ConvBlock1D.forward (blocks.py:57-71): act(conv3(conv2(conv1(x))) [+ downsample(x)])."""
+        y = self.conv_layer(a, blk.conv1, mask, raw)
+        y = self.conv_layer(y, blk.conv2, mask)
+        y = self.conv_layer(y, blk.conv3, mask)
+        if not blk.use_residual:
+            return self.affine_act(y, blk.activation_name, mask=mask)
+        r = self.conv(a, blk.downsample.weight, None, (a.shape[1] - 1) // 2 + 1, stride=2, mask=mask, raw=raw)
+        if r.shape[1] != y.shape[1]:
+            raise ValueError(f"residual length {r.shape[1]} != conv path length {y.shape[1]}")
+        return self.affine_act(y, blk.activation_name, res=r, mask=mask)
+
+    def dilated_blocks(self, x_BSF: Tensor, blocks) -> Tensor:
+        """Sequential(DilatedConvBlock) in eval mode (blocks.py:115-126)."""
+        cur = x_BSF
+        for blk in blocks:
+            blk_in = cur
+            for layer in blk.conv_layers:
+                cur = self.conv_layer(cur, layer)
+            cur = self.affine_act(cur, blk.activation_name, res=blk_in)
+        return cur
+
     # ------------------------------------------------------------------ stages
     def encode(self, enc, x_BT: Tensor):
         """SignalEncoder.forward (wav2sleep.py:235-267) -> (z [B, S, F], mask [B] uint8)."""
@@ -137,16 +159,7 @@ class GeneralEngine:
             m = mask
         raw = 1
         for blk in enc.cnn:
-            y = self.conv_layer(a, blk.conv1, m, raw)
-            y = self.conv_layer(y, blk.conv2, m)
-            y = self.conv_layer(y, blk.conv3, m)
-            if blk.use_residual:
-                r = self.conv(a, blk.downsample.weight, None, (a.shape[1] - 1) // 2 + 1, stride=2, mask=m, raw=raw)
-                if r.shape[1] != y.shape[1]:
-                    raise ValueError(f"residual length {r.shape[1]} != conv path length {y.shape[1]}")
-                a = self.affine_act(y, blk.activation_name, res=r, mask=m)
-            else:
-                a = self.affine_act(y, blk.activation_name, mask=m)
+            a = self.conv_block(a, blk, m, raw)
             raw = 0
         Bp, L4, Cc = a.shape
         if L4 % 4 or (Bp * L4) // 4 != B * S:
@@ -199,13 +212,7 @@ class GeneralEngine:
 
     def sequence_mixer(self, x_BSF: Tensor) -> Tensor:
         """SequenceCNN.forward (wav2sleep.py:379-390) + DilatedConvBlock.forward (blocks.py:115-126), eval mode."""
-        cur = x_BSF
-        for blk in self.model.sequence_mixer.dilated_convs:
-            blk_in = cur
-            for layer in blk.conv_layers:
-                cur = self.conv_layer(cur, layer)
-            cur = self.affine_act(cur, blk.activation_name, res=blk_in)
-        return cur
+        return self.dilated_blocks(x_BSF, self.model.sequence_mixer.dilated_convs)
 
     # ------------------------------------------------------------------ model
     @torch.no_grad()
