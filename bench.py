@@ -11,11 +11,20 @@ night, N(0,1) fp32), random-init weights.  Recordings are independent, so N GPUs
 with no data-path collective ("scaling": "weak").
 
 One "step" = one forward pass (signal encoders -> epoch mixer -> sequence mixer -> classifier -> argmax) over one
-batch.  `value` times K steps with inputs resident in HBM (CUDA events, barrier + synchronize on both sides, max
-over ranks).  `e2e` times the same K steps through the public API with HOST (pinned) inputs: every step copies its
-196.6 MB of inputs host->device and reads the int64 predictions back; copies are double-buffered on a side stream
-but all inside the timed region.  Inputs (196.6 MB/step) and activations (GBs) exceed the 126 MB L2, so no
-explicit L2 flush is needed ("l2": "inputs+activations > L2").
+batch, through ``Wav2Sleep.predict_async`` (the forward runs on streams owned by the engine; results are awaited in
+order).  `value` times K steps with inputs resident in HBM (CUDA events, barrier + synchronize on both sides, max
+over ranks).  `e2e` times the same K steps with HOST (pinned) inputs: every step copies its 196.6 MB of inputs
+host->device (copy stream, two batches ahead) and reads the int64 predictions back, all inside the timed region.
+Inputs (196.6 MB/step) and activations (GBs) exceed the 126 MB L2, so no explicit L2 flush is needed
+("l2": "inputs+activations > L2").
+
+Secondary objects on the same JSON line, each with its own clock samples:
+  train           BASELINE configs[3]: cardio training step (polarity flip + config masker + forward + CE + loss-scaled
+                  backward + bucketed all-reduce + fused clip/AdamW), 16 nights per GPU; per-rank times and, for N > 1,
+                  the same step with identical masks on every rank (mask stragglers vs communication)
+  train_ecg_only  BASELINE configs[4]: the same step at batch 32 with PPG / ABD / THX missing for every night
+  eog             BASELINE configs[1]: EOG model, 16 x 14-h nights, 1 GPU (N = 1 only)
+  e2e_staged      the e2e loop with int16 transport + on-device z-score
 """
 from __future__ import annotations
 

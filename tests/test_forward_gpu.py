@@ -184,7 +184,10 @@ def test_predict_is_argmax(cuda_device):
     logits = model(x)
     pred = model.predict(x)
     assert pred.dtype == torch.int64 and pred.shape == (2, 6)
-    assert (pred == logits.argmax(-1)).float().mean().item() > 0.9  # two runs differ only by atomic order
+    # two runs of the same kernels: statistics go through fp64 atomics, so the logits are reproducible and the argmax
+    # kernel must agree with torch.argmax on them (first maximum wins in both)
+    assert (logits - model(x)).abs().max().item() < 1e-5
+    assert torch.equal(pred, logits.argmax(-1))
 
 
 def test_errors_on_gpu(cuda_device):
@@ -216,8 +219,9 @@ def test_stage_outputs_match_oracle(cuda_device):
         assert e < 2e-2 * zref[live].abs().max().item()  # features are O(2-5): relative bound
         assert buf["mask"][n].cpu().bool().tolist() == (~live).tolist()
     e = (buf["mix"].float().cpu() - inter["mixer"]).abs().max().item()
-    print("mixer max-abs", e)
-    assert e < 3e-2
+    scale = inter["mixer"].abs().max().item()
+    print("mixer max-abs", e, "of max", scale)
+    assert e < 5e-3 * scale  # CLS features are O(3-4): fp16 inputs / operands, fp32 residual stream
 
 
 def test_randomised_shapes_subsets_and_masks(cuda_device):
@@ -249,6 +253,24 @@ def test_randomised_shapes_subsets_and_masks(cuda_device):
         worst = max(worst, err)
         assert err < TOL, (trial, B, S, present, err)
     print(f"randomised sweep: worst max-abs {worst:.3e}")
+
+
+def test_fp32_check_mode_on_full_nights(cuda_device):
+    """The fp32 gate (1e-4) where it is hardest: whole-night InstanceNorm statistics over 1.2 M (cardio) and 6.9 M (EOG)
+    samples per channel (reference models/wav2sleep.py:256-261 non-causal path)."""
+    from wav2sleep_b200.check import forward_fp32
+    for smap, ncls, S, cfg in ((CARDIO, 4, 1200, oracle.cardio_config()), (EOG, 5, 1680, oracle.eog_config())):
+        model = build_default(smap, ncls, seed=0)
+        x = make_inputs(smap, 1, S, seed=42)
+        ref = oracle.forward(x, model.state_dict(), cfg)
+        model = model.to(cuda_device).eval()
+        out = forward_fp32(model, {k: v.to(cuda_device) for k, v in x.items()}).float().cpu()
+        err = (out - ref).abs().max().item()
+        agree = (out.argmax(-1) == ref.argmax(-1)).float().mean().item()
+        print(f"fp32 check mode, full night {list(smap)}: max-abs {err:.3e} argmax agreement {agree:.5f}")
+        assert err < 1e-4 and agree >= 0.999
+        del model, out
+        torch.cuda.empty_cache()
 
 
 def test_predict_async_lanes_match_predict(cuda_device):

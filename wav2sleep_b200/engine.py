@@ -170,6 +170,7 @@ class ForwardEngine:
         # per step) - every kernel of the forward claims 150-230 KB of shared memory, so the mixer tail of one batch and
         # the encoder kernels of the next cannot be co-resident on an SM - and it doubles the workspaces (EOG: 70 GB).
         self.n_lanes = int(os.environ.get("W2S_LANES", "1"))
+        self.seq_groups = int(os.environ.get("W2S_SEQ_GROUPS", "4"))  # night groups of the sequence mixer (see _seq_head)
         self._lane = 0
 
     # ------------------------------------------------------------------ weights
@@ -256,7 +257,10 @@ class ForwardEngine:
         for n in names:
             pe = self.enc[self.model.signal_encoders.signal_map[n]]
             sizes[n] = lib.w2s_encoder_workspace_bytes(C.byref(pe.desc), B, S * pe.samples_per_epoch, 0)
-        seq_ws = lib.w2s_seqmixer_workspace_bytes(C.byref(self.seq_desc), B, S, 0)
+        G = max(1, min(self.seq_groups, B))
+        per = (B + G - 1) // G
+        seq_ws = max(lib.w2s_seqmixer_workspace_bytes(C.byref(self.seq_desc), B, S, 0),
+                     G * lib.w2s_seqmixer_workspace_bytes(C.byref(self.seq_desc), per, S, 0))
         concurrent = (self.enc_streams and len(names) > 1) or lane >= 0
         if concurrent:  # encoders run side by side: one workspace each
             enc_ws = {n: torch.empty(sizes[n], dtype=torch.uint8, device=device) for n in names}
@@ -267,6 +271,7 @@ class ForwardEngine:
             "enc_ws": enc_ws,
             "streams": [torch.cuda.Stream(device=device) for _ in names] if concurrent else None,
             "tail": torch.cuda.Stream(device=device) if lane >= 0 else None,   # mixer + sequence mixer + head of a lane
+            "seq_streams": [torch.cuda.Stream(device=device) for _ in range(G)] if (G > 1 and self.enc_streams) else None,
             "tail_done": None,
             "seq_ws": torch.empty(seq_ws, dtype=torch.uint8, device=device),
             "z": {n: torch.empty(B, S, 128, dtype=torch.float16, device=device) for n in names},
@@ -302,6 +307,35 @@ class ForwardEngine:
             raise ValueError("empty batch")
         return B, S, device
 
+    def _seq_head(self, buf, B: int, S: int, logits: Tensor, stream: "torch.cuda.Stream") -> None:
+        """Sequence mixer + classifier on `stream`, the nights split into groups that run on side streams: each of the 12
+        dependent layer launches is 10 one-tile CTAs per night (160 for 16 nights = two waves on 148 SMs, the second one
+        12 CTAs wide); independent groups make the schedule work-conserving - a group's next layer starts as soon as
+        its own CTAs are done."""
+        lib = self.lib
+        G = min(self.seq_groups, B)
+        if G <= 1 or buf.get("seq_streams") is None:
+            _lib.check(lib.w2s_seqmixer_head_fwd(C.byref(self.seq_desc), buf["mix"].data_ptr(), B, S, buf["seq_ws"].data_ptr(),
+                                                 buf["seq_ws"].numel(), 0, None, logits.data_ptr(), stream.cuda_stream))
+            return
+        fork = torch.cuda.Event()
+        fork.record(stream)
+        per = (B + G - 1) // G
+        ws_per = lib.w2s_seqmixer_workspace_bytes(C.byref(self.seq_desc), per, S, 0)
+        ncls = self.model.num_classes
+        for g in range(G):
+            b0, nb = g * per, min(per, B - g * per)
+            if nb <= 0:
+                break
+            st = buf["seq_streams"][g]
+            st.wait_event(fork)
+            _lib.check(lib.w2s_seqmixer_head_fwd(C.byref(self.seq_desc), buf["mix"].data_ptr() + b0 * S * 128 * 2, nb, S,
+                                                 buf["seq_ws"].data_ptr() + g * ws_per, ws_per, 0, None,
+                                                 logits.data_ptr() + b0 * S * ncls * 4, st.cuda_stream))
+            join = torch.cuda.Event()
+            join.record(st)
+            stream.wait_event(join)
+
     def _launch(self, buf, xs: dict[str, Tensor], names, B: int, S: int, logits: Tensor) -> None:
         """Enqueue the three stage calls on the current stream (also what gets captured into a CUDA graph)."""
         lib, st = self.lib, _stream()
@@ -329,8 +363,7 @@ class ForwardEngine:
         zs = (C.c_void_p * len(names))(*[buf["z"][n].data_ptr() for n in names])
         ms = (C.c_void_p * len(names))(*[buf["mask"][n].data_ptr() for n in names])
         _lib.check(lib.w2s_epoch_mixer_fwd(C.byref(self.mixer_desc), zs, ms, len(names), B, S, buf["mix"].data_ptr(), st))
-        _lib.check(lib.w2s_seqmixer_head_fwd(C.byref(self.seq_desc), buf["mix"].data_ptr(), B, S, buf["seq_ws"].data_ptr(),
-                                             buf["seq_ws"].numel(), 0, None, logits.data_ptr(), st))
+        self._seq_head(buf, B, S, logits, torch.cuda.current_stream())
 
     def _launch_async(self, buf, xs: dict[str, Tensor], names, B: int, S: int, argmax: bool) -> Pending:
         """The whole forward on the lane's own streams: nothing is enqueued on the current stream except the fork event."""
@@ -359,9 +392,7 @@ class ForwardEngine:
             ms = (C.c_void_p * len(names))(*[buf["mask"][n].data_ptr() for n in names])
             ts = tail.cuda_stream
             _lib.check(lib.w2s_epoch_mixer_fwd(C.byref(self.mixer_desc), zs, ms, len(names), B, S, buf["mix"].data_ptr(), ts))
-            _lib.check(lib.w2s_seqmixer_head_fwd(C.byref(self.seq_desc), buf["mix"].data_ptr(), B, S,
-                                                 buf["seq_ws"].data_ptr(), buf["seq_ws"].numel(), 0, None,
-                                                 logits.data_ptr(), ts))
+            self._seq_head(buf, B, S, logits, tail)
             out = logits
             if argmax:
                 out = torch.empty(B, S, dtype=torch.int64, device=logits.device)
