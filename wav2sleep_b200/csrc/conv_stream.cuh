@@ -438,8 +438,11 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
           }
         }
       };
-      // TMEM columns [col, col + SEG) of this warp's 32 lanes -> staging (lane = row)
+      // TMEM columns [col, col + SEG) of this warp's 32 lanes -> staging (lane = row).  All loads of the segment are
+      // issued before the single tcgen05.wait::ld: the round trip of a TMEM load while the MMA unit is accumulating
+      // into the other stage is several hundred cycles, and it used to be paid once per 16 columns.
       auto stage_in = [&](uint32_t taddr) {
+#ifdef W2S_EPI_LD16  // A/B build: one wait per 16 columns (round-2 first version)
 #pragma unroll
         for (int q = 0; q < SEG / 16; ++q) {
           float v[16];
@@ -449,6 +452,20 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
           sts128(stg + lane * SEGB + (((2 * q) ^ swz(lane)) * 16), lo);
           sts128(stg + lane * SEGB + (((2 * q + 1) ^ swz(lane)) * 16), hi);
         }
+#else
+        uint32_t r[SEG];
+#pragma unroll
+        for (int q = 0; q < SEG / 32; ++q) tmem_ld32(taddr + q * 32, r + q * 32);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < SEG / 8; ++c) {
+          const uint4 w = make_uint4(pack_h2(__uint_as_float(r[8 * c]), __uint_as_float(r[8 * c + 1])),
+                                     pack_h2(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3])),
+                                     pack_h2(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5])),
+                                     pack_h2(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7])));
+          sts128(stg + lane * SEGB + ((c ^ swz(lane)) * 16), w);
+        }
+#endif
       };
       TilePos tp = pos0;
       for (int tile = tile_begin; tile < tile_end; ++tile, advance(tp)) {
