@@ -277,6 +277,62 @@ def test_seq_conv_layer(cuda_device, dil, S, res):
         assert (logits - (ref @ hw.t() + hb)).abs().max().item() < 5e-3
 
 
+@pytest.mark.parametrize("B,S,n_blocks,n_dil,ncls", [(1, 1, 2, 6, 4), (3, 40, 2, 6, 5), (2, 129, 1, 2, 4), (2, 300, 2, 6, 4),
+                                                     (3, 1200, 2, 6, 4), (2, 1680, 2, 6, 5), (1, 2048, 2, 3, 4),
+                                                     (1, 2100, 2, 6, 4)])
+def test_seqmixer_stage(cuda_device, B, S, n_blocks, n_dil, ncls):
+    """w2s_seqmixer_head_fwd (SequenceCNN + classifier, models/wav2sleep.py:379-390, 66) against fp32 torch on the
+    fp16-rounded operands and inter-layer activations.  S <= 2048 runs the cluster-per-night kernel (seq_mixer.cuh: 1 CTA
+    for S <= 128 ... 8 CTAs x 256 rows), S = 2100 the layer-per-launch kernels; both must give the same numbers."""
+    lib = _lib.load()
+    torch.manual_seed(S + n_dil)
+    dev = cuda_device
+    x = torch.randn(B, S, 128, device=dev).half()
+    d = _lib.SeqDesc()
+    d.n_blocks, d.n_dilations, d.kernel_size, d.feature_dim, d.n_classes, d.ln_eps = n_blocks, n_dil, 7, 128, ncls, 1e-5
+    keep, ws, gs, bs = [], [], [], []
+    for bl in range(n_blocks):
+        for k in range(n_dil):
+            w = torch.randn(128, 128, 7, device=dev) / (7 * 128) ** 0.5 * 1.5
+            g, b = torch.randn(128, device=dev) * 0.2 + 1, torch.randn(128, device=dev) * 0.1
+            pw = G.pack_conv(w)
+            keep += [pw, g, b]
+            ws.append(w), gs.append(g), bs.append(b)
+            d.w[bl][k], d.ln_w[bl][k], d.ln_b[bl][k] = pw.data_ptr(), g.data_ptr(), b.data_ptr()
+    hw, hb = torch.randn(ncls, 128, device=dev) / 11, torch.randn(ncls, device=dev)
+    d.head_w, d.head_b = hw.data_ptr(), hb.data_ptr()
+    nbytes = lib.w2s_seqmixer_workspace_bytes(C.byref(d), B, S, 0)
+    work = torch.full((nbytes,), 0x7F, dtype=torch.uint8, device=dev)  # garbage (NaN patterns): padding must be written
+    feat = torch.full((B, S, 128), float("nan"), dtype=torch.float16, device=dev)
+    logits = torch.full((B, S, ncls), float("nan"), device=dev)
+    for rep in range(2):  # second call re-uses the dirty workspace
+        _lib.check(lib.w2s_seqmixer_head_fwd(C.byref(d), x.data_ptr(), B, S, work.data_ptr(), nbytes, 0, feat.data_ptr(),
+                                             logits.data_ptr(), G.stream()))
+    torch.cuda.synchronize()
+    cur = x.float()
+    i = 0
+    for bl in range(n_blocks):
+        blk_in = cur
+        for k in range(n_dil):
+            c = G.conv_ref(cur, ws[i], stride=1, pad=3 * 2 ** k, dil=2 ** k)
+            mu = c.mean(-1, keepdim=True)
+            var = (c - mu).pow(2).mean(-1, keepdim=True)
+            a = G.gelu((c - mu) / torch.sqrt(var + 1e-5) * gs[i] + bs[i])
+            if k == n_dil - 1:
+                a = G.gelu(a + blk_in)
+            last = (bl == n_blocks - 1 and k == n_dil - 1)
+            final = a
+            cur = a if last else a.half().float()
+            i += 1
+    ref_logits = final @ hw.t() + hb
+    assert torch.isfinite(logits).all() and torch.isfinite(feat.float()).all()
+    e_feat = (feat.float() - final).abs().max().item()
+    e_log = (logits - ref_logits).abs().max().item()
+    print(f"seq mixer B={B} S={S}: feature max-abs {e_feat:.3e}, logits max-abs {e_log:.3e}")
+    # fp16 re-rounding of 1-ulp-different intermediates over n_blocks * n_dil layers
+    assert e_feat < 1.5e-2 and e_log < 1.5e-2
+
+
 def test_pack_batch_matches_single_packs(cuda_device):
     """w2s_pack_batch (strided sources, one launch) against w2s_pack_conv_weight / w2s_pack_linear_frag, incl. the
     flipped + transposed view used for data-gradient weights and the taps-major view of a Linear."""

@@ -237,7 +237,7 @@ def _main():
             Policy(wide_blocks=10, split_max=128, gelu="erf", mixer="f32", seq="f32", lin="f32", z_store="f32"),
         ]
         if len(sys.argv) > 3:
-            pols = [eval(sys.argv[3])]
+            pols = [eval(a) for a in sys.argv[3:]]  # any number of Policy(...) expressions
     model = build_default(smap, ncls, seed=0)
     sd = {k: v.detach().float() for k, v in model.state_dict().items()}
     x = make_inputs(smap, nights, S, seed=42)

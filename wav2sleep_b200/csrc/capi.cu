@@ -21,6 +21,7 @@
 #include "check_fp32.cuh"
 #include "general.cuh"
 #include "staging.cuh"
+#include "seq_mixer.cuh"
 
 using namespace w2s;
 
@@ -766,7 +767,19 @@ int w2s_epoch_mixer_fwd(const w2s_mixer_desc* d, const void* const* z, const uin
 size_t w2s_seqmixer_workspace_bytes(const w2s_seq_desc* d, int B, int S, int keep) {
   if (d == nullptr || B <= 0 || S <= 0) return 0;
   const size_t t = align_up((size_t)B * S * 128 * sizeof(__half), 256);
-  return keep ? t * ((size_t)d->n_blocks * d->n_dilations + 1) : t * 4;
+  if (keep) return t * ((size_t)d->n_blocks * d->n_dilations + 1);
+  const size_t fused = seq_fused_workspace_bytes(B, S, d->n_dilations);  // 0 when the shape is not served by it
+  return t * 4 > fused ? t * 4 : fused;
+}
+
+// W2S_SEQ_FUSED=0 in the environment selects the layer-per-launch sequence mixer (A/B measurements).
+static bool seq_fused_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("W2S_SEQ_FUSED");
+    on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
 }
 
 int w2s_seqmixer_head_fwd(const w2s_seq_desc* d, const void* x, int B, int S, void* workspace, size_t ws_bytes,
@@ -779,6 +792,29 @@ int w2s_seqmixer_head_fwd(const w2s_seq_desc* d, const void* x, int B, int S, vo
   if (ws_bytes < w2s_seqmixer_workspace_bytes(d, B, S, keep)) return fail("seqmixer: workspace too small");
   const size_t t = align_up((size_t)B * S * 128 * sizeof(__half), 256);
   uint8_t* ws = (uint8_t*)workspace;
+  SeqGeom geom;
+  static const int nc_force = getenv("W2S_SEQ_NC") ? atoi(getenv("W2S_SEQ_NC")) : 0;  // A/B: pin the cluster size
+  if (!keep && seq_fused_enabled() && d->n_blocks * d->n_dilations <= kSeqMaxLayers &&
+      seq_fused_geometry(B, S, d->n_dilations, geom, nc_force)) {
+    // inference: all layers of a night inside one thread-block cluster (seq_mixer.cuh)
+    SeqArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int bl = 0; bl < d->n_blocks; ++bl)
+      for (int k = 0; k < d->n_dilations; ++k) {
+        const int l = bl * d->n_dilations + k;
+        a.w[l] = (const act_t*)d->w[bl][k];
+        a.ln_w[l] = d->ln_w[bl][k];
+        a.ln_b[l] = d->ln_b[bl][k];
+      }
+    a.x = (const act_t*)x; a.buf = (act_t*)ws; a.feat_out = (act_t*)feat_out;
+    a.head_w = d->head_w; a.head_b = d->head_b; a.logits = logits; a.n_classes = d->n_classes;
+    a.n_blocks = d->n_blocks; a.n_dil = d->n_dilations; a.S = S; a.ln_eps = d->ln_eps;
+    const double rows = (double)B * S, layers = (double)d->n_blocks * d->n_dilations;
+    LaunchScope scope((cudaStream_t)stream, "seq_mixer fused", rows * 128 * 2.0 * 2.0 * layers,
+                      2.0 * 7 * 128 * 128 * rows * layers);
+    cudaError_t e = launch_seq_mixer(a, geom, B, (cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "seq_mixer launch");
+  }
   // keep = 0: slots 0/1 ping-pong inside a block, slots 2/3 alternate as block outputs (a block's input is the
   // previous block's output or x, so it is never overwritten while it is still the residual source).
   int next = 0;

@@ -170,7 +170,7 @@ class ForwardEngine:
         # per step) - every kernel of the forward claims 150-230 KB of shared memory, so the mixer tail of one batch and
         # the encoder kernels of the next cannot be co-resident on an SM - and it doubles the workspaces (EOG: 70 GB).
         self.n_lanes = int(os.environ.get("W2S_LANES", "1"))
-        self.seq_groups = int(os.environ.get("W2S_SEQ_GROUPS", "4"))  # night groups of the sequence mixer (see _seq_head)
+        self.seq_groups = int(os.environ.get("W2S_SEQ_GROUPS", "1"))  # night groups of the sequence mixer (see _seq_head)
         self._lane = 0
 
     # ------------------------------------------------------------------ weights
