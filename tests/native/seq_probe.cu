@@ -42,8 +42,8 @@ int main(int argc, char** argv) {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  const int dbgs[] = {0, 1, 2, 4, 8, 7, 15, 16};
-  for (int B : {1, 8, 16, 32}) {
+  const int dbgs[] = {0, 4, 7, 256, 4 + 256, 4 + 256 + 224};
+  for (int B : {16}) {
     SeqGeom g;
     if (!seq_fused_geometry(B, S, n_dil, g, nc_force)) return 1;
     printf("B=%d S=%d nc=%d rpc=%d ntiles=%d AR=%d stages=%d smem=%zu active clusters=%d\n", B, S, g.nc, g.rpc, g.ntiles, g.AR,

@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_mixer_kernel(const SeqArgs
       const int d = 1 << k;
       const uint8_t* src = reinterpret_cast<const uint8_t*>(in_buf(k));
       const uint32_t nld = (uint32_t)(nrows + 6 * d) * 16;
-      fence_proxy_async_all();
+      if (!(p.dbg & 128)) fence_proxy_async_all();
       if (stage_loops && elect_one()) {
         for (int h = 0; h < 2; ++h) {
           if (p.dbg & 8) {
@@ -345,7 +345,8 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_mixer_kernel(const SeqArgs
             for (int q = 0; q < 4; ++q) {
               const float2 a = make_float2(__uint_as_float(r[c8 * 8 + 2 * q]), __uint_as_float(r[c8 * 8 + 2 * q + 1]));
               const float2 xh = __ffma2_rn(a, rs2, nm2);
-              v[q] = gelu_acc2(__ffma2_rn(xh, ww[q], bb[q]));
+              v[q] = __ffma2_rn(xh, ww[q], bb[q]);
+              if (!(p.dbg & 256)) v[q] = gelu_acc2(v[q]);
             }
             if (last_of_block) {  // + block input (DilatedConvBlock.forward: act(out + x)), same row, read by its writer
               const uint4 rz = __ldcg(reinterpret_cast<const uint4*>(resb + ((size_t)ch * p.SP + grow) * 16));
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_mixer_kernel(const SeqArgs
             const uint4 o = make_uint4(pack_h2(v[0].x, v[0].y), pack_h2(v[1].x, v[1].y), pack_h2(v[2].x, v[2].y),
                                        pack_h2(v[3].x, v[3].y));
             if (!last) {
-              *reinterpret_cast<uint4*>(outb + ((size_t)ch * p.SP + grow) * 16) = o;
+              if (!(p.dbg & 32)) *reinterpret_cast<uint4*>(outb + ((size_t)ch * p.SP + grow) * 16) = o;
             } else {
               if (p.feat_out != nullptr)
                 *(reinterpret_cast<uint4*>(p.feat_out + ((size_t)b * p.S + r0 + row) * 128) + ch) = o;
@@ -398,7 +399,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_mixer_kernel(const SeqArgs
         }
       }
       tc_fence_before_sync();
-      fence_proxy_async_all();  // this layer's rows are read by bulk copies of the whole cluster after the barrier
+      if (!(p.dbg & 64)) fence_proxy_async_all();  // this layer's rows are read by bulk copies of the whole cluster after the barrier
       __syncwarp();
       cluster_arrive();
       cluster_wait();
