@@ -101,3 +101,46 @@ def test_grad_reducer_buckets_gloo_world2():
         assert torch.equal(after_tail[6:], base[6:] * 3)            # tail bucket summed over ranks (1x + 2x)
         assert torch.equal(after_tail[:6], base[:6] * (rank + 1))   # encoder bucket still local
         assert torch.equal(final, base * 3)
+
+
+def test_validation_and_test_steps_re_evaluate_signal_subsets():
+    """reference trainer/main.py:188-226: unified models are re-evaluated on ECG, ECG+THX, PPG, PPG+THX per dataset;
+    host-side control flow only, so a stub model that records the signal sets it was called with is enough."""
+    from wav2sleep_b200.trainer import SleepLightningModule
+
+    class Stub(torch.nn.Module):
+        valid_signals = ["ABD", "THX", "ECG", "PPG"]
+
+        def __init__(self):
+            super().__init__()
+            self.signal_encoders = [0, 1, 2, 3]  # len() > 1 -> unified
+            self.calls = []
+
+        def forward(self, x):
+            self.calls.append(tuple(x.keys()))
+            B, T = next(iter(x.values())).shape
+            return torch.zeros(B, T // 4, 4)
+
+        def predict(self, x):
+            return self.forward(x).argmax(-1)
+
+    stub = Stub()
+    pl = SleepLightningModule(stub, num_classes=4, masker=None)
+    pl.val_dataset_map = {0: "all", 1: "shhs", 2: "mesa", 3: "cfs"}
+    pl.test_dataset_map = {0: "shhs", 1: "mesa"}
+    batch = ({k: torch.zeros(2, 16) for k in ("ABD", "THX", "ECG", "PPG")}, torch.zeros(2, 4, dtype=torch.long))
+    full = ("ABD", "THX", "ECG", "PPG")
+    pl.validation_step(batch, dataloader_idx=0)
+    assert stub.calls == [full]                                        # combined loader: no subsets
+    stub.calls.clear(); pl.validation_step(batch, dataloader_idx=1)    # SHHS: ECG, ECG+THX (no PPG there)
+    assert stub.calls == [full, ("ECG",), ("ECG", "THX")]
+    stub.calls.clear(); pl.validation_step(batch, dataloader_idx=2)    # MESA: + PPG, PPG+THX
+    assert stub.calls == [full, ("ECG",), ("ECG", "THX"), ("PPG",), ("PPG", "THX")]
+    stub.calls.clear(); pl.validation_step(batch, dataloader_idx=3)    # CFS: ECG, PPG
+    assert stub.calls == [full, ("ECG",), ("PPG",)]
+    stub.calls.clear(); pl.test_step(batch, dataloader_idx=0)          # test: ECG+THX wherever THX exists
+    assert stub.calls == [full, ("ECG",), ("ECG", "THX")]
+    assert set(pl.aux_outputs["val"]) >= {(None, "all"), ("ECG", "shhs"), ("ECG_THX", "mesa"), ("PPG_THX", "mesa")}
+    assert int(pl.aux_outputs["val"][("ECG", "mesa")].sum()) == 8 and int(pl.cmats["val"].sum()) == 4 * 8
+    out = pl.predict_step(batch)
+    assert set(out) == {"labels", "preds_ECG", "preds_ECG_THX", "preds"} and out["preds"].shape == (2, 4)

@@ -22,7 +22,11 @@ constexpr int kMixHeads = 8;     // nhead
 constexpr int kMixHd = 16;       // head dim
 constexpr int kMixFF = 512;      // dim_feedforward
 constexpr int kMixEp = 16;       // epochs per tile
-constexpr int kMixThreads = 256;
+#ifndef W2S_MIX_THREADS
+#define W2S_MIX_THREADS 256  // measured on B200: 512 threads (16 warps) give the same 395 us per 19200 epochs
+#endif
+constexpr int kMixThreads = W2S_MIX_THREADS;
+constexpr int kMixWarps = kMixThreads / 32;
 constexpr int kMixMaxLayers = 8;
 constexpr int kMixMaxSig = 4;
 
@@ -77,6 +81,7 @@ W2S_DEVINL void mma_16816(float (&c)[4], const uint32_t (&a)[4], const uint2 b) 
 }
 
 // C[m_tiles*16, n8-tiles nt0..nt0+ntn) = A[., KT*16] * W^T ; epi(row, col, v0, v1) gets two adjacent columns.
+// n-tiles are taken two at a time (one A fragment feeds two MMAs); an odd count ends with a single one.
 template <int D, int KT, class Epi>
 W2S_DEVINL void warp_gemm(const __half* sAop, int lda, int m_tiles, const uint2* __restrict__ Wp, int nt0, int ntn,
                           int lane, Epi epi) {
@@ -84,6 +89,7 @@ W2S_DEVINL void warp_gemm(const __half* sAop, int lda, int m_tiles, const uint2*
   const int lcol = (lane >> 4) * 8;
 #pragma unroll 1
   for (int nc = 0; nc < ntn; nc += 2) {
+    const bool two = nc + 1 < ntn;
     float acc[D][2][4];
 #pragma unroll
     for (int m = 0; m < D; ++m)
@@ -95,9 +101,10 @@ W2S_DEVINL void warp_gemm(const __half* sAop, int lda, int m_tiles, const uint2*
     for (int kc = 0; kc < KT; kc += 8) {
       uint2 bf[2][8];
 #pragma unroll
-      for (int n = 0; n < 2; ++n)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) bf[n][k] = __ldg(Wp + ((size_t)(nt0 + nc + n) * KT + kc + k) * 32 + lane);
+      for (int k = 0; k < 8; ++k) {
+        bf[0][k] = __ldg(Wp + ((size_t)(nt0 + nc) * KT + kc + k) * 32 + lane);
+        bf[1][k] = two ? __ldg(Wp + ((size_t)(nt0 + nc + 1) * KT + kc + k) * 32 + lane) : make_uint2(0u, 0u);
+      }
 #pragma unroll
       for (int m = 0; m < D; ++m) {
         if (m < m_tiles) {
@@ -106,7 +113,7 @@ W2S_DEVINL void warp_gemm(const __half* sAop, int lda, int m_tiles, const uint2*
             uint32_t a[4];
             ldmatrix_x4(a, sAop + (size_t)(m * 16 + lrow) * lda + (kc + k) * 16 + lcol);
             mma_16816(acc[m][0], a, bf[0][k]);
-            mma_16816(acc[m][1], a, bf[1][k]);
+            if (two) mma_16816(acc[m][1], a, bf[1][k]);
           }
         }
       }
@@ -116,6 +123,7 @@ W2S_DEVINL void warp_gemm(const __half* sAop, int lda, int m_tiles, const uint2*
       if (m < m_tiles) {
 #pragma unroll
         for (int n = 0; n < 2; ++n) {
+          if (n == 1 && !two) continue;
           const int row = m * 16 + (lane >> 2);
           const int col = (nt0 + nc + n) * 8 + (lane & 3) * 2;
           epi(row, col, acc[m][n][0], acc[m][n][1]);
@@ -218,10 +226,10 @@ __global__ void __launch_bounds__(kMixThreads, 1) epoch_mixer_kernel(const Mixer
           *reinterpret_cast<uint32_t*>(sQ + (size_t)row * kMixLdQ + col) = pack_h2(v0 + bv.x, v1 + bv.y);
         };
         if (!last) {
-          warp_gemm<D, 8>(sA, kMixLdA, D, W.in_w, warp * 6, 6, lane, epi);  // 48 n-tiles over 8 warps
+          warp_gemm<D, 8>(sA, kMixLdA, D, W.in_w, warp * (48 / kMixWarps), 48 / kMixWarps, lane, epi);  // 48 n-tiles
         } else {
-          warp_gemm<D, 8>(sA, kMixLdA, D, W.in_w, 16 + warp * 4, 4, lane, epi);  // K,V: n-tiles 16..47
-          warp_gemm<D, 8>(sA, kMixLdA, 1, W.in_w, warp * 2, 2, lane, epi);       // Q of the CLS tile
+          warp_gemm<D, 8>(sA, kMixLdA, D, W.in_w, 16 + warp * (32 / kMixWarps), 32 / kMixWarps, lane, epi);  // K,V: n-tiles 16..47
+          warp_gemm<D, 8>(sA, kMixLdA, 1, W.in_w, warp * (16 / kMixWarps), 16 / kMixWarps, lane, epi);  // Q of the CLS tile
         }
       }
       __syncthreads();
@@ -292,7 +300,7 @@ __global__ void __launch_bounds__(kMixThreads, 1) epoch_mixer_kernel(const Mixer
           xv.y += v1 + bv.y;
           *x = xv;
         };
-        warp_gemm<D, 8>(sA, kMixLdA, mq, W.out_w, warp * 2, 2, lane, epi);
+        warp_gemm<D, 8>(sA, kMixLdA, mq, W.out_w, warp * (16 / kMixWarps), 16 / kMixWarps, lane, epi);
       }
       __syncthreads();
 
@@ -307,7 +315,7 @@ __global__ void __launch_bounds__(kMixThreads, 1) epoch_mixer_kernel(const Mixer
           *reinterpret_cast<uint32_t*>(sQ + (size_t)row * kMixLdH + col) =
               pack_h2(gelu_erf(v0 + bv.x), gelu_erf(v1 + bv.y));
         };
-        warp_gemm<D, 8>(sA, kMixLdA, mq, W.ff1_w, warp * 8, 8, lane, epi);
+        warp_gemm<D, 8>(sA, kMixLdA, mq, W.ff1_w, warp * (64 / kMixWarps), 64 / kMixWarps, lane, epi);
       }
       __syncthreads();
 
@@ -321,7 +329,7 @@ __global__ void __launch_bounds__(kMixThreads, 1) epoch_mixer_kernel(const Mixer
           xv.y += v1 + bv.y;
           *x = xv;
         };
-        warp_gemm<D, 32>(sQ, kMixLdH, mq, W.ff2_w, warp * 2, 2, lane, epi);
+        warp_gemm<D, 32>(sQ, kMixLdH, mq, W.ff2_w, warp * (16 / kMixWarps), 16 / kMixWarps, lane, epi);
       }
       __syncthreads();
     }

@@ -23,6 +23,9 @@ from torch import Tensor, nn
 from .optim import ExpWarmUpScheduler, FusedAdamW
 
 TRAIN, VAL, TEST = "train", "val", "test"
+# signal / dataset names of the reference (settings.py:2-5, 35-39)
+ECG, PPG, THX = "ECG", "PPG", "THX"
+SHHS, MESA, CFS, CHAT, CCSHS = "shhs", "mesa", "cfs", "chat", "ccshs"
 
 
 class SignalMasker:
@@ -188,6 +191,10 @@ class SleepLightningModule(nn.Module):
         self.causal = causal
         self.unified = len(model.signal_encoders) > 1
         self.cmats = {m: torch.zeros(num_classes, num_classes, dtype=torch.long) for m in (TRAIN, VAL, TEST)}
+        # per (signal prefix, dataset) confusion matrices, as the reference's aux_outputs (trainer/main.py:91)
+        self.aux_outputs = {m: {} for m in (TRAIN, VAL, TEST)}
+        self.val_dataset_map: dict[int, str] = {}
+        self.test_dataset_map: dict[int, str] = {}
         self._opt = self._sched = self._reducer = None
 
     def forward(self, x: dict[str, Tensor], y: Tensor | None = None) -> Tensor:
@@ -205,24 +212,80 @@ class SleepLightningModule(nn.Module):
                 self.masker(x)
         return x, y
 
+    def get_ds_name(self, dataloader_idx: int, mode: str) -> str:
+        """Dataset behind a dataloader index (reference trainer/main.py:118-126; the maps come from the datamodule there,
+        here they are plain attributes ``val_dataset_map`` / ``test_dataset_map`` a caller may set)."""
+        if mode == TRAIN:
+            return "all"
+        ds_map = self.val_dataset_map if mode == VAL else self.test_dataset_map
+        return ds_map.get(dataloader_idx, "all") if isinstance(ds_map, dict) else ds_map[dataloader_idx]
+
     def _step(self, batch, mode: str, dataloader_idx: int = 0, signals=None) -> Tensor:
+        """Generic step (reference trainer/main.py:140-186): optionally on a subset of the signals; the confusion matrix
+        is accumulated per (mode, signal prefix, dataset) as the reference's ``aux_outputs`` are."""
         x, y = batch
         if signals is not None:
             x = {s: x[s] for s in signals}
+            sig_prefix = "_".join(signals)
+        else:
+            sig_prefix = None if self.unified else "_".join(x.keys())
         logits = self(x, y)
         logits_NC, y_N = self.reshape_for_loss(logits, y)
         loss = self.criterion(logits_NC, y_N.long())
         with torch.no_grad():
             cm = sum_if_distributed(confusion_matrix(logits_NC.detach(), y_N, self.num_classes))
-            self.cmats[mode] = self.cmats[mode].to(cm.device) + cm
+            if signals is None:
+                self.cmats[mode] = self.cmats[mode].to(cm.device) + cm
+            key = (sig_prefix, self.get_ds_name(dataloader_idx, mode))
+            prev = self.aux_outputs[mode].get(key)
+            self.aux_outputs[mode][key] = cm if prev is None else prev.to(cm.device) + cm
         return loss
 
     def training_step(self, batch, batch_idx: int = 0) -> Tensor:
         return self._step(batch, TRAIN)
 
+    def _subset_steps(self, batch, mode: str, dataloader_idx: int, ecg_thx_on, ppg_on, ppg_thx_on) -> None:
+        """Re-evaluation on the modality subsets a deployment may see (reference trainer/main.py:188-226)."""
+        x = batch[0]
+        valid = self.model.valid_signals
+        ds_name = self.get_ds_name(dataloader_idx, mode)
+        if ECG in x and ECG in valid:
+            self._step(batch, mode, dataloader_idx, signals=(ECG,))
+            if THX in x and THX in valid and (ecg_thx_on is None or ds_name in ecg_thx_on):
+                self._step(batch, mode, dataloader_idx, signals=(ECG, THX))
+        if PPG in x and PPG in valid and ds_name in ppg_on:
+            self._step(batch, mode, dataloader_idx, signals=(PPG,))
+            if THX in x and THX in valid and ds_name in ppg_thx_on:
+                self._step(batch, mode, dataloader_idx, signals=(PPG, THX))
+
     def validation_step(self, batch, batch_idx: int = 0, dataloader_idx: int = 0) -> Tensor:
         with torch.no_grad():
-            return self._step(batch, VAL, dataloader_idx)
+            loss = self._step(batch, VAL, dataloader_idx)
+            if dataloader_idx == 0 or not self.unified:  # the combined loader / single-modality models: no subsets
+                return loss
+            self._subset_steps(batch, VAL, dataloader_idx, ecg_thx_on=(SHHS, MESA), ppg_on=(MESA, CFS, CCSHS, CHAT),
+                               ppg_thx_on=(MESA,))
+            return loss
+
+    def test_step(self, batch, batch_idx: int = 0, dataloader_idx: int = 0) -> Tensor:
+        with torch.no_grad():
+            loss = self._step(batch, TEST, dataloader_idx)
+            if self.unified:
+                self._subset_steps(batch, TEST, dataloader_idx, ecg_thx_on=None, ppg_on=(MESA, CFS, CCSHS, CHAT),
+                                   ppg_thx_on=(MESA,))
+            return loss
+
+    def predict_step(self, batch) -> dict:
+        """Predictions from ECG only, ECG + THX and all modalities (reference trainer/main.py:228-243)."""
+        x, y = batch
+        out = {"labels": y}
+        with torch.no_grad():
+            if ECG in x:
+                out[f"preds_{ECG}"] = self.model.predict({ECG: x[ECG]})
+            if ECG in x and THX in x:
+                out[f"preds_{ECG}_{THX}"] = self.model.predict({ECG: x[ECG], THX: x[THX]})
+            out["preds"] = self.model.predict(x)
+        return out
 
     # EMACallback hooks (reference trainer/callbacks.py:88-110): evaluate with the averaged weights kept by the optimizer
     def on_validation_epoch_start(self) -> None:
