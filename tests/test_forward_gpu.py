@@ -113,6 +113,40 @@ def test_full_night_argmax_eog(cuda_device):
     assert res[0][0] < 2.5e-2 and res[0][1] >= 0.99
 
 
+def test_reference_arithmetic_on_gpu_vs_cpu_eog(cuda_device):
+    """Context for the 99.9 % argmax gate on the EOG model (informational, only sanity is asserted): the reference's
+    OWN arithmetic (the oracle's plain torch ops) run on this GPU - once with PyTorch's defaults (cuDNN convolutions may
+    use TF32: 10-bit mantissa operands, like fp16) and once with TF32 disabled (fp32, different summation order) -
+    against the same CPU fp32 logits the CUDA path is judged against, on the same three 14-h nights."""
+    model = build_default(EOG, 5, seed=0)
+    x = make_inputs(EOG, 3, 1680, seed=42)
+    cfg = oracle.eog_config()
+    ref = oracle.forward(x, model.state_dict(), cfg)
+    sd = {k: v.detach().to(cuda_device) for k, v in model.state_dict().items()}
+    old = torch.backends.cudnn.allow_tf32
+    res = {}
+    try:
+        for tf32 in (True, False):
+            torch.backends.cudnn.allow_tf32 = tf32
+            outs = []
+            with torch.no_grad():
+                for b in range(3):  # one night at a time: the eager graph keeps fp32 [16, 6.9 M] intermediates
+                    xb = {k: v[b:b + 1].to(cuda_device) for k, v in x.items()}
+                    z = oracle.signal_encoders(xb, sd, cfg)   # (oracle.forward itself moves everything to the CPU)
+                    s = oracle.sequence_mixer(oracle.epoch_mixer(z, sd, cfg), sd, cfg)
+                    outs.append((s @ sd["classifier.weight"].t() + sd["classifier.bias"]).float().cpu())
+            out = torch.cat(outs)
+            err = (out - ref).abs()
+            flips = int((out.argmax(-1) != ref.argmax(-1)).sum())
+            res[tf32] = (err.max().item(), err.mean().item(), flips)
+            print(f"reference arithmetic on GPU, cudnn.allow_tf32={tf32}: max-abs {err.max().item():.3e} mean "
+                  f"{err.mean().item():.3e} argmax flips {flips} of {ref.shape[0] * ref.shape[1]} "
+                  f"({100 * (1 - flips / (ref.shape[0] * ref.shape[1])):.3f} %)")
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert res[False][0] < 1e-3 and res[True][0] < 0.2
+
+
 def test_masked_equals_absent_and_batch_independence(cuda_device):
     """SURVEY section 4 invariants on the CUDA path."""
     model = build_default(CARDIO, 4, seed=0)
