@@ -8,6 +8,12 @@
 // both operands transposed on load (ldmatrix.trans from row-major [row][channel] tiles); each CTA reduces a
 // contiguous row range into registers and finishes with fp32 atomics into C (stride-addressed, so C can be a
 // tap slice of a [Cout, Cin, taps] conv weight gradient).
+//
+// Measured and rejected (round 2, same-box A/B on the 4-signal and the ECG-only training step): (i) forcing 2 or 3
+// resident CTAs per SM through __launch_bounds__ (spills: 37.0 -> 37.9 / 44.4 ms per step); (ii) replacing the register
+// double buffering by a 3-5 stage cp.async ring with one CTA per SM (equal step time; 16-channel layers 20 % slower,
+// 128-channel layers 25 % faster in isolation).  Inside the step these kernels share the GPU with the other encoders'
+// streams, so their isolated rate is not what bounds the step.
 #pragma once
 #include "common.cuh"
 
