@@ -57,7 +57,7 @@ def summarize_launches(csvf: Path, out: Path, last=102):
     tot = sum(t for *_, t in seq)
     agg = {}
     for k, g, b, t in seq:
-        m = re.search(r"(conv_stream_kernel|conv_igemm_kernel|epoch_mixer_kernel|first_conv_kernel|argmax_kernel)(<[^>]*>)?", k)
+        m = re.search(r"(conv_stream_kernel|conv_igemm_kernel|epoch_mixer_kernel|seq_mixer_kernel|first_conv_kernel|argmax_kernel)(<[^>]*>)?", k)
         name = (m.group(1) + (m.group(2) or "")).replace("(int)", "").replace("(bool)", "") if m else k[:60]
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1
@@ -68,7 +68,7 @@ def summarize_launches(csvf: Path, out: Path, last=102):
         txt.append(f"{name:75s} {n:4d} {t:10.1f} {100 * t / tot:6.2f}%")
     txt += ["", "# every launch in order: kernel | grid | block | us"]
     for k, g, b, t in seq:
-        m = re.search(r"(conv_stream_kernel|conv_igemm_kernel|epoch_mixer_kernel|first_conv_kernel|argmax_kernel)(<[^>]*>)?", k)
+        m = re.search(r"(conv_stream_kernel|conv_igemm_kernel|epoch_mixer_kernel|seq_mixer_kernel|first_conv_kernel|argmax_kernel)(<[^>]*>)?", k)
         name = (m.group(1) + (m.group(2) or "")).replace("(int)", "").replace("(bool)", "") if m else k[:60]
         txt.append(f"{name:75s} {g:16s} {b:12s} {t:9.1f}")
     out.write_text("\n".join(txt))
