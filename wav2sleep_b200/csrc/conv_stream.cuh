@@ -57,7 +57,10 @@ struct WaitClock {
 // warp 0 producer, 1 MMA, 2..2+E-1 epilogue, then transform.  E = 4 or 8: with 8, two warps share each TMEM lane
 // quadrant (a warp may only read the quadrant warp_id % 4) and split the (column group, sub-tile) items.  Measured for
 // COUT >= 64, where the epilogue is the busiest stage (93 %): no gain from 8 warps, and none from software-pipelining
-// the tcgen05.ld of the next item behind the current one (register pressure eats it) - so E stays 4.
+// the tcgen05.ld of the next item behind the current one (register pressure eats it) - so E stays 4.  Re-measured in
+// round 2 on top of the staged epilogue (a second warp per quadrant taking every other 32 x 32/64 item of the 32- and
+// 64-channel kernels, 768 threads at 80 registers): same step time (6.68 vs 6.70 ms, 3 alternating rounds) - with the
+// epilogue relieved, the transform warps (81 % busy) and the shared issue slots are the next limit.
 constexpr int stream_epi_warps(int /*cout*/) { return 4; }
 constexpr int stream_first_transform_warp(int cout) { return 2 + stream_epi_warps(cout); }
 constexpr int stream_threads(int ntw, int cout) { return 32 * (stream_first_transform_warp(cout) + ntw); }
