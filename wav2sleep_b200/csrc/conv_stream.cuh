@@ -65,6 +65,17 @@ constexpr int stream_epi_warps(int /*cout*/) { return 4; }
 constexpr int stream_first_transform_warp(int cout) { return 2 + stream_epi_warps(cout); }
 constexpr int stream_threads(int ntw, int cout) { return 32 * (stream_first_transform_warp(cout) + ntw); }
 
+// Named-barrier hand-over (transform warps -> MMA issuer / producer): bar.arrive does not block the arriving warp and
+// bar.sync parks the waiting warp in hardware until the count is reached - no polling.  ncu source view of the round-2
+// kernels: 15 % of the executed warp instructions were still mbarrier polls of waiting roles (SYNCS 6.4 %, NANOSLEEP 2.9 %
+// and their branches), because a parked try_wait is woken by every mbarrier event of the CTA and the transform warps
+// produced 36 such events per tile.  -DW2S_NAMED_BARS=0 restores the mbarrier hand-over (A/B).
+#ifndef W2S_NAMED_BARS
+#define W2S_NAMED_BARS 1
+#endif
+W2S_DEVINL void named_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+W2S_DEVINL void named_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 W2S_DEVINL void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -174,6 +185,11 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
 #else
   constexpr int kTransformArrives = NTW;
 #endif
+  // named barriers: ids 1 .. NA = "A stage written" (transform -> MMA issuer), NA+1 .. NA+NR = "raw stage read"
+  // (transform -> producer); each is joined by the NTW transform warps (bar.arrive) and the one waiting warp (bar.sync)
+  constexpr bool NAMED = W2S_NAMED_BARS != 0;
+  constexpr int kNamedCount = 32 * (NTW + 1);
+  static_assert(NA + NR < 16, "named barrier ids");
 
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sRaw = smem;
@@ -277,7 +293,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
         }
       }
       __syncwarp();
-      int s = 0;
+      int s = 0, n_issued = 0;
       uint32_t ph = 0;
       WaitClock wc;
       const long long cta_t0 = clock64();
@@ -298,7 +314,12 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
         int xhi = xs0 + Cfg::XN;
         xhi = (xhi > p.T_raw ? p.T_raw : xhi) & ~3;
         const uint32_t xbytes = (Cfg::XN > 0 && xhi > xlo) ? (uint32_t)(xhi - xlo) * 4 : 0u;
-        wc.wait(p, &raw_empty[s], ph ^ 1);
+        if (NAMED) {
+          if (n_issued >= NR) named_sync(1 + NA + s, kNamedCount);  // (the first NR fills find the ring empty)
+          ++n_issued;
+        } else {
+          wc.wait(p, &raw_empty[s], ph ^ 1);
+        }
         uint8_t* dst = sRaw + s * Cfg::RAW_BYTES + (size_t)(lo - i0) * CIN * ESZ;
         const size_t goff = ((size_t)b * p.L_in + lo) * CIN * ESZ;  // byte offset
         if (elect_one()) {
@@ -334,7 +355,8 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
       for (int tile = tile_begin; tile < tile_end; ++tile, advance(tp)) {
         int b;
         if (!sample_of(tp, b)) continue;
-        wc.wait(p, &a_full[as], aph);
+        if (NAMED) named_sync(1 + as, kNamedCount);
+        else wc.wait(p, &a_full[as], aph);
         wc.wait(p, &t_empty[ts], tph ^ 1);
         tc_fence_after_sync();
         const uint32_t a_base = smem_u32(sA + as * Cfg::A_BYTES);
@@ -818,10 +840,15 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
         mbar_arrive(&raw_empty[rs]);
       }
 #else
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&a_full[as]);
-        mbar_arrive(&raw_empty[rs]);
+      if (NAMED) {
+        named_arrive(1 + as, kNamedCount);
+        named_arrive(1 + NA + rs, kNamedCount);
+      } else {
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&a_full[as]);
+          mbar_arrive(&raw_empty[rs]);
+        }
       }
 #endif
       if (++rs == NR) {
