@@ -176,6 +176,15 @@ W2S_DEVINL uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t 
   d |= (uint64_t)1 << 46;  // descriptor version (sm_100)
   return d;                // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
 }
+// The same descriptor in two 32-bit halves.  Within one staged operand only the start-address field (low 14 bits, units
+// of 16 bytes) changes from MMA to MMA, and it cannot carry into the LBO field because shared-memory addresses stay
+// below 256 KB: a descriptor is `umma_desc(lo0 + (byte_offset >> 4), hi)` - ONE integer add on the issuing thread
+// instead of shift / mask / or per operand (the MMA issuer of the 16-channel kernels was 95 % busy on this arithmetic).
+W2S_DEVINL uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+W2S_DEVINL uint64_t umma_desc(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 // kind::f16 instruction descriptor: fp32 accumulate, A/B both K-major, M x N tile.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, bool bf16) {
   return (1u << 4)                      // c_format = F32

@@ -348,8 +348,12 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
       int as = 0, ts = 0;
       uint32_t aph = 0, tph = 0;
       WaitClock wc;
-      const uint32_t b_base = smem_u32(sB);
       constexpr uint32_t lbo_a = RP * 16, lbo_b = COUT * 16;
+      // descriptors = (stage / operand base) + compile-time offset: one integer add per operand on the issuing thread
+      constexpr uint32_t DHI = umma_desc_hi(128);
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(sB), lbo_b);
+      const uint32_t a_lo_first = umma_desc_lo(smem_u32(sA), lbo_a);
+      uint32_t a_lo0 = a_lo_first;
       TilePos tp = pos0;
       if (tile_begin < tile_end) mbar_wait(w_full, 0);
       for (int tile = tile_begin; tile < tile_end; ++tile, advance(tp)) {
@@ -359,7 +363,6 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
         else wc.wait(p, &a_full[as], aph);
         wc.wait(p, &t_empty[ts], tph ^ 1);
         tc_fence_after_sync();
-        const uint32_t a_base = smem_u32(sA + as * Cfg::A_BYTES);
         const uint32_t d_base = tmem_base + ts * Cfg::STAGE_COLS;
         if (elect_one()) {
 #pragma unroll
@@ -370,16 +373,16 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
             const int rowoff = t / STRIDE + j * 128;
 #pragma unroll
             for (int kk = 0; kk < KSTEPS; ++kk) {
-              const uint32_t a_off = ((uint32_t)(phase * CH + 2 * kk) * RP + rowoff) * 16;
-              const uint32_t b_off = (uint32_t)(t * CH + 2 * kk) * COUT * 16;
-              const uint64_t da = umma_smem_desc(a_base + a_off, lbo_a, 128);
-              const uint64_t db = umma_smem_desc(b_base + b_off, lbo_b, 128);
+              const uint32_t a_off = (uint32_t)((phase * CH + 2 * kk) * RP + rowoff);       // in 16-byte units
+              const uint32_t b_off = (uint32_t)((t * CH + 2 * kk) * COUT);
+              const uint64_t da = umma_desc(a_lo0 + a_off, DHI);
+              const uint64_t db = umma_desc(b_lo0 + b_off, DHI);
               if (!W2S_DBG(p, 2)) umma_f16(d_base + j * COUT, da, db, IDESC, (t > 0 || kk > 0) ? 1u : 0u);
               if (SPLIT && !W2S_DBG(p, 3)) {
                 if (!W2S_DBG(p, 128) && !(CIN == 32 && W2S_DBG(p, 512)))
-                  umma_f16(d_base + j * COUT, umma_smem_desc(a_base + Cfg::A_ONE + a_off, lbo_a, 128), db, IDESC, 1u);
+                  umma_f16(d_base + j * COUT, umma_desc(a_lo0 + (Cfg::A_ONE >> 4) + a_off, DHI), db, IDESC, 1u);
                 if (!W2S_DBG(p, 256) && !(CIN == 32 && W2S_DBG(p, 1024)))
-                  umma_f16(d_base + j * COUT, da, umma_smem_desc(b_base + Cfg::B_ONE + b_off, lbo_b, 128), IDESC, 1u);
+                  umma_f16(d_base + j * COUT, da, umma_desc(b_lo0 + (Cfg::B_ONE >> 4) + b_off, DHI), IDESC, 1u);
               }
             }
           }
@@ -387,16 +390,16 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
             const int rowoff = 1 + j * 128;
 #pragma unroll
             for (int kk = 0; kk < KSTEPS; ++kk) {
-              const uint32_t a_off = ((uint32_t)(2 * kk) * RP + rowoff) * 16;
-              const uint32_t b_off = (uint32_t)(3 * CH + 2 * kk) * COUT * 16;
-              const uint64_t da = umma_smem_desc(a_base + a_off, lbo_a, 128);
-              const uint64_t db = umma_smem_desc(b_base + b_off, lbo_b, 128);
+              const uint32_t a_off = (uint32_t)((2 * kk) * RP + rowoff);
+              const uint32_t b_off = (uint32_t)((3 * CH + 2 * kk) * COUT);
+              const uint64_t da = umma_desc(a_lo0 + a_off, DHI);
+              const uint64_t db = umma_desc(b_lo0 + b_off, DHI);
               umma_f16(d_base + (MT + j) * COUT, da, db, IDESC, kk > 0 ? 1u : 0u);
               if (SPLIT) {
                 if (!W2S_DBG(p, 128))
-                  umma_f16(d_base + (MT + j) * COUT, umma_smem_desc(a_base + Cfg::A_ONE + a_off, lbo_a, 128), db, IDESC, 1u);
+                  umma_f16(d_base + (MT + j) * COUT, umma_desc(a_lo0 + (Cfg::A_ONE >> 4) + a_off, DHI), db, IDESC, 1u);
                 if (!W2S_DBG(p, 256))
-                  umma_f16(d_base + (MT + j) * COUT, da, umma_smem_desc(b_base + Cfg::B_ONE + b_off, lbo_b, 128), IDESC, 1u);
+                  umma_f16(d_base + (MT + j) * COUT, da, umma_desc(b_lo0 + (Cfg::B_ONE >> 4) + b_off, DHI), IDESC, 1u);
               }
             }
           }
@@ -405,9 +408,11 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
         umma_commit(&t_full[ts]);   // accumulators ready for the epilogue
         }
         __syncwarp();
+        a_lo0 += Cfg::A_BYTES >> 4;
         if (++as == NA) {
           as = 0;
           aph ^= 1;
+          a_lo0 = a_lo_first;
         }
         if (++ts == 2) {
           ts = 0;
