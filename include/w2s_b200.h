@@ -42,7 +42,7 @@ const char* w2s_last_error(void);
  * Also used for nn.Linear(4*C -> F) of SignalEncoder (models/wav2sleep.py:230,264) by viewing its
  * weight [F, 4*C] as [F, taps=4, C] -> pass taps_major = 1 (input index = tap*cin + c). */
 int w2s_pack_conv_weight(const float* w, int cout, int cin, int taps, int taps_major, int split, void* out_fp16,
-                         void* stream);
+                         void* stream);  /* split: 0 = fp16, 1 = fp16 hi block + lo block, 2 = bf16 (measurement hook) */
 size_t w2s_packed_conv_weight_bytes(int cout, int cin, int taps, int split);
 /* 1 if the (cin, cout) encoder conv kernels carry operands as fp16 hi + fp16 lo pairs by default; their weights must
  * then be packed with split = 1 (hi block followed by lo block, twice the bytes).  True for cin <= 16 and cout <= 16. */
@@ -142,7 +142,10 @@ int w2s_stage_zscore(const void* raw, int raw_dtype, float* out, const uint8_t* 
  * (optionally) the [512][2] entry/exit table of the last launch to the host (synchronises). */
 int w2s_debug_timestamps(uint64_t* out16, uint64_t* cta1024);
 /* Kernel selection for the encoder convs (testing / A-B measurement): 0 = auto (persistent warp-specialised
- * streaming kernel, conv_stream.cuh), 1 = tile-per-CTA kernel only (conv_igemm.cuh).  Same results either way. */
+ * streaming kernel, conv_stream.cuh), 1 = tile-per-CTA kernel only (conv_igemm.cuh).  Same results either way.
+ * 3 = measurement hook: tile-per-CTA kernel with BF16 MMA operands (k3 32->32 / 64->64 / 128->128 W2S_EPI_STATS convs
+ * without the 1x1 branch only; weights packed with split = 2 = one block of bf16) - the hardware evidence behind the
+ * fp16-over-bf16 operand decision (DESIGN.md "Numerics"); never used by the model path. */
 int w2s_set_conv_impl(int impl);
 
 /* ---------------------------------------------------------------------------------------------------------

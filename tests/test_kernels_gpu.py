@@ -333,6 +333,39 @@ def test_seqmixer_stage(cuda_device, B, S, n_blocks, n_dil, ncls):
     assert e_feat < 1.5e-2 and e_log < 1.5e-2
 
 
+@pytest.mark.parametrize("c", [32, 64, 128])
+def test_bf16_operands_on_hardware(cuda_device, c):
+    """The north star names bf16; this path multiplies fp16 operands.  Hardware evidence at the kernel level: the same
+    encoder conv (InstanceNorm + GELU prologue, k3, fp32 accumulate in TMEM) with the MMA operand type flipped to bf16
+    (w2s_set_conv_impl(3): bf16 rounding in the prologue, bf16-packed weights, bf16 instruction descriptor), both
+    against fp32 torch on UNROUNDED operands.  bf16 keeps 8 mantissa bits instead of 11: its operand error is ~8x the
+    fp16 one, on top of the common fp16 output rounding (the model-level consequence - 7.6e-2 / 99.4 % against
+    1.05e-2 / 100 % on two cardio nights - is tools/emulate_16bit.py, profiles/r02_emulation_16bit.txt)."""
+    lib = _lib.load()
+    torch.manual_seed(c)
+    dev, B, L = cuda_device, 2, 4096
+    y = torch.randn(B, L, c, device=dev).half()
+    w = torch.randn(c, c, 3, device=dev) / (3 * c) ** 0.5
+    ref = G.conv_ref(G.prologue_ref(y), w, split=1)  # fp32, operands not rounded
+    err = {}
+    try:
+        for name, impl, split in (("fp16", 1, 0), ("bf16", 3, 2)):
+            _lib.check(lib.w2s_set_conv_impl(impl))
+            out = torch.full((B, L, c), float("nan"), dtype=torch.float16, device=dev)
+            stats = torch.zeros(B, c, 2, dtype=torch.float64, device=dev)
+            G.run_conv(cin=c, cout=c, taps=3, stride=1, dilation=1, pad=1, prologue=_lib.PRO_NORM, epilogue=_lib.EPI_STATS,
+                       has_ds=0, B=B, L_in=L, L_out=L, **{"in": y}, in_stats=G.sums(y), w=G.pack_conv(w, split=split),
+                       out=out, out_stats=stats, in_eps=1e-2)
+            assert torch.isfinite(out.float()).all()
+            err[name] = ((out.float() - ref).abs().mean() / ref.abs().mean()).item()
+    finally:
+        _lib.check(lib.w2s_set_conv_impl(0))
+    print(f"conv {c}->{c}: mean relative error with fp16 operands {err['fp16']:.3e}, with bf16 operands {err['bf16']:.3e} "
+          f"({err['bf16'] / err['fp16']:.1f}x)")
+    assert err["fp16"] < 1e-3 and err["bf16"] < 1e-2   # both compute the same convolution ...
+    assert err["bf16"] > 2.5 * err["fp16"]              # ... bf16 operands are markedly less accurate
+
+
 def test_pack_batch_matches_single_packs(cuda_device):
     """w2s_pack_batch (strided sources, one launch) against w2s_pack_conv_weight / w2s_pack_linear_frag, incl. the
     flipped + transposed view used for data-gradient weights and the taps-major view of a Linear."""

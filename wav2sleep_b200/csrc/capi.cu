@@ -2,6 +2,8 @@
 // carving, kernel dispatch.  No allocation, no synchronisation, no CPU fallback.
 #include "../../include/w2s_b200.h"
 
+#include <cuda_bf16.h>
+
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -108,6 +110,10 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, int cout, int cin,
     const int t = r / (cin / 8);
     const int c = c8 * 8 + k;
     const float v = taps_major ? w[(size_t)n * taps * cin + (size_t)t * cin + c] : w[((size_t)n * cin + c) * taps + t];
+    if (split == 2) {  // bf16 operand (measurement hook): one block of bf16 bit patterns
+      reinterpret_cast<__nv_bfloat16*>(out)[idx] = __float2bfloat16_rn(v);
+      continue;
+    }
     const __half hi = __float2half_rn(v);
     out[idx] = hi;
     if (split) out[total + idx] = __float2half_rn(v - __half2float(hi));  // W = hi + lo
@@ -233,7 +239,8 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
   if (ilog2_exact(c.stride) < 0 || c.stride > 4) return fail("conv1d: stride %d unsupported", c.stride);
   if (c.B > 65535) return fail("conv1d: B=%d exceeds grid.y", c.B);
   if (c.n_classes > 8) return fail("conv1d: n_classes=%d > 8", c.n_classes);
-  if ((c.in_wide || c.out_wide || c.force_split) && (c.epilogue != W2S_EPI_STATS || g_conv_impl.load() != 0))
+  const int impl = g_conv_impl.load();
+  if ((c.in_wide || c.out_wide || c.force_split) && (c.epilogue != W2S_EPI_STATS || impl != 0))
     return fail("conv1d: wide storage / forced split operands are only built for the streaming encoder kernels");
   if (c.epilogue == W2S_EPI_ACT_BWD) {
     if (!c.act_y || !c.act_stats || !c.out_stats || (c.act_r && !c.act_dr))
@@ -260,7 +267,7 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
                           : 0.0;
   const double fl = 2.0 * c.B * (double)c.L_out * c.cout * c.cin * (c.taps + (c.has_ds ? 0.5 : 0.0));
   LaunchScope scope(st, label, in_b + out_b + ab_b, fl);
-  if (c.epilogue == W2S_EPI_STATS && c.taps == 3 && c.dilation == 1 && c.pad == 1 && g_conv_impl.load() == 0 &&
+  if (c.epilogue == W2S_EPI_STATS && c.taps == 3 && c.dilation == 1 && c.pad == 1 && impl == 0 &&
       ((c.stride == 1 && c.L_out == c.L_in) || (c.stride == 2 && c.L_out == (c.L_in + 1) / 2))) {
     const int sms = sm_count();
     const bool want_split = c.force_split != 0 || w2s_conv_uses_split(c.cin, c.cout) != 0;
@@ -326,6 +333,20 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
       if (e != cudaSuccess) return cuda_fail(e, "conv_stream launch");
       return 0;
     }
+  }
+  if (impl == 3) {  // bf16 operands on the tile-per-CTA kernel: un-split encoder convs without the 1x1 branch only
+#define W2S_BF16(CIN, COUT)                                                                                          \
+  if (!found && c.cin == CIN && c.cout == COUT && c.taps == 3 && c.prologue == PRO_NORM && c.epilogue == EPI_STATS && \
+      !c.has_ds) {                                                                                                   \
+    found = true;                                                                                                    \
+    e = launch_conv_igemm<CIN, COUT, 3, 3, PRO_NORM, EPI_STATS, false, true>(a, c.B, st);                            \
+  }
+    W2S_BF16(32, 32)
+    W2S_BF16(64, 64)
+    W2S_BF16(128, 128)
+#undef W2S_BF16
+    if (!found) return fail("conv1d: bf16-operand hook is built for k3 32->32 / 64->64 / 128->128 EPI_STATS convs only");
+    return e == cudaSuccess ? 0 : cuda_fail(e, "conv_igemm (bf16 operands) launch");
   }
 #define W2S_CASE(CIN, COUT, TAPS, GT, PRO, EPI, DS)                                                       \
   if (!found && c.cin == CIN && c.cout == COUT && c.taps == TAPS && c.prologue == PRO && c.epilogue == EPI && \
@@ -1222,7 +1243,7 @@ int w2s_gen_attn(const float* q, const float* k, const float* v, float* o, const
 }
 
 int w2s_set_conv_impl(int impl) {
-  if (impl != 0 && impl != 1) return fail("set_conv_impl: %d", impl);
+  if (impl != 0 && impl != 1 && impl != 3) return fail("set_conv_impl: %d", impl);
   g_conv_impl.store(impl);
   return 0;
 }

@@ -264,6 +264,12 @@ W2S_DEVINL uint32_t pack_h2(float lo, float hi) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
+// {lo, hi} -> packed bf16x2, round-to-nearest (bf16 operand measurement hook)
+W2S_DEVINL uint32_t pack_bf2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 W2S_DEVINL float2 unpack_h2(uint32_t u) {
   __half2 h = *reinterpret_cast<__half2*>(&u);
   return __half22float2(h);

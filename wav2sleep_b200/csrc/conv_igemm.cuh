@@ -111,9 +111,13 @@ __host__ __device__ inline size_t conv_smem_bytes(int stride, int taps, int dil)
   return (SPLIT ? 2 : 1) * (a + b) + kConvCtlBytes;
 }
 
+// BF16OP (measurement hook, w2s_set_conv_impl(3)): the MMA operands are bf16 instead of fp16 - activated inputs are
+// rounded to bf16 in the prologue, the weights come packed as bf16, the instruction descriptor selects bf16 A / B.
+// Storage stays fp16.  Evidence for the fp16-over-bf16 decision on the hardware itself (tests/test_kernels_gpu.py).
 template <int CIN, int COUT, int TAPS, int GT /*taps resident per weight group*/, int PRO, int EPI, bool HAS_DS,
-          bool SPLIT>
+          bool SPLIT, bool BF16OP = false>
 __global__ void __launch_bounds__(kConvThreads, (EPI == EPI_ACT_BWD && COUT <= 64) ? 3 : 1) conv_igemm_kernel(const ConvArgs p) {
+  static_assert(!BF16OP || (!SPLIT && PRO != PRO_NONE), "bf16 operands: computed prologue, single operand");
   static_assert(!SPLIT || (GT == TAPS && PRO != PRO_NONE), "split operands: single weight group, computed prologue");
   static_assert(CIN % 16 == 0 && COUT % 16 == 0 && COUT <= 128, "UMMA shape");
   static_assert(EPI == EPI_STATS || EPI == EPI_PLAIN || EPI == EPI_ACT_BWD || COUT == 128,
@@ -124,7 +128,7 @@ __global__ void __launch_bounds__(kConvThreads, (EPI == EPI_ACT_BWD && COUT <= 6
   constexpr int KSTEPS = CIN / 16;            // UMMA K=16 steps per tap
   constexpr int NGROUPS = (TAPS + GT - 1) / GT;
   constexpr uint32_t TMEM_COLS = HAS_DS ? 256 : 128;
-  constexpr uint32_t IDESC = umma_idesc_f16(128, COUT, false);
+  constexpr uint32_t IDESC = umma_idesc_f16(128, COUT, BF16OP);
 
   const int b = blockIdx.y;
   if (p.row_mask != nullptr && p.row_mask[b]) return;
@@ -233,7 +237,7 @@ __global__ void __launch_bounds__(kConvThreads, (EPI == EPI_ACT_BWD && COUT <= 6
                 a0 = gelu_fast(a0 + rv.x);
                 a1 = gelu_fast(a1 + rv.y);
               }
-              oo[q] = pack_h2(a0, a1);
+              oo[q] = BF16OP ? pack_bf2(a0, a1) : pack_h2(a0, a1);
               if (SPLIT) {
                 const float2 hi = unpack_h2(oo[q]);
                 ol[q] = pack_h2(a0 - hi.x, a1 - hi.y);
@@ -600,10 +604,10 @@ __global__ void __launch_bounds__(kConvThreads, (EPI == EPI_ACT_BWD && COUT <= 6
 }
 
 // Host-side launcher.  Returns cudaError_t of the launch.
-template <int CIN, int COUT, int TAPS, int GT, int PRO, int EPI, bool HAS_DS>
+template <int CIN, int COUT, int TAPS, int GT, int PRO, int EPI, bool HAS_DS, bool BF16OP = false>
 inline cudaError_t launch_conv_igemm(const ConvArgs& a, int B, cudaStream_t stream) {
-  constexpr bool SPLIT = ConvSplit<CIN, COUT>::value && EPI == EPI_STATS;
-  auto kern = conv_igemm_kernel<CIN, COUT, TAPS, GT, PRO, EPI, HAS_DS, SPLIT>;
+  constexpr bool SPLIT = ConvSplit<CIN, COUT>::value && EPI == EPI_STATS && !BF16OP;
+  auto kern = conv_igemm_kernel<CIN, COUT, TAPS, GT, PRO, EPI, HAS_DS, SPLIT, BF16OP>;
   const int stride = 1 << a.stride_log2;
   const size_t smem = conv_smem_bytes<CIN, COUT, GT, HAS_DS, SPLIT>(stride, TAPS, a.dil);
   static size_t configured = 0;  // per instantiation
