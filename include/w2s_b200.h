@@ -72,7 +72,7 @@ int w2s_pack_linear_frag(const float* w, int n, int k, void* out_fp16, void* str
  * One generic implicit-GEMM conv layer (kernel-level entry, used by the tests and by the stage calls below).
  * Replaces ConvLayer1D.forward (models/blocks.py:173-186) + the consumer-side InstanceNorm/GELU of its input.
  * ------------------------------------------------------------------------------------------------------- */
-enum { W2S_PRO_NONE = 0, W2S_PRO_NORM = 1, W2S_PRO_NORM_RES = 2, W2S_PRO_FIR = 3, W2S_PRO_NORM_RES_X = 4 };
+enum { W2S_PRO_NONE = 0, W2S_PRO_NORM = 1, W2S_PRO_NORM_RES = 2, W2S_PRO_FIR = 3, W2S_PRO_NORM_RES_X = 4, W2S_PRO_DNORM = 5 };
 enum { W2S_EPI_STATS = 0, W2S_EPI_BIAS_GELU = 1, W2S_EPI_LN_GELU = 2, W2S_EPI_LN_GELU_RES = 3, W2S_EPI_PLAIN = 4,
        W2S_EPI_ACT_BWD = 5 };
 
@@ -123,6 +123,15 @@ typedef struct w2s_conv_call {
   void* act_a;
   void* act_dr;
   float act_eps;
+  /* W2S_PRO_DNORM (training, data-gradient convs; ABI v3): the conv input is dy = InstanceNorm-backward of `in` =
+   * d(x_hat) with `in_res` = the layer's stored pre-norm output y, `in_stats` = its forward sums and dn_sums =
+   * [B, cin, 2] (sum d(x_hat), sum d(x_hat) x_hat), computed on the way into shared memory; every tile also writes the
+   * dy rows it owns to dn_out [B, L_in, cin] (operand of the weight gradient).  dn_upsample = 1: the layer was a
+   * stride-2 conv (in / in_res have L_in / 2 rows): row i of the conv input is source row i / 2 for even i and zero for
+   * odd i, dn_out is written zero-stuffed.  Replaces a separate w2s_enc_norm_bwd pass. */
+  const double* dn_sums;
+  void* dn_out;
+  int32_t dn_upsample;
 } w2s_conv_call;
 
 int w2s_conv1d_fwd(const w2s_conv_call* call, void* stream);

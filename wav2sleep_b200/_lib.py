@@ -23,9 +23,9 @@ MAX_MIXER_LAYERS = 8
 MAX_SIGNALS = 4
 MAX_SEQ_BLOCKS = 4
 MAX_DILATIONS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 
-PRO_NONE, PRO_NORM, PRO_NORM_RES, PRO_FIR, PRO_NORM_RES_X = 0, 1, 2, 3, 4
+PRO_NONE, PRO_NORM, PRO_NORM_RES, PRO_FIR, PRO_NORM_RES_X, PRO_DNORM = 0, 1, 2, 3, 4, 5
 EPI_STATS, EPI_BIAS_GELU, EPI_LN_GELU, EPI_LN_GELU_RES, EPI_PLAIN, EPI_ACT_BWD = 0, 1, 2, 3, 4, 5
 
 
@@ -80,6 +80,7 @@ class ConvCall(C.Structure):
         ("in_wide", C.c_int32), ("out_wide", C.c_int32), ("force_split", C.c_int32),
         ("act_y", C.c_void_p), ("act_r", C.c_void_p), ("act_stats", C.c_void_p), ("act_a", C.c_void_p),
         ("act_dr", C.c_void_p), ("act_eps", C.c_float),
+        ("dn_sums", C.c_void_p), ("dn_out", C.c_void_p), ("dn_upsample", C.c_int32),
     ]
 
 

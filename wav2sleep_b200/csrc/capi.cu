@@ -230,6 +230,7 @@ ConvArgs to_args(const w2s_conv_call& c) {
   a.out_rows = c.out_rows > 0 ? c.out_rows : c.L_out;
   a.ab_y = (const act_t*)c.act_y; a.ab_r = (const act_t*)c.act_r; a.ab_stats = c.act_stats;
   a.ab_a = (act_t*)c.act_a; a.ab_dr = (act_t*)c.act_dr; a.ab_eps = c.act_eps;
+  a.dn_sums = c.dn_sums; a.dn_out = (act_t*)c.dn_out; a.dn_upsample = c.dn_upsample;
   { const char* dbg = getenv("W2S_DEBUG_FLAGS"); a.debug_flags = dbg ? atoi(dbg) : 0; }
   return a;
 }
@@ -242,6 +243,12 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
   const int impl = g_conv_impl.load();
   if ((c.in_wide || c.out_wide || c.force_split) && (c.epilogue != W2S_EPI_STATS || impl != 0))
     return fail("conv1d: wide storage / forced split operands are only built for the streaming encoder kernels");
+  if (c.prologue == W2S_PRO_DNORM) {
+    if (c.epilogue != W2S_EPI_ACT_BWD || c.stride != 1 || c.taps != 3 || c.L_in != c.L_out)
+      return fail("conv1d: W2S_PRO_DNORM is built for the k3 stride-1 data-gradient convs (W2S_EPI_ACT_BWD) only");
+    if (!c.in_res || !c.in_stats || !c.dn_sums || !c.dn_out) return fail("conv1d: W2S_PRO_DNORM needs in_res (y), in_stats, dn_sums, dn_out");
+    if (c.dn_upsample && (c.L_in & 1)) return fail("conv1d: W2S_PRO_DNORM upsample needs an even L_in");
+  }
   if (c.epilogue == W2S_EPI_ACT_BWD) {
     if (!c.act_y || !c.act_stats || !c.out_stats || (c.act_r && !c.act_dr))
       return fail("conv1d: W2S_EPI_ACT_BWD needs act_y, act_stats, out_stats (and act_dr with act_r)");
@@ -257,7 +264,9 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
            c.in_wide ? (c.out_wide ? " w32/32" : " w32/16") : (c.out_wide ? " w16/32" : ""), c.B, c.L_in);
   const double ein = c.in_wide ? 4.0 : 2.0, eout = c.out_wide ? 4.0 : 2.0;
   // algorithmic traffic: every input element read once (+ residual), every output written once; fp16
-  const double in_b = c.prologue == W2S_PRO_FIR ? (double)c.B * c.L_in * 4.0
+  const double in_b = c.prologue == W2S_PRO_DNORM  // d(x_hat) + y read (half length when zero-stuffed), dy written
+                          ? (double)c.B * c.L_in * c.cin * 2.0 * (c.dn_upsample ? 2.0 : 3.0)
+                      : c.prologue == W2S_PRO_FIR ? (double)c.B * c.L_in * 4.0
                       : (double)c.B * c.L_in * c.cin * ein * (c.prologue == W2S_PRO_NORM_RES ? 2.0 : 1.0) +
                             (c.prologue == W2S_PRO_NORM_RES_X ? (double)c.B * c.L_in * 8.0 : 0.0);
   const double out_b = (double)c.B * c.L_out * c.cout * eout * (c.has_ds ? 1.5 : 1.0) +
@@ -394,6 +403,14 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
   W2S_CASE(64, 64, 3, 3, PRO_NONE, EPI_ACT_BWD, false)
   W2S_CASE(128, 64, 3, 3, PRO_NONE, EPI_ACT_BWD, false)
   W2S_CASE(128, 128, 3, 3, PRO_NONE, EPI_ACT_BWD, false)
+  // ... with the InstanceNorm backward of the incoming gradient fused into the prologue
+  W2S_CASE(16, 16, 3, 3, PRO_DNORM, EPI_ACT_BWD, false)
+  W2S_CASE(32, 16, 3, 3, PRO_DNORM, EPI_ACT_BWD, false)
+  W2S_CASE(32, 32, 3, 3, PRO_DNORM, EPI_ACT_BWD, false)
+  W2S_CASE(64, 32, 3, 3, PRO_DNORM, EPI_ACT_BWD, false)
+  W2S_CASE(64, 64, 3, 3, PRO_DNORM, EPI_ACT_BWD, false)
+  W2S_CASE(128, 64, 3, 3, PRO_DNORM, EPI_ACT_BWD, false)
+  W2S_CASE(128, 128, 3, 3, PRO_DNORM, EPI_ACT_BWD, false)
   W2S_CASE(16, 16, 1, 1, PRO_NONE, EPI_PLAIN, false)
   W2S_CASE(32, 16, 1, 1, PRO_NONE, EPI_PLAIN, false)
   W2S_CASE(32, 32, 1, 1, PRO_NONE, EPI_PLAIN, false)
@@ -456,7 +473,7 @@ int check_encoder_desc(const w2s_encoder_desc* d) {
 
 extern "C" {
 
-int w2s_abi_version(void) { return 2; }
+int w2s_abi_version(void) { return 3; }
 const char* w2s_last_error(void) { return g_err.c_str(); }
 
 int w2s_conv_uses_split(int cin, int cout) { return (cin <= 16 && cout <= 16) ? 1 : 0; }

@@ -25,12 +25,19 @@
 //                   gradient); sum d(x_hat), sum d(x_hat) x_hat per (sample, channel) -> out_stats (fp64)
 //   EPI_PLAIN     : (+ bias) (+ residual tensor) -> fp16, output rows at o*out_stride + out_offset (plain GEMMs and
 //                   data-gradient convolutions of the training path)
+// Training prologue PRO_DNORM (data-gradient convs): the conv input is the gradient dy of the layer's pre-norm output,
+//   which is the InstanceNorm backward of d(x_hat): dy = rstd (d(x_hat) - mean(d x_hat) - x_hat mean(d x_hat . x_hat)),
+//   x_hat = (y - mu) rstd.  It is computed on the way to shared memory from `in` = d(x_hat) and `in_res` = y (the layer's
+//   stored forward output) with the per-(sample, channel) constants from in_stats (sum y, sum y^2) and dn_sums
+//   (sum d x_hat, sum d x_hat . x_hat); each tile also writes the dy rows it owns to dn_out, for the weight-gradient
+//   GEMM that follows.  dn_upsample: the layer was a stride-2 conv - its gradient enters the (stride-1) data-gradient
+//   conv zero-stuffed: input row i = source row i / 2 for even i, zero for odd i.
 #pragma once
 #include "common.cuh"
 
 namespace w2s {
 
-enum : int { PRO_NONE = 0, PRO_NORM = 1, PRO_NORM_RES = 2, PRO_FIR = 3, PRO_NORM_RES_X = 4 };
+enum : int { PRO_NONE = 0, PRO_NORM = 1, PRO_NORM_RES = 2, PRO_FIR = 3, PRO_NORM_RES_X = 4, PRO_DNORM = 5 };
 enum : int { EPI_STATS = 0, EPI_BIAS_GELU = 1, EPI_LN_GELU = 2, EPI_LN_GELU_RES = 3, EPI_PLAIN = 4, EPI_ACT_BWD = 5 };
 
 struct ConvArgs {
@@ -73,6 +80,10 @@ struct ConvArgs {
   const float* w_first;   // [16, 3]
   const float* w_first_ds;  // [16]
   int T_raw;
+  // PRO_DNORM
+  const double* dn_sums;  // [B, CIN, 2] sum d(x_hat), sum d(x_hat) x_hat over the layer's output length
+  act_t* dn_out;          // [B, L_in, CIN] dy (zero-stuffed when dn_upsample)
+  int dn_upsample;
   // Profiling experiments only (W2S_DEBUG_FLAGS in the environment; 0 in production, results are wrong otherwise):
   //   1 skip the lo-operand MMAs, 2 skip all MMAs, 4 skip GELU, 8 skip epilogue stores, 16 skip epilogue TMEM loads,
   //   32 skip the transform, 64 record timestamps / per-role wait cycles (results stay correct), 128 / 256 skip only the
@@ -102,7 +113,7 @@ template <int CIN, int COUT>
 struct ConvSplit {
   static constexpr bool value = (CIN <= 16 && COUT <= 16);
 };
-constexpr int kConvCtlBytes = 16 + 2 * 128 * 4 + 2 * 512 * 4;  // barrier+tmem slot, scale/shift, stats partials
+constexpr int kConvCtlBytes = 16 + 2 * 128 * 4 + 2 * 512 * 4 + 4 * 128 * 4;  // barrier+tmem slot, scale/shift, stats partials, PRO_DNORM constants
 template <int CIN, int COUT, int GT, bool HAS_DS, bool SPLIT>
 __host__ __device__ inline size_t conv_smem_bytes(int stride, int taps, int dil) {
   const int rp = conv_rows_per_phase(ConvTile<COUT>::POS, stride, taps, dil);
@@ -154,6 +165,8 @@ __global__ void __launch_bounds__(kConvThreads, (EPI == EPI_ACT_BWD && COUT <= 6
   float* sShift = sScale + 128;                                 // [128]
   float* sPartSum = sShift + 128;                               // [8 warps][4 units][16 ch]
   float* sPartSq = sPartSum + 512;
+  float* sDn = sPartSq + 512;                                   // PRO_DNORM: [mean | rstd | m1 | m2][128]
+  (void)sDn;
 
   // ---------------- setup ----------------
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -161,7 +174,18 @@ __global__ void __launch_bounds__(kConvThreads, (EPI == EPI_ACT_BWD && COUT <= 6
     mbar_init(bar, 1);
     fence_mbar_init();
   }
-  if (PRO != PRO_NONE && tid >= 64 && tid < 64 + CIN) {
+  if (PRO == PRO_DNORM && tid >= 64 && tid < 64 + CIN) {
+    const int c = tid - 64;
+    const int Ls = p.dn_upsample ? (p.L_in >> 1) : p.L_in;  // length of the layer output the statistics run over
+    float mean, rstd;
+    in_consts(p.in_stats, b, CIN, c, Ls, p.in_eps, mean, rstd);
+    const float invL = 1.0f / (float)Ls;
+    sDn[c] = mean;
+    sDn[128 + c] = rstd;
+    sDn[256 + c] = (float)p.dn_sums[((size_t)b * CIN + c) * 2] * invL;
+    sDn[384 + c] = (float)p.dn_sums[((size_t)b * CIN + c) * 2 + 1] * invL;
+  }
+  if (PRO != PRO_NONE && PRO != PRO_DNORM && tid >= 64 && tid < 64 + CIN) {
     const int c = tid - 64;
     const double s0 = p.in_stats[((size_t)b * CIN + c) * 2 + 0];
     const double s1 = p.in_stats[((size_t)b * CIN + c) * 2 + 1];
@@ -184,7 +208,64 @@ __global__ void __launch_bounds__(kConvThreads, (EPI == EPI_ACT_BWD && COUT <= 6
   const uint32_t tmem_base = *tmem_slot;
 
   // ---------------- prologue: global -> (norm, GELU) -> smem A ----------------
-  {
+  if constexpr (PRO == PRO_DNORM) {
+    // InstanceNorm backward on the way in (see the header): 4 row chunks in flight per thread, two tensors each
+    const int cch = tid & (CH - 1);
+    float mean[8], rstd[8], m1[8], m2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      mean[k] = sDn[cch * 8 + k];
+      rstd[k] = sDn[128 + cch * 8 + k];
+      m1[k] = sDn[256 + cch * 8 + k];
+      m2[k] = sDn[384 + cch * 8 + k];
+    }
+    const int total = R * CH;
+    const int up = p.dn_upsample;
+    const int Ls = up ? (p.L_in >> 1) : p.L_in;
+    const act_t* gb = p.in + (size_t)b * Ls * CIN;        // d(x_hat)
+    const act_t* yb = p.in_res + (size_t)b * Ls * CIN;    // y
+    act_t* dyb = p.dn_out + (size_t)b * p.L_in * CIN;
+    constexpr int UN = 4;
+    for (int base = tid; base < total; base += kConvThreads * UN) {
+      uint4 g[UN], y[UN];
+#pragma unroll
+      for (int k = 0; k < UN; ++k) {
+        const int id = base + k * kConvThreads;
+        const int i = i0 + id / CH;
+        g[k] = y[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (id < total && i >= 0 && i < p.L_in && !(up && (i & 1))) {
+          const size_t off = (size_t)(up ? (i >> 1) : i) * CIN + cch * 8;
+          g[k] = __ldg(reinterpret_cast<const uint4*>(gb + off));
+          y[k] = __ldg(reinterpret_cast<const uint4*>(yb + off));
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < UN; ++k) {
+        const int id = base + k * kConvThreads;
+        if (id >= total) break;
+        const int u = id / CH;
+        const int i = i0 + u;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (i >= 0 && i < p.L_in && !(up && (i & 1))) {
+          const uint32_t* gg = reinterpret_cast<const uint32_t*>(&g[k]);
+          const uint32_t* yy = reinterpret_cast<const uint32_t*>(&y[k]);
+          uint32_t* oo = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 gv = unpack_h2(gg[q]), yv = unpack_h2(yy[q]);
+            const float xh0 = (yv.x - mean[2 * q]) * rstd[2 * q], xh1 = (yv.y - mean[2 * q + 1]) * rstd[2 * q + 1];
+            oo[q] = pack_h2(rstd[2 * q] * (gv.x - m1[2 * q] - xh0 * m2[2 * q]),
+                            rstd[2 * q + 1] * (gv.y - m1[2 * q + 1] - xh1 * m2[2 * q + 1]));
+          }
+        }
+        const int phase = u & (stride - 1);
+        const int row = u >> p.stride_log2;
+        *reinterpret_cast<uint4*>(sA + ((size_t)(phase * CH + cch) * Rp + row) * 16) = o;
+        // rows this tile owns (the POS input rows aligned with its outputs; halo rows belong to the neighbours)
+        if (u >= p.pad && u < p.pad + POS && i < p.L_in) *reinterpret_cast<uint4*>(dyb + (size_t)i * CIN + cch * 8) = o;
+      }
+    }
+  } else {
     const int cch = tid & (CH - 1);  // this thread's channel chunk is fixed (256 % CH == 0)
     float sc[8], sh[8];
     if (PRO != PRO_NONE) {

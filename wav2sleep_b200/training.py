@@ -24,13 +24,14 @@ exactly (powers of two), and nothing outside this file sees the scale.
 from __future__ import annotations
 
 import contextlib
+import os
 import ctypes as C
 
 import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import ConvCall, EPI_ACT_BWD, EPI_PLAIN, PRO_NONE
+from ._lib import PRO_DNORM, ConvCall, EPI_ACT_BWD, EPI_PLAIN, PRO_NONE
 from .engine import ForwardEngine, _stream
 
 F16 = torch.float16
@@ -57,6 +58,9 @@ class TrainEngine(ForwardEngine):
         self.dropout_seed = None  # int: fixed seed for every step (tests); None: drawn from torch's CPU generator
         self.last_dropout_seed = 0
         self._side_streams = {}   # device -> per-encoder CUDA streams (same overlap of kernel tails as in inference)
+        # InstanceNorm backward of a layer's gradient inside the prologue of the data-gradient conv that consumes it
+        # (W2S_PRO_DNORM) instead of a separate enc_norm_bwd pass; W2S_FUSE_NORM_BWD=0 keeps the separate kernels (A/B)
+        self.fuse_norm_bwd = os.environ.get("W2S_FUSE_NORM_BWD", "1") != "0"
         self.loss_scale = None    # power of two applied to the fp16 activation gradients; None = from B*S (see below)
         self._inv_scale = 1.0
         self.last_loss_scale = 1.0
@@ -169,16 +173,26 @@ class TrainEngine(ForwardEngine):
         c.out_stride, c.out_offset, c.out_rows = out_stride, out_offset, out_rows
         _lib.check(self.lib.w2s_conv1d_fwd(C.byref(c), _stream()))
 
-    def conv_act_bwd(self, dy, w, cin, cout, B, L, y, stats, sums, dxh, a_out, eps, row_mask, res=None, r=None, dr=None):
+    def conv_act_bwd(self, dy, w, cin, cout, B, L, y, stats, sums, dxh, a_out, eps, row_mask, res=None, r=None, dr=None,
+                     dnorm=None):
         """Data gradient of a k=3 / pad=1 / stride-1 conv (flipped, transposed weights w) fused with the backward through
         the activation of the layer that produced the conv's input: writes d(x_hat) of that layer (dxh), its activated
         output (a_out, operand of this conv's weight gradient), d(residual branch) (dr, block outputs) and accumulates
-        the two InstanceNorm-backward reductions into sums."""
+        the two InstanceNorm-backward reductions into sums.
+
+        dnorm = (dxh_in, y_in, stats_in, sums_in, upsample): the conv input dy is not given but computed in the kernel's
+        prologue as the InstanceNorm backward of this layer's own d(x_hat) (W2S_PRO_DNORM) and written to `dy` for the
+        weight gradient - one pass over the tensors instead of a separate enc_norm_bwd launch."""
         c = ConvCall()
         c.cin, c.cout, c.taps, c.stride, c.dilation, c.pad = cin, cout, 3, 1, 1, 1
         c.prologue, c.epilogue, c.has_ds = PRO_NONE, EPI_ACT_BWD, 0
         c.B, c.L_in, c.L_out = B, L, L
         c.in_, c.w, c.out = dy.data_ptr(), w.data_ptr(), dxh.data_ptr()
+        if dnorm is not None:
+            dxh_in, y_in, stats_in, sums_in, upsample = dnorm
+            c.prologue = PRO_DNORM
+            c.in_, c.in_res, c.in_stats = dxh_in.data_ptr(), y_in.data_ptr(), stats_in.data_ptr()
+            c.dn_sums, c.dn_out, c.dn_upsample, c.in_eps = sums_in.data_ptr(), dy.data_ptr(), int(upsample), eps
         c.res = res.data_ptr() if res is not None else None
         c.row_mask = row_mask.data_ptr() if row_mask is not None else None
         c.out_stats = sums.data_ptr()
@@ -579,27 +593,38 @@ class TrainEngine(ForwardEngine):
             Lh = L // 2
             # here: dxh / dr / sums = backward through this block's output activation GELU(GELU(IN(y3)) + r)
             dy_up = new(B, L, Cc)  # even rows = dy, odd rows = zeros (written by the kernel): transposed stride-2 conv
-            _lib.check(lib.w2s_enc_norm_bwd(dxh.data_ptr(), bk["y3"].data_ptr(), bk["s3"].data_ptr(), sums.data_ptr(),
-                                            dy_up.data_ptr(), mask.data_ptr(), B, Lh, Cc, 1, eps, st))
+            fuse = self.fuse_norm_bwd
+            if not fuse:
+                _lib.check(lib.w2s_enc_norm_bwd(dxh.data_ptr(), bk["y3"].data_ptr(), bk["s3"].data_ptr(), sums.data_ptr(),
+                                                dy_up.data_ptr(), mask.data_ptr(), B, Lh, Cc, 1, eps, st))
             # ---- conv3 (stride 2): data gradient + backward through GELU(IN(y2)) in one kernel ----
+            dn = (dxh, bk["y3"], bk["s3"], sums, 1) if fuse else None
             dxh, a2, sums = new(B, L, Cc), new(B, L, Cc), zeros64(Cc)
-            self.conv_act_bwd(dy_up, tw["conv"][i][2], Cc, Cc, B, L, bk["y2"], bk["s2"], sums, dxh, a2, eps, mask)
+            self.conv_act_bwd(dy_up, tw["conv"][i][2], Cc, Cc, B, L, bk["y2"], bk["s2"], sums, dxh, a2, eps, mask, dnorm=dn)
             self.gemm_tn(dy_up, a2, G(blk.conv3.conv.weight), Cc, Cc, B, L, L, Cc * 3, 3, y_offset=-1, row_mask=mask,
                          taps=3, ldc_t=1)
             del dy_up
             # ---- conv2 ----
             dy2 = a2  # a2 is consumed: reuse its storage
-            _lib.check(lib.w2s_enc_norm_bwd(dxh.data_ptr(), bk["y2"].data_ptr(), bk["s2"].data_ptr(), sums.data_ptr(),
-                                            dy2.data_ptr(), mask.data_ptr(), B, L, Cc, 0, eps, st))
+            if not fuse:
+                _lib.check(lib.w2s_enc_norm_bwd(dxh.data_ptr(), bk["y2"].data_ptr(), bk["s2"].data_ptr(), sums.data_ptr(),
+                                                dy2.data_ptr(), mask.data_ptr(), B, L, Cc, 0, eps, st))
+                dn, dxh_next = None, dxh  # (the un-fused kernel may overwrite d(x_hat) in place)
+            else:
+                dn, dxh_next = (dxh, bk["y2"], bk["s2"], sums, 0), new(B, L, Cc)
             a1, sums = new(B, L, Cc), zeros64(Cc)
-            self.conv_act_bwd(dy2, tw["conv"][i][1], Cc, Cc, B, L, bk["y1"], bk["s1"], sums, dxh, a1, eps, mask)
+            self.conv_act_bwd(dy2, tw["conv"][i][1], Cc, Cc, B, L, bk["y1"], bk["s1"], sums, dxh_next, a1, eps, mask, dnorm=dn)
+            dxh = dxh_next
             self.gemm_tn(dy2, a1, G(blk.conv2.conv.weight), Cc, Cc, B, L, L, Cc * 3, 3, y_offset=-1, row_mask=mask, taps=3,
                          ldc_t=1)
             del dy2, a2
             # ---- conv1 (+ 1x1 stride-2 residual branch) ----
             dy1 = a1
-            _lib.check(lib.w2s_enc_norm_bwd(dxh.data_ptr(), bk["y1"].data_ptr(), bk["s1"].data_ptr(), sums.data_ptr(),
-                                            dy1.data_ptr(), mask.data_ptr(), B, L, Cc, 0, eps, st))
+            fuse1 = fuse and i > 0  # block 0 has no data gradient to fuse into (its input is the raw signal)
+            if not fuse1:
+                _lib.check(lib.w2s_enc_norm_bwd(dxh.data_ptr(), bk["y1"].data_ptr(), bk["s1"].data_ptr(), sums.data_ptr(),
+                                                dy1.data_ptr(), mask.data_ptr(), B, L, Cc, 0, eps, st))
+            dn = (dxh, bk["y1"], bk["s1"], sums, 0) if fuse1 else None
             del dxh
             if i == 0:
                 _lib.check(lib.w2s_first_conv_wgrad(e["x"].data_ptr(), dy1.data_ptr(), dr.data_ptr(),
@@ -614,7 +639,8 @@ class TrainEngine(ForwardEngine):
             # block's output activation; a_in is this block's input, needed by the two weight gradients below
             dxh_p, dr_p, a_in, sums = new(B, L, Ci), new(B, L, Ci), new(B, L, Ci), zeros64(Ci)
             self.conv_act_bwd(dy1, tw["conv"][i][0], Cc, Ci, B, L, pb["y3"], pb["s3"], sums, dxh_p, a_in, eps, mask,
-                              res=tmp, r=pb["r"], dr=dr_p)
+                              res=tmp, r=pb["r"], dr=dr_p, dnorm=dn)
+            dn = None
             del tmp
             self.gemm_tn(dy1, a_in, G(blk.conv1.conv.weight), Cc, Ci, B, L, L, Ci * 3, 3, y_offset=-1, row_mask=mask,
                          taps=3, ldc_t=1)
