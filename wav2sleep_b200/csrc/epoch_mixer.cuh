@@ -81,7 +81,8 @@ W2S_DEVINL void mma_16816(float (&c)[4], const uint32_t (&a)[4], const uint2 b) 
 }
 
 // C[m_tiles*16, n8-tiles nt0..nt0+ntn) = A[., KT*16] * W^T ; epi(row, col, v0, v1) gets two adjacent columns.
-// n-tiles are taken two at a time (one A fragment feeds two MMAs); an odd count ends with a single one.
+// n-tiles are taken two at a time (one A fragment feeds two MMAs); an odd count ends with a single one.  (Measured:
+// four at a time - half the ldmatrix traffic, 220 registers, weight fragments in chunks of 4 k-tiles - is 7 % slower.)
 template <int D, int KT, class Epi>
 W2S_DEVINL void warp_gemm(const __half* sAop, int lda, int m_tiles, const uint2* __restrict__ Wp, int nt0, int ntn,
                           int lane, Epi epi) {
