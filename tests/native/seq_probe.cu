@@ -1,5 +1,5 @@
 // Stand-alone timing probe of the fused sequence mixer (seq_mixer.cuh): random data, knock-outs of single stages.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o seq_probe seq_probe.cu && ./seq_probe
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DW2S_SEQ_PROBE -o seq_probe seq_probe.cu && ./seq_probe
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>

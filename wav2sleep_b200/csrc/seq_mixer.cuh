@@ -73,6 +73,14 @@ W2S_DEVINL float2 gelu_acc2(float2 x) {
   return make_float2(__fdividef(x.x, d.x), __fdividef(x.y, d.y));
 }
 
+// Profiling knock-outs of single stages are compiled in only for the stand-alone probe (tests/native/seq_probe.cu builds
+// with -DW2S_SEQ_PROBE); in the library SeqArgs::dbg is ignored and the checks cost nothing.
+#ifdef W2S_SEQ_PROBE
+#define SEQ_DBG(p, mask) ((p).dbg & (mask))
+#else
+#define SEQ_DBG(p, mask) 0
+#endif
+
 W2S_DEVINL void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 W2S_DEVINL void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 // generic-proxy global writes <-> async-proxy (bulk copy) reads
@@ -167,7 +175,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_mixer_kernel(const SeqArgs
   //   input, same rows, same thread) and writes the block output back into X.
   auto in_buf = [&](int k) -> act_t* { return k == 0 ? bufX : (((k - 1) & 1) ? bufP1 : bufP0); };
   auto out_buf = [&](int k) -> act_t* { return k == p.n_dil - 1 ? bufX : ((k & 1) ? bufP1 : bufP0); };
-  const bool stage_loops = !(p.dbg & 16);
+  const bool stage_loops = !SEQ_DBG(p, 16);
 
   if (warp == 0) {
     // ---------------- weight producer: free-running ring, one 16 KB stage per (tap, K half) ----------------
@@ -178,7 +186,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_mixer_kernel(const SeqArgs
       for (int st = 0; stage_loops && st < kSeqStagesPerLayer; ++st) {
         mbar_wait(&w_empty[s], ph ^ 1);
         if (elect_one()) {
-          if (p.dbg & 2) {
+          if (SEQ_DBG(p, 2)) {
             mbar_arrive(&w_full[s]);
           } else {
             mbar_arrive_expect_tx(&w_full[s], kSeqStageBytes);
@@ -206,10 +214,10 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_mixer_kernel(const SeqArgs
       const int d = 1 << k;
       const uint8_t* src = reinterpret_cast<const uint8_t*>(in_buf(k));
       const uint32_t nld = (uint32_t)(nrows + 6 * d) * 16;
-      if (!(p.dbg & 128)) fence_proxy_async_all();
+      if (!SEQ_DBG(p, 128)) fence_proxy_async_all();
       if (stage_loops && elect_one()) {
         for (int h = 0; h < 2; ++h) {
-          if (p.dbg & 8) {
+          if (SEQ_DBG(p, 8)) {
             mbar_arrive(&a_full[h]);
             continue;
           }
@@ -227,7 +235,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_mixer_kernel(const SeqArgs
     constexpr uint32_t IDESC = umma_idesc_f16(128, 128, false);
     const uint32_t a_base = smem_u32(sA);
     const uint32_t lbo_a = (uint32_t)p.AR * 16;
-    const int ntm = (p.dbg & 4) ? 0 : p.ntiles;
+    const int ntm = SEQ_DBG(p, 4) ? 0 : p.ntiles;
     int s = 0;
     uint32_t ph = 0;
     for (int l = 0; l < n_layers; ++l) {
@@ -291,7 +299,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_mixer_kernel(const SeqArgs
       const uint8_t* resb = reinterpret_cast<const uint8_t*>(bufX);
       for (int tile = 0; tile < p.ntiles; ++tile) {
         if (tile * 128 + quad * 32 >= nrows) break;  // warp-uniform; the partner warps (same quadrant) take the same path
-        if (p.dbg & 1) continue;
+        if (SEQ_DBG(p, 1)) continue;
         const int row = tile * 128 + quad * 32 + lane;  // row inside this CTA
         const bool valid = row < nrows;
         const size_t grow = (size_t)p.PAD + r0 + row;   // row in the padded scratch tensors
@@ -346,7 +354,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_mixer_kernel(const SeqArgs
               const float2 a = make_float2(__uint_as_float(r[c8 * 8 + 2 * q]), __uint_as_float(r[c8 * 8 + 2 * q + 1]));
               const float2 xh = __ffma2_rn(a, rs2, nm2);
               v[q] = __ffma2_rn(xh, ww[q], bb[q]);
-              if (!(p.dbg & 256)) v[q] = gelu_acc2(v[q]);
+              if (!SEQ_DBG(p, 256)) v[q] = gelu_acc2(v[q]);
             }
             if (last_of_block) {  // + block input (DilatedConvBlock.forward: act(out + x)), same row, read by its writer
               const uint4 rz = __ldcg(reinterpret_cast<const uint4*>(resb + ((size_t)ch * p.SP + grow) * 16));
@@ -357,7 +365,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_mixer_kernel(const SeqArgs
             const uint4 o = make_uint4(pack_h2(v[0].x, v[0].y), pack_h2(v[1].x, v[1].y), pack_h2(v[2].x, v[2].y),
                                        pack_h2(v[3].x, v[3].y));
             if (!last) {
-              if (!(p.dbg & 32)) *reinterpret_cast<uint4*>(outb + ((size_t)ch * p.SP + grow) * 16) = o;
+              if (!SEQ_DBG(p, 32)) *reinterpret_cast<uint4*>(outb + ((size_t)ch * p.SP + grow) * 16) = o;
             } else {
               if (p.feat_out != nullptr)
                 *(reinterpret_cast<uint4*>(p.feat_out + ((size_t)b * p.S + r0 + row) * 128) + ch) = o;
@@ -399,7 +407,7 @@ __global__ void __launch_bounds__(kSeqThreads, 1) seq_mixer_kernel(const SeqArgs
         }
       }
       tc_fence_before_sync();
-      if (!(p.dbg & 64)) fence_proxy_async_all();  // this layer's rows are read by bulk copies of the whole cluster after the barrier
+      if (!SEQ_DBG(p, 64)) fence_proxy_async_all();  // this layer's rows are read by bulk copies of the whole cluster after the barrier
       __syncwarp();
       cluster_arrive();
       cluster_wait();
