@@ -158,6 +158,11 @@ W2S_DEVINL void mixer_layernorm(const float* sX, __half* sA, int rows, const flo
   }
 }
 
+// ncu source view (round 2, profiles/r02_src_epoch_mixer.txt): the exact-erf GELU of the FFN hidden layer is 54 % of the
+// executed instructions (FSEL / FFMA / FADD of erff, 49 k GELUs per tile) against 10 % HMMA - yet replacing it by the
+// one-ex2 form only moves the kernel from 396 to 379 us: the tile is a chain of 14 barrier-separated phases whose
+// length is set by dependent latencies (stalls: wait 26 %, short scoreboard 18 %, long scoreboard 16 %), not by issue
+// slots.  The exact form stays.
 template <int D>  // D = 1 (CLS) + number of signals
 __global__ void __launch_bounds__(kMixThreads, 1) epoch_mixer_kernel(const MixerArgs p) {
   constexpr int R = 16 * D;
