@@ -10,8 +10,10 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN
+from conftest import GOLDEN, make_inputs
 from oracle import make_golden_general as G
+from oracle import wav2sleep_oracle as oracle
+from wav2sleep_b200 import build_default
 from wav2sleep_b200 import model as M
 
 TOL = 2e-4  # fp32 kernels vs fp32 reference; logits are O(1)
@@ -94,6 +96,46 @@ def test_reference_causality_test_on_cuda_path(cuda_device):
     L_out = y2.shape[1]
     assert y.shape == (1, 1200, 4) and L_out == 600
     assert torch.allclose(y[:, :L_out], y2[:, :L_out])
+
+
+@pytest.mark.gpu
+def test_reference_compile_test_on_cuda_path(cuda_device):
+    """/root/reference/tests/model/test_compile.py:11-40, same configuration and call sequence: ``encoders.compile(...)``,
+    ``model.compile(mode='max-autotune', fullgraph=True)``, a stand-alone ``encoders({...})`` call and ``model({...})`` on
+    one 10-h night.  Here ``compile`` has nothing to trace (the forward is CUDA behind a C ABI) and is accepted as a
+    no-op; the one difference to the reference test is ``eval()`` + ``no_grad`` - non-default configurations are
+    inference-only on this path.  The stand-alone encoders call must follow models/wav2sleep.py:146-161: fp32
+    [B, S, F] per signal, rows of missing signals filled with -inf, and agree with what the model consumes."""
+    torch.manual_seed(0)
+    feature_dim = 16
+    encoders = M.SignalEncoders(signal_map={"ECG": "ECG", "PPG": "PPG"}, feature_dim=feature_dim, activation="relu",
+                                norm="instance").to(cuda_device)
+    assert encoders.compile(fullgraph=True) is None
+    model = M.Wav2Sleep(signal_encoders=encoders, epoch_mixer=M.MultiModalAttentionEmbedder(feature_dim=feature_dim),
+                        sequence_mixer=M.SequenceCNN(feature_dim=feature_dim), num_classes=1).to(cuda_device).eval()
+    assert model.compile(mode="max-autotune", fullgraph=True) is None
+    x = torch.randn(1, 1_228_800, device=cuda_device)
+    with torch.no_grad():
+        z = encoders({"ECG": x, "PPG": x})
+        out = model({"ECG": x, "PPG": x})
+    assert set(z) == {"ECG", "PPG"} and z["ECG"].shape == (1, 1200, feature_dim) and z["ECG"].dtype == torch.float32
+    assert out.shape == (1, 1200, 1) and torch.isfinite(out).all() and torch.isfinite(z["PPG"]).all()
+    # missing-signal convention and agreement with the features the model itself computes
+    xs = torch.randn(2, 8 * 1024, device=cuda_device)
+    xs[1] = float("-inf")
+    with torch.no_grad():
+        zs = encoders({"ECG": xs})["ECG"]
+        ref, mask = model._get_general().encode(encoders.get_encoder("ECG"), xs)
+    assert torch.isinf(zs[1]).all() and (zs[1] < 0).all() and torch.isfinite(zs[0]).all()
+    assert mask.tolist() == [0, 1] and torch.equal(zs[0], ref[0])
+    # the default model family takes the same entry (fp32 general kernels) and matches the oracle's encoder features
+    enc = build_default({"ABD": "ABD"}, 4, seed=0).signal_encoders.to(cuda_device)
+    xa = make_inputs({"ABD": "ABD"}, 2, 6, seed=3)
+    want = oracle.signal_encoders(xa, {k: v.detach().cpu() for k, v in enc.state_dict(prefix="signal_encoders.").items()},
+                                  oracle.OracleConfig(signal_map={"ABD": "ABD"}, num_classes=4))["ABD"]
+    with torch.no_grad():
+        got = enc({"ABD": xa["ABD"].to(cuda_device)})["ABD"].cpu()
+    assert (got - want).abs().max().item() < 1e-4
 
 
 @pytest.mark.gpu

@@ -229,6 +229,35 @@ class SignalEncoders(nn.Module):
     def get_encoder(self, signal_name: str) -> SignalEncoder:
         return self.encoders[self.signal_map[signal_name]]  # type: ignore[return-value]
 
+    def compile(self, *args, **kwargs) -> None:
+        """``nn.Module.compile`` of the reference (tests/model/test_compile.py:27, api.py:96-97) has nothing to trace here:
+        the forward is pre-compiled CUDA behind a C ABI.  Accepted and ignored, so that callers need no change."""
+
+    def forward(self, x: dict[str, Tensor]) -> dict[str, Tensor]:
+        """Stand-alone call of the encoders (reference models/wav2sleep.py:146-161): {signal: [B, T]} ->
+        {signal: fp32 [B, S, feature_dim]}, rows of samples whose signal is missing (-inf input) filled with -inf,
+        plus the optional signal-source embedding.  ``Wav2Sleep.forward`` does not come through here (its fused path
+        keeps the features in fp16 and hands masks over separately); this entry runs the dimension-generic fp32 CUDA
+        kernels for every configuration."""
+        from .general import GeneralEngine  # deferred: loads the CUDA library
+        if getattr(self, "_general", None) is None:
+            object.__setattr__(self, "_general", GeneralEngine(None))
+        eng, out = self._general, {}
+        for name, x_BT in x.items():
+            if name not in self.signal_map:
+                raise KeyError(f"Signal {name!r} has no encoder (valid: {list(self.signal_map)})")
+            if not x_BT.is_cuda:
+                raise RuntimeError("wav2sleep_b200 runs on CUDA (sm_100a) only: move inputs with .to('cuda'); "
+                                   "there is no CPU fallback")
+            with torch.no_grad(), torch.cuda.device(x_BT.device):
+                z, mask = eng.encode(self.get_encoder(name), x_BT)
+                if self.embed_signals:  # wav2sleep.py:155-159 (the reference adds it to the -inf rows as well)
+                    e = self.embedder.weight[self.sig_to_embedding_idx[name]].detach().float().contiguous()
+                    z = eng.affine_act(z, "linear", shift=e, mask=mask, per_channel=1)
+                z = z.masked_fill(mask.bool()[:, None, None], float("-inf"))  # data movement, no arithmetic
+            out[name] = z
+        return out
+
 
 class MultiModalAttentionEmbedder(nn.Module):
     """CLS-token set transformer over the modality tokens of one epoch.  models/wav2sleep.py:270-346."""
@@ -253,6 +282,9 @@ class MultiModalAttentionEmbedder(nn.Module):
         self.register_tokens = nn.Parameter(torch.randn(1, 1, feature_dim, register_tokens + 1))
         self.fast_path = (feature_dim == 128 and nhead == 8 and dim_ff == 512 and activation == "gelu" and norm_first
                           and register_tokens == 0 and 1 <= layers <= 8)
+
+    def compile(self, *args, **kwargs) -> None:
+        """Accepted and ignored (see SignalEncoders.compile): the CUDA path needs no tracing compiler."""
 
 
 class DilatedConvBlock(nn.Module):
@@ -288,6 +320,9 @@ class SequenceCNN(nn.Module):
         self.fast_path = (feature_dim == 128 and kernel_size == 7 and activation == "gelu" and norm == "layer"
                           and not causal and 1 <= num_layers <= 4 and 1 <= num_dilations <= 8)
 
+    def compile(self, *args, **kwargs) -> None:
+        """Accepted and ignored (see SignalEncoders.compile): the CUDA path needs no tracing compiler."""
+
 
 class Wav2Sleep(nn.Module):
     """Sleep-staging model: encoders -> epoch mixer -> sequence mixer -> classifier.  models/wav2sleep.py:16-80."""
@@ -311,6 +346,11 @@ class Wav2Sleep(nn.Module):
     @property
     def valid_signals(self) -> list[str]:
         return list(self.signal_encoders.signal_map.keys())
+
+    def compile(self, *args, **kwargs) -> None:
+        """``model.compile(mode='max-autotune')`` of the reference (api.py:96-97, tests/model/test_compile.py:35): accepted
+        and ignored - the forward is hand-written CUDA behind a C ABI, there is nothing for a tracing compiler to do (and
+        tracing it with ``fullgraph=True`` would stop at the first library call)."""
 
     def _get_engine(self):
         from .training import TrainEngine  # deferred: loads the CUDA library
