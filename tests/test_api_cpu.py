@@ -75,3 +75,16 @@ def test_predict_sharded_gloo_world2():
     assert res[0][1] == [[0, 1, 2]] and res[1][1] == [[3, 4]]  # disjoint contiguous shards
     for _, _, out in res:
         assert torch.equal(out, expect)  # every rank sees all predictions, in recording order
+
+
+def test_top_level_functions_mirror_the_reference_package():
+    """`from wav2sleep import load_model, predict, save_predictions, predict_on_folder` (reference __init__.py:3-19)."""
+    import inspect
+    import wav2sleep_b200 as pkg
+    for name in ("load_model", "predict", "save_predictions", "predict_on_folder"):
+        assert callable(getattr(pkg, name)), name
+    params = list(inspect.signature(pkg.load_model).parameters)
+    assert params == ["folder", "device", "compile", "revision", "cache_dir"]  # api.py:53-59
+    import pytest
+    with pytest.raises(NotImplementedError):
+        pkg.load_model("hf://joncarter/wav2sleep")

@@ -17,5 +17,17 @@ from .model import (  # noqa: F401
 
 __all__ = [
     "COLS_TO_SAMPLES_PER_EPOCH", "MultiModalAttentionEmbedder", "SequenceCNN", "SignalEncoder", "SignalEncoders",
-    "Wav2Sleep", "build_default",
+    "Wav2Sleep", "build_default", "load_model", "predict", "save_predictions", "predict_on_folder",
 ]
+
+# The reference's top-level functions (src/wav2sleep/__init__.py:3-19), resolved on first use so that importing the
+# package stays light (folder.py pulls in pandas / pyarrow).  ``prepare`` / ``load_dataset`` (EDF ingestion) stay with
+# the reference.
+_LAZY = {"load_model": "api", "predict": "api", "save_predictions": "folder", "predict_on_folder": "folder"}
+
+
+def __getattr__(name):
+    if name in _LAZY:
+        import importlib
+        return getattr(importlib.import_module(f"{__name__}.{_LAZY[name]}"), name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

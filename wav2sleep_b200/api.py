@@ -56,9 +56,15 @@ def _resolve_device(device: str) -> str:
     return device
 
 
-def load_model(folder: str, device: str = "auto", compile: bool = False):
-    """Load ``config.yaml`` + ``state_dict.pth`` from a local folder (reference api.py:53-99; hub download is out
-    of scope).  ``compile`` is accepted for signature compatibility and ignored (there is no tracing compiler here)."""
+def load_model(folder: str, device: str = "auto", compile: bool = False, revision: str | None = None,
+               cache_dir: str | None = None):
+    """Load ``config.yaml`` + ``state_dict.pth`` from a local folder (reference api.py:53-99, same signature).
+    Hub download is out of scope: an ``hf://`` URI raises (fetch the two files with the reference's ``hub`` module
+    first); ``revision`` / ``cache_dir`` only apply to hub URIs.  ``compile`` is accepted and ignored (there is no
+    tracing compiler on this path, see ``Wav2Sleep.compile``)."""
+    if str(folder).startswith("hf://"):
+        raise NotImplementedError("wav2sleep_b200.load_model reads local checkpoint folders only; download "
+                                  f"{folder} (config.yaml + state_dict.pth) first")
     config_fp = os.path.join(folder, "config.yaml")
     if not os.path.exists(config_fp):
         raise FileNotFoundError(f"No config file found at {config_fp}. Has the model been downloaded?")
