@@ -89,3 +89,15 @@ def test_predict_on_folder_matches_oracle_pipeline(cuda_device, tmp_path):
         assert torch.equal(preds[i][clear], ref.argmax(-1)[clear])
     out = pd.read_csv(tmp_path / "out" / "sub" / "n3.preds.csv", index_col=0)
     assert list(out["Pred"]) == preds[2].tolist() and list(out.index) == [30.0 * (k + 1) for k in range(S)]
+
+    # the reference's three-call form of the same pipeline (api.py:143-220): load_dataset -> predict -> save_predictions
+    import wav2sleep_b200 as pkg
+    ds = pkg.load_dataset(str(tmp_path / "in"), model.valid_signals, num_classes=4, max_length_hours=10)
+    assert len(ds) == 3 and ds.files == files and set(ds[2][0]) == {"ECG", "ABD"}
+    P, L = pkg.predict(model, ds, device=str(cuda_device), batch_size=2)
+    assert P.shape == (3, S) and P.dtype == torch.int64 and L is not None and L.shape == (3, S)
+    for i in range(3):
+        assert torch.equal(P[i], preds[i])
+    pkg.save_predictions(P, str(tmp_path / "in"), str(tmp_path / "out3"), ds, labels=L, overwrite=True)
+    again = pd.read_csv(tmp_path / "out3" / "sub" / "n3.preds.csv", index_col=0)
+    assert list(again["Pred"]) == preds[2].tolist() and list(again["Stage"]) == [-1.0] * S

@@ -17,13 +17,14 @@ from .model import (  # noqa: F401
 
 __all__ = [
     "COLS_TO_SAMPLES_PER_EPOCH", "MultiModalAttentionEmbedder", "SequenceCNN", "SignalEncoder", "SignalEncoders",
-    "Wav2Sleep", "build_default", "load_model", "predict", "save_predictions", "predict_on_folder",
+    "Wav2Sleep", "build_default", "load_model", "load_dataset", "predict", "save_predictions", "predict_on_folder",
 ]
 
 # The reference's top-level functions (src/wav2sleep/__init__.py:3-19), resolved on first use so that importing the
-# package stays light (folder.py pulls in pandas / pyarrow).  ``prepare`` / ``load_dataset`` (EDF ingestion) stay with
-# the reference.
-_LAZY = {"load_model": "api", "predict": "api", "save_predictions": "folder", "predict_on_folder": "folder"}
+# package stays light (folder.py pulls in pandas / pyarrow).  ``prepare`` (EDF / CSV ingestion) stays with the
+# reference.
+_LAZY = {"load_model": "api", "predict": "api", "load_dataset": "folder", "save_predictions": "folder",
+         "predict_on_folder": "folder"}
 
 
 def __getattr__(name):

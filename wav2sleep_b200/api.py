@@ -96,9 +96,14 @@ def default_config(signal_map: dict, num_classes: int) -> dict:
 
 
 @torch.inference_mode()
-def predict(model, batches: Iterable[dict], device: str = "auto") -> torch.Tensor:
-    """``model(x).argmax(-1)`` over an iterable of input dicts (reference api.py:163-190); returns int64 [N, S] on CPU.
-    Device->host copies are queued per batch and synchronised once at the end."""
+def predict(model, batches, device: str = "auto", batch_size: int = 4, num_workers: int = 4):
+    """Reference ``predict`` (api.py:163-190).  With a dataset from ``load_dataset`` (``.files`` / ``.columns``): the
+    reference's call and return value - ``(predictions int64 [N, S], labels or None)``.  With an iterable of input
+    dicts: ``model(x).argmax(-1)`` per batch, returned as one int64 [N, S] tensor on the CPU (device -> host copies are
+    queued per batch and synchronised once at the end)."""
+    if hasattr(batches, "files") and hasattr(batches, "columns"):
+        from .folder import predict_dataset
+        return predict_dataset(model, batches, device=device, batch_size=batch_size, num_workers=num_workers)
     device = _resolve_device(device)
     outs, pending = [], []
     for x in batches:

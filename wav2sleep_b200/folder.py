@@ -67,6 +67,52 @@ def load_night(fp: str, columns: list[str], num_classes: int, max_length_hours: 
     return signals, labels
 
 
+class NightDataset:
+    """What the reference's ``load_dataset`` returns, as far as its callers use it (``ParquetDataset``: ``.files``,
+    ``.columns``, ``len()``, ``dataset[i] -> (signal dict, labels)``, data/dataset.py:20-75, 132-186).  Items are the RAW
+    night (fp32 per signal, labels fp32 [S]); the whole-night z-score and the ``-inf`` fill of missing signals happen on
+    the device when ``predict`` stages a batch (staging.stage_batch) instead of per item on the CPU."""
+
+    def __init__(self, parquet_fps: list[str], num_classes: int, columns: list[str],
+                 max_length_hours: Optional[int] = None):
+        if num_classes not in INTEGER_LABEL_MAPS:
+            raise ValueError(f"Unsupported num_classes={num_classes}")
+        self.files, self.num_classes, self.columns = list(parquet_fps), num_classes, list(columns)
+        self.max_length_hours = max_length_hours
+
+    def __len__(self) -> int:
+        return len(self.files)
+
+    def __getitem__(self, idx):
+        return load_night(self.files[idx], self.columns, self.num_classes, self.max_length_hours)
+
+
+def load_dataset(parquet_folder: str, signals: Iterable[str], num_classes: int = 4,
+                 max_length_hours: Optional[int] = None) -> NightDataset:
+    """reference api.py:143-160"""
+    files = parquet_files(parquet_folder)
+    if len(files) == 0:
+        raise ValueError(f"No parquet files found in {parquet_folder}.")
+    return NightDataset(files, num_classes, list(signals), max_length_hours)
+
+
+def predict_dataset(model, dataset: NightDataset, device: str = "auto", batch_size: int = 4, num_workers: int = 4):
+    """reference ``predict(model, dataset, device, batch_size, num_workers)`` (api.py:163-190): -> (predictions int64
+    [N, S], labels [N, S] or None when no night has labels).  Nights of different lengths come back padded with -1
+    (the reference's default collate would refuse them).  ``num_workers`` is accepted for compatibility: one reader
+    thread prefetches into pinned memory."""
+    device = _resolve_device(device)
+    preds, labels = predict_files(model.to(device).eval(), dataset.files, dataset.columns, device, batch_size,
+                                  dataset.max_length_hours)
+    S = max((len(p) for p in preds), default=0)
+    P = torch.full((len(preds), S), -1, dtype=torch.int64)
+    L = torch.full((len(preds), S), -1.0)
+    for i, (p_, l_) in enumerate(zip(preds, labels)):
+        P[i, : len(p_)] = p_
+        L[i, : len(l_)] = l_
+    return P, (None if bool((L == -1).all()) else L)
+
+
 def iter_batches(files: list[str], columns: list[str], num_classes: int, batch_size: int,
                  max_length_hours: Optional[int] = None, pin: bool = True, prefetch: int = 2):
     """Yields (indices, {signal: raw [b, T_sig]} pinned, labels [b, S]) for runs of consecutive files of equal length
@@ -128,11 +174,19 @@ def predict_files(model, files: list[str], signals: list[str], device, batch_siz
     return out_p, out_l
 
 
-def save_predictions(predictions, files: list[str], parquet_folder: str, output_folder: str, columns: list[str],
-                     labels=None, overwrite: bool = False) -> None:
+def save_predictions(predictions, files, parquet_folder, output_folder, columns=None, labels=None,
+                     overwrite: bool = False, max_length_hours: Optional[int] = None) -> None:
     """CSV per night mirroring the input tree: index ``Timestamp`` (end of each 30-s epoch, or datetimes when the input
-    has a DatetimeIndex), column ``Pred`` (+ ``Stage``).  Reference api.py:193-220."""
+    has a DatetimeIndex), column ``Pred`` (+ ``Stage``).  Reference api.py:193-220.
+
+    Two calling conventions: ``(predictions, files, parquet_folder, output_folder, columns, ...)`` and the reference's
+    ``(predictions, parquet_folder, output_folder, dataset, labels=None, overwrite=False, max_length_hours=None)`` where
+    ``dataset`` carries ``.files`` / ``.columns``.  Rows padded with -1 (ragged nights) are cut at the night's length."""
     import pandas as pd
+    if isinstance(files, (str, os.PathLike)) and hasattr(output_folder, "files"):  # the reference's argument order
+        dataset, ref_labels = output_folder, columns
+        files, parquet_folder, output_folder, columns = dataset.files, files, parquet_folder, dataset.columns
+        labels = ref_labels if ref_labels is not None else labels
     for idx, fp in enumerate(files):
         out_fp = str(Path(output_folder) / Path(fp).relative_to(parquet_folder).with_suffix(".preds.csv"))
         if os.path.exists(out_fp) and not overwrite:
@@ -141,6 +195,7 @@ def save_predictions(predictions, files: list[str], parquet_folder: str, output_
         input_df = pd.read_parquet(fp)
         input_df = input_df[list(set(columns) & set(input_df.columns))]
         pred = predictions[idx]
+        pred = pred[np.asarray(pred) >= 0] if len(pred) and int(np.asarray(pred).min()) < 0 else pred  # -1 padding
         n = int(len(pred))
         index = pd.Index(np.arange(0, 60 * n / 2, step=30) + 30.0, name=TIMESTAMP)
         if isinstance(input_df.index, pd.DatetimeIndex):
