@@ -144,3 +144,23 @@ def test_validation_and_test_steps_re_evaluate_signal_subsets():
     assert int(pl.aux_outputs["val"][("ECG", "mesa")].sum()) == 8 and int(pl.cmats["val"].sum()) == 4 * 8
     out = pl.predict_step(batch)
     assert set(out) == {"labels", "preds_ECG", "preds_ECG_THX", "preds"} and out["preds"].shape == (2, 4)
+
+
+def test_lightning_module_with_a_unimodal_model():
+    """reference trainer/main.py:97-114: for SleepPPGNet the module drops the masker, is not 'unified' and hands the
+    model the single tensor of a one-key input dict."""
+    from wav2sleep_b200.trainer import SignalMasker, SleepLightningModule
+
+    class Uni(torch.nn.Module):  # no signal_encoders attribute, like SleepPPGNet
+        valid_signals = ["PPG"]
+
+        def forward(self, x_BT):
+            assert isinstance(x_BT, torch.Tensor)
+            return torch.zeros(x_BT.shape[0], x_BT.shape[1] // 4, 4)
+
+    pl = SleepLightningModule(Uni(), num_classes=4, masker=SignalMasker({"PPG": 0.1}))
+    assert pl.masker is None and not pl.unified
+    batch = ({"PPG": torch.zeros(2, 16)}, torch.zeros(2, 4, dtype=torch.long))
+    assert pl.validation_step(batch).ndim == 0 and ("PPG", "all") in pl.aux_outputs["val"]
+    with pytest.raises(ValueError):
+        pl({"PPG": torch.zeros(2, 16), "ECG": torch.zeros(2, 16)})

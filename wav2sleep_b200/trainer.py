@@ -189,7 +189,10 @@ class SleepLightningModule(nn.Module):
         self.masker = masker
         self.flip_polarity = flip_polarity
         self.causal = causal
-        self.unified = len(model.signal_encoders) > 1
+        # is the model unified, i.e. does it work on multiple modalities (reference trainer/main.py:103-106)
+        self.unified = hasattr(model, "signal_encoders") and len(model.signal_encoders) > 1
+        if not hasattr(model, "signal_encoders"):
+            self.masker = None  # trainer/main.py:97-100: the masker applies to Wav2Sleep models only
         self.cmats = {m: torch.zeros(num_classes, num_classes, dtype=torch.long) for m in (TRAIN, VAL, TEST)}
         # per (signal prefix, dataset) confusion matrices, as the reference's aux_outputs (trainer/main.py:91)
         self.aux_outputs = {m: {} for m in (TRAIN, VAL, TEST)}
@@ -198,6 +201,10 @@ class SleepLightningModule(nn.Module):
         self._opt = self._sched = self._reducer = None
 
     def forward(self, x: dict[str, Tensor], y: Tensor | None = None) -> Tensor:
+        if not hasattr(self.model, "signal_encoders"):  # SleepPPGNet: one tensor (reference trainer/main.py:108-114)
+            if len(x) != 1:
+                raise ValueError(f"x.keys()={x.keys()} but expected unimodal input!")
+            x = x[list(x.keys())[0]]
         return self.model(x)
 
     def reshape_for_loss(self, outputs: Tensor, labels: Tensor):
