@@ -241,11 +241,13 @@ def run_cuda(args):
         stage = [{k: torch.empty_like(v) for k, v in devb[0].items()} for _ in range(NS)]
         out_host = [torch.empty(BATCH, S_EPOCHS, dtype=torch.int64).pin_memory() for _ in range(NS)]
         ready = [torch.cuda.Event() for _ in range(NS)]
+        sig_ready = [{k: torch.cuda.Event() for k in devb[0]} for _ in range(NS)]  # per signal: its copy has landed
         free = [None] * NS  # event after which staging buffer b may be overwritten
 
-        def pipelined(n, upload_one, make_inputs):
+        def pipelined(n, upload_one, make_inputs, per_signal=False):
             """Every step: H2D copy of its inputs (copy stream, pinned source) -> forward (predict_async, two in
-            flight) -> D2H copy of its predictions; all inside the caller's timed region."""
+            flight) -> D2H copy of its predictions; all inside the caller's timed region.  per_signal: every signal's
+            encoder waits for its own copy only (largest signals are uploaded first), instead of the whole batch."""
             for b in range(NS):
                 free[b] = None
 
@@ -260,9 +262,10 @@ def run_cuda(args):
                 upload(i)
             pend = []
             for i in range(n):
-                main.wait_event(ready[i % NS])
+                if not per_signal:
+                    main.wait_event(ready[i % NS])
                 x, released = make_inputs(i)
-                p = model.predict_async(x)
+                p = model.predict_async(x, ready=sig_ready[i % NS] if per_signal else None)
                 free[i % NS] = released if released is not None else p.done
                 pend.append((p, i, x))
                 if i + 2 < n:
@@ -275,11 +278,12 @@ def run_cuda(args):
             torch.cuda.synchronize()
 
         def upload_f32(i):
-            for k in stage[i % NS]:
+            for k in sorted(stage[i % NS], key=lambda k: -stage[i % NS][k].numel()):  # longest encoder chains first
                 stage[i % NS][k].copy_(host[i % 2][k], non_blocking=True)
+                sig_ready[i % NS][k].record(copy_stream)
 
         def e2e_loop(n):
-            pipelined(n, upload_f32, lambda i: (stage[i % NS], None))
+            pipelined(n, upload_f32, lambda i: (stage[i % NS], None), per_signal=True)
 
         e2e_loop(min(args.warmup, 3))
         barrier()

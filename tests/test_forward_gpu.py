@@ -323,3 +323,26 @@ def test_predict_async_lanes_match_predict(cuda_device):
     for a, b in zip(outs, ref):
         assert (a == b).float().mean().item() >= 0.98  # same kernels; only exact logit ties may resolve differently
     assert half.shape == (3, 8)
+
+
+def test_predict_async_with_per_signal_ready_events(cuda_device):
+    """``predict_async(x, ready={signal: event})``: each encoder waits for its own signal's upload only.  The inputs are
+    copied from pinned memory on a side stream AFTER the forward has been enqueued on buffers holding garbage; the
+    result must be that of the blocking call on the real data."""
+    model = build_default(CARDIO, 4, seed=0).to(cuda_device).eval()
+    host = {k: v.pin_memory() for k, v in make_inputs(CARDIO, 2, 16, seed=8).items()}
+    with torch.inference_mode():
+        ref = model.predict({k: v.to(cuda_device) for k, v in host.items()}).clone()
+        dev = {k: torch.full_like(v, float("nan"), device=cuda_device) for k, v in host.items()}
+        copy = torch.cuda.Stream(device=cuda_device)
+        gate = torch.cuda.Event()
+        ready = {}
+        with torch.cuda.stream(copy):
+            torch.cuda._sleep(50_000_000)  # ~25 ms: the forward below is enqueued long before the data arrives
+            for k in sorted(dev, key=lambda k: -dev[k].numel()):
+                dev[k].copy_(host[k], non_blocking=True)
+                ready[k] = torch.cuda.Event()
+                ready[k].record(copy)
+        out = model.predict_async(dev, ready=ready).wait().clone()
+        torch.cuda.synchronize()
+    assert torch.equal(out, ref)

@@ -365,8 +365,11 @@ class ForwardEngine:
         _lib.check(lib.w2s_epoch_mixer_fwd(C.byref(self.mixer_desc), zs, ms, len(names), B, S, buf["mix"].data_ptr(), st))
         self._seq_head(buf, B, S, logits, torch.cuda.current_stream())
 
-    def _launch_async(self, buf, xs: dict[str, Tensor], names, B: int, S: int, argmax: bool) -> Pending:
-        """The whole forward on the lane's own streams: nothing is enqueued on the current stream except the fork event."""
+    def _launch_async(self, buf, xs: dict[str, Tensor], names, B: int, S: int, argmax: bool, ready=None) -> Pending:
+        """The whole forward on the lane's own streams: nothing is enqueued on the current stream except the fork event.
+        ready: optional {signal: event} - the signal's encoder additionally waits for its event (e.g. the end of that
+        signal's host -> device copy on another stream), so the first encoders start while the other signals still
+        arrive."""
         lib = self.lib
         cur = torch.cuda.current_stream()
         fork = torch.cuda.Event()
@@ -376,6 +379,8 @@ class ForwardEngine:
         for i, n in enumerate(sorted(names, key=lambda k: -xs[k].size(1))):
             st = streams[i]
             st.wait_event(fork)
+            if ready is not None and ready.get(n) is not None:
+                st.wait_event(ready[n])
             if buf["tail_done"] is not None:
                 st.wait_event(buf["tail_done"])  # the lane's previous batch has finished reading z / masks
             xs[n].record_stream(st)
@@ -403,7 +408,7 @@ class ForwardEngine:
         return Pending(out, done)
 
     @torch.no_grad()
-    def forward_async(self, x: dict[str, Tensor], argmax: bool = False) -> Pending:
+    def forward_async(self, x: dict[str, Tensor], argmax: bool = False, ready=None) -> Pending:
         """Enqueue a forward on the next lane and return at once; ``.wait()`` on the result orders the current stream
         after it.  Up to ``n_lanes`` batches are in flight on the GPU; inputs must stay untouched until then."""
         B, S, device = self._check_inputs(x)
@@ -417,10 +422,10 @@ class ForwardEngine:
             for n in names:
                 t = x[n].detach()
                 xs[n] = t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
-            return self._launch_async(buf, xs, names, B, S, argmax)
+            return self._launch_async(buf, xs, names, B, S, argmax, ready)
 
-    def predict_async(self, x: dict[str, Tensor]) -> Pending:
-        return self.forward_async(x, argmax=True)
+    def predict_async(self, x: dict[str, Tensor], ready=None) -> Pending:
+        return self.forward_async(x, argmax=True, ready=ready)
 
     # Small batches are launch-latency bound (~100 launches for ~2 ms of GPU work at B = 1): from the second call with
     # the same shape on, the whole forward is replayed from one CUDA graph over static input / output buffers.

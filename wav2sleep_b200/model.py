@@ -395,17 +395,22 @@ class Wav2Sleep(nn.Module):
             return self._get_general().predict(x)
         return self._get_engine().predict(x)
 
-    def predict_async(self, x: dict[str, Tensor]):
+    def predict_async(self, x: dict[str, Tensor], ready=None):
         """``predict`` without ordering the current stream after it: returns a handle whose ``wait()`` does (and hands
         back the int64 [B, S] tensor).  Consecutive calls alternate between two sets of streams and workspaces, so the
-        latency-bound tail of one batch overlaps the encoders of the next (throughput mode for loops over batches)."""
+        latency-bound tail of one batch overlaps the encoders of the next (throughput mode for loops over batches).
+        ``ready``: optional ``{signal: torch.cuda.Event}``; a signal's encoder starts once its event has completed (e.g.
+        that signal's host -> device copy on a copy stream), so a batch need not be fully uploaded before work begins."""
         if not self.fast_path:
             from .engine import Pending
+            for ev in (ready or {}).values():
+                if ev is not None:
+                    torch.cuda.current_stream().wait_event(ev)
             out = self._get_general().predict(x)
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(out.device))
             return Pending(out, ev)
-        return self._get_engine().predict_async(x)
+        return self._get_engine().predict_async(x, ready=ready)
 
     def forward_fp32_check(self, x: dict[str, Tensor]) -> Tensor:
         """The same forward through the un-fused fp32 CUDA-core check kernels (check.py): slow, <= 1e-4 from the
