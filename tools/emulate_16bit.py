@@ -50,9 +50,29 @@ def gelu_tanh_fit(x, approx_amp=0.0):
     return 0.5 * x * (1.0 + th)
 
 
+def gelu_half(x, tanh_ulp=0.0):
+    """The prologue GELU evaluated in fp16 arithmetic (HMUL2 / HFMA2 / tanh.approx.f16x2: every operation rounds to
+    fp16, x_hat itself is rounded first).  tanh_ulp > 0 adds a deterministic error of that many fp16 ulps (of 1.0) to
+    the tanh value, modelling tanh.approx.f16x2's stated max absolute error of 2^-10.987."""
+    h = lambda v: v.half().float()
+    c2, c1, c0 = (h(torch.tensor(c)) for c in (-3.5159264e-4, 0.037005995, 0.79750759))
+    x = h(x)
+    t = h(x * x).clamp(max=25.0)
+    q = h(t * c2 + c1)
+    q = h(q * t + c0)
+    u = h(x * q)
+    th = torch.tanh(u)
+    if tanh_ulp > 0:
+        th = th + tanh_ulp * 2.0 ** -11 * torch.sin(u * 4096.0)
+    th = h(th)
+    hx = 0.5 * x
+    return h(hx * th + hx)
+
+
 class Policy:
     def __init__(self, store="f16", wide_blocks=0, op="f16", split_max=32, lin="f16", mixer="f16", seq="f16",
-                 gelu="tanh", z_store="f16", split_kind="split", split_min=0):
+                 gelu="tanh", z_store="f16", split_kind="split", split_min=0, half_min=0, tanh_ulp=0.0):
+        self.half_min, self.tanh_ulp = half_min, tanh_ulp  # half_min > 0: prologues of kernels with CIN >= half_min use fp16 math
         self.store, self.wide_blocks, self.op, self.split_max = store, wide_blocks, op, split_max
         self.split_kind, self.split_min = split_kind, split_min
         self.lin, self.mixer, self.seq, self.gelu, self.z_store = lin, mixer, seq, gelu, z_store
@@ -64,14 +84,17 @@ class Policy:
         lo, hi = min(cin, cout), max(cin, cout)
         return self.split_kind if (hi <= self.split_max and lo >= self.split_min) else self.op
 
-    def act(self, x):
+    def act(self, x, cin=0):
+        if self.half_min and cin >= self.half_min:
+            return gelu_half(x, self.tanh_ulp)
         if self.gelu == "tanh_approx":
             return gelu_tanh_fit(x, approx_amp=2.0 ** -11.5)
         return gelu_tanh_fit(x) if self.gelu == "tanh" else oracle.gelu(x)
 
     def __repr__(self):
         return (f"store={self.store} wide={self.wide_blocks} op={self.op} {self.split_kind}<={self.split_max} lin={self.lin} "
-                f"mixer={self.mixer} seq={self.seq} gelu={self.gelu}")
+                f"mixer={self.mixer} seq={self.seq} gelu={self.gelu}"
+                + (f" half-gelu>={self.half_min} tanh_ulp={self.tanh_ulp}" if self.half_min else ""))
 
 
 def norm_apply(y_acc, y_st, eps):
@@ -103,13 +126,14 @@ def encoder(x_BT, sd, prefix, spe, eps, pol: Policy):
         y1 = conv(a_in, w1, k1)
         r = rnd(conv(a_in, wd, k1, stride=2, pad=0), "f32" if i == 0 else st)  # block 0: recomputed, never stored
         y1s = y1 if i == 0 else rnd(y1, st)       # block-0 conv1 is recomputed in the consumer: never stored
-        a1 = pol.act(norm_apply(y1, y1s, eps))
+        a1 = pol.act(norm_apply(y1, y1s, eps), c)
         k = pol.op_kind(c, c)
         y2 = conv(a1, w2, k)
-        a2 = pol.act(norm_apply(y2, rnd(y2, st), eps))
+        a2 = pol.act(norm_apply(y2, rnd(y2, st), eps), c)
         y3 = conv(a2, w3, k, stride=2)
-        a3 = pol.act(norm_apply(y3, rnd(y3, st), eps))
-        a_in = pol.act(a3 + r)
+        last = i == nb - 1  # the last block's output is activated in the Linear's prologue (fp32 math)
+        a3 = pol.act(norm_apply(y3, rnd(y3, st), eps), 0 if last else c)
+        a_in = pol.act(a3 + r, 0 if last else c)
         cin = c
     C = a_in.size(1)
     y = rnd(a_in, pol.lin).transpose(1, 2).reshape(B, -1, 4 * C)
