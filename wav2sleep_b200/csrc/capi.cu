@@ -290,30 +290,38 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
   W2S_STREAMX(CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW, WIN, WOUT, (CIN <= 16 && COUT <= 16))
 #define W2S_STREAM(CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW) \
   W2S_STREAMW(CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW, false, false)
-    //          cin cout s  prologue      ds    MT NR NA NTW
+    // W2S_STREAMD: kernels with CIN >= W2S_DIRECT_MIN_CIN drop the raw ring (NR = 0: the transform warps read global
+    // memory directly through a register prefetch ring, conv_stream.cuh) and use NAD A stages instead of NA.  Default
+    // 128: only the 128-channel kernels, whose weights left room for a single A stage next to a raw ring.
+#ifndef W2S_DIRECT_MIN_CIN
+#define W2S_DIRECT_MIN_CIN 128
+#endif
+#define W2S_STREAMD(CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW, NAD) \
+  W2S_STREAM(CIN, COUT, STRIDE, PRO, DS, MT, (CIN >= W2S_DIRECT_MIN_CIN ? 0 : NR), (CIN >= W2S_DIRECT_MIN_CIN ? NAD : NA), NTW)
+    //          cin cout s  prologue      ds    MT NR NA NTW [NA direct]
     W2S_STREAM(16, 16, 1, PRO_FIR, false, 8, 3, 2, 18)
     W2S_STREAM(16, 16, 1, PRO_NORM_RES_X, true, 8, 2, 2, 14)
-    W2S_STREAM(16, 16, 1, PRO_NORM, false, 8, 2, 2, 18)
-    W2S_STREAM(16, 16, 2, PRO_NORM, false, 4, 2, 2, 18)
-    W2S_STREAM(16, 16, 1, PRO_NORM_RES, true, 4, 3, 2, 14)
-    W2S_STREAM(16, 32, 1, PRO_NORM_RES, true, 4, 3, 2, 10)
-#ifdef W2S_TUNE_MT32  // A/B build: larger tiles for the (now un-split) 32-channel kernels
-    W2S_STREAM(32, 32, 1, PRO_NORM, false, 6, 2, 2, 14)
-    W2S_STREAM(32, 32, 2, PRO_NORM, false, 3, 2, 2, 14)
-    W2S_STREAM(32, 32, 1, PRO_NORM_RES, true, 4, 2, 2, 10)
-#else
-    W2S_STREAM(32, 32, 1, PRO_NORM, false, 4, 2, 2, 14)
-    W2S_STREAM(32, 32, 2, PRO_NORM, false, 2, 2, 2, 14)
-    W2S_STREAM(32, 32, 1, PRO_NORM_RES, true, 2, 3, 2, 10)
-#endif
-    W2S_STREAM(32, 64, 1, PRO_NORM_RES, true, 2, 3, 2, 14)
-    W2S_STREAM(64, 64, 1, PRO_NORM, false, 2, 2, 2, 14)
-    W2S_STREAM(64, 64, 2, PRO_NORM, false, 1, 3, 2, 14)
-    W2S_STREAM(64, 64, 1, PRO_NORM_RES, true, 1, 3, 2, 14)
-    W2S_STREAM(64, 128, 1, PRO_NORM_RES, true, 1, 3, 2, 14)
+    W2S_STREAMD(16, 16, 1, PRO_NORM, false, 8, 2, 2, 18, 3)
+    W2S_STREAMD(16, 16, 2, PRO_NORM, false, 4, 2, 2, 18, 3)
+    W2S_STREAMD(16, 16, 1, PRO_NORM_RES, true, 4, 3, 2, 14, 3)
+    W2S_STREAMD(16, 32, 1, PRO_NORM_RES, true, 4, 3, 2, 10, 3)
+    W2S_STREAMD(32, 32, 1, PRO_NORM, false, 4, 2, 2, 14, 3)
+    W2S_STREAMD(32, 32, 2, PRO_NORM, false, 2, 2, 2, 14, 3)
+    W2S_STREAMD(32, 32, 1, PRO_NORM_RES, true, 2, 3, 2, 10, 3)
+    W2S_STREAMD(32, 64, 1, PRO_NORM_RES, true, 2, 3, 2, 14, 3)
+    W2S_STREAMD(64, 64, 1, PRO_NORM, false, 2, 2, 2, 14, 3)
+    W2S_STREAMD(64, 64, 2, PRO_NORM, false, 1, 3, 2, 14, 3)
+    W2S_STREAMD(64, 64, 1, PRO_NORM_RES, true, 1, 3, 2, 14, 3)
+    W2S_STREAMD(64, 128, 1, PRO_NORM_RES, true, 1, 3, 2, 14, 3)
+#ifdef W2S_C128_RING  // A/B build: raw ring + ONE A stage (round-1 / early round-2 configuration)
     W2S_STREAM(128, 128, 1, PRO_NORM, false, 1, 2, 1, 14)
     W2S_STREAM(128, 128, 2, PRO_NORM, false, 1, 1, 1, 14)
     W2S_STREAM(128, 128, 1, PRO_NORM_RES, true, 1, 1, 1, 14)
+#else  // NR = 0, 2-3 A stages
+    W2S_STREAM(128, 128, 1, PRO_NORM, false, 1, 0, 3, 14)
+    W2S_STREAM(128, 128, 2, PRO_NORM, false, 1, 0, 2, 14)
+    W2S_STREAM(128, 128, 1, PRO_NORM_RES, true, 1, 0, 2, 14)
+#endif
     // wide (fp32) storage of the leading <= 32-channel blocks            MT NR NA NTW  in     out
     W2S_STREAMW(16, 16, 1, PRO_FIR, false, 8, 3, 2, 18, false, true)
     W2S_STREAMW(16, 16, 1, PRO_NORM_RES_X, true, 4, 3, 2, 14, true, true)
@@ -333,6 +341,7 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
     W2S_STREAMX(64, 64, 1, PRO_NORM_RES, true, 1, 1, 2, 14, true, true, true)
     W2S_STREAMX(64, 128, 1, PRO_NORM_RES, true, 1, 1, 2, 14, true, false, false)
 #undef W2S_STREAM
+#undef W2S_STREAMD
 #undef W2S_STREAMW
 #undef W2S_STREAMX
     if (!found && (c.in_wide || c.out_wide || c.force_split))

@@ -124,6 +124,11 @@ template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, bool SPLIT, int M
           bool WIN = false, bool WOUT = false>
 struct StreamCfg {
   static constexpr int CH = CIN / 8;
+  // NR == 0: no raw ring - the transform warps read their 16-byte chunks straight from global memory (coalesced: a
+  // tile's input rows are one contiguous byte range) through a register prefetch ring that runs one tile ahead, and
+  // the shared memory of the ring goes to a second / third A stage.  Built for the 128-channel kernels, whose 96-128 KB
+  // of weights left room for only ONE A stage next to a raw ring (transform and MMA of consecutive tiles serialised).
+  static constexpr bool DIRECT = (NR == 0);
   static constexpr int ESZ = WIN ? 4 : 2;  // bytes per stored input element
   static constexpr int POS = 128 * MT;
   static constexpr int R = (POS - 1) * STRIDE + 3;            // input rows per tile (with halo)
@@ -159,6 +164,10 @@ struct StreamCfg {
   static_assert(2 * STAGE_COLS <= 512, "TMEM budget");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert((NTW * 32) % CH == 0, "fixed channel chunk per transform thread");
+  static_assert(!DIRECT || ((PRO == PRO_NORM || PRO == PRO_NORM_RES) && !WIN), "direct-from-global transform: fp16 PRO_NORM[_RES] only");
+  // direct mode: 16-byte chunks per transform thread and tile, and the depth of the register prefetch ring
+  static constexpr int NIT = (R * CH + NTW * 32 - 1) / (NTW * 32);
+  static constexpr int PF = NIT <= 5 ? NIT : (NIT + 1) / 2;
 };
 
 template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, bool SPLIT, int MT, int NR, int NA, int NTW, bool WIN, bool WOUT>
@@ -242,6 +251,11 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
     mbar_init(w_full, 1);
     fence_mbar_init();
   }
+  // Programmatic dependent launch: the next stream kernel of this CUDA stream may be scheduled onto SMs as this grid's
+  // CTAs exit (launch latency, TMEM allocation and barrier set-up then overlap this grid's tail); everything that reads
+  // or writes global memory comes after the wait, which returns when the preceding grid has completed and flushed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (compact && tid == 64) {
     int n = 0;
     for (int b = 0; b < n_samples; ++b)
@@ -298,7 +312,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
       WaitClock wc;
       const long long cta_t0 = clock64();
       TilePos tp = pos0;
-      for (int tile = tile_begin; tile < tile_end; ++tile, advance(tp)) {
+      for (int tile = tile_begin; tile < (Cfg::DIRECT ? tile_begin : tile_end); ++tile, advance(tp)) {
         int b;
         if (!sample_of(tp, b)) continue;
         const int o0 = tp.r * POS;
@@ -710,121 +724,255 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
         fw[q][0] = make_float2(__ldg(p.w_first_ds + c), __ldg(p.w_first_ds + c + 1));
       }
     }
+    // per-sample constants of this thread's 8 channels
+    auto load_consts = [&](int b) {
+      const double inv_len = 1.0 / (double)p.L_in;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = cch * 8 + k;
+        const double s0 = p.in_stats[((size_t)b * CIN + c) * 2 + 0];
+        const double s1 = p.in_stats[((size_t)b * CIN + c) * 2 + 1];
+        const double mean = s0 * inv_len;
+        const double var = fmax(s1 * inv_len - mean * mean, 0.0);
+        // mean / variance need fp64 (sumsq / L - mean^2 cancels); the reciprocal square root does not
+        const float rstd = 1.0f / sqrtf((float)(var + (double)p.in_eps));
+        if (k & 1) {
+          sc[k >> 1].y = rstd;
+          sh[k >> 1].y = (float)(-mean) * rstd;
+        } else {
+          sc[k >> 1].x = rstd;
+          sh[k >> 1].x = (float)(-mean) * rstd;
+        }
+      }
+      if (PRO == PRO_FIR) {  // taps re-read (L1/L2 hits) on a sample change instead of living in registers
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = cch * 8 + 2 * q;
+#pragma unroll
+          for (int t = 0; t < 3; ++t)
+            fws[q][t] = __fmul2_rn(make_float2(__ldg(p.w_first + c * 3 + t), __ldg(p.w_first + (c + 1) * 3 + t)), sc[q]);
+        }
+      }
+    };
+    // per-tile state read by the chunk transform below
+    int i0 = 0, xs0 = 0;
+    uint32_t adst = 0;
+    const float* xraw = nullptr;  // staged x window (block-0 fusion modes)
+    bool x_interior = false;      // whole x window inside the sample
+    auto xat = [&](int j) -> float {  // x[j] of this sample with conv1's zero padding and the -inf -> 0 rule
+      if (!x_interior && (j < 0 || j >= p.T_raw)) return 0.0f;
+      const float v = xraw[j - xs0];
+      return isinf(v) ? 0.0f : v;
+    };
+    // 8 channels of input row u = id / CH (y [, y2]: stored conv output, r [, r2]: residual branch) -> activated fp16
+    // operand chunk(s) in the A stage
+    auto core = [&](int id, bool valid, const uint4& y, const uint4& y2, const uint4& r, const uint4& r2) {
+      const int u = id / CH;
+      uint4 o = make_uint4(0u, 0u, 0u, 0u), olo = make_uint4(0u, 0u, 0u, 0u);
+      if (valid) {
+        float xm = 0.0f, x0 = 0.0f, xp = 0.0f;
+        auto fin = [](float v) { return isinf(v) ? 0.0f : v; };  // the reference's -inf -> 0 rule, element-wise
+        if (PRO == PRO_FIR) {
+          if (x_interior) {  // whole window staged: no per-element bounds checks
+            const float* xp3 = xraw + (i0 + u - 1 - xs0);
+            xm = fin(xp3[0]);
+            x0 = fin(xp3[1]);
+            xp = fin(xp3[2]);
+          } else {
+            xm = xat(i0 + u - 1);
+            x0 = xat(i0 + u);
+            xp = xat(i0 + u + 1);
+          }
+        } else if (PRO == PRO_NORM_RES_X) {
+          x0 = x_interior ? fin(xraw[2 * (i0 + u) - xs0]) : xat(2 * (i0 + u));
+        }
+        const uint32_t yy[8] = {y.x, y.y, y.z, y.w, y2.x, y2.y, y2.z, y2.w};
+        const uint32_t rr[8] = {r.x, r.y, r.z, r.w, r2.x, r2.y, r2.z, r2.w};
+        auto pair = [&](const uint32_t (&w)[8], int q) -> float2 {  // channels 2q, 2q+1 of the 8 as fp32
+          return WIN ? make_float2(__uint_as_float(w[2 * q]), __uint_as_float(w[2 * q + 1])) : unpack_h2(w[q]);
+        };
+        uint32_t* oo = reinterpret_cast<uint32_t*>(&o);
+        uint32_t* ol = reinterpret_cast<uint32_t*>(&olo);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float2 yv;
+          float2 a;
+          if (PRO == PRO_FIR) {
+            // conv1 of block 0 recomputed in fp32 (never stored, never rounded); the InstanceNorm scale is folded
+            // into the taps (fws = w * rstd), the shift is the FMA addend: 3 packed FMAs give x_hat directly
+            a = __ffma2_rn(fws[q][2], make_float2(xp, xp),
+                           __ffma2_rn(fws[q][1], make_float2(x0, x0), __ffma2_rn(fws[q][0], make_float2(xm, xm), sh[q])));
+          } else {
+            yv = pair(yy, q);
+            a = __ffma2_rn(yv, sc[q], sh[q]);
+          }
+          if (!W2S_DBG(p, 4)) a = gelu_fast2(a);
+          if (PRO == PRO_NORM_RES) a = gelu_fast2(__fadd2_rn(a, pair(rr, q)));
+          if (PRO == PRO_NORM_RES_X) a = gelu_fast2(__ffma2_rn(fw[q][0], make_float2(x0, x0), a));
+          oo[q] = pack_h2(a.x, a.y);
+          if (SPLIT) {
+            const float2 lo = __ffma2_rn(unpack_h2(oo[q]), make_float2(-1.0f, -1.0f), a);
+            ol[q] = pack_h2(lo.x, lo.y);
+          }
+        }
+      }
+      const uint32_t soff = (uint32_t)((u & (STRIDE - 1)) * CH * RP + u / STRIDE) * 16;
+      sts128(adst + soff, o);
+      if (SPLIT) sts128(adst + Cfg::A_ONE + soff, olo);
+    };
+    // Hand-over: every transform thread publishes its shared-memory writes to the async proxy, then each warp signals
+    auto hand_over = [&]() {
+      fence_proxy_async_smem();
+#ifdef W2S_TILE_ARRIVE
+      asm volatile("bar.sync 1, %0;" ::"n"(NTT) : "memory");
+      if (tt == 0) {
+        mbar_arrive(&a_full[as]);
+        if (!Cfg::DIRECT) mbar_arrive(&raw_empty[rs]);
+      }
+#else
+      if (NAMED) {
+        named_arrive(1 + as, kNamedCount);
+        if (!Cfg::DIRECT) named_arrive(1 + NA + rs, kNamedCount);
+      } else {
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&a_full[as]);
+          if (!Cfg::DIRECT) mbar_arrive(&raw_empty[rs]);
+        }
+      }
+#endif
+      if (!Cfg::DIRECT && ++rs == NR) {
+        rs = 0;
+        rph ^= 1;
+      }
+      if (++as == NA) {
+        as = 0;
+        aph ^= 1;
+      }
+    };
+    if constexpr (Cfg::DIRECT) {
+      constexpr int NCHUNK = R * CH, NIT = Cfg::NIT, PF = Cfg::PF;
+      constexpr int NITP = (NIT + PF - 1) / PF * PF;
+      constexpr bool RES = PRO == PRO_NORM_RES;
+      struct TileRef {
+        const uint8_t* y;  // row i0 of the sample (may lie one row before its start: never dereferenced there)
+        const uint8_t* r;
+        int i0;
+        bool interior;
+      };
+      auto tile_ref = [&](const TilePos& t, int b) {
+        const int ti0 = t.r * POS * STRIDE - 1;
+        const long long off = ((long long)b * p.L_in + ti0) * (CIN * 2);
+        TileRef tr;
+        tr.y = reinterpret_cast<const uint8_t*>(p.in) + off;
+        tr.r = RES ? reinterpret_cast<const uint8_t*>(p.in_res) + off : nullptr;
+        tr.i0 = ti0;
+        tr.interior = (ti0 >= 0) && (ti0 + R <= p.L_in);
+        return tr;
+      };
+      auto chunk_ok = [&](const TileRef& tr, int k, int id) {
+        bool ok = (k < NIT - 1) || id < NCHUNK;
+        if (!tr.interior) {
+          const int i = tr.i0 + id / CH;
+          ok = ok && i >= 0 && i < p.L_in;
+        }
+        return ok;
+      };
+      auto fetch = [&](const TileRef& tr, int k, uint4& y, uint4& r) {
+        const int id = tt + k * NTT;
+        if (chunk_ok(tr, k, id)) {
+          y = ldg128_stream(tr.y + (size_t)id * 16);
+          if (RES) r = ldg128_stream(tr.r + (size_t)id * 16);
+        }
+      };
+      // next tile of this CTA whose sample is live (b < 0: none)
+      auto seek = [&](TilePos& t, int& tl) -> int {
+        for (; tl < tile_end; ++tl, advance(t)) {
+          int bb;
+          if (sample_of(t, bb)) return bb;
+        }
+        return -1;
+      };
+      const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+      uint4 ybuf[PF], rbuf[PF];
+#pragma unroll
+      for (int k = 0; k < PF; ++k) ybuf[k] = rbuf[k] = zero4;
+      TilePos tp = pos0;
+      int tile = tile_begin;
+      int b = seek(tp, tile);
+      TileRef cur = {nullptr, nullptr, 0, true};
+      if (b >= 0) {
+        cur = tile_ref(tp, b);
+#pragma unroll
+        for (int k = 0; k < PF; ++k) fetch(cur, k, ybuf[k], rbuf[k]);
+      }
+      while (b >= 0) {
+        if (b != cur_b) {
+          cur_b = b;
+          load_consts(b);
+        }
+        TilePos tn = tp;
+        int tilen = tile + 1;
+        advance(tn);
+        const int bn = seek(tn, tilen);
+        TileRef nxt = {nullptr, nullptr, 0, true};
+        if (bn >= 0) nxt = tile_ref(tn, bn);
+        i0 = cur.i0;
+        wc_a.wait(p, &a_empty[as], aph ^ 1);
+        adst = smem_u32(sA + as * Cfg::A_BYTES) + (uint32_t)cch * RP * 16;
+#pragma unroll
+        for (int k = 0; k < NITP; ++k) {
+          const int id = tt + k * NTT;
+          const uint4 y = ybuf[k % PF], r = rbuf[k % PF];
+          // refill the slot: PF chunks ahead, in this tile or (slots of the tail) in the next one
+          if (k + PF < NITP) {
+            if (k + PF < NIT) fetch(cur, k + PF, ybuf[k % PF], rbuf[k % PF]);
+          } else if (k + PF - NITP < NIT) {
+            if (bn >= 0) fetch(nxt, k + PF - NITP, ybuf[k % PF], rbuf[k % PF]);
+          }
+          if (k < NIT && ((k < NIT - 1) || id < NCHUNK)) core(id, chunk_ok(cur, k, id), y, zero4, r, zero4);
+        }
+        hand_over();
+        tp = tn;
+        tile = tilen;
+        b = bn;
+        cur = nxt;
+      }
+    } else {
     TilePos tp = pos0;
     for (int tile = tile_begin; tile < tile_end; ++tile, advance(tp)) {
       int b;
       if (!sample_of(tp, b)) continue;
       if (b != cur_b) {
         cur_b = b;
-        const double inv_len = 1.0 / (double)p.L_in;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int c = cch * 8 + k;
-          const double s0 = p.in_stats[((size_t)b * CIN + c) * 2 + 0];
-          const double s1 = p.in_stats[((size_t)b * CIN + c) * 2 + 1];
-          const double mean = s0 * inv_len;
-          const double var = fmax(s1 * inv_len - mean * mean, 0.0);
-          // mean / variance need fp64 (sumsq / L - mean^2 cancels); the reciprocal square root does not
-          const float rstd = 1.0f / sqrtf((float)(var + (double)p.in_eps));
-          if (k & 1) {
-            sc[k >> 1].y = rstd;
-            sh[k >> 1].y = (float)(-mean) * rstd;
-          } else {
-            sc[k >> 1].x = rstd;
-            sh[k >> 1].x = (float)(-mean) * rstd;
-          }
-        }
-        if (PRO == PRO_FIR) {  // taps re-read (L1/L2 hits) on a sample change instead of living in registers
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int c = cch * 8 + 2 * q;
-#pragma unroll
-            for (int t = 0; t < 3; ++t)
-              fws[q][t] = __fmul2_rn(make_float2(__ldg(p.w_first + c * 3 + t), __ldg(p.w_first + (c + 1) * 3 + t)), sc[q]);
-          }
-        }
+        load_consts(b);
       }
       const int o0 = tp.r * POS;
-      const int i0 = o0 * STRIDE - 1;
+      i0 = o0 * STRIDE - 1;
       if (tt == 0 && tile == tile_begin) dbg_ts(p, 3);
       wc_raw.wait(p, &raw_full[rs], rph);
       wc_a.wait(p, &a_empty[as], aph ^ 1);
       if (tt == 0 && tile == tile_begin) dbg_ts(p, 4);
       const uint32_t raw = smem_u32(sRaw + rs * Cfg::RAW_BYTES);
-      const uint32_t adst = smem_u32(sA + as * Cfg::A_BYTES) + (uint32_t)cch * RP * 16;
+      adst = smem_u32(sA + as * Cfg::A_BYTES) + (uint32_t)cch * RP * 16;
       const bool interior = (i0 >= 0) && (i0 + R <= p.L_in);  // no zero-padding rows in this tile
-      const int xs0 = (PRO == PRO_FIR) ? ((i0 - 1) & ~3) : ((2 * i0) & ~3);
-      const float* xraw = reinterpret_cast<const float*>(sRaw + rs * Cfg::RAW_BYTES + Cfg::RAW_ONE);  // staged x window
-      const bool x_interior = xs0 >= 0 && xs0 + Cfg::XN <= p.T_raw;  // whole x window inside the sample
-      auto xat = [&](int j) -> float {  // x[j] of this sample with conv1's zero padding and the -inf -> 0 rule
-        if (!x_interior && (j < 0 || j >= p.T_raw)) return 0.0f;
-        const float v = xraw[j - xs0];
-        return isinf(v) ? 0.0f : v;
-      };
+      xs0 = (PRO == PRO_FIR) ? ((i0 - 1) & ~3) : ((2 * i0) & ~3);
+      xraw = reinterpret_cast<const float*>(sRaw + rs * Cfg::RAW_BYTES + Cfg::RAW_ONE);
+      x_interior = xs0 >= 0 && xs0 + Cfg::XN <= p.T_raw;
       auto chunk = [&](int id, bool valid) {
-        const int u = id / CH;
-        uint4 o = make_uint4(0u, 0u, 0u, 0u), olo = make_uint4(0u, 0u, 0u, 0u);
+        // 8 channels of one input row: one 16-B load (fp16) or two (wide fp32 storage)
+        uint4 y = make_uint4(0u, 0u, 0u, 0u), y2 = y, r = y, r2 = y;
         if (valid) {
-          // 8 channels of one input row: one 16-B load (fp16) or two (wide fp32 storage)
-          uint4 y = make_uint4(0u, 0u, 0u, 0u), y2 = y;
           if (PRO != PRO_FIR) {
             y = lds128(raw + (uint32_t)id * (8 * ESZ));
             if (WIN) y2 = lds128(raw + (uint32_t)id * 32 + 16);
           }
-          uint4 r = make_uint4(0u, 0u, 0u, 0u), r2 = r;
           if (PRO == PRO_NORM_RES) {
             r = lds128(raw + Cfg::RAW_ONE + (uint32_t)id * (8 * ESZ));
             if (WIN) r2 = lds128(raw + Cfg::RAW_ONE + (uint32_t)id * 32 + 16);
           }
-          float xm = 0.0f, x0 = 0.0f, xp = 0.0f;
-          auto fin = [](float v) { return isinf(v) ? 0.0f : v; };  // the reference's -inf -> 0 rule, element-wise
-          if (PRO == PRO_FIR) {
-            if (x_interior) {  // whole window staged: no per-element bounds checks
-              const float* xp3 = xraw + (i0 + u - 1 - xs0);
-              xm = fin(xp3[0]);
-              x0 = fin(xp3[1]);
-              xp = fin(xp3[2]);
-            } else {
-              xm = xat(i0 + u - 1);
-              x0 = xat(i0 + u);
-              xp = xat(i0 + u + 1);
-            }
-          } else if (PRO == PRO_NORM_RES_X) {
-            x0 = x_interior ? fin(xraw[2 * (i0 + u) - xs0]) : xat(2 * (i0 + u));
-          }
-          const uint32_t yy[8] = {y.x, y.y, y.z, y.w, y2.x, y2.y, y2.z, y2.w};
-          const uint32_t rr[8] = {r.x, r.y, r.z, r.w, r2.x, r2.y, r2.z, r2.w};
-          auto pair = [&](const uint32_t (&w)[8], int q) -> float2 {  // channels 2q, 2q+1 of the 8 as fp32
-            return WIN ? make_float2(__uint_as_float(w[2 * q]), __uint_as_float(w[2 * q + 1])) : unpack_h2(w[q]);
-          };
-          uint32_t* oo = reinterpret_cast<uint32_t*>(&o);
-          uint32_t* ol = reinterpret_cast<uint32_t*>(&olo);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float2 yv;
-            float2 a;
-            if (PRO == PRO_FIR) {
-              // conv1 of block 0 recomputed in fp32 (never stored, never rounded); the InstanceNorm scale is folded
-              // into the taps (fws = w * rstd), the shift is the FMA addend: 3 packed FMAs give x_hat directly
-              a = __ffma2_rn(fws[q][2], make_float2(xp, xp),
-                             __ffma2_rn(fws[q][1], make_float2(x0, x0), __ffma2_rn(fws[q][0], make_float2(xm, xm), sh[q])));
-            } else {
-              yv = pair(yy, q);
-              a = __ffma2_rn(yv, sc[q], sh[q]);
-            }
-            if (!W2S_DBG(p, 4)) a = gelu_fast2(a);
-            if (PRO == PRO_NORM_RES) a = gelu_fast2(__fadd2_rn(a, pair(rr, q)));
-            if (PRO == PRO_NORM_RES_X) a = gelu_fast2(__ffma2_rn(fw[q][0], make_float2(x0, x0), a));
-            oo[q] = pack_h2(a.x, a.y);
-            if (SPLIT) {
-              const float2 lo = __ffma2_rn(unpack_h2(oo[q]), make_float2(-1.0f, -1.0f), a);
-              ol[q] = pack_h2(lo.x, lo.y);
-            }
-          }
         }
-        const uint32_t soff = (uint32_t)((u & (STRIDE - 1)) * CH * RP + u / STRIDE) * 16;
-        sts128(adst + soff, o);
-        if (SPLIT) sts128(adst + Cfg::A_ONE + soff, olo);
+        core(id, valid, y, y2, r, r2);
       };
       if (W2S_DBG(p, 32)) {
       } else if (interior) {
@@ -836,34 +984,8 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
           chunk(id, i >= 0 && i < p.L_in);
         }
       }
-      // Hand-over: every transform thread publishes its shared-memory writes to the async proxy, then each warp signals
-      fence_proxy_async_smem();
-#ifdef W2S_TILE_ARRIVE
-      asm volatile("bar.sync 1, %0;" ::"n"(NTT) : "memory");
-      if (tt == 0) {
-        mbar_arrive(&a_full[as]);
-        mbar_arrive(&raw_empty[rs]);
-      }
-#else
-      if (NAMED) {
-        named_arrive(1 + as, kNamedCount);
-        named_arrive(1 + NA + rs, kNamedCount);
-      } else {
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&a_full[as]);
-          mbar_arrive(&raw_empty[rs]);
-        }
-      }
-#endif
-      if (++rs == NR) {
-        rs = 0;
-        rph ^= 1;
-      }
-      if (++as == NA) {
-        as = 0;
-        aph ^= 1;
-      }
+      hand_over();
+    }
     }
     if (tt == 0) {
       wc_a.publish(p, 14);
@@ -900,8 +1022,21 @@ inline cudaError_t launch_conv_stream(const ConvArgs& a, int B, int sm_count, cu
   if (total > 0x7fffffffLL) return cudaErrorInvalidValue;
   const int ctas = sm_count * (Cfg::THREADS <= 384 ? 2 : 1);  // small CTAs run two per SM
   const int grid = total < ctas ? (int)total : ctas;
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a, tiles_per_sample, (int)total);
-  return cudaGetLastError();
+  // W2S_PDL=0 launches without programmatic stream serialization (A/B); never used while the stream is being captured
+  static const bool pdl_enabled = [] { const char* e = getenv("W2S_PDL"); return !e || atoi(e) != 0; }();
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (pdl_enabled) cudaStreamIsCapturing(stream, &cap);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_enabled && cap == cudaStreamCaptureStatusNone) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, a, tiles_per_sample, (int)total);
 }
 
 }  // namespace w2s
