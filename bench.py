@@ -169,6 +169,12 @@ def run_cuda(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # Multi-rank runs: every rank stages its pinned host batches on the NUMA node of its own GPU (placement only; the
+    # single-GPU run keeps all host cores for its cpu_baseline leg).
+    host_cpus = 0
+    if world > 1:
+        from wav2sleep_b200 import hostmem
+        host_cpus = hostmem.bind_to_gpu_numa(local_rank)
     if world > 1:
         # NCCL prints its version banner on stdout when the communicator is created: route fd 1 to stderr while that
         # happens so that stdout carries exactly one JSON line.
@@ -420,7 +426,8 @@ def run_cuda(args):
         "config": {"workload": WORKLOAD, "nights_per_gpu_per_step": BATCH, "epochs_per_night": S_EPOCHS,
                    "parallelism": f"replicas x{world} (no data-path collective)",
                    "api": "Wav2Sleep.predict_async (engine-owned streams, results awaited in order)",
-                   "l2": "inputs+activations > L2, 2 alternating batches"},
+                   "l2": "inputs+activations > L2, 2 alternating batches",
+                   "host_affinity": f"rank bound to {host_cpus} GPU-local CPUs" if host_cpus else "unbound"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e / args.steps},
         "e2e_staged": {"value": hours_per_step * args.steps / (ms_staged * 1e-3), "unit": UNIT,

@@ -251,9 +251,10 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
     mbar_init(w_full, 1);
     fence_mbar_init();
   }
-  // Programmatic dependent launch: the next stream kernel of this CUDA stream may be scheduled onto SMs as this grid's
-  // CTAs exit (launch latency, TMEM allocation and barrier set-up then overlap this grid's tail); everything that reads
-  // or writes global memory comes after the wait, which returns when the preceding grid has completed and flushed.
+  // Programmatic dependent launch (only with W2S_PDL=1, see launch_conv_stream; both instructions are no-ops for a
+  // normally launched grid): the next stream kernel of this CUDA stream may be scheduled onto SMs as this grid's CTAs
+  // exit (launch latency, TMEM allocation and barrier set-up then overlap this grid's tail); everything that reads or
+  // writes global memory comes after the wait, which returns when the preceding grid has completed and flushed.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (compact && tid == 64) {
@@ -1022,8 +1023,11 @@ inline cudaError_t launch_conv_stream(const ConvArgs& a, int B, int sm_count, cu
   if (total > 0x7fffffffLL) return cudaErrorInvalidValue;
   const int ctas = sm_count * (Cfg::THREADS <= 384 ? 2 : 1);  // small CTAs run two per SM
   const int grid = total < ctas ? (int)total : ctas;
-  // W2S_PDL=0 launches without programmatic stream serialization (A/B); never used while the stream is being captured
-  static const bool pdl_enabled = [] { const char* e = getenv("W2S_PDL"); return !e || atoi(e) != 0; }();
+  // W2S_PDL=1 launches with programmatic stream serialization (never while the stream is being captured).  Measured
+  // (3 alternating rounds, one box): the serialised kernel sum drops 1 % (7.40 vs 7.49 ms) but the step gets 2.4 % SLOWER
+  // (6.72 vs 6.55 ms): the four encoder streams fill each other's tails with useful CTAs, and an early-scheduled
+  // dependent CTA holds its SM idle at griddepcontrol.wait instead.  Off by default.
+  static const bool pdl_enabled = [] { const char* e = getenv("W2S_PDL"); return e && atoi(e) != 0; }();
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (pdl_enabled) cudaStreamIsCapturing(stream, &cap);
   cudaLaunchConfig_t cfg = {};
