@@ -252,6 +252,29 @@ W2S_DEVINL uint4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
 }
+// Compacted list of the samples a row mask leaves alive (mask[b] == 0), built by ONE WARP: all loads of the mask are
+// issued before the first ballot (one global-memory round trip instead of one per sample on a single thread - the
+// serial scan cost every launch ~2 us of set-up).  Returns the number of live samples.
+W2S_DEVINL int build_live_list(const uint8_t* __restrict__ mask, int n, uint16_t* live, int lane) {
+  int count = 0;
+#pragma unroll 1
+  for (int r0 = 0; r0 < n; r0 += 128) {
+    uint8_t m[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int b = r0 + j * 32 + lane;
+      m[j] = b < n ? mask[b] : (uint8_t)1;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool alive = m[j] == 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, alive);
+      if (alive) live[count + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(r0 + j * 32 + lane);
+      count += __popc(bal);
+    }
+  }
+  return count;
+}
 // 16 bytes of a tensor written by an earlier launch, streamed past L1
 W2S_DEVINL uint4 ldg128_stream(const void* ptr) {
   uint4 v;

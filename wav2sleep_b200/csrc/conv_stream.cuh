@@ -257,12 +257,19 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   // writes global memory comes after the wait, which returns when the preceding grid has completed and flushed.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef W2S_SERIAL_LIVE  // A/B build: one thread scans the mask (one dependent global load per sample)
   if (compact && tid == 64) {
     int n = 0;
     for (int b = 0; b < n_samples; ++b)
       if (!p.row_mask[b]) sLive[n++] = (uint16_t)b;
     sNLive = n;
   }
+#else
+  if (compact && warp == 2) {
+    const int n = build_live_list(p.row_mask, n_samples, sLive, lane);
+    if (lane == 0) sNLive = n;
+  }
+#endif
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();

@@ -109,11 +109,9 @@ __global__ void __launch_bounds__(kGemmTNThreads) gemm_tn_kernel(const GemmTNArg
   __shared__ int sNLive;
   const bool compact = p.row_mask != nullptr && p.B <= kMaxLive;
   if (compact) {
-    if (tid == 0) {
-      int n = 0;
-      for (int b = 0; b < p.B; ++b)
-        if (!p.row_mask[b]) sLive[n++] = (uint16_t)b;
-      sNLive = n;
+    if (warp == 0) {
+      const int n = build_live_list(p.row_mask, p.B, sLive, lane);
+      if (lane == 0) sNLive = n;
     }
     __syncthreads();
   }
