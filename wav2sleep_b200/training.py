@@ -61,6 +61,10 @@ class TrainEngine(ForwardEngine):
         # InstanceNorm backward of a layer's gradient inside the prologue of the data-gradient conv that consumes it
         # (W2S_PRO_DNORM) instead of a separate enc_norm_bwd pass; W2S_FUSE_NORM_BWD=0 keeps the separate kernels (A/B)
         self.fuse_norm_bwd = os.environ.get("W2S_FUSE_NORM_BWD", "1") != "0"
+        # weight gradients of the classifier / mixer backward on a side stream (W2S_WGRAD_STREAM=0: in stream order, A/B)
+        self.wgrad_stream = os.environ.get("W2S_WGRAD_STREAM", "1") != "0"
+        self._wg = None
+        self._wg_streams = {}
         self.loss_scale = None    # power of two applied to the fp16 activation gradients; None = from B*S (see below)
         self._inv_scale = 1.0
         self.last_loss_scale = 1.0
@@ -202,11 +206,28 @@ class TrainEngine(ForwardEngine):
         c.act_dr = dr.data_ptr() if dr is not None else None
         _lib.check(self.lib.w2s_conv1d_fwd(C.byref(c), _stream()))
 
+    def _wgrad_stream(self, *tensors):
+        """Stream for a parameter-gradient launch.  Inside the classifier / mixer part of the backward (`_wg` set) these
+        launches leave the critical path: that part is a chain of ~150 small dependent kernels, of which only the data
+        gradients (convs, LayerNorm / attention backward) depend on each other - the weight-gradient GEMMs and bias
+        column sums (more than half of the launches) only have to be done before the optimizer / the gradient bucket
+        hook.  They run on a side stream ordered after the current position of the main stream."""
+        side = self._wg
+        if side is None:
+            return _stream()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        side.wait_event(ev)
+        for t in tensors:
+            if t is not None:
+                t.record_stream(side)
+        return side.cuda_stream
+
     def gemm_tn(self, X, Y, Cbuf, M, N, B, LX, LY, ldc_m, ldc_n, y_stride=1, y_offset=0, row_mask=None, c_off=0, taps=1,
                 ldc_t=0, tap_stride=1):
         _lib.check(self.lib.w2s_gemm_tn(X.data_ptr(), Y.data_ptr(), Cbuf.data_ptr() + 4 * c_off, M, N, taps, tap_stride, B,
                                         LX, LY, y_stride, y_offset, ldc_m, ldc_n, ldc_t, self._inv_scale, _p(row_mask),
-                                        _stream()))
+                                        self._wgrad_stream(X, Y, Cbuf, row_mask)))
 
     def ln_fwd(self, x, g, b, rows, gelu, eps, res=None):
         out = torch.empty_like(x)
@@ -224,7 +245,7 @@ class TrainEngine(ForwardEngine):
 
     def colsum(self, x, out, rows, Cc, row_stride=1, row_offset=0, row_mask=None, rows_per_sample=0, out_off=0):
         _lib.check(self.lib.w2s_colsum(x.data_ptr(), out.data_ptr() + 4 * out_off, rows, Cc, row_stride, row_offset,
-                                       _p(row_mask), rows_per_sample, self._inv_scale, _stream()))
+                                       _p(row_mask), rows_per_sample, self._inv_scale, self._wgrad_stream(x, out, row_mask)))
 
     # ------------------------------------------------------------------ gradients storage
     def _grad(self, p: Tensor) -> Tensor:
@@ -420,6 +441,7 @@ class TrainEngine(ForwardEngine):
         N = B * S
         self.grads = {}
         self.direct = set()
+        self._wg = None
         scale = float(self.loss_scale) if self.loss_scale is not None else self.auto_loss_scale(N)
         if scale <= 0 or (scale != 2.0 ** round(__import__("math").log2(scale))):
             raise ValueError(f"loss_scale must be a positive power of two, got {scale}")
@@ -428,6 +450,8 @@ class TrainEngine(ForwardEngine):
             st = _stream()
             G = self._grad
             dlogits = dlogits.detach().to(torch.float32).contiguous()
+            if self.wgrad_stream:
+                self._wg = self._wg_streams.setdefault(str(device), torch.cuda.Stream(device=device))
             # ---- classifier ----
             dfeat = torch.empty(N, 128, dtype=F16, device=device)
             _lib.check(lib.w2s_head_bwd(sv["feat"].data_ptr(), sv["wc"].data_ptr(), dlogits.data_ptr(), dfeat.data_ptr(),
@@ -522,6 +546,9 @@ class TrainEngine(ForwardEngine):
             _lib.check(lib.w2s_tokens_bwd(dx.data_ptr(), dzs, ms, G(mix.register_tokens).data_ptr(), N, S, len(names),
                                           self._inv_scale, st))
             # ---- encoders ----
+            if self._wg is not None:  # the side stream's weight gradients are part of the "tail" bucket
+                torch.cuda.current_stream(device).wait_stream(self._wg)
+                self._wg = None
             for hook in self.bucket_hooks:
                 hook("tail")  # classifier + sequence mixer + epoch mixer gradients are final
             if self.bucket_hooks and len(self.direct) != len(self.grads):
