@@ -193,6 +193,15 @@ int w2s_encoder_layout(const w2s_encoder_desc* d, int B, int64_t T, int64_t* off
 int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T, void* workspace,
                     size_t workspace_bytes, int keep_activations, void* z_out, uint8_t* row_mask, void* stream);
 
+/* Two encoders of the SAME architecture (e.g. ECG + PPG, ABD + THX: SignalEncoders builds one SignalEncoder per
+ * signal from one set of constructor arguments, models/wav2sleep.py:117-133) on inputs of the same shape: every
+ * encoder conv layer of the two runs in ONE launch, half of the grid each (results identical to two w2s_encoder_fwd
+ * calls).  Each encoder has its own workspace of workspace_bytes.  Different architectures fall back to two plain
+ * forwards in stream order.  (ABI v4) */
+int w2s_encoder_fwd_pair(const w2s_encoder_desc* d0, const float* x0, void* workspace0, void* z_out0, uint8_t* row_mask0,
+                         const w2s_encoder_desc* d1, const float* x1, void* workspace1, void* z_out1, uint8_t* row_mask1,
+                         int B, int64_t T, size_t workspace_bytes, int keep_activations, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Stage 2: epoch mixer.  Replaces MultiModalAttentionEmbedder.forward (models/wav2sleep.py:301-346).
  * ------------------------------------------------------------------------------------------------------- */

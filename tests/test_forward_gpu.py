@@ -162,6 +162,34 @@ def test_masked_equals_absent_and_batch_independence(cuda_device):
     assert (full[1:2] - one).abs().max().item() < 2e-3  # fp32 atomic-order noise through fp16 re-rounding
 
 
+@pytest.mark.parametrize("smap,ncls,B,S,masked", [(CARDIO, 4, 3, 40, [("ABD", 0), ("ECG", 1), ("PPG", 1), ("PPG", 2)]),
+                                                  (CARDIO, 4, 5, 7, []), (EOG, 5, 2, 12, [("EOG-R", 1)])])
+def test_paired_encoder_launches_equal_single_launches(cuda_device, smap, ncls, B, S, masked):
+    """Encoders of identical architecture (ECG + PPG, ABD + THX, EOG-L + EOG-R) share their conv launches, half of the
+    grid each (w2s_encoder_fwd_pair).  Same kernels, same arithmetic per tile; what changes is which CTA owns which
+    tiles, i.e. the order of the fp32 per-CTA partial sums behind the InstanceNorm statistics - the same ~1e-7 relative
+    noise as between two batch compositions (test_masked_equals_absent_and_batch_independence), which moves a few
+    fp16 roundings of stored activations and with them the logits by ~1e-3.  A wrong pointer in the second group (its
+    weights, statistics or mask) would show as an O(0.1-1) difference.  Per-signal row masks (the two halves of a grid
+    see different live-sample lists), odd batch sizes and lengths that leave partial tiles are covered."""
+    model = build_default(smap, ncls, seed=0)
+    x = make_inputs(smap, B, S, masked=masked, seed=5)
+    eng = model._get_engine()
+    assert eng.enc_pairs  # the default
+    ref = oracle.forward(x, model.state_dict(), oracle.OracleConfig(signal_map=smap, num_classes=ncls))
+    paired = run_cuda(model, x, cuda_device)
+    groups = eng._enc_groups(sorted(x), {k: v for k, v in x.items()}, paired=True)
+    assert all(len(g) == 2 for g in groups), groups
+    eng.enc_pairs = False
+    try:
+        single = run_cuda(model, x, cuda_device)
+    finally:
+        eng.enc_pairs = True
+    print(f"paired vs single max-abs {(paired - single).abs().max().item():.2e}, vs oracle {(paired - ref).abs().max().item():.2e}")
+    assert (paired - single).abs().max().item() < 4e-3 and (paired - single).abs().mean().item() < 5e-4
+    assert (paired - ref).abs().max().item() < TOL and (single - ref).abs().max().item() < TOL
+
+
 @pytest.mark.parametrize("smap,ncls,B,S,masked", [(CARDIO, 4, 2, 24, [("ABD", 0), ("ECG", 1)]), (EOG, 5, 1, 12, [])])
 def test_fp32_check_mode_within_1e4(cuda_device, smap, ncls, B, S, masked):
     """North-star fp32 gate: the fp32 check mode (plain fp32 CUDA-core kernels, fp32 storage) reproduces the reference

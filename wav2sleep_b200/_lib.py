@@ -23,7 +23,7 @@ MAX_MIXER_LAYERS = 8
 MAX_SIGNALS = 4
 MAX_SEQ_BLOCKS = 4
 MAX_DILATIONS = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 PRO_NONE, PRO_NORM, PRO_NORM_RES, PRO_FIR, PRO_NORM_RES_X, PRO_DNORM = 0, 1, 2, 3, 4, 5
 EPI_STATS, EPI_BIAS_GELU, EPI_LN_GELU, EPI_LN_GELU_RES, EPI_PLAIN, EPI_ACT_BWD = 0, 1, 2, 3, 4, 5
@@ -135,6 +135,9 @@ SYMBOLS = {
     "w2s_encoder_layout": (C.c_int, [C.POINTER(EncoderDesc), C.c_int, C.c_int64, C.POINTER(C.c_int64)]),
     "w2s_encoder_fwd": (C.c_int, [C.POINTER(EncoderDesc), C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_size_t,
                                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "w2s_encoder_fwd_pair": (C.c_int, [C.POINTER(EncoderDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.POINTER(EncoderDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_int, C.c_int64, C.c_size_t, C.c_int, C.c_void_p]),
     "w2s_epoch_mixer_fwd": (C.c_int, [C.POINTER(MixerDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int,
                                       C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "w2s_seqmixer_workspace_bytes": (C.c_size_t, [C.POINTER(SeqDesc), C.c_int, C.c_int, C.c_int]),

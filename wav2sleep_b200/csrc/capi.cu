@@ -235,7 +235,20 @@ ConvArgs to_args(const w2s_conv_call& c) {
   return a;
 }
 
-int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
+// c2 != nullptr: a second call of the same shape and configuration (the same layer of a second encoder with identical
+// architecture) to run in the same launch (paired stream kernel, conv_stream.cuh).  Returns kNotPaired - nothing was
+// launched - if the pair cannot share a launch; the caller then dispatches the two calls one after the other.
+constexpr int kNotPaired = -77;
+static bool conv_calls_pairable(const w2s_conv_call& a, const w2s_conv_call& b) {
+  return a.cin == b.cin && a.cout == b.cout && a.taps == b.taps && a.stride == b.stride && a.dilation == b.dilation &&
+         a.pad == b.pad && a.prologue == b.prologue && a.epilogue == b.epilogue && a.has_ds == b.has_ds && a.B == b.B &&
+         a.L_in == b.L_in && a.L_out == b.L_out && a.in_wide == b.in_wide && a.out_wide == b.out_wide &&
+         a.force_split == b.force_split && a.T_raw == b.T_raw && a.in_eps == b.in_eps && a.epilogue == W2S_EPI_STATS &&
+         (a.row_mask != nullptr) == (b.row_mask != nullptr) && stream_pairable(a.cout, a.has_ds != 0);
+}
+
+int conv_dispatch(const w2s_conv_call& c, cudaStream_t st, const w2s_conv_call* c2 = nullptr) {
+  if (c2 != nullptr && !conv_calls_pairable(c, *c2)) return kNotPaired;
   if (c.B <= 0 || c.L_in <= 0 || c.L_out <= 0) return fail("conv1d: empty shape B=%d L_in=%d L_out=%d", c.B, c.L_in, c.L_out);
   if (ilog2_exact(c.stride) < 0 || c.stride > 4) return fail("conv1d: stride %d unsupported", c.stride);
   if (c.B > 65535) return fail("conv1d: B=%d exceeds grid.y", c.B);
@@ -256,12 +269,20 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
       return fail("conv1d: W2S_EPI_ACT_BWD writes dense rows only");
   }
   const ConvArgs a = to_args(c);
+  ConvArgs a2s;
+  const ConvArgs* a2 = nullptr;
+  if (c2 != nullptr) {
+    a2s = to_args(*c2);
+    a2 = &a2s;
+  }
+  const double npair = c2 != nullptr ? 2.0 : 1.0;
   cudaError_t e = cudaErrorInvalidValue;
   bool found = false;
   char label[96];
-  snprintf(label, sizeof(label), "conv c%d->%d k%d s%d d%d pro%d epi%d%s%s B%d L%d", c.cin, c.cout, c.taps, c.stride,
+  snprintf(label, sizeof(label), "conv c%d->%d k%d s%d d%d pro%d epi%d%s%s B%d L%d%s", c.cin, c.cout, c.taps, c.stride,
            c.dilation, c.prologue, c.epilogue, c.has_ds ? " +ds" : "",
-           c.in_wide ? (c.out_wide ? " w32/32" : " w32/16") : (c.out_wide ? " w16/32" : ""), c.B, c.L_in);
+           c.in_wide ? (c.out_wide ? " w32/32" : " w32/16") : (c.out_wide ? " w16/32" : ""), c.B, c.L_in,
+           c2 != nullptr ? " x2" : "");
   const double ein = c.in_wide ? 4.0 : 2.0, eout = c.out_wide ? 4.0 : 2.0;
   // algorithmic traffic: every input element read once (+ residual), every output written once; fp16
   const double in_b = c.prologue == W2S_PRO_DNORM  // d(x_hat) + y read (half length when zero-stuffed), dy written
@@ -275,16 +296,19 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
                           ? (double)c.B * c.L_out * c.cout * 2.0 * (1.0 + (c.res ? 1.0 : 0.0) + (c.act_r ? 2.0 : 0.0) + (c.act_a ? 1.0 : 0.0))
                           : 0.0;
   const double fl = 2.0 * c.B * (double)c.L_out * c.cout * c.cin * (c.taps + (c.has_ds ? 0.5 : 0.0));
-  LaunchScope scope(st, label, in_b + out_b + ab_b, fl);
-  if (c.epilogue == W2S_EPI_STATS && c.taps == 3 && c.dilation == 1 && c.pad == 1 && impl == 0 &&
-      ((c.stride == 1 && c.L_out == c.L_in) || (c.stride == 2 && c.L_out == (c.L_in + 1) / 2))) {
+  // a pair whose shape has no stream kernel is not launched here (checked before the launch is counted / timed)
+  const bool stream_shape = c.epilogue == W2S_EPI_STATS && c.taps == 3 && c.dilation == 1 && c.pad == 1 && impl == 0 &&
+                            ((c.stride == 1 && c.L_out == c.L_in) || (c.stride == 2 && c.L_out == (c.L_in + 1) / 2));
+  if (c2 != nullptr && !stream_shape) return kNotPaired;
+  LaunchScope scope(st, label, npair * (in_b + out_b + ab_b), npair * fl);
+  if (stream_shape) {
     const int sms = sm_count();
     const bool want_split = c.force_split != 0 || w2s_conv_uses_split(c.cin, c.cout) != 0;
 #define W2S_STREAMX(CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW, WIN, WOUT, SPLIT)                          \
   if (!found && c.cin == CIN && c.cout == COUT && c.stride == STRIDE && c.prologue == PRO && (c.has_ds != 0) == DS && \
       (c.in_wide != 0) == WIN && (c.out_wide != 0) == WOUT && want_split == SPLIT) {                        \
     found = true;                                                                                           \
-    e = launch_conv_stream<CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW, WIN, WOUT, SPLIT>(a, c.B, sms, st); \
+    e = launch_conv_stream<CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW, WIN, WOUT, SPLIT>(a, a2, c.B, sms, st); \
   }
 #define W2S_STREAMW(CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW, WIN, WOUT) \
   W2S_STREAMX(CIN, COUT, STRIDE, PRO, DS, MT, NR, NA, NTW, WIN, WOUT, (CIN <= 16 && COUT <= 16))
@@ -352,6 +376,7 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st) {
       return 0;
     }
   }
+  if (c2 != nullptr) return kNotPaired;  // no stream kernel for this configuration: the caller dispatches the two calls singly
   if (impl == 3) {  // bf16 operands on the tile-per-CTA kernel: un-split encoder convs without the 1x1 branch only
 #define W2S_BF16(CIN, COUT)                                                                                          \
   if (!found && c.cin == CIN && c.cout == COUT && c.taps == 3 && c.prologue == PRO_NORM && c.epilogue == EPI_STATS && \
@@ -482,7 +507,7 @@ int check_encoder_desc(const w2s_encoder_desc* d) {
 
 extern "C" {
 
-int w2s_abi_version(void) { return 3; }
+int w2s_abi_version(void) { return 4; }
 const char* w2s_last_error(void) { return g_err.c_str(); }
 
 int w2s_conv_uses_split(int cin, int cout) { return (cin <= 16 && cout <= 16) ? 1 : 0; }
@@ -602,8 +627,20 @@ int w2s_encoder_layout(const w2s_encoder_desc* d, int B, int64_t T, int64_t* off
   return 0;
 }
 
-int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T, void* workspace, size_t ws_bytes,
-                    int keep, void* z_out, uint8_t* row_mask, void* stream) {
+// One encoder forward as a list of launches: built first, then issued - singly (w2s_encoder_fwd) or zipped with the list of
+// a second encoder of identical architecture, whose stream-kernel layers then share their launches (w2s_encoder_fwd_pair).
+struct EncStep {
+  enum Kind { MEMSET, XSTATS, FIRST, CONV } kind;
+  w2s_conv_call cc;       // CONV
+  void* ptr; size_t bytes;  // MEMSET
+  XStatsArgs xa;          // XSTATS (+ the finalize kernel's arguments)
+  const float* x; const double* xs; const float* w_first; const uint8_t* row_mask; double* s1;
+  FirstConvArgs fa;       // FIRST
+  int B, L;
+};
+
+static int encoder_plan(const w2s_encoder_desc* d, const float* x, int B, int64_t T, void* workspace, size_t ws_bytes,
+                        int keep, void* z_out, uint8_t* row_mask, std::vector<EncStep>& plan) {
   if (check_encoder_desc(d) != 0) return 1;
   if (x == nullptr || z_out == nullptr || row_mask == nullptr || workspace == nullptr) return fail("encoder: null pointer");
   const int64_t spe = (int64_t)4 << d->n_blocks;  // samples per epoch = 2^(n_blocks+2)
@@ -612,12 +649,24 @@ int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T,
   if (T > 0x7fffffff / 2) return fail("encoder: T=%lld too long", (long long)T);
   const size_t need = w2s_encoder_workspace_bytes(d, B, T, keep);
   if (ws_bytes < need) return fail("encoder: workspace %zu < required %zu", ws_bytes, need);
-  cudaStream_t st = (cudaStream_t)stream;
+  EncStep blank;
+  memset(&blank, 0, sizeof(blank));
+  auto emit_conv = [&](const w2s_conv_call& cc) {
+    EncStep s = blank;
+    s.kind = EncStep::CONV;
+    s.cc = cc;
+    plan.push_back(s);
+  };
 
   const size_t stats_bytes = align_up(enc_stats_count(d, B) * sizeof(double), 256);
   double* stats = (double*)workspace;
-  cudaError_t ce = cudaMemsetAsync(stats, 0, stats_bytes, st);
-  if (ce != cudaSuccess) return cuda_fail(ce, "encoder memset");
+  {
+    EncStep s = blank;
+    s.kind = EncStep::MEMSET;
+    s.ptr = stats;
+    s.bytes = stats_bytes;
+    plan.push_back(s);
+  }
   uint8_t* act_base = (uint8_t*)workspace + stats_bytes;
 
   Slots slots;
@@ -668,16 +717,10 @@ int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T,
       double* xs = stats + enc_layer_stats_count(d, B);  // zeroed with the rest of the statistics region
       XStatsArgs xa;
       xa.x = x; xa.xs = xs; xa.row_mask = row_mask; xa.T = L;
-      {
-        LaunchScope scope(st, "x_stats", (double)B * L * 4.0, (double)B * L * 8.0);
-        int gx = (L / 4 + 255) / 256;
-        const int cap = (4 * sm_count() + B - 1) / B;  // ~4 long-lived blocks per SM over the whole batch
-        if (gx > cap) gx = cap;
-        x_stats_kernel<<<dim3(gx < 1 ? 1 : gx, B), 256, 0, st>>>(xa);
-        x_stats_finalize_kernel<<<(B * 16 + 127) / 128, 128, 0, st>>>(x, xs, d->w_first, row_mask, s1, B, L);
-      }
-      ce = cudaGetLastError();
-      if (ce != cudaSuccess) return cuda_fail(ce, "x_stats launch");
+      EncStep s = blank;
+      s.kind = EncStep::XSTATS;
+      s.xa = xa; s.x = x; s.xs = xs; s.w_first = d->w_first; s.row_mask = row_mask; s.s1 = s1; s.B = B; s.L = L;
+      plan.push_back(s);
     } else if (i == 0) {
       FirstConvArgs fa;
       fa.x = x;
@@ -688,13 +731,10 @@ int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T,
       fa.stats = s1;
       fa.row_mask = row_mask;
       fa.T = L;
-      {
-        char fl_label[64];
-        snprintf(fl_label, sizeof(fl_label), "first_conv c1->16 k3 B%d L%d", B, L);
-        LaunchScope scope(st, fl_label, (double)B * L * (4.0 + 32.0 + 16.0), 2.0 * B * (double)L * 16 * 3.5);
-        ce = launch_first_conv(fa, B, st);
-      }
-      if (ce != cudaSuccess) return cuda_fail(ce, "first_conv launch");
+      EncStep s = blank;
+      s.kind = EncStep::FIRST;
+      s.fa = fa; s.B = B; s.L = L;
+      plan.push_back(s);
     } else {
       w2s_conv_call cc;
       memset(&cc, 0, sizeof(cc));
@@ -710,7 +750,7 @@ int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T,
       cc.out = y1; cc.out_ds = r; cc.out_stats = s1; cc.row_mask = row_mask; cc.in_eps = d->norm_eps;
       cc.in_wide = wide(i - 1); cc.out_wide = wide(i);
       cc.force_split = keep ? 0 : w2s_encoder_conv_split(d->wide_blocks, i, prev_c, c);
-      if (conv_dispatch(cc, st) != 0) return 1;
+      emit_conv(cc);
       release(prev_y3);
       release(prev_r);
     }
@@ -730,7 +770,7 @@ int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T,
       cc.out = y2; cc.out_stats = s2; cc.row_mask = row_mask; cc.in_eps = d->norm_eps;
       cc.in_wide = wide(i) && !(i == 0 && fuse0); cc.out_wide = wide(i);
       cc.force_split = keep ? 0 : w2s_encoder_conv_split(d->wide_blocks, i, c, c);
-      if (conv_dispatch(cc, st) != 0) return 1;
+      emit_conv(cc);
     }
     release(y1);
     void* y3 = alloc((size_t)B * (L / 2) * c * e);
@@ -745,7 +785,7 @@ int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T,
       cc.out = y3; cc.out_stats = s3; cc.row_mask = row_mask; cc.in_eps = d->norm_eps;
       cc.in_wide = wide(i); cc.out_wide = wide(i);
       cc.force_split = keep ? 0 : w2s_encoder_conv_split(d->wide_blocks, i, c, c);
-      if (conv_dispatch(cc, st) != 0) return 1;
+      emit_conv(cc);
     }
     release(y2);
     prev_y3 = y3;
@@ -762,7 +802,77 @@ int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T,
     cc.B = B; cc.L_in = L; cc.L_out = L / 4;
     cc.in = prev_y3; cc.in_res = prev_r; cc.in_stats = prev_s3; cc.w = d->w_lin; cc.bias = d->b_lin;
     cc.out = z_out; cc.row_mask = row_mask; cc.in_eps = d->norm_eps;
-    if (conv_dispatch(cc, st) != 0) return 1;
+    emit_conv(cc);
+  }
+  return 0;
+}
+
+static int run_enc_step(const EncStep& s, cudaStream_t st) {
+  switch (s.kind) {
+    case EncStep::MEMSET: {
+      cudaError_t ce = cudaMemsetAsync(s.ptr, 0, s.bytes, st);
+      return ce == cudaSuccess ? 0 : cuda_fail(ce, "encoder memset");
+    }
+    case EncStep::XSTATS: {
+      {
+        LaunchScope scope(st, "x_stats", (double)s.B * s.L * 4.0, (double)s.B * s.L * 8.0);
+        int gx = (s.L / 4 + 255) / 256;
+        const int cap = (4 * sm_count() + s.B - 1) / s.B;  // ~4 long-lived blocks per SM over the whole batch
+        if (gx > cap) gx = cap;
+        x_stats_kernel<<<dim3(gx < 1 ? 1 : gx, s.B), 256, 0, st>>>(s.xa);
+        x_stats_finalize_kernel<<<(s.B * 16 + 127) / 128, 128, 0, st>>>(s.x, s.xs, s.w_first, s.row_mask, s.s1, s.B, s.L);
+      }
+      cudaError_t ce = cudaGetLastError();
+      return ce == cudaSuccess ? 0 : cuda_fail(ce, "x_stats launch");
+    }
+    case EncStep::FIRST: {
+      cudaError_t ce;
+      {
+        char fl_label[64];
+        snprintf(fl_label, sizeof(fl_label), "first_conv c1->16 k3 B%d L%d", s.B, s.L);
+        LaunchScope scope(st, fl_label, (double)s.B * s.L * (4.0 + 32.0 + 16.0), 2.0 * s.B * (double)s.L * 16 * 3.5);
+        ce = launch_first_conv(s.fa, s.B, st);
+      }
+      return ce == cudaSuccess ? 0 : cuda_fail(ce, "first_conv launch");
+    }
+    case EncStep::CONV:
+      return conv_dispatch(s.cc, st);
+  }
+  return fail("encoder: bad plan step");
+}
+
+int w2s_encoder_fwd(const w2s_encoder_desc* d, const float* x, int B, int64_t T, void* workspace, size_t ws_bytes,
+                    int keep, void* z_out, uint8_t* row_mask, void* stream) {
+  std::vector<EncStep> plan;
+  if (encoder_plan(d, x, B, T, workspace, ws_bytes, keep, z_out, row_mask, plan) != 0) return 1;
+  for (const EncStep& s : plan)
+    if (run_enc_step(s, (cudaStream_t)stream) != 0) return 1;
+  return 0;
+}
+
+int w2s_encoder_fwd_pair(const w2s_encoder_desc* d0, const float* x0, void* workspace0, void* z_out0, uint8_t* row_mask0,
+                         const w2s_encoder_desc* d1, const float* x1, void* workspace1, void* z_out1, uint8_t* row_mask1,
+                         int B, int64_t T, size_t ws_bytes, int keep, void* stream) {
+  std::vector<EncStep> p0, p1;
+  if (encoder_plan(d0, x0, B, T, workspace0, ws_bytes, keep, z_out0, row_mask0, p0) != 0) return 1;
+  if (encoder_plan(d1, x1, B, T, workspace1, ws_bytes, keep, z_out1, row_mask1, p1) != 0) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  bool same = p0.size() == p1.size();
+  for (size_t i = 0; same && i < p0.size(); ++i) same = p0[i].kind == p1[i].kind;
+  if (!same) {  // different architectures: one encoder after the other
+    for (const EncStep& s : p0)
+      if (run_enc_step(s, st) != 0) return 1;
+    for (const EncStep& s : p1)
+      if (run_enc_step(s, st) != 0) return 1;
+    return 0;
+  }
+  for (size_t i = 0; i < p0.size(); ++i) {
+    if (p0[i].kind == EncStep::CONV) {
+      const int rc = conv_dispatch(p0[i].cc, st, &p1[i].cc);
+      if (rc == 0) continue;
+      if (rc != kNotPaired) return 1;
+    }
+    if (run_enc_step(p0[i], st) != 0 || run_enc_step(p1[i], st) != 0) return 1;
   }
   return 0;
 }

@@ -13,6 +13,8 @@
 //                                   flushed with fp64 atomics only when the sample changes
 // Stages hand over through mbarriers (raw full/empty, A full/empty, TMEM full/empty); weights are loaded once.
 #pragma once
+#include <cstring>
+
 #include "conv_igemm.cuh"
 
 namespace w2s {
@@ -53,6 +55,42 @@ struct WaitClock {
     if (W2S_DBG(p, 64) && blockIdx.x == 0) g_stream_ts[slot] = (unsigned long long)acc;
   }
 };
+
+// Paired launch: two encoders with identical layer shapes (ECG + PPG, ABD + THX) run a layer in ONE launch - the first
+// half of the grid works on group 0, the second half on group 1.  Only the tensors differ between the groups: the second
+// group's pointers ride in this block (ngroups == 1: ignored), every scalar of ConvArgs is shared.  Halves the number of
+// stream-kernel launches of a forward and with it the per-launch fixed cost (set-up, pipeline fill, drain, exit spread:
+// ~8 us of every CTA's life, profiles/r02_fixed_cost_small_layers.txt), and gives each CTA twice the tiles per launch.
+struct ConvGroup2 {
+  const act_t* in;
+  const act_t* in_res;
+  const double* in_stats;
+  const act_t* w;
+  const act_t* w_ds;
+  act_t* out;
+  act_t* out_ds;
+  double* out_stats;
+  const uint8_t* row_mask;
+  const float* x_raw;
+  const float* w_first;
+  const float* w_first_ds;
+  int ngroups;
+};
+// Kernels that are already at their register cap stay single-group (the second group's pointers would be selected into
+// registers: 72 -> 330 bytes of spills in the staged two-accumulator epilogue of the 128-channel conv1 kernels).
+__host__ __device__ constexpr bool stream_pairable(int cout, bool has_ds) { return !(cout == 128 && has_ds); }
+inline ConvGroup2 conv_group2(const ConvArgs* a) {
+  ConvGroup2 g;
+  memset(&g, 0, sizeof(g));
+  g.ngroups = 1;
+  if (a != nullptr) {
+    g.in = a->in; g.in_res = a->in_res; g.in_stats = a->in_stats; g.w = a->w; g.w_ds = a->w_ds;
+    g.out = a->out; g.out_ds = a->out_ds; g.out_stats = a->out_stats; g.row_mask = a->row_mask;
+    g.x_raw = a->x_raw; g.w_first = a->w_first; g.w_first_ds = a->w_first_ds;
+    g.ngroups = 2;
+  }
+  return g;
+}
 
 // warp 0 producer, 1 MMA, 2..2+E-1 epilogue, then transform.  E = 4 or 8: with 8, two warps share each TMEM lane
 // quadrant (a warp may only read the quadrant warp_id % 4) and split the (column group, sub-tile) items.  Measured for
@@ -172,7 +210,17 @@ struct StreamCfg {
 
 template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, bool SPLIT, int MT, int NR, int NA, int NTW, bool WIN, bool WOUT>
 __global__ void __launch_bounds__(stream_threads(NTW, COUT), (stream_threads(NTW, COUT) <= 384 ? 2 : 1))
-conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
+conv_stream_kernel(const ConvArgs pa, const ConvGroup2 pb, int tiles_per_sample, int total_tiles) {
+  // group of this CTA and the argument block it works on (scalars stay kernel-parameter constants, pointers are selected)
+  const int grid_half = (int)gridDim.x >> 1;
+  constexpr bool kPairable = stream_pairable(COUT, HAS_DS);
+  const bool grp1 = kPairable && pb.ngroups > 1 && (int)blockIdx.x >= grid_half;
+  const int cta = grp1 ? (int)blockIdx.x - grid_half : (int)blockIdx.x;
+  const int nctas = (kPairable && pb.ngroups > 1) ? (grp1 ? (int)gridDim.x - grid_half : grid_half) : (int)gridDim.x;
+  // (each role overrides only the pointers it uses, inside its own branch: keeps the selects out of the other roles'
+  // register budgets)
+  ConvArgs p = pa;
+  if (grp1) p.row_mask = pb.row_mask;
   using Cfg = StreamCfg<CIN, COUT, STRIDE, PRO, HAS_DS, SPLIT, MT, NR, NA, NTW, WIN, WOUT>;
   constexpr int ESZ = Cfg::ESZ;
   constexpr int kStreamThreads = Cfg::THREADS;
@@ -276,8 +324,8 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   tc_fence_after_sync();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const int live_tiles = compact ? sNLive * tiles_per_sample : total_tiles;
-  const int tile_begin = (int)((long long)blockIdx.x * live_tiles / gridDim.x);
-  const int tile_end = (int)((long long)(blockIdx.x + 1) * live_tiles / gridDim.x);
+  const int tile_begin = (int)((long long)cta * live_tiles / nctas);
+  const int tile_end = (int)((long long)(cta + 1) * live_tiles / nctas);
   // Position of a tile as (entry of the sample list, tile inside the sample), advanced incrementally: no division in
   // the per-tile loops of the four roles.
   struct TilePos {
@@ -299,6 +347,9 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
   // ======================================================================================================
   if (warp == 0) {
     // ---------------- producer (whole warp runs the loop; one elected lane issues) ----------------
+    if (grp1) {
+      p.in = pb.in; p.in_res = pb.in_res; p.x_raw = pb.x_raw; p.w = pb.w; p.w_ds = pb.w_ds;
+    }
     {
       // weights -> smem once per CTA (hi [, lo] blocks; the 1x1 branch after the taps): plain bulk copies of the packed
       // layout, off every other role's critical path (only the MMA issuer waits for them)
@@ -445,6 +496,9 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
     }
   } else if (warp < kStreamFirstTransformWarp) {
     // ---------------- epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) ----------------
+    if (grp1) {
+      p.out = pb.out; p.out_ds = pb.out_ds; p.out_stats = pb.out_stats;
+    }
     if constexpr (STAGED) {
       static_assert(Cfg::EPI_WARPS == 4, "one epilogue warp per TMEM lane quadrant");
       constexpr int SEG = Cfg::SEG, SEGB = SEG * 2;
@@ -715,6 +769,12 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
     }
   } else {
     // ---------------- transform warps ----------------
+    if (grp1) {
+      p.in_stats = pb.in_stats; p.w_first = pb.w_first; p.w_first_ds = pb.w_first_ds;
+      if (Cfg::DIRECT) {
+        p.in = pb.in; p.in_res = pb.in_res;
+      }
+    }
     const int tt = tid - kStreamFirstTransformWarp * 32;  // 0..255
     constexpr int NTT = kStreamTransformWarps * 32;
     const int cch = tt & (CH - 1);
@@ -1016,7 +1076,7 @@ conv_stream_kernel(const ConvArgs p, int tiles_per_sample, int total_tiles) {
 // SPLIT defaults to the (CIN, COUT) rule of ConvSplit; the wide-storage 64-channel kernels of deep encoders override it.
 template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, int MT, int NR, int NA, int NTW, bool WIN = false, bool WOUT = false,
           bool SPLIT = ConvSplit<CIN, COUT>::value>
-inline cudaError_t launch_conv_stream(const ConvArgs& a, int B, int sm_count, cudaStream_t stream) {
+inline cudaError_t launch_conv_stream(const ConvArgs& a, const ConvArgs* a2, int B, int sm_count, cudaStream_t stream) {
   using Cfg = StreamCfg<CIN, COUT, STRIDE, PRO, HAS_DS, SPLIT, MT, NR, NA, NTW, WIN, WOUT>;
   auto kern = conv_stream_kernel<CIN, COUT, STRIDE, PRO, HAS_DS, SPLIT, MT, NR, NA, NTW, WIN, WOUT>;
   static bool configured = false;
@@ -1029,7 +1089,13 @@ inline cudaError_t launch_conv_stream(const ConvArgs& a, int B, int sm_count, cu
   const long long total = (long long)tiles_per_sample * B;
   if (total > 0x7fffffffLL) return cudaErrorInvalidValue;
   const int ctas = sm_count * (Cfg::THREADS <= 384 ? 2 : 1);  // small CTAs run two per SM
-  const int grid = total < ctas ? (int)total : ctas;
+  int grid = total < ctas ? (int)total : ctas;
+  if (a2 != nullptr && !stream_pairable(COUT, HAS_DS)) return cudaErrorInvalidValue;  // (conv_dispatch never asks for it)
+  if (a2 != nullptr) {  // paired launch: half of the grid per group (same B, L for both)
+    const int per = total < ctas / 2 ? (int)total : ctas / 2;
+    grid = 2 * per;
+  }
+  const ConvGroup2 g2 = conv_group2(a2);
   // W2S_PDL=1 launches with programmatic stream serialization (never while the stream is being captured).  Measured
   // (3 alternating rounds, one box): the serialised kernel sum drops 1 % (7.40 vs 7.49 ms) but the step gets 2.4 % SLOWER
   // (6.72 vs 6.55 ms): the four encoder streams fill each other's tails with useful CTAs, and an early-scheduled
@@ -1047,7 +1113,7 @@ inline cudaError_t launch_conv_stream(const ConvArgs& a, int B, int sm_count, cu
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (pdl_enabled && cap == cudaStreamCaptureStatusNone) ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, a, tiles_per_sample, (int)total);
+  return cudaLaunchKernelEx(&cfg, kern, a, g2, tiles_per_sample, (int)total);
 }
 
 }  // namespace w2s

@@ -164,6 +164,9 @@ class ForwardEngine:
         # fill and tail of one encoder are covered by the other encoders' work.  W2S_ENC_STREAMS=0 serialises them.
         import os
         self.enc_streams = os.environ.get("W2S_ENC_STREAMS", "1") != "0"
+        # encoders of identical architecture on inputs of equal length (ECG + PPG, ABD + THX) share their conv launches
+        # (w2s_encoder_fwd_pair); W2S_ENC_PAIRS=0: one launch chain per signal (A/B)
+        self.enc_pairs = os.environ.get("W2S_ENC_PAIRS", "1") != "0"
         # Asynchronous forwards (forward_async / predict_async) run on the engine's own streams (the current stream only
         # records the fork event), alternating between n_lanes independent sets of streams and workspaces.  One lane is
         # the default: with two, consecutive batches could overlap, but measured on B200 it buys nothing (6.91 vs 6.89 ms
@@ -336,6 +339,48 @@ class ForwardEngine:
             join.record(st)
             stream.wait_event(join)
 
+    def _enc_groups(self, names, xs, paired: bool):
+        """Signals in launch order (longest chains first - they set the critical path when the encoders overlap), grouped
+        in pairs where two encoders have the same architecture and input length."""
+        order = sorted(names, key=lambda k: -xs[k].size(1))
+        if not (paired and self.enc_pairs):
+            return [(n,) for n in order]
+        smap = self.model.signal_encoders.signal_map
+
+        def arch(n):
+            d = self.enc[smap[n]].desc
+            return (d.n_blocks, tuple(d.channels[:d.n_blocks]), d.feature_dim, d.wide_blocks, d.norm_eps, xs[n].size(1))
+
+        groups, used = [], set()
+        for i, n in enumerate(order):
+            if n in used:
+                continue
+            used.add(n)
+            mate = next((m for m in order[i + 1:] if m not in used and arch(m) == arch(n)), None)
+            if mate is None:
+                groups.append((n,))
+            else:
+                used.add(mate)
+                groups.append((n, mate))
+        return groups
+
+    def _encode(self, buf, xs, grp, B: int, stream_ptr) -> None:
+        """One signal encoder, or two of the same architecture in shared launches, on the given stream."""
+        lib, smap = self.lib, self.model.signal_encoders.signal_map
+        n = grp[0]
+        pe, ws = self.enc[smap[n]], buf["enc_ws"][n]
+        if len(grp) == 1:
+            _lib.check(lib.w2s_encoder_fwd(C.byref(pe.desc), xs[n].data_ptr(), B, xs[n].size(1), ws.data_ptr(), ws.numel(), 0,
+                                           buf["z"][n].data_ptr(), buf["mask"][n].data_ptr(), stream_ptr), ValueError)
+            return
+        m = grp[1]
+        pm, wm = self.enc[smap[m]], buf["enc_ws"][m]
+        assert ws.numel() == wm.numel() and ws.data_ptr() != wm.data_ptr()
+        _lib.check(lib.w2s_encoder_fwd_pair(C.byref(pe.desc), xs[n].data_ptr(), ws.data_ptr(), buf["z"][n].data_ptr(),
+                                            buf["mask"][n].data_ptr(), C.byref(pm.desc), xs[m].data_ptr(), wm.data_ptr(),
+                                            buf["z"][m].data_ptr(), buf["mask"][m].data_ptr(), B, xs[n].size(1), ws.numel(),
+                                            0, stream_ptr), ValueError)
+
     def _launch(self, buf, xs: dict[str, Tensor], names, B: int, S: int, logits: Tensor) -> None:
         """Enqueue the three stage calls on the current stream (also what gets captured into a CUDA graph)."""
         lib, st = self.lib, _stream()
@@ -344,18 +389,14 @@ class ForwardEngine:
             cur = torch.cuda.current_stream()
             fork = torch.cuda.Event()
             fork.record(cur)
-        # longest chains first (they set the critical path when the encoders overlap)
-        for i, n in enumerate(sorted(names, key=lambda k: -xs[k].size(1))):
-            pe = self.enc[self.model.signal_encoders.signal_map[n]]
-            ws = buf["enc_ws"][n]
+        # (pairs need one workspace per encoder: only when the encoders have their own streams / workspaces)
+        for i, grp in enumerate(self._enc_groups(names, xs, paired=streams is not None)):
             if streams is not None:
                 streams[i].wait_event(fork)
                 est = streams[i].cuda_stream
             else:
                 est = st
-            _lib.check(lib.w2s_encoder_fwd(C.byref(pe.desc), xs[n].data_ptr(), B, xs[n].size(1), ws.data_ptr(),
-                                           ws.numel(), 0, buf["z"][n].data_ptr(), buf["mask"][n].data_ptr(), est),
-                       ValueError)
+            self._encode(buf, xs, grp, B, est)
             if streams is not None:
                 join = torch.cuda.Event()
                 join.record(streams[i])
@@ -376,18 +417,16 @@ class ForwardEngine:
         fork.record(cur)
         tail, streams = buf["tail"], buf["streams"]
         tail.wait_event(fork)
-        for i, n in enumerate(sorted(names, key=lambda k: -xs[k].size(1))):
+        for i, grp in enumerate(self._enc_groups(names, xs, paired=True)):
             st = streams[i]
             st.wait_event(fork)
-            if ready is not None and ready.get(n) is not None:
-                st.wait_event(ready[n])
+            for n in grp:
+                if ready is not None and ready.get(n) is not None:
+                    st.wait_event(ready[n])
+                xs[n].record_stream(st)
             if buf["tail_done"] is not None:
                 st.wait_event(buf["tail_done"])  # the lane's previous batch has finished reading z / masks
-            xs[n].record_stream(st)
-            pe = self.enc[self.model.signal_encoders.signal_map[n]]
-            ws = buf["enc_ws"][n]
-            _lib.check(lib.w2s_encoder_fwd(C.byref(pe.desc), xs[n].data_ptr(), B, xs[n].size(1), ws.data_ptr(), ws.numel(), 0,
-                                           buf["z"][n].data_ptr(), buf["mask"][n].data_ptr(), st.cuda_stream), ValueError)
+            self._encode(buf, xs, grp, B, st.cuda_stream)
             ev = torch.cuda.Event()
             ev.record(st)
             tail.wait_event(ev)
