@@ -335,7 +335,9 @@ def run_cuda(args):
         prof = []
         if rank == 0:
             eng = model._get_engine()
-            streams_on, eng.enc_streams = eng.enc_streams, False  # isolated per-kernel durations: encoders back to back
+            # isolated per-kernel durations of exactly the launches of a timed step (paired encoder launches included):
+            # the encoder streams run one after the other
+            eng.serial_groups = True
             model.predict(devb[0])
             lib.w2s_profile_enable(1)
             for i in range(2):
@@ -343,7 +345,7 @@ def run_cuda(args):
             torch.cuda.synchronize()
             prof = collect_profile(lib)
             lib.w2s_profile_enable(0)
-            eng.enc_streams = streams_on
+            eng.serial_groups = False
             eng._release_buffers()
 
     del stage, stage16, host16, devb

@@ -20,7 +20,7 @@ dev = torch.device("cuda:0")
 rt = torch.cuda.cudart()
 if mode == "infer":
     model = build_default(bench.CARDIO, 4, seed=0).to(dev).eval()
-    model._get_engine().enc_streams = False
+    model._get_engine().serial_groups = True  # the launches of a normal step (paired encoders), one stream after the other
     x = {k: v.to(dev) for k, v in bench.make_night_batch(B, seed=42).items()}
     if len(sys.argv) > 3:
         for k in x:

@@ -279,10 +279,10 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st, const w2s_conv_call* 
   cudaError_t e = cudaErrorInvalidValue;
   bool found = false;
   char label[96];
-  snprintf(label, sizeof(label), "conv c%d->%d k%d s%d d%d pro%d epi%d%s%s B%d L%d%s", c.cin, c.cout, c.taps, c.stride,
+  snprintf(label, sizeof(label), "conv c%d->%d k%d s%d d%d pro%d epi%d%s%s%s B%d L%d", c.cin, c.cout, c.taps, c.stride,
            c.dilation, c.prologue, c.epilogue, c.has_ds ? " +ds" : "",
-           c.in_wide ? (c.out_wide ? " w32/32" : " w32/16") : (c.out_wide ? " w16/32" : ""), c.B, c.L_in,
-           c2 != nullptr ? " x2" : "");
+           c.in_wide ? (c.out_wide ? " w32/32" : " w32/16") : (c.out_wide ? " w16/32" : ""),
+           c2 != nullptr ? " x2" : "", c.B, c.L_in);  // x2: paired launch (two encoders, B nights each)
   const double ein = c.in_wide ? 4.0 : 2.0, eout = c.out_wide ? 4.0 : 2.0;
   // algorithmic traffic: every input element read once (+ residual), every output written once; fp16
   const double in_b = c.prologue == W2S_PRO_DNORM  // d(x_hat) + y read (half length when zero-stuffed), dy written

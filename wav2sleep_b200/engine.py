@@ -165,8 +165,13 @@ class ForwardEngine:
         import os
         self.enc_streams = os.environ.get("W2S_ENC_STREAMS", "1") != "0"
         # encoders of identical architecture on inputs of equal length (ECG + PPG, ABD + THX) share their conv launches
-        # (w2s_encoder_fwd_pair); W2S_ENC_PAIRS=0: one launch chain per signal (A/B)
-        self.enc_pairs = os.environ.get("W2S_ENC_PAIRS", "1") != "0"
+        # (w2s_encoder_fwd_pair); W2S_ENC_PAIRS=0: one launch chain per signal (A/B).
+        # 1 (default): only while at least two launch chains remain to overlap each other's kernel tails - the two-signal
+        # EOG model keeps one chain per signal (paired: 44.4 vs 42.3 ms per 16 x 14-h nights); 2: always
+        self.enc_pairs = int(os.environ.get("W2S_ENC_PAIRS", "1"))
+        # measurement mode: the encoder streams run one after the other (isolated per-kernel durations of exactly the
+        # launches of a normal step, paired launches included)
+        self.serial_groups = False
         # Asynchronous forwards (forward_async / predict_async) run on the engine's own streams (the current stream only
         # records the fork event), alternating between n_lanes independent sets of streams and workspaces.  One lane is
         # the default: with two, consecutive batches could overlap, but measured on B200 it buys nothing (6.91 vs 6.89 ms
@@ -362,6 +367,8 @@ class ForwardEngine:
             else:
                 used.add(mate)
                 groups.append((n, mate))
+        if len(groups) < 2 and self.enc_pairs < 2:
+            return [(n,) for n in order]
         return groups
 
     def _encode(self, buf, xs, grp, B: int, stream_ptr) -> None:
@@ -390,9 +397,12 @@ class ForwardEngine:
             fork = torch.cuda.Event()
             fork.record(cur)
         # (pairs need one workspace per encoder: only when the encoders have their own streams / workspaces)
+        prev = None
         for i, grp in enumerate(self._enc_groups(names, xs, paired=streams is not None)):
             if streams is not None:
                 streams[i].wait_event(fork)
+                if self.serial_groups and prev is not None:
+                    streams[i].wait_event(prev)
                 est = streams[i].cuda_stream
             else:
                 est = st
@@ -401,6 +411,7 @@ class ForwardEngine:
                 join = torch.cuda.Event()
                 join.record(streams[i])
                 cur.wait_event(join)
+                prev = join
         zs = (C.c_void_p * len(names))(*[buf["z"][n].data_ptr() for n in names])
         ms = (C.c_void_p * len(names))(*[buf["mask"][n].data_ptr() for n in names])
         _lib.check(lib.w2s_epoch_mixer_fwd(C.byref(self.mixer_desc), zs, ms, len(names), B, S, buf["mix"].data_ptr(), st))
