@@ -177,8 +177,10 @@ def test_paired_encoder_launches_equal_single_launches(cuda_device, smap, ncls, 
     eng = model._get_engine()
     assert eng.enc_pairs == 1  # the default: pairs while two launch chains remain (cardio yes, the two-signal EOG model no)
     ref = oracle.forward(x, model.state_dict(), oracle.OracleConfig(signal_map=smap, num_classes=ncls))
+    default = run_cuda(model, x, cuda_device)  # (also packs the weights: the grouping below reads the encoder descriptors)
     groups = eng._enc_groups(sorted(x), {k: v for k, v in x.items()}, paired=True)
     assert all(len(g) == (2 if len(smap) == 4 else 1) for g in groups), groups
+    assert (default - ref).abs().max().item() < TOL
     try:
         eng.enc_pairs = 2  # always
         assert all(len(g) == 2 for g in eng._enc_groups(sorted(x), {k: v for k, v in x.items()}, paired=True))
