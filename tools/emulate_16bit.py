@@ -87,6 +87,8 @@ class Policy:
     def act(self, x, cin=0):
         if self.half_min and cin >= self.half_min:
             return gelu_half(x, self.tanh_ulp)
+        if self.gelu == "tanh_std":  # textbook tanh form (no clamp needed: monotone argument), max abs error ~3e-4 vs erf
+            return 0.5 * x * (1.0 + torch.tanh(0.7978845608 * (x + 0.044715 * x * x * x)))
         if self.gelu == "tanh_approx":
             return gelu_tanh_fit(x, approx_amp=2.0 ** -11.5)
         return gelu_tanh_fit(x) if self.gelu == "tanh" else oracle.gelu(x)

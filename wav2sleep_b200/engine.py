@@ -369,6 +369,9 @@ class ForwardEngine:
                 groups.append((n, mate))
         if len(groups) < 2 and self.enc_pairs < 2:
             return [(n,) for n in order]
+        if self.enc_pairs == 3:  # A/B: pair only the shorter signals, the longest ones keep one chain each
+            tmax = max(xs[n].size(1) for n in order)
+            groups = [g2 for g in groups for g2 in ([(n,) for n in g] if xs[g[0]].size(1) == tmax else [g])]
         return groups
 
     def _encode(self, buf, xs, grp, B: int, stream_ptr) -> None:
