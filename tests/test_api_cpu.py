@@ -88,3 +88,22 @@ def test_top_level_functions_mirror_the_reference_package():
     import pytest
     with pytest.raises(NotImplementedError):
         pkg.load_model("hf://joncarter/wav2sleep")
+
+
+def test_hostmem_binding_is_placement_only():
+    """hostmem.bind_to_gpu_numa narrows the process's CPU affinity to the GPU-local CPUs and never widens or empties it;
+    without NVML / a GPU it is a silent no-op (multi-rank bench.py calls it before allocating pinned batches)."""
+    import os
+    from wav2sleep_b200 import hostmem
+    before = os.sched_getaffinity(0)
+    cpus = hostmem.gpu_local_cpus(0)
+    assert isinstance(cpus, list) and all(isinstance(c, int) and 0 <= c < (os.cpu_count() or 1) for c in cpus)
+    n = hostmem.bind_to_gpu_numa(0)
+    after = os.sched_getaffinity(0)
+    try:
+        assert after <= before and len(after) > 0
+        assert n in (0, len(after))
+        if not cpus:
+            assert n == 0 and after == before
+    finally:
+        os.sched_setaffinity(0, before)
