@@ -163,7 +163,11 @@ def test_masked_equals_absent_and_batch_independence(cuda_device):
 
 
 @pytest.mark.parametrize("smap,ncls,B,S,masked", [(CARDIO, 4, 3, 40, [("ABD", 0), ("ECG", 1), ("PPG", 1), ("PPG", 2)]),
-                                                  (CARDIO, 4, 5, 7, []), (EOG, 5, 2, 12, [("EOG-R", 1)])])
+                                                  (CARDIO, 4, 5, 7, []), (EOG, 5, 2, 12, [("EOG-R", 1)]),
+                                                  # one signal of a pair missing on every night, the other pair 1 : 4 -
+                                                  # the grid of a paired launch is split in proportion to the live samples
+                                                  (CARDIO, 4, 4, 9, [("PPG", 0), ("PPG", 1), ("PPG", 2), ("PPG", 3),
+                                                                     ("THX", 0), ("THX", 1), ("THX", 2)])])
 def test_paired_encoder_launches_equal_single_launches(cuda_device, smap, ncls, B, S, masked):
     """Encoders of identical architecture (ECG + PPG, ABD + THX, EOG-L + EOG-R) share their conv launches, half of the
     grid each (w2s_encoder_fwd_pair).  Same kernels, same arithmetic per tile; what changes is which CTA owns which

@@ -1,2 +1,2 @@
 #!/bin/bash
-bash tools/gpu_env_ab.sh "W2S_LANES=2" 2
+bash tools/gpu_ab2.sh "equal" 3

@@ -185,7 +185,7 @@ struct StreamCfg {
   static constexpr int B_BYTES = B_ONE * (SPLIT ? 2 : 1);
   static constexpr int STAGE_COLS = MT * COUT * (HAS_DS ? 2 : 1);
   static constexpr int TMEM_COLS = (2 * STAGE_COLS <= 32) ? 32 : (2 * STAGE_COLS <= 64) ? 64 : (2 * STAGE_COLS <= 128) ? 128 : (2 * STAGE_COLS <= 256) ? 256 : 512;
-  static constexpr int CTL_BYTES = 512;  // mbarriers + TMEM slot (first 256 B), live-sample list (second 256 B)
+  static constexpr int CTL_BYTES = 768;  // mbarriers + TMEM slot (first 256 B), live-sample lists of the two groups (256 B each)
   static constexpr int SMEM_BASE = NR * RAW_BYTES + NA * A_BYTES + B_BYTES + CTL_BYTES;
   // per-thread statistics accumulators across tiles for COUT = 16 (and for the 32-channel conv1 kernels, whose epilogue
   // also drains the residual-branch accumulator: measured faster)
@@ -212,15 +212,11 @@ template <int CIN, int COUT, int STRIDE, int PRO, bool HAS_DS, bool SPLIT, int M
 __global__ void __launch_bounds__(stream_threads(NTW, COUT), (stream_threads(NTW, COUT) <= 384 ? 2 : 1))
 conv_stream_kernel(const ConvArgs pa, const ConvGroup2 pb, int tiles_per_sample, int total_tiles) {
   // group of this CTA and the argument block it works on (scalars stay kernel-parameter constants, pointers are selected)
-  const int grid_half = (int)gridDim.x >> 1;
+  // (the group of a CTA is decided after the set-up barrier, from the two groups' live-sample counts; each role then
+  // overrides only the pointers it uses, inside its own branch: keeps the selects out of the other roles' registers)
   constexpr bool kPairable = stream_pairable(COUT, HAS_DS);
-  const bool grp1 = kPairable && pb.ngroups > 1 && (int)blockIdx.x >= grid_half;
-  const int cta = grp1 ? (int)blockIdx.x - grid_half : (int)blockIdx.x;
-  const int nctas = (kPairable && pb.ngroups > 1) ? (grp1 ? (int)gridDim.x - grid_half : grid_half) : (int)gridDim.x;
-  // (each role overrides only the pointers it uses, inside its own branch: keeps the selects out of the other roles'
-  // register budgets)
+  const bool paired = kPairable && pb.ngroups > 1;
   ConvArgs p = pa;
-  if (grp1) p.row_mask = pb.row_mask;
   using Cfg = StreamCfg<CIN, COUT, STRIDE, PRO, HAS_DS, SPLIT, MT, NR, NA, NTW, WIN, WOUT>;
   constexpr int ESZ = Cfg::ESZ;
   constexpr int kStreamThreads = Cfg::THREADS;
@@ -269,10 +265,12 @@ conv_stream_kernel(const ConvArgs pa, const ConvGroup2 pb, int tiles_per_sample,
   // nights cost nothing and the remaining work stays balanced (training with the modality masker, inference with
   // missing signals).  sLive[i] = i-th live sample; batches larger than the list fall back to skipping tile by tile.
   constexpr int kMaxLive = 120;
-  uint16_t* sLive = reinterpret_cast<uint16_t*>(sCtl + 256);
-  int& sNLive = *reinterpret_cast<int*>(sCtl + 256 + 2 * kMaxLive);
+  uint16_t* sLive0 = reinterpret_cast<uint16_t*>(sCtl + 256);
+  uint16_t* sLive1 = reinterpret_cast<uint16_t*>(sCtl + 512);  // second group of a paired launch
+  int* sNLive = reinterpret_cast<int*>(sCtl + 256 + 2 * kMaxLive);  // [0] group 0; group 1 at the same place of its block
+  int* sNLive1 = reinterpret_cast<int*>(sCtl + 512 + 2 * kMaxLive);
   const int n_samples = total_tiles / tiles_per_sample;
-  const bool compact = p.row_mask != nullptr && n_samples <= kMaxLive;
+  const bool compact = pa.row_mask != nullptr && n_samples <= kMaxLive;
 
   // ---------------- one-time setup ----------------
   if (tid == 0) dbg_ts(p, 0);
@@ -309,21 +307,47 @@ conv_stream_kernel(const ConvArgs pa, const ConvGroup2 pb, int tiles_per_sample,
   if (compact && tid == 64) {
     int n = 0;
     for (int b = 0; b < n_samples; ++b)
-      if (!p.row_mask[b]) sLive[n++] = (uint16_t)b;
-    sNLive = n;
+      if (!pa.row_mask[b]) sLive0[n++] = (uint16_t)b;
+    *sNLive = n;
   }
 #else
   if (compact && warp == 2) {
-    const int n = build_live_list(p.row_mask, n_samples, sLive, lane);
-    if (lane == 0) sNLive = n;
+    const int n = build_live_list(pa.row_mask, n_samples, sLive0, lane);
+    if (lane == 0) *sNLive = n;
   }
 #endif
+  if (compact && paired && warp == 3) {
+    const int n = build_live_list(pb.row_mask, n_samples, sLive1, lane);
+    if (lane == 0) *sNLive1 = n;
+  }
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-  const int live_tiles = compact ? sNLive * tiles_per_sample : total_tiles;
+  // Paired launch: the grid is split between the two encoders in proportion to their live samples (the modality masks
+  // of the two signals differ: a night without PPG costs the ECG + PPG launch nothing on the PPG side, and the CTAs it
+  // would have had work on ECG instead); without compaction, half each.
+  int ctas0 = (int)gridDim.x;
+  if (paired) {
+    ctas0 = (int)gridDim.x >> 1;
+#ifndef W2S_EQUAL_SPLIT  // (A/B build: always half of the grid per group)
+    if (compact) {
+      const int n0 = *sNLive, n1 = *sNLive1;
+      if (n0 != n1) {  // (equal counts: half each, nothing to compute; 32-bit: gridDim.x * n0 <= 296 * 120)
+        ctas0 = (int)(((unsigned)gridDim.x * (unsigned)n0 + ((unsigned)(n0 + n1) >> 1)) / (unsigned)(n0 + n1));
+        if (n0 > 0 && ctas0 < 1) ctas0 = 1;
+        if (n1 > 0 && ctas0 > (int)gridDim.x - 1) ctas0 = (int)gridDim.x - 1;
+      }
+    }
+#endif
+  }
+  const bool grp1 = paired && (int)blockIdx.x >= ctas0;
+  const int cta = grp1 ? (int)blockIdx.x - ctas0 : (int)blockIdx.x;
+  const int nctas = grp1 ? (int)gridDim.x - ctas0 : ctas0;
+  if (grp1) p.row_mask = pb.row_mask;
+  const uint16_t* sLive = grp1 ? sLive1 : sLive0;
+  const int live_tiles = compact ? (grp1 ? *sNLive1 : *sNLive) * tiles_per_sample : total_tiles;
   const int tile_begin = (int)((long long)cta * live_tiles / nctas);
   const int tile_end = (int)((long long)(cta + 1) * live_tiles / nctas);
   // Position of a tile as (entry of the sample list, tile inside the sample), advanced incrementally: no division in
