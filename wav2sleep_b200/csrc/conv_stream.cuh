@@ -301,7 +301,9 @@ conv_stream_kernel(const ConvArgs pa, const ConvGroup2 pb, int tiles_per_sample,
   // normally launched grid): the next stream kernel of this CUDA stream may be scheduled onto SMs as this grid's CTAs
   // exit (launch latency, TMEM allocation and barrier set-up then overlap this grid's tail); everything that reads or
   // writes global memory comes after the wait, which returns when the preceding grid has completed and flushed.
+#ifndef W2S_PDL_LATE_TRIGGER
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
   asm volatile("griddepcontrol.wait;" ::: "memory");
 #ifdef W2S_SERIAL_LIVE  // A/B build: one thread scans the mask (one dependent global load per sample)
   if (compact && tid == 64) {
@@ -1086,6 +1088,9 @@ conv_stream_kernel(const ConvArgs pa, const ConvGroup2 pb, int tiles_per_sample,
   }
 
   // ---------------- teardown ----------------
+#ifdef W2S_PDL_LATE_TRIGGER  // A/B build: dependents may be scheduled only when this CTA is done with its tiles
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
   tc_fence_before_sync();
   __syncthreads();
   if (tid == 0) dbg_ts(p, 9);
@@ -1123,7 +1128,9 @@ inline cudaError_t launch_conv_stream(const ConvArgs& a, const ConvArgs* a2, int
   // W2S_PDL=1 launches with programmatic stream serialization (never while the stream is being captured).  Measured
   // (3 alternating rounds, one box): the serialised kernel sum drops 1 % (7.40 vs 7.49 ms) but the step gets 2.4 % SLOWER
   // (6.72 vs 6.55 ms): the four encoder streams fill each other's tails with useful CTAs, and an early-scheduled
-  // dependent CTA holds its SM idle at griddepcontrol.wait instead.  Off by default.
+  // dependent CTA holds its SM idle at griddepcontrol.wait instead.  Re-measured on top of the paired launches (two
+  // streams): 6.73 / 6.70 vs 6.55 / 6.62 ms; with the trigger moved to the end of each CTA's work (-DW2S_PDL_LATE_TRIGGER)
+  // 6.58 / 6.57 / 6.57 vs 6.56 / 6.61 / 6.56 ms - neutral.  Off by default.
   static const bool pdl_enabled = [] { const char* e = getenv("W2S_PDL"); return e && atoi(e) != 0; }();
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (pdl_enabled) cudaStreamIsCapturing(stream, &cap);
