@@ -12,6 +12,9 @@
 //   warps 2..5       : epilogue   - tcgen05.ld, fp16 store, sum / sum-of-squares kept in registers across tiles and
 //                                   flushed with fp64 atomics only when the sample changes
 // Stages hand over through mbarriers (raw full/empty, A full/empty, TMEM full/empty); weights are loaded once.
+// Variants: NR = 0 (StreamCfg::DIRECT) drops the raw ring - the transform warps read global memory directly through a
+// register prefetch ring (128-channel kernels); a paired launch (ConvGroup2) runs the same layer of two encoders of
+// identical architecture in one grid, split in proportion to the encoders' live samples.
 #pragma once
 #include <cstring>
 
