@@ -103,7 +103,8 @@ def test_full_night_argmax_eog(cuda_device):
             print(f"    {int(flipped.sum())} flipped epochs, largest reference top-2 margin among them {worst:.2e}")
             assert worst < 2 * err.max().item()
     assert build_default(EOG, 5).signal_encoders.get_encoder("EOG-L").wide_blocks == 6  # the default policy
-    # Default policy: max-abs gate with 3x margin.  Argmax: measured 99.86 % (7 of 5040 epochs flip; flips scale with the
+    # Default policy: max-abs gate with 3x margin.  Argmax: measured 99.86-99.90 % (5-7 of 5040 epochs flip, depending on
+    # the build's rounding order - e.g. which epilogue the 128-channel conv1 kernels use; flips scale with the
     # mean logit error: 22 / 8 / 7 at 4.4e-3 / 1.8e-3 / 1.0e-3), i.e. statistically AT the 99.9 % north-star figure, not
     # safely above it: tools/emulate_16bit.py shows the remaining error is the fp16 operands of the 128-channel layers
     # and of the two mixers (DESIGN.md "Numerics").  Asserted at 99.8 % so that the test is not a coin flip.
