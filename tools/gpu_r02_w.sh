@@ -1,11 +1,13 @@
 #!/bin/bash
-# PDL with the trigger at the end of each CTA's work (build "late") vs no PDL
+# staged epilogue + 14 transform warps for the 32-channel conv1 kernels (build "st32") vs per-thread statistics + 10 warps
 mkdir -p gpurun_out
-for r in 1 2 3; do
-  for v in nopdl late_pdl; do
-    if [ $v == nopdl ]; then envs="W2S_PDL=0"; else envs="W2S_PDL=1 W2S_LIB_VARIANT=late"; fi
-    env $envs timeout 200 python bench.py --steps 30 --warmup 5 --no-train --no-eog --no-cpu-baseline > gpurun_out/ab_${v}_$r.json 2> gpurun_out/ab_${v}_$r.err
-    python -c "
-import json; d=json.load(open('gpurun_out/ab_${v}_$r.json')); print('$v round $r: %.3f ms/step e2e %.3f serial %.3f clocks %s' % (d['ms_per_step'], d['e2e']['ms_per_step'], d['roofline']['whole_step']['kernel_ms_per_step'], d['clocks']['sm_mhz']))"
-  done
-done
+W2S_LIB_VARIANT=st32 timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_forward_gpu.py -m gpu -x -q > gpurun_out/w_tests.log 2>&1
+echo "tests st32 rc=$?"; tail -n 3 gpurun_out/w_tests.log
+bash tools/gpu_ab2.sh "st32" 3
+python - <<'PY'
+import json
+ks = {v: {k["kernel"]: k for k in json.load(open(f"gpurun_out/ab_{v}_2_kernels.json"))} for v in ("default", "st32")}
+for name, k in ks["default"].items():
+    if "pro2" in name and ("c16->32" in name or "c32->32" in name):
+        print(f"{name:62s} default {k['avg_ms']*1e3:7.1f} us   st32 {ks['st32'][name]['avg_ms']*1e3:7.1f} us")
+PY

@@ -192,6 +192,8 @@ struct StreamCfg {
   static constexpr int SMEM_BASE = NR * RAW_BYTES + NA * A_BYTES + B_BYTES + CTL_BYTES;
   // per-thread statistics accumulators across tiles for COUT = 16 (and for the 32-channel conv1 kernels, whose epilogue
   // also drains the residual-branch accumulator: measured faster)
+  // (re-measured against the staged epilogue with 14 instead of 10 transform warps, which the lower register count
+  // would allow: 16 -> 32 conv1 273 -> 354 us, 32 -> 32 conv1 219 -> 237 us per paired launch - slower)
   static constexpr bool REG_STATS = (COUT <= 16) || (COUT <= 32 && HAS_DS);
   // Staged epilogue (all other fp16-output kernels, where shared memory allows): each epilogue warp transposes its
   // 32 rows through a private, XOR-swizzled staging buffer, so that (i) global stores are full 128-byte lines written
