@@ -328,6 +328,8 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st, const w2s_conv_call* 
     W2S_STREAMD(16, 16, 1, PRO_NORM, false, 8, 2, 2, 18, 3)
     W2S_STREAMD(16, 16, 2, PRO_NORM, false, 4, 2, 2, 18, 3)
     W2S_STREAMD(16, 16, 1, PRO_NORM_RES, true, 4, 3, 2, 14, 3)
+    // (10 transform warps at 120 registers; 12 / 14 warps cap the kernel at 96 registers and spill: 16 -> 32 conv1
+    //  265 -> 339 / 361 us per paired launch, 32 -> 32 conv1 227 -> 214 / 241 us, step +2-3 %)
     W2S_STREAMD(16, 32, 1, PRO_NORM_RES, true, 4, 3, 2, 10, 3)
     W2S_STREAMD(32, 32, 1, PRO_NORM, false, 4, 2, 2, 14, 3)
     W2S_STREAMD(32, 32, 2, PRO_NORM, false, 2, 2, 2, 14, 3)
