@@ -362,8 +362,11 @@ def test_two_forwards_before_backward(cuda_device):
     got_a = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
     lb.backward()  # accumulates
     for n, p in model.named_parameters():
-        assert torch.allclose(got_a[n], ga[n], rtol=1e-4, atol=1e-6), n
-        assert torch.allclose(p.grad, ga[n] + gb[n], rtol=1e-3, atol=1e-5), n
+        # (weight gradients are sums over up to 1e5 positions accumulated with fp32 atomics: two runs of the same
+        #  backward differ by the summation order; a backward through the WRONG forward's activations differs by O(1))
+        scale = ga[n].abs().max().item() + 1e-6
+        assert (got_a[n] - ga[n]).abs().max().item() <= 1e-3 * scale, n
+        assert (p.grad - (ga[n] + gb[n])).abs().max().item() <= 2e-3 * scale, n
     with pytest.raises(RuntimeError):
         la.backward()  # a graph can be back-propagated once
     assert w.grad is not None
