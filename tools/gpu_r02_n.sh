@@ -1,7 +1,10 @@
 #!/bin/bash
-# fixed cost of a stream-kernel launch: CTA-0 milestones and CTA exit spread on small layers (debug build)
-for a in "--cin 64 --cout 64 --L 9600" "--cin 64 --cout 64 --L 38400" "--cin 128 --cout 128 --L 9600" "--cin 16 --cout 16 --stride 2 --L 153600" "--cin 32 --cout 32 --L 38400"; do
-  echo "== profile_conv $a"
-  W2S_LIB_VARIANT=dbg W2S_DEBUG_FLAGS=64 python tools/profile_conv.py $a --iters 5 2>&1 | cut -c1-400
-done
-W2S_LIB_VARIANT=ring timeout 300 python -m pytest tests/test_forward_gpu.py -m gpu -x -q -k eog -s 2>&1 | grep -E "EOG wide|passed|failed"
+# ncu --set full of every launch of the dominant kernel FUNCTION of the step (the 16-channel stride-2 stream kernel, 8
+# launches per step) for profiles/traffic.json
+mkdir -p gpurun_out
+NCU="ncu --clock-control none --profile-from-start off"
+timeout 500 $NCU --set full --kernel-name-base demangled -k 'regex:conv_stream_kernel<\(int\)16, \(int\)16, \(int\)2,' -c 8 \
+   -o gpurun_out/r02_c16s2 python tools/profile_step.py infer 16 > gpurun_out/ncu_c16s2.log 2>&1
+tail -1 gpurun_out/ncu_c16s2.log
+ncu -i gpurun_out/r02_c16s2.ncu-rep --page raw --csv > gpurun_out/r02_c16s2.csv 2>/dev/null
+rm -f gpurun_out/r02_c16s2.ncu-rep; ls -la gpurun_out/r02_c16s2.csv
