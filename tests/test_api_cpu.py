@@ -107,3 +107,53 @@ def test_hostmem_binding_is_placement_only():
             assert n == 0 and after == before
     finally:
         os.sched_setaffinity(0, before)
+
+
+def test_encoder_pairing_rules():
+    """Host logic of the paired encoder launches (engine._enc_groups): signals are paired when their encoders have the
+    same architecture and their inputs the same length; the longest chains come first; in the default mode pairs are
+    formed only while at least two launch chains remain (the two-signal EOG model keeps one chain per signal)."""
+    import types
+    import torch
+    from wav2sleep_b200 import _lib
+    from wav2sleep_b200.engine import ForwardEngine
+
+    def desc(channels, wide=0):
+        d = _lib.EncoderDesc()
+        d.n_blocks, d.feature_dim, d.norm_eps, d.wide_blocks = len(channels), 128, 1e-2, wide
+        for i, c in enumerate(channels):
+            d.channels[i] = c
+        return d
+
+    hi, lo = [16, 16, 32, 32, 64, 64, 128, 128], [16, 16, 32, 32, 64, 64]
+
+    def stub(smap, descs, mode):
+        model = types.SimpleNamespace(signal_encoders=types.SimpleNamespace(signal_map=smap))
+        return types.SimpleNamespace(enc_pairs=mode, model=model,
+                                     enc={k: types.SimpleNamespace(desc=d) for k, d in descs.items()})
+
+    groups = ForwardEngine._enc_groups
+    smap = {n: n for n in ("ABD", "THX", "ECG", "PPG")}
+    descs = {"ABD": desc(lo), "THX": desc(lo), "ECG": desc(hi), "PPG": desc(hi)}
+    xs = {"ABD": torch.empty(2, 256 * 8), "THX": torch.empty(2, 256 * 8), "ECG": torch.empty(2, 1024 * 8),
+          "PPG": torch.empty(2, 1024 * 8)}
+    names = sorted(xs)
+    assert groups(stub(smap, descs, 1), names, xs, True) == [("ECG", "PPG"), ("ABD", "THX")]
+    assert groups(stub(smap, descs, 0), names, xs, True) == [("ECG",), ("PPG",), ("ABD",), ("THX",)]
+    assert groups(stub(smap, descs, 1), names, xs, False) == [("ECG",), ("PPG",), ("ABD",), ("THX",)]
+    assert groups(stub(smap, descs, 3), names, xs, True) == [("ECG",), ("PPG",), ("ABD", "THX")]
+    # a different architecture (wide storage) or input length is never paired
+    odd = dict(descs, PPG=desc(hi, wide=2))
+    assert groups(stub(smap, odd, 1), names, xs, True) == [("ECG",), ("PPG",), ("ABD", "THX")]
+    # three signals: one pair + one single = two chains
+    three = {k: xs[k] for k in ("ABD", "ECG", "PPG")}
+    assert groups(stub(smap, descs, 1), sorted(three), three, True) == [("ECG", "PPG"), ("ABD",)]
+    # two signals of one architecture: default keeps two chains, mode 2 pairs
+    eog = {"EOG-L": "EOG-L", "EOG-R": "EOG-R"}
+    de = {k: desc(hi + [128, 128], wide=6) for k in eog}
+    xe = {k: torch.empty(1, 4096 * 4) for k in eog}
+    assert groups(stub(eog, de, 1), sorted(xe), xe, True) == [("EOG-L",), ("EOG-R",)]
+    assert groups(stub(eog, de, 2), sorted(xe), xe, True) == [("EOG-L", "EOG-R")]
+    # two signals sharing ONE encoder (same weights) may be paired too
+    shared = {"EOG-L": "EOG", "EOG-R": "EOG"}
+    assert groups(stub(shared, {"EOG": de["EOG-L"]}, 2), sorted(xe), xe, True) == [("EOG-L", "EOG-R")]
