@@ -243,8 +243,8 @@ static bool conv_calls_pairable(const w2s_conv_call& a, const w2s_conv_call& b) 
   return a.cin == b.cin && a.cout == b.cout && a.taps == b.taps && a.stride == b.stride && a.dilation == b.dilation &&
          a.pad == b.pad && a.prologue == b.prologue && a.epilogue == b.epilogue && a.has_ds == b.has_ds && a.B == b.B &&
          a.L_in == b.L_in && a.L_out == b.L_out && a.in_wide == b.in_wide && a.out_wide == b.out_wide &&
-         a.force_split == b.force_split && a.T_raw == b.T_raw && a.in_eps == b.in_eps && a.epilogue == W2S_EPI_STATS &&
-         (a.row_mask != nullptr) == (b.row_mask != nullptr) && stream_pairable(a.cout, a.has_ds != 0);
+         a.force_split == b.force_split && a.T_raw == b.T_raw && a.in_eps == b.in_eps &&
+         (a.row_mask != nullptr) == (b.row_mask != nullptr) && (a.bias != nullptr) == (b.bias != nullptr);
 }
 
 int conv_dispatch(const w2s_conv_call& c, cudaStream_t st, const w2s_conv_call* c2 = nullptr) {
@@ -299,7 +299,13 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st, const w2s_conv_call* 
   // a pair whose shape has no stream kernel is not launched here (checked before the launch is counted / timed)
   const bool stream_shape = c.epilogue == W2S_EPI_STATS && c.taps == 3 && c.dilation == 1 && c.pad == 1 && impl == 0 &&
                             ((c.stride == 1 && c.L_out == c.L_in) || (c.stride == 2 && c.L_out == (c.L_in + 1) / 2));
-  if (c2 != nullptr && !stream_shape) return kNotPaired;
+  // the encoder Linear (4-tap stride-4 conv + bias + GELU, tile-per-CTA kernel): paired through blockIdx.z
+  const bool linear_shape = c.epilogue == W2S_EPI_BIAS_GELU && c.taps == 4 && c.stride == 4 && c.dilation == 1 && c.pad == 0 &&
+                            c.prologue == W2S_PRO_NORM_RES && !c.has_ds && impl == 0 && c.cout == 128 &&
+                            (c.cin == 64 || c.cin == 128) && !c.in_wide && !c.out_wide && !c.force_split;
+  static const bool pair_linear = [] { const char* e = getenv("W2S_PAIR_LINEAR"); return !e || atoi(e) != 0; }();
+  if (c2 != nullptr && !((stream_shape && stream_pairable(c.cout, c.has_ds != 0)) || (linear_shape && pair_linear)))
+    return kNotPaired;
   LaunchScope scope(st, label, npair * (in_b + out_b + ab_b), npair * fl);
   if (stream_shape) {
     const int sms = sm_count();
@@ -377,6 +383,11 @@ int conv_dispatch(const w2s_conv_call& c, cudaStream_t st, const w2s_conv_call* 
       if (e != cudaSuccess) return cuda_fail(e, "conv_stream launch");
       return 0;
     }
+  }
+  if (c2 != nullptr && linear_shape && pair_linear) {
+    e = c.cin == 64 ? launch_conv_igemm_pair<64, 128, 4, 4, PRO_NORM_RES, EPI_BIAS_GELU, false>(a, a2s, c.B, st)
+                    : launch_conv_igemm_pair<128, 128, 4, 2, PRO_NORM_RES, EPI_BIAS_GELU, false>(a, a2s, c.B, st);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "conv_igemm pair launch");
   }
   if (c2 != nullptr) return kNotPaired;  // no stream kernel for this configuration: the caller dispatches the two calls singly
   if (impl == 3) {  // bf16 operands on the tile-per-CTA kernel: un-split encoder convs without the 1x1 branch only
@@ -809,24 +820,31 @@ static int encoder_plan(const w2s_encoder_desc* d, const float* x, int B, int64_
   return 0;
 }
 
+// closed-form block-0 statistics of one signal, or of two signals of equal shape in the same two launches
+static int run_x_stats(const EncStep& s, const EncStep* s2, cudaStream_t st) {
+  const int n = s2 != nullptr ? 2 : 1;
+  {
+    LaunchScope scope(st, s2 != nullptr ? "x_stats x2" : "x_stats", n * (double)s.B * s.L * 4.0, n * (double)s.B * s.L * 8.0);
+    int gx = (s.L / 4 + 255) / 256;
+    const int cap = (4 * sm_count() + n * s.B - 1) / (n * s.B);  // ~4 long-lived blocks per SM over the whole batch
+    if (gx > cap) gx = cap;
+    const EncStep& t = s2 != nullptr ? *s2 : s;
+    const XFinalizeArgs f0 = {s.x, s.xs, s.w_first, s.row_mask, s.s1}, f1 = {t.x, t.xs, t.w_first, t.row_mask, t.s1};
+    x_stats_kernel<<<dim3(gx < 1 ? 1 : gx, s.B, n), 256, 0, st>>>(s.xa, t.xa);
+    x_stats_finalize_kernel<<<dim3((s.B * 16 + 127) / 128, n), 128, 0, st>>>(f0, f1, s.B, s.L);
+  }
+  cudaError_t ce = cudaGetLastError();
+  return ce == cudaSuccess ? 0 : cuda_fail(ce, "x_stats launch");
+}
+
 static int run_enc_step(const EncStep& s, cudaStream_t st) {
   switch (s.kind) {
     case EncStep::MEMSET: {
       cudaError_t ce = cudaMemsetAsync(s.ptr, 0, s.bytes, st);
       return ce == cudaSuccess ? 0 : cuda_fail(ce, "encoder memset");
     }
-    case EncStep::XSTATS: {
-      {
-        LaunchScope scope(st, "x_stats", (double)s.B * s.L * 4.0, (double)s.B * s.L * 8.0);
-        int gx = (s.L / 4 + 255) / 256;
-        const int cap = (4 * sm_count() + s.B - 1) / s.B;  // ~4 long-lived blocks per SM over the whole batch
-        if (gx > cap) gx = cap;
-        x_stats_kernel<<<dim3(gx < 1 ? 1 : gx, s.B), 256, 0, st>>>(s.xa);
-        x_stats_finalize_kernel<<<(s.B * 16 + 127) / 128, 128, 0, st>>>(s.x, s.xs, s.w_first, s.row_mask, s.s1, s.B, s.L);
-      }
-      cudaError_t ce = cudaGetLastError();
-      return ce == cudaSuccess ? 0 : cuda_fail(ce, "x_stats launch");
-    }
+    case EncStep::XSTATS:
+      return run_x_stats(s, nullptr, st);
     case EncStep::FIRST: {
       cudaError_t ce;
       {
@@ -873,6 +891,11 @@ int w2s_encoder_fwd_pair(const w2s_encoder_desc* d0, const float* x0, void* work
       const int rc = conv_dispatch(p0[i].cc, st, &p1[i].cc);
       if (rc == 0) continue;
       if (rc != kNotPaired) return 1;
+    }
+    static const bool pair_xstats = [] { const char* e = getenv("W2S_PAIR_XSTATS"); return !e || atoi(e) != 0; }();
+    if (pair_xstats && p0[i].kind == EncStep::XSTATS && p0[i].B == p1[i].B && p0[i].L == p1[i].L) {
+      if (run_x_stats(p0[i], &p1[i], st) != 0) return 1;
+      continue;
     }
     if (run_enc_step(p0[i], st) != 0 || run_enc_step(p1[i], st) != 0) return 1;
   }

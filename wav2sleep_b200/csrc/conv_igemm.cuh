@@ -33,6 +33,7 @@
 //   GEMM that follows.  dn_upsample: the layer was a stride-2 conv - its gradient enters the (stride-1) data-gradient
 //   conv zero-stuffed: input row i = source row i / 2 for even i, zero for odd i.
 #pragma once
+#include <cstring>
 #include "common.cuh"
 
 namespace w2s {
@@ -91,6 +92,42 @@ struct ConvArgs {
   int debug_flags;
 };
 
+// Paired launch: two encoders with identical layer shapes (ECG + PPG, ABD + THX) run a layer in ONE launch - the first
+// half of the grid works on group 0, the second half on group 1.  Only the tensors differ between the groups: the second
+// group's pointers ride in this block (ngroups == 1: ignored), every scalar of ConvArgs is shared.  Halves the number of
+// stream-kernel launches of a forward and with it the per-launch fixed cost (set-up, pipeline fill, drain, exit spread:
+// ~8 us of every CTA's life, profiles/r02_fixed_cost_small_layers.txt), and gives each CTA twice the tiles per launch.
+struct ConvGroup2 {
+  const act_t* in;
+  const act_t* in_res;
+  const double* in_stats;
+  const act_t* w;
+  const act_t* w_ds;
+  act_t* out;
+  act_t* out_ds;
+  double* out_stats;
+  const uint8_t* row_mask;
+  const float* x_raw;
+  const float* w_first;
+  const float* w_first_ds;
+  int ngroups;
+};
+// Kernels that are already at their register cap stay single-group (the second group's pointers would be selected into
+// registers: 72 -> 330 bytes of spills in the staged two-accumulator epilogue of the 128-channel conv1 kernels).
+__host__ __device__ constexpr bool stream_pairable(int cout, bool has_ds) { return !(cout == 128 && has_ds); }
+inline ConvGroup2 conv_group2(const ConvArgs* a) {
+  ConvGroup2 g;
+  memset(&g, 0, sizeof(g));
+  g.ngroups = 1;
+  if (a != nullptr) {
+    g.in = a->in; g.in_res = a->in_res; g.in_stats = a->in_stats; g.w = a->w; g.w_ds = a->w_ds;
+    g.out = a->out; g.out_ds = a->out_ds; g.out_stats = a->out_stats; g.row_mask = a->row_mask;
+    g.x_raw = a->x_raw; g.w_first = a->w_first; g.w_first_ds = a->w_first_ds;
+    g.ngroups = 2;
+  }
+  return g;
+}
+
 constexpr int kConvThreads = 256;
 
 template <int COUT>
@@ -127,7 +164,7 @@ __host__ __device__ inline size_t conv_smem_bytes(int stride, int taps, int dil)
 // Storage stays fp16.  Evidence for the fp16-over-bf16 decision on the hardware itself (tests/test_kernels_gpu.py).
 template <int CIN, int COUT, int TAPS, int GT /*taps resident per weight group*/, int PRO, int EPI, bool HAS_DS,
           bool SPLIT, bool BF16OP = false>
-__global__ void __launch_bounds__(kConvThreads, (EPI == EPI_ACT_BWD && COUT <= 64) ? 3 : 1) conv_igemm_kernel(const ConvArgs p) {
+W2S_DEVINL void conv_igemm_body(const ConvArgs& p, const int b) {
   static_assert(!BF16OP || (!SPLIT && PRO != PRO_NONE), "bf16 operands: computed prologue, single operand");
   static_assert(!SPLIT || (GT == TAPS && PRO != PRO_NONE), "split operands: single weight group, computed prologue");
   static_assert(CIN % 16 == 0 && COUT % 16 == 0 && COUT <= 128, "UMMA shape");
@@ -141,7 +178,6 @@ __global__ void __launch_bounds__(kConvThreads, (EPI == EPI_ACT_BWD && COUT <= 6
   constexpr uint32_t TMEM_COLS = HAS_DS ? 256 : 128;
   constexpr uint32_t IDESC = umma_idesc_f16(128, COUT, BF16OP);
 
-  const int b = blockIdx.y;
   if (p.row_mask != nullptr && p.row_mask[b]) return;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -682,6 +718,38 @@ __global__ void __launch_bounds__(kConvThreads, (EPI == EPI_ACT_BWD && COUT <= 6
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int CIN, int COUT, int TAPS, int GT, int PRO, int EPI, bool HAS_DS, bool SPLIT, bool BF16OP = false>
+__global__ void __launch_bounds__(kConvThreads, (EPI == EPI_ACT_BWD && COUT <= 64) ? 3 : 1) conv_igemm_kernel(const ConvArgs p) {
+  conv_igemm_body<CIN, COUT, TAPS, GT, PRO, EPI, HAS_DS, SPLIT, BF16OP>(p, (int)blockIdx.y);
+}
+// The same tile program for two argument sets in one grid (blockIdx.z selects): the encoder Linear of two encoders of
+// identical architecture (w2s_encoder_fwd_pair).  Instantiated for those configurations only.
+template <int CIN, int COUT, int TAPS, int GT, int PRO, int EPI, bool HAS_DS, bool SPLIT>
+__global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_pair_kernel(const ConvArgs pa, const ConvArgs pb) {
+  // two copies of the tile program, each reading its own argument block straight from the parameter space (selecting
+  // single pointers into a local ConvArgs instead lost the override of `in` in the generated code: the second
+  // encoder's Linear read the first encoder's activations - caught by the paired-vs-single parity test)
+  if (blockIdx.z != 0) conv_igemm_body<CIN, COUT, TAPS, GT, PRO, EPI, HAS_DS, SPLIT, false>(pb, (int)blockIdx.y);
+  else conv_igemm_body<CIN, COUT, TAPS, GT, PRO, EPI, HAS_DS, SPLIT, false>(pa, (int)blockIdx.y);
+}
+
+template <int CIN, int COUT, int TAPS, int GT, int PRO, int EPI, bool HAS_DS>
+inline cudaError_t launch_conv_igemm_pair(const ConvArgs& a, const ConvArgs& a2, int B, cudaStream_t stream) {
+  constexpr bool SPLIT = ConvSplit<CIN, COUT>::value && EPI == EPI_STATS;
+  auto kern = conv_igemm_pair_kernel<CIN, COUT, TAPS, GT, PRO, EPI, HAS_DS, SPLIT>;
+  const int stride = 1 << a.stride_log2;
+  const size_t smem = conv_smem_bytes<CIN, COUT, GT, HAS_DS, SPLIT>(stride, TAPS, a.dil);
+  static size_t configured = 0;  // per instantiation
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  dim3 grid((a.L_out + ConvTile<COUT>::POS - 1) / ConvTile<COUT>::POS, B, 2);
+  kern<<<grid, kConvThreads, smem, stream>>>(a, a2);
+  return cudaGetLastError();
 }
 
 // Host-side launcher.  Returns cudaError_t of the launch.

@@ -59,42 +59,6 @@ struct WaitClock {
   }
 };
 
-// Paired launch: two encoders with identical layer shapes (ECG + PPG, ABD + THX) run a layer in ONE launch - the first
-// half of the grid works on group 0, the second half on group 1.  Only the tensors differ between the groups: the second
-// group's pointers ride in this block (ngroups == 1: ignored), every scalar of ConvArgs is shared.  Halves the number of
-// stream-kernel launches of a forward and with it the per-launch fixed cost (set-up, pipeline fill, drain, exit spread:
-// ~8 us of every CTA's life, profiles/r02_fixed_cost_small_layers.txt), and gives each CTA twice the tiles per launch.
-struct ConvGroup2 {
-  const act_t* in;
-  const act_t* in_res;
-  const double* in_stats;
-  const act_t* w;
-  const act_t* w_ds;
-  act_t* out;
-  act_t* out_ds;
-  double* out_stats;
-  const uint8_t* row_mask;
-  const float* x_raw;
-  const float* w_first;
-  const float* w_first_ds;
-  int ngroups;
-};
-// Kernels that are already at their register cap stay single-group (the second group's pointers would be selected into
-// registers: 72 -> 330 bytes of spills in the staged two-accumulator epilogue of the 128-channel conv1 kernels).
-__host__ __device__ constexpr bool stream_pairable(int cout, bool has_ds) { return !(cout == 128 && has_ds); }
-inline ConvGroup2 conv_group2(const ConvArgs* a) {
-  ConvGroup2 g;
-  memset(&g, 0, sizeof(g));
-  g.ngroups = 1;
-  if (a != nullptr) {
-    g.in = a->in; g.in_res = a->in_res; g.in_stats = a->in_stats; g.w = a->w; g.w_ds = a->w_ds;
-    g.out = a->out; g.out_ds = a->out_ds; g.out_stats = a->out_stats; g.row_mask = a->row_mask;
-    g.x_raw = a->x_raw; g.w_first = a->w_first; g.w_first_ds = a->w_first_ds;
-    g.ngroups = 2;
-  }
-  return g;
-}
-
 // warp 0 producer, 1 MMA, 2..2+E-1 epilogue, then transform.  E = 4 or 8: with 8, two warps share each TMEM lane
 // quadrant (a warp may only read the quadrant warp_id % 4) and split the (column group, sub-tile) items.  Measured for
 // COUT >= 64, where the epilogue is the busiest stage (93 %): no gain from 8 warps, and none from software-pipelining

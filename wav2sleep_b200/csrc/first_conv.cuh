@@ -106,7 +106,9 @@ struct XStatsArgs {
   uint8_t* row_mask;  // [B]
   int T;
 };
-__global__ void __launch_bounds__(256) x_stats_kernel(const XStatsArgs p) {
+// (blockIdx.z selects the argument set: two signals of equal length in one launch, w2s_encoder_fwd_pair)
+__global__ void __launch_bounds__(256) x_stats_kernel(const XStatsArgs p0, const XStatsArgs p1) {
+  const XStatsArgs p = blockIdx.z ? p1 : p0;
   const int b = blockIdx.y;
   const float* xb = p.x + (size_t)b * p.T;
   const bool masked = isinf(__ldg(xb));
@@ -150,8 +152,20 @@ __global__ void __launch_bounds__(256) x_stats_kernel(const XStatsArgs p) {
   }
 }
 // stats1[b, c] = (sum y_c, sum y_c^2) from the four sums; one thread per (b, c)
-__global__ void x_stats_finalize_kernel(const float* x, const double* xs, const float* w, const uint8_t* row_mask,
-                                        double* stats1, int B, int T) {
+struct XFinalizeArgs {
+  const float* x;
+  const double* xs;
+  const float* w;
+  const uint8_t* row_mask;
+  double* stats1;
+};
+__global__ void x_stats_finalize_kernel(const XFinalizeArgs f0, const XFinalizeArgs f1, int B, int T) {
+  const XFinalizeArgs f = blockIdx.y ? f1 : f0;
+  const float* x = f.x;
+  const double* xs = f.xs;
+  const float* w = f.w;
+  const uint8_t* row_mask = f.row_mask;
+  double* stats1 = f.stats1;
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= B * 16) return;
   const int b = id / 16, c = id % 16;
